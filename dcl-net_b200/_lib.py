@@ -1,0 +1,86 @@
+"""ctypes binding of libdcl_b200.so (C-ABI: include/dcl_b200.h).  Fails loudly."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcl_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dcl_b200.h")
+
+_I, _F, _P, _SZ, _I64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
+
+# name -> (restype, argtypes); must list every function include/dcl_b200.h declares
+SIGNATURES = {
+    "dcl_b200_abi_version": (_I, []),
+    "dcl_b200_arch": (_I, []),
+    "dcl_lib_furthest_point_sampling_kernel_launcher": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "dcl_lib_gather_points_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "dcl_lib_gather_points_grad_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "dcl_lib_ball_query_kernel_launcher_fast": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P]),
+    "dcl_lib_group_points_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "dcl_lib_group_points_grad_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "dcl_lib_three_nn_kernel_launcher_fast": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_lib_knn_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_lib_three_interpolate_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_lib_three_interpolate_grad_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_sp_three_nn_kernel_launcher_fast": (_I, [_I, _I, _P, _P, _P, _P, _P]),
+    "dcl_sp_three_nn_workspace_bytes": (_SZ, [_I, _I]),
+    "dcl_sp_three_nn_segmented": (_I, [_I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_sp_three_interpolate_kernel_launcher_fast": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_sp_three_interpolate_grad_kernel_launcher_fast": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_sp_nn_interpolate_fused": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "dcl_fda_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "dcl_fda_align_fwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_attention_map": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
+    "dcl_weighted_kabsch": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    "dcl_pose_compose": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no CUDA needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C dcl-net_b200/csrc`).  dcl_net_b200 has no CPU / PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if lib.dcl_b200_abi_version() != 1:
+            raise RuntimeError("libdcl_b200.so ABI version mismatch with dcl_net_b200/_lib.py")
+        _lib = lib
+    return _lib
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor that must already be a contiguous CUDA tensor."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("dcl_net_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("dcl_net_b200 ops need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def check(err, what):
+    if err != 0:
+        raise RuntimeError(f"{what} failed: cudaError {err}")
+
+
+def require(t, dtype, what):
+    if t.dtype != dtype:
+        raise TypeError(f"{what}: expected {dtype}, got {t.dtype}")
+    return t

@@ -1,0 +1,475 @@
+// Flat, batch-id-aware three_nn / three_interpolate — the variants DCL-Net's
+// Network.forward actually calls (models/Modules.py:213-251).
+// Semantics: libs/pointnet_sp/src/interpolate_gpu.cu:9-56 (three_nn),
+//            :80-102 (three_interpolate), :124-146 (grad).
+//
+// three_nn in the reference is O(n*m): every query scans every known row and skips
+// the ones whose batch id differs.  Two implementations here, bit-identical:
+//  * full scan (reference signature, no scratch): known rows streamed through shared
+//    memory by TMA bulk copies;
+//  * segmented (caller-provided scratch): known rows are bucketed by batch id on the
+//    device (histogram -> scan -> scatter), each query scans only its bucket.  The
+//    scatter is not order-preserving, so candidates are ranked by the explicit
+//    lexicographic key (d, original index) — which is exactly the order the
+//    reference's ascending scan with strict '<' produces.
+// three_interpolate uses one lane per 4 channels of a row so that both the three
+// feature-row reads and the output write are coalesced 128-bit accesses (the
+// reference strides by C between lanes).
+#include "common.cuh"
+#include "tile_pipe.cuh"
+#include "../../include/dcl_b200.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int SP_THREADS = 128;
+constexpr int SP_TILE_ROWS = 1024;  // 16 KB per stage
+constexpr int SP_TILE_FLOATS = SP_TILE_ROWS * 4;
+
+__device__ __forceinline__ void nn3_insert_strict(float d, int k, float& b1, float& b2, float& b3, int& i1, int& i2,
+                                                  int& i3) {
+    if (d < b3) {
+        if (d < b2) {
+            b3 = b2;
+            i3 = i2;
+            if (d < b1) {
+                b2 = b1;
+                i2 = i1;
+                b1 = d;
+                i1 = k;
+            } else {
+                b2 = d;
+                i2 = k;
+            }
+        } else {
+            b3 = d;
+            i3 = k;
+        }
+    }
+}
+
+// (d,k) < (b,i) lexicographically
+__device__ __forceinline__ bool lex_lt(float d, int k, float b, int i) { return d < b || (d == b && k < i); }
+
+__device__ __forceinline__ void nn3_insert_lex(float d, int k, float& b1, float& b2, float& b3, int& i1, int& i2,
+                                               int& i3) {
+    if (lex_lt(d, k, b3, i3)) {
+        if (lex_lt(d, k, b2, i2)) {
+            b3 = b2;
+            i3 = i2;
+            if (lex_lt(d, k, b1, i1)) {
+                b2 = b1;
+                i2 = i1;
+                b1 = d;
+                i1 = k;
+            } else {
+                b2 = d;
+                i2 = k;
+            }
+        } else {
+            b3 = d;
+            i3 = k;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- full scan
+__global__ void __launch_bounds__(SP_THREADS) sp_three_nn_scan_kernel(int n, int m, const float* __restrict__ unknown,
+                                                                      const float* __restrict__ known,
+                                                                      float* __restrict__ dist2,
+                                                                      int* __restrict__ idx) {
+    __shared__ __align__(16) float s_tile[2 * SP_TILE_FLOATS];
+    __shared__ uint64_t s_bar[2];
+    const int qi = blockIdx.x * SP_THREADS + threadIdx.x;
+    const int qc = min(qi, n - 1);
+    const float4 u = reinterpret_cast<const float4*>(unknown)[qc];
+    float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+    int i1 = 0, i2 = 0, i3 = 0;
+    DclTilePipe<SP_TILE_FLOATS> pipe;
+    pipe.init(s_tile, s_bar, known, m * 4);
+    for (int t = 0; t < pipe.ntiles; ++t) {
+        const int cnt = pipe.acquire(t) / 4;
+        const float4* tile = reinterpret_cast<const float4*>(pipe.tile(t));
+        const int kbase = t * SP_TILE_ROWS;
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const float4 k4 = tile[j];
+            if (k4.x != u.x) continue;
+            const float d = dcl_dist2(u.y, u.z, u.w, k4.y, k4.z, k4.w);
+            nn3_insert_strict(d, kbase + j, b1, b2, b3, i1, i2, i3);
+        }
+        pipe.release(t);
+    }
+    if (qi < n) {
+        dist2[qi * 3 + 0] = b1;
+        dist2[qi * 3 + 1] = b2;
+        dist2[qi * 3 + 2] = b3;
+        idx[qi * 3 + 0] = i1;
+        idx[qi * 3 + 1] = i2;
+        idx[qi * 3 + 2] = i3;
+    }
+}
+
+// ---------------------------------------------------------------- segmented
+// Workspace layout (ints unless noted):
+//   [0]              flag: 1 if some known batch id is not an integer in [0, MAXB)
+//   [1]              max batch id seen (+1), i.e. number of buckets in use
+//   [4 .. 4+MAXB]    bucket offsets (MAXB+1 entries; counts before the scan)
+//   [.. +MAXB]       scatter cursors
+//   then 16-B aligned float4 sorted[m] = (x, y, z, bits(original index))
+constexpr int WS_FLAG = 0, WS_NB = 1, WS_OFF = 4;
+constexpr int WS_CUR = WS_OFF + DCL_SP_MAX_BATCH + 4;
+constexpr int WS_HDR_INTS = WS_CUR + DCL_SP_MAX_BATCH;  // multiple of 4 -> sorted[] is 16-B aligned
+
+__device__ __forceinline__ bool batch_id_ok(float b, int& ib) {
+    ib = (int)b;
+    return (b == (float)ib) && ib >= 0 && ib < DCL_SP_MAX_BATCH;
+}
+
+__global__ void sp_bucket_hist_kernel(int m, const float* __restrict__ known, int* __restrict__ ws) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    int ib;
+    if (batch_id_ok(known[k * 4], ib)) {
+        atomicAdd(ws + WS_OFF + ib, 1);
+        atomicMax(ws + WS_NB, ib + 1);
+    } else {
+        atomicOr(ws + WS_FLAG, 1);
+    }
+}
+
+// Single CTA: exclusive scan of the bucket counts in place; off[nb] = total.
+__global__ void __launch_bounds__(1024) sp_bucket_scan_kernel(int* __restrict__ ws) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int nb = ws[WS_NB];
+    int* off = ws + WS_OFF;
+    int* cur = ws + WS_CUR;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nb) ? off[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int warp_prefix = (threadIdx.x >= 32) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int incl = x + warp_prefix + s_carry;
+        if (i < nb) {
+            off[i] = incl - v;
+            cur[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[nb] = s_carry;
+}
+
+__global__ void sp_bucket_scatter_kernel(int m, const float* __restrict__ known, int* __restrict__ ws,
+                                         float4* __restrict__ sorted) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const float4 r = reinterpret_cast<const float4*>(known)[k];
+    int ib;
+    if (!batch_id_ok(r.x, ib)) return;
+    const int pos = ws[WS_OFF + ib] + atomicAdd(ws + WS_CUR + ib, 1);
+    sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
+}
+
+// Per-lane 3-NN over the lane's own bucket; a warp walks the distinct batch ids
+// present among its lanes so that every candidate load is a warp-uniform broadcast.
+__device__ __forceinline__ void sp_segmented_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
+                                                    const float4* __restrict__ known4, int m, bool valid, float4 u,
+                                                    float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+    b1 = b2 = b3 = CUDART_INF_F;
+    i1 = i2 = i3 = 0;
+    if (ws[WS_FLAG] != 0) {
+        // Some batch id is not a small non-negative integer: buckets are unusable, do the
+        // reference's full ascending scan (float equality on the id) straight from global.
+        for (int k = 0; k < m; ++k) {
+            const float4 c = __ldg(known4 + k);
+            if (c.x != u.x) continue;
+            const float d = dcl_dist2(u.y, u.z, u.w, c.y, c.z, c.w);
+            nn3_insert_strict(d, k, b1, b2, b3, i1, i2, i3);
+        }
+        return;
+    }
+    int my_b;
+    const int nb = ws[WS_NB];
+    const bool has_bucket = valid && batch_id_ok(u.x, my_b) && my_b < nb;
+    unsigned todo = __ballot_sync(0xffffffffu, has_bucket);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int bid = __shfl_sync(0xffffffffu, my_b, leader);
+        const bool mine = has_bucket && (my_b == bid);
+        const int beg = ws[WS_OFF + bid], end = ws[WS_OFF + bid + 1];
+#pragma unroll 4
+        for (int j = beg; j < end; ++j) {
+            const float4 c = __ldg(sorted + j);
+            if (mine) {
+                const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
+                nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+            }
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int m, const float* __restrict__ unknown,
+                                                                     const float* __restrict__ known,
+                                                                     const int* __restrict__ ws,
+                                                                     const float4* __restrict__ sorted,
+                                                                     float* __restrict__ dist2,
+                                                                     int* __restrict__ idx) {
+    const int qi = blockIdx.x * SP_THREADS + threadIdx.x;
+    const bool valid = qi < n;
+    const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
+    float b1, b2, b3;
+    int i1, i2, i3;
+    sp_segmented_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, b1, b2, b3, i1, i2, i3);
+    if (valid) {
+        dist2[qi * 3 + 0] = b1;
+        dist2[qi * 3 + 1] = b2;
+        dist2[qi * 3 + 2] = b3;
+        idx[qi * 3 + 0] = i1;
+        idx[qi * 3 + 1] = i2;
+        idx[qi * 3 + 2] = i3;
+    }
+}
+
+// ------------------------------------------------------------ interpolation
+// out[i, c] = fma(w2,f2, fma(w0,f0, w1*f1)); one thread per (row, 4 channels).
+__global__ void __launch_bounds__(256) sp_interp_v4_kernel(int c4, int n, const float4* __restrict__ points,
+                                                           const int* __restrict__ idx,
+                                                           const float* __restrict__ weight,
+                                                           float4* __restrict__ out) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)n * c4) return;
+    const int i = (int)(g / c4), cc = (int)(g - (long)i * c4);
+    const int j0 = __ldg(idx + i * 3), j1 = __ldg(idx + i * 3 + 1), j2 = __ldg(idx + i * 3 + 2);
+    const float w0 = __ldg(weight + i * 3), w1 = __ldg(weight + i * 3 + 1), w2 = __ldg(weight + i * 3 + 2);
+    const float4 f0 = __ldg(points + (size_t)j0 * c4 + cc);
+    const float4 f1 = __ldg(points + (size_t)j1 * c4 + cc);
+    const float4 f2 = __ldg(points + (size_t)j2 * c4 + cc);
+    float4 o;
+    o.x = dcl_interp3(w0, f0.x, w1, f1.x, w2, f2.x);
+    o.y = dcl_interp3(w0, f0.y, w1, f1.y, w2, f2.y);
+    o.z = dcl_interp3(w0, f0.z, w1, f1.z, w2, f2.z);
+    o.w = dcl_interp3(w0, f0.w, w1, f1.w, w2, f2.w);
+    out[(size_t)i * c4 + cc] = o;
+}
+
+__global__ void __launch_bounds__(256) sp_interp_v1_kernel(int c, int n, const float* __restrict__ points,
+                                                           const int* __restrict__ idx,
+                                                           const float* __restrict__ weight,
+                                                           float* __restrict__ out) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)n * c) return;
+    const int i = (int)(g / c), cc = (int)(g - (long)i * c);
+    const int j0 = idx[i * 3], j1 = idx[i * 3 + 1], j2 = idx[i * 3 + 2];
+    out[(size_t)i * c + cc] =
+        dcl_interp3(weight[i * 3], points[(size_t)j0 * c + cc], weight[i * 3 + 1], points[(size_t)j1 * c + cc],
+                    weight[i * 3 + 2], points[(size_t)j2 * c + cc]);
+}
+
+// grad_points[idx[i,j], c] += grad_out[i, c] * w[i, j]
+__global__ void __launch_bounds__(256) sp_interp_grad_v4_kernel(int c4, int n, const float4* __restrict__ grad_out,
+                                                                const int* __restrict__ idx,
+                                                                const float* __restrict__ weight,
+                                                                float4* __restrict__ grad_points) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)n * c4) return;
+    const int i = (int)(g / c4), cc = (int)(g - (long)i * c4);
+    const float4 go = __ldg(grad_out + (size_t)i * c4 + cc);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int r = __ldg(idx + i * 3 + j);
+        const float w = __ldg(weight + i * 3 + j);
+        const float4 v = make_float4(__fmul_rn(go.x, w), __fmul_rn(go.y, w), __fmul_rn(go.z, w), __fmul_rn(go.w, w));
+        atomicAdd(grad_points + (size_t)r * c4 + cc, v);  // red.global.add.v4.f32 (sm_90+)
+    }
+}
+
+__global__ void __launch_bounds__(256) sp_interp_grad_v1_kernel(int c, int n, const float* __restrict__ grad_out,
+                                                                const int* __restrict__ idx,
+                                                                const float* __restrict__ weight,
+                                                                float* __restrict__ grad_points) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)n * c) return;
+    const int i = (int)(g / c), cc = (int)(g - (long)i * c);
+    const float go = grad_out[(size_t)i * c + cc];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        atomicAdd(grad_points + (size_t)idx[i * 3 + j] * c + cc, __fmul_rn(go, weight[i * 3 + j]));
+}
+
+// ------------------------------------------------ fused search + interpolation
+// Phase 1: lane = query, segmented 3-NN, weights as models/Modules.py:222-224:
+//   dist = sqrt(d2); r = 1/(dist+1e-8); w = r / ((r0+r1)+r2)
+// Phase 2: the warp walks its 32 queries; lanes spread over channels (float4 each).
+__global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, int m, int c,
+                                                                        const float* __restrict__ unknown,
+                                                                        const float* __restrict__ known,
+                                                                        const int* __restrict__ ws,
+                                                                        const float4* __restrict__ sorted,
+                                                                        const float* __restrict__ feats,
+                                                                        float* __restrict__ out, int out_stride,
+                                                                        int out_col0, int vec_ok) {
+    const int qi = blockIdx.x * SP_THREADS + threadIdx.x;
+    const bool valid = qi < n;
+    const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
+    float b1, b2, b3;
+    int i1, i2, i3;
+    sp_segmented_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, b1, b2, b3, i1, i2, i3);
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+
+    const int lane = threadIdx.x & 31;
+    const int q_base = qi - lane;
+    for (int q = 0; q < 32; ++q) {
+        if (q_base + q >= n) break;
+        const int j0 = __shfl_sync(0xffffffffu, i1, q), j1 = __shfl_sync(0xffffffffu, i2, q),
+                  j2 = __shfl_sync(0xffffffffu, i3, q);
+        const float a0 = __shfl_sync(0xffffffffu, w0, q), a1 = __shfl_sync(0xffffffffu, w1, q),
+                    a2 = __shfl_sync(0xffffffffu, w2, q);
+        float* orow = out + (size_t)(q_base + q) * out_stride + out_col0;
+        if (vec_ok) {
+            const float4* f0 = reinterpret_cast<const float4*>(feats + (size_t)j0 * c);
+            const float4* f1 = reinterpret_cast<const float4*>(feats + (size_t)j1 * c);
+            const float4* f2 = reinterpret_cast<const float4*>(feats + (size_t)j2 * c);
+            for (int cc = lane; cc < (c >> 2); cc += 32) {
+                const float4 x0 = __ldg(f0 + cc), x1 = __ldg(f1 + cc), x2 = __ldg(f2 + cc);
+                float4 o;
+                o.x = dcl_interp3(a0, x0.x, a1, x1.x, a2, x2.x);
+                o.y = dcl_interp3(a0, x0.y, a1, x1.y, a2, x2.y);
+                o.z = dcl_interp3(a0, x0.z, a1, x1.z, a2, x2.z);
+                o.w = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
+                reinterpret_cast<float4*>(orow)[cc] = o;
+            }
+        } else {
+            for (int cc = lane; cc < c; cc += 32)
+                orow[cc] = dcl_interp3(a0, feats[(size_t)j0 * c + cc], a1, feats[(size_t)j1 * c + cc], a2,
+                                       feats[(size_t)j2 * c + cc]);
+        }
+    }
+}
+
+int build_buckets(int m, const float* known, int* ws, float4* sorted, cudaStream_t st) {
+    // only the header words that are read before being written need clearing
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(WS_OFF + DCL_SP_MAX_BATCH + 4) * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    if (m > 0) sp_bucket_hist_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws);
+    sp_bucket_scan_kernel<<<1, 1024, 0, st>>>(ws);
+    if (m > 0) sp_bucket_scatter_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws, sorted);
+    return dcl_launch_status();
+}
+
+}  // namespace
+
+DCL_API int dcl_sp_three_nn_kernel_launcher_fast(int n, int m, const float* unknown, const float* known,
+                                                 float* dist2, int* idx, void* stream) {
+    DCL_RETURN_IF_BAD(n >= 0 && m >= 0);
+    DCL_RETURN_IF_BAD(((uintptr_t)unknown & 15u) == 0);
+    if (n == 0) return 0;
+    sp_three_nn_scan_kernel<<<DCL_DIVUP(n, SP_THREADS), SP_THREADS, 0, (cudaStream_t)stream>>>(
+        n, m, unknown, known, dist2, idx);
+    return dcl_launch_status();
+}
+
+DCL_API size_t dcl_sp_three_nn_workspace_bytes(int n, int m) {
+    (void)n;
+    return (size_t)WS_HDR_INTS * sizeof(int) + (size_t)(m > 0 ? m : 0) * sizeof(float4) + 16;
+}
+
+DCL_API int dcl_sp_three_nn_segmented(int n, int m, const float* unknown, const float* known, float* dist2, int* idx,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(n >= 0 && m >= 0 && workspace != nullptr);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_three_nn_workspace_bytes(n, m));
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
+                      ((uintptr_t)known & 15u) == 0);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* ws = (int*)workspace;
+    float4* sorted = (float4*)(ws + WS_HDR_INTS);
+    int err = build_buckets(m, known, ws, sorted, st);
+    if (err) return err;
+    const int grid = DCL_DIVUP(n, SP_THREADS);
+    sp_three_nn_seg_kernel<<<grid, SP_THREADS, 0, st>>>(n, m, unknown, known, ws, sorted, dist2, idx);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_sp_three_interpolate_kernel_launcher_fast(int c, int m, int n, const float* points, const int* idx,
+                                                          const float* weight, float* out, void* stream) {
+    DCL_RETURN_IF_BAD(c >= 0 && m >= 0 && n >= 0);
+    if (c == 0 || n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = ((c & 3) == 0) && ((((uintptr_t)points) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
+    if (vec) {
+        const long total = (long)n * (c >> 2);
+        sp_interp_v4_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, st>>>(c >> 2, n, (const float4*)points, idx,
+                                                                              weight, (float4*)out);
+    } else {
+        const long total = (long)n * c;
+        sp_interp_v1_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, st>>>(c, n, points, idx, weight, out);
+    }
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_sp_three_interpolate_grad_kernel_launcher_fast(int c, int n, int m, const float* grad_out,
+                                                               const int* idx, const float* weight,
+                                                               float* grad_points, void* stream) {
+    DCL_RETURN_IF_BAD(c >= 0 && m >= 0 && n >= 0);
+    if (c == 0 || n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec =
+        ((c & 3) == 0) && ((((uintptr_t)grad_out) & 15u) == 0) && ((((uintptr_t)grad_points) & 15u) == 0);
+    if (vec) {
+        const long total = (long)n * (c >> 2);
+        sp_interp_grad_v4_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, st>>>(
+            c >> 2, n, (const float4*)grad_out, idx, weight, (float4*)grad_points);
+    } else {
+        const long total = (long)n * c;
+        sp_interp_grad_v1_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, st>>>(c, n, grad_out, idx, weight,
+                                                                                   grad_points);
+    }
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_sp_nn_interpolate_fused(int n, int m, int c, const float* unknown, const float* known,
+                                        const float* feats, float* out, int out_stride, int out_col0,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(n >= 0 && m >= 0 && c >= 0 && workspace != nullptr && out_stride >= out_col0 + c);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_three_nn_workspace_bytes(n, m));
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
+                      ((uintptr_t)known & 15u) == 0);
+    if (n == 0 || c == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* ws = (int*)workspace;
+    float4* sorted = (float4*)(ws + WS_HDR_INTS);
+    int err = build_buckets(m, known, ws, sorted, st);
+    if (err) return err;
+    const int vec_ok = ((c & 3) == 0) && ((out_stride & 3) == 0) && ((out_col0 & 3) == 0) &&
+                       ((((uintptr_t)feats) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
+    sp_nn_interp_fused_kernel<<<DCL_DIVUP(n, SP_THREADS), SP_THREADS, 0, st>>>(
+        n, m, c, unknown, known, ws, sorted, feats, out, out_stride, out_col0, vec_ok);
+    return dcl_launch_status();
+}

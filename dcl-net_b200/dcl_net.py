@@ -1,0 +1,138 @@
+"""Drop-in for the hot-path part of the reference's models/DCL_Net.py.
+
+    ortho9d2matrix(x_raw, y_raw, z_raw) -> (B,3,3)         :15-36   dcl_svd3_project kernel
+    Network(cfg, mode).forward(data) -> dict                :38-259  same modules / parameter names
+
+The two sparse-conv backbones (libs/spconv, libs/pointgroup_ops) are outside this path
+(SURVEY.md §2/§8f): `Network` takes them as an injected `backbone` callable and otherwise offers
+`forward_from_backbone` (pyramid levels -> pose: point-feature interpolation, FDA, pose) and
+`forward_from_point_feats` (FDA + pose).  Everything after the backbone is implemented here.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from functools import partial
+
+from . import _lib as L
+from .modules import (BasicBlock_3DCONV, Head_MultiLayerPerceptron, Ops_GetPointFeat_spconv, fda_align,
+                      fda_attention_map)
+
+
+def svd3_project(m9, normalize_columns):
+    """(B,9) fp32 -> (B,3,3) rotation; see include/dcl_b200.h:dcl_svd3_project."""
+    m9 = L.require(m9.contiguous(), torch.float32, "svd3_project input")
+    B = m9.shape[0]
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=m9.device)
+    L.check(L.load().dcl_svd3_project(B, L.ptr(m9), int(normalize_columns), L.ptr(R), L.stream_ptr()), "svd3_project")
+    return R
+
+
+def ortho9d2matrix(x_raw, y_raw, z_raw):
+    """Rotation from three raw 3-vectors: columns normalised by (|v| + 1e-8), then the SO(3) projection
+    U diag(1,1,det(UV^T)) V^T.  Inference path (no autograd through the kernel)."""
+    return svd3_project(torch.cat((x_raw, y_raw, z_raw), dim=1), True)
+
+
+def weighted_kabsch(src, dst, w):
+    """Confidence-weighted rigid fit  min sum_i w_i |R src_i + t - dst_i|^2.
+    src, dst (B,N,3), w (B,N) fp32 -> R (B,3,3), t (B,3)."""
+    src, dst, w = src.contiguous(), dst.contiguous(), w.contiguous()
+    B, N, _ = src.shape
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=src.device)
+    t = torch.empty(B, 3, dtype=torch.float32, device=src.device)
+    L.check(L.load().dcl_weighted_kabsch(B, N, L.ptr(src), L.ptr(dst), L.ptr(w), L.ptr(R), L.ptr(t), L.stream_ptr()),
+            "weighted_kabsch")
+    return R, t
+
+
+class Network(nn.Module):
+    def __init__(self, cfg, mode="train", backbone=None, c_m=64) -> None:
+        """cfg needs n_inp, n_tmp, unit_voxel_extent (reference configs/*.yaml: model section).
+        backbone: optional callable data -> (levels_inp, levels_tmp, points_inp (b*n,3), points_tmp (b*n,3), b),
+        each `levels_*` a list of four objects with .features (Mv,C_l) / .indices (Mv,4).
+        c_m: width of the pose-insensitive branch (64 in the reference; 128 in BASELINE.json's config)."""
+        super().__init__()
+        self.mode = mode
+        self.n_inp, self.n_tmp = cfg.n_inp, cfg.n_tmp
+        self.unit_voxel_extent = np.array(cfg.unit_voxel_extent)
+        self.backbone = backbone
+        self.stage1_get_point_feats = Ops_GetPointFeat_spconv(
+            scale_lists=[2, 4, 6, 8], unit_voxel_extent=self.unit_voxel_extent, voxel_num_limit=[64, 64, 64])
+        blk = partial(BasicBlock_3DCONV, size=1, bias=False, stride=1, padding=0, norm=True, act="relu", drop=0.0)
+        for name in ("Xc_p1", "Xc_m1", "Yo_p1", "Yo_m1", "Xc_p2", "Xc_m2", "Yo_p2", "Yo_m2"):
+            setattr(self, "disengage_" + name,
+                    nn.Sequential(blk(dim_in=480, dim_out=256), blk(dim_in=256, dim_out=256 if "_p" in name else c_m)))
+        plain = (["relu", "relu", "none"], [False] * 3, [0.0] * 3)
+        fuse = (["relu"] * 3, [True] * 3, [0.0] * 3)
+        self.regressor_Xo = Head_MultiLayerPerceptron([256, 256, 128, 3], *plain)
+        self.regressor_Yc = Head_MultiLayerPerceptron([256, 256, 128, 3], *plain)
+        self.regressor_conf = Head_MultiLayerPerceptron([c_m * 2, 128, 128, 1], *plain)
+        self.regressor_conf_bi = Head_MultiLayerPerceptron([c_m * 2, 128, 128, 1], *plain)
+        self.neck_fuser = Head_MultiLayerPerceptron([256 * 2, 512, 512, 1024], *fuse)
+        self.neck_fuser_bi = Head_MultiLayerPerceptron([256 * 2, 512, 512, 1024], *fuse)
+        self.regressor_rot = Head_MultiLayerPerceptron([1024, 512, 128, 9], *plain)
+        self.regressor_trans = Head_MultiLayerPerceptron([1024, 512, 128, 3], *plain)
+
+    # ---- entry points -----------------------------------------------------------------
+    def forward(self, data):
+        if self.backbone is None:
+            raise RuntimeError("Network.forward(data) needs a sparse-conv backbone provider (out of this path's "
+                               "scope); use forward_from_backbone / forward_from_point_feats")
+        levels_inp, levels_tmp, points_inp, points_tmp, b = self.backbone(data)
+        pred = self.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, b)
+        if self.mode != "test" and "flags" in data:
+            pred["sym_flag"] = data["flags"].to(points_inp.device)
+        data.setdefault("labels", {})
+        data["labels"]["points_tmp"] = points_tmp.view(b, self.n_tmp, -1)
+        data["labels"]["points_inp"] = points_inp.view(b, self.n_inp, -1)
+        return pred
+
+    def forward_from_backbone(self, levels_inp, levels_tmp, points_inp, points_tmp, b):
+        """Pyramid levels of both towers -> prediction dict (models/DCL_Net.py:182-255)."""
+        dev = points_inp.device
+        ids_inp = torch.arange(b, device=dev).repeat_interleave(points_inp.shape[0] // b)
+        ids_tmp = torch.arange(b, device=dev).repeat_interleave(points_tmp.shape[0] // b)
+        F_Xc = self.stage1_get_point_feats(points_inp, ids_inp, *levels_inp)
+        F_Yo = self.stage1_get_point_feats(points_tmp, ids_tmp, *levels_tmp)
+        return self.forward_from_point_feats(F_Xc, F_Yo, b)
+
+    def forward_from_point_feats(self, F_Xc, F_Yo, b):
+        """F_Xc (b*n_inp, 480), F_Yo (b*n_tmp, 480) -> prediction dict (models/DCL_Net.py:187-255)."""
+        F_Xc = F_Xc.view(b, self.n_inp, -1).transpose(1, 2)[:, :, :, None, None]
+        F_Yo = F_Yo.view(b, self.n_tmp, -1).transpose(1, 2)[:, :, :, None, None]
+        sq = lambda t: t.squeeze(-1).squeeze(-1)
+        F_Xc_p1, F_Xc_m1 = sq(self.disengage_Xc_p1(F_Xc)), sq(self.disengage_Xc_m1(F_Xc))
+        F_Xc_p2, F_Xc_m2 = sq(self.disengage_Xc_p2(F_Xc)), sq(self.disengage_Xc_m2(F_Xc))
+        F_Yo_p1, F_Yo_m1 = sq(self.disengage_Yo_p1(F_Yo)), sq(self.disengage_Yo_m1(F_Yo))
+        F_Yo_p2, F_Yo_m2 = sq(self.disengage_Yo_p2(F_Yo)), sq(self.disengage_Yo_m2(F_Yo))
+
+        # dual FDA: both attention products of each direction in one fused kernel
+        F_Xo_p, F_Xo_m = fda_align(F_Xc_m1, F_Yo_m1, F_Yo_p1)
+        F_Yc_p, F_Yc_m = fda_align(F_Yo_m2, F_Xc_m2, F_Xc_p2)
+        Xo_pred = self.regressor_Xo(F_Xo_p) if self.mode != "test" else None
+        Yc_pred = self.regressor_Yc(F_Yc_p) if self.mode != "test" else None
+
+        conf_1 = self.regressor_conf(torch.cat([F_Xc_m1, F_Xo_m], dim=1))
+        conf_2 = self.regressor_conf_bi(torch.cat([F_Yc_m, F_Yo_m2], dim=1))
+        conf = torch.sigmoid(torch.cat([conf_1, conf_2], dim=2))
+        conf_softmax = torch.softmax(conf, dim=2)
+
+        F_p1 = self.neck_fuser(torch.cat([F_Xc_p1, F_Xo_p], dim=1))
+        F_p2 = self.neck_fuser_bi(torch.cat([F_Yc_p, F_Yo_p2], dim=1))
+        F_p_wei = torch.sum(torch.cat([F_p1, F_p2], dim=2) * conf_softmax, dim=2, keepdim=True)
+
+        ortho9d_pred = self.regressor_rot(F_p_wei).squeeze(-1)
+        rot_pred = svd3_project(ortho9d_pred, True)
+        trans_pred = self.regressor_trans(F_p_wei).squeeze(-1)
+
+        prediction = {"trans_pred": trans_pred, "rot_pred": rot_pred, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p}
+        if self.mode != "test":
+            prediction.update({"Xo_pred": Xo_pred.transpose(1, 2), "Yc_pred": Yc_pred.transpose(1, 2)})
+        prediction["_debug"] = {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d_pred}
+        return prediction
+
+    def attention_maps(self, F_Xc_m1, F_Yo_m1, F_Yo_m2, F_Xc_m2):
+        """The two (B,M,N) attention maps the reference keeps in `attention_map` / `attention_map_bi`."""
+        _, _, lse1 = fda_align(F_Xc_m1, F_Yo_m1, F_Yo_m1.new_zeros(F_Yo_m1.shape[0], 256, F_Yo_m1.shape[2]), True)
+        _, _, lse2 = fda_align(F_Yo_m2, F_Xc_m2, F_Xc_m2.new_zeros(F_Xc_m2.shape[0], 256, F_Xc_m2.shape[2]), True)
+        return fda_attention_map(F_Xc_m1, F_Yo_m1, lse1), fda_attention_map(F_Yo_m2, F_Xc_m2, lse2)

@@ -1,0 +1,177 @@
+"""Drop-ins for the hot-path pieces of the reference's models/Modules.py.
+
+    Aligner                          :162-169   fused tcgen05 kernel (dcl_fda_align_fwd)
+    Head_MultiLayerPerceptron        :173-201   same layers / parameter names (library GEMMs)
+    BasicBlock_3DCONV                :58-97     same layers / parameter names
+    Ops_tensor2points                :204-211
+    Ops_nearest_neighbor_interpolate :213-226   pointnet_sp kernels (fused in inference)
+    Ops_GetPointFeat_spconv          :227-251
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .pointnet_sp import pointnet2_utils as pointnet2_utils_sp
+
+_fda_ws = {}
+
+
+def _fda_workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _fda_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _fda_ws[key] = ws
+    return ws
+
+
+def fda_align(RI_1, RI_2, RE_2, return_lse=False):
+    """One FDA direction, fused:  A = softmax_m(RI_2^T RI_1) is never materialised.
+
+    RI_1 (B,C,N) queries, RI_2 (B,C,M) keys, RE_2 (B,P,M) values, fp32, C in {64,128}, P=256,
+    N % 128 == 0, M % 64 == 0.  Returns RE_embed = RE_2 A (B,P,N) and RI_embed = RI_2 A (B,C,N)
+    (models/Modules.py:167-168 and models/DCL_Net.py:213/215), optionally the per-query
+    log-sum-exp (B,N).  Inference path: no autograd graph is recorded.
+    """
+    RI_1 = L.require(RI_1.contiguous(), torch.float32, "RI_1")
+    RI_2 = L.require(RI_2.contiguous(), torch.float32, "RI_2")
+    RE_2 = L.require(RE_2.contiguous(), torch.float32, "RE_2")
+    B, C, N = RI_1.shape
+    M, P = RI_2.shape[2], RE_2.shape[1]
+    if RI_2.shape[:2] != (B, C) or RE_2.shape[0] != B or RE_2.shape[2] != M:
+        raise ValueError("fda_align: inconsistent shapes")
+    lib = L.load()
+    nbytes = lib.dcl_fda_workspace_bytes(B, C, P, N, M)
+    if nbytes == 0 or N % 128 or M % 64:
+        raise ValueError(f"fda_align: unsupported shape C={C} P={P} N={N} M={M} "
+                         "(need C in {64,128}, P=256, N%128==0, M%64==0)")
+    ws = _fda_workspace(nbytes, RI_1.device)
+    RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=RI_1.device)
+    RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=RI_1.device)
+    lse = torch.empty(B, N, dtype=torch.float32, device=RI_1.device) if return_lse else None
+    L.check(lib.dcl_fda_align_fwd(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(RE_embed),
+                                  L.ptr(RI_embed), L.ptr(lse), L.ptr(ws), ws.numel(), L.stream_ptr()),
+            "fda_align")
+    return (RE_embed, RI_embed, lse) if return_lse else (RE_embed, RI_embed)
+
+
+def fda_attention_map(RI_1, RI_2, lse):
+    """A (B,M,N) = exp(RI_2^T RI_1 - lse): the reference's `attention_map` (Modules.py:167)."""
+    RI_1, RI_2, lse = RI_1.contiguous(), RI_2.contiguous(), lse.contiguous()
+    B, C, N = RI_1.shape
+    M = RI_2.shape[2]
+    A = torch.empty(B, M, N, dtype=torch.float32, device=RI_1.device)
+    L.check(L.load().dcl_fda_attention_map(B, C, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(lse), L.ptr(A),
+                                           L.stream_ptr()), "fda_attention_map")
+    return A
+
+
+class Aligner(nn.Module):
+    """forward(RI_1, RI_2, RE_2) -> (RE_embed, attention_map), as models/Modules.py:162-169.
+
+    RE_embed comes from the fused kernel.  attention_map is what the reference returns second;
+    it is rebuilt from the kernel's log-sum-exp only because this signature demands it —
+    Network.forward uses `fda_align` directly and never materialises it.
+    """
+
+    def forward(self, RI_1, RI_2, RE_2):
+        RE_embed, _, lse = fda_align(RI_1, RI_2, RE_2, return_lse=True)
+        return RE_embed, fda_attention_map(RI_1, RI_2, lse)
+
+
+class BasicBlock_3DCONV(nn.Module):
+    def __init__(self, dim_in, dim_out, bias, size, stride, padding, norm, act, drop):
+        super().__init__()
+        layers = [nn.Conv3d(dim_in, dim_out, size, stride, padding, bias=bias)]
+        if norm:
+            layers.append(nn.BatchNorm3d(dim_out))
+        layers += _activation(act)
+        if drop > 0:
+            layers.append(nn.Dropout(drop))
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, input):
+        return self.layers(input)
+
+
+def _activation(act):
+    if act == "relu":
+        return [nn.ReLU()]
+    if act == "sigmoid":
+        return [nn.Sigmoid()]
+    if act == "tanh":
+        return [nn.Tanh()]
+    if act == "none":
+        return []
+    raise NotImplementedError(act)
+
+
+class Head_MultiLayerPerceptron(nn.Module):
+    """Conv1d(k=1) -> activation -> [BatchNorm1d] -> [Dropout] per layer (BN after the activation)."""
+
+    def __init__(self, list_dim, list_act, list_bn, list_drop):
+        super().__init__()
+        layers, dim_inp = [], list_dim[0]
+        for dim, act, bn, drop in zip(list_dim[1:], list_act, list_bn, list_drop):
+            layers.append(nn.Conv1d(dim_inp, dim, 1))
+            layers += _activation(act)
+            if bn:
+                layers.append(nn.BatchNorm1d(dim))
+            if drop > 0.0:
+                layers.append(nn.Dropout(drop))
+            dim_inp = dim
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, input):
+        return self.layers(input)
+
+
+def Ops_tensor2points(tensor, offset=(0., -40., -3.), voxel_extent=(.1, .1, .2)):
+    """Sparse tensor (.features (Mv,C), .indices (Mv,4) int bxyz) -> (features, voxel centres bxyz)."""
+    indices = tensor.indices.float()
+    offset = torch.as_tensor(np.asarray(offset), dtype=torch.float32, device=indices.device)
+    voxel_extent = torch.as_tensor(np.asarray(voxel_extent), dtype=torch.float32, device=indices.device)
+    indices[:, 1:] = indices[:, 1:] * voxel_extent + offset + .5 * voxel_extent
+    return tensor.features, indices
+
+
+def Ops_nearest_neighbor_interpolate(target_points, query_points, query_feats):
+    """(n,4) bxyz targets, (m,4) bxyz sources, (m,C) features -> (n,C)."""
+    if not (torch.is_grad_enabled() and query_feats.requires_grad):
+        return pointnet2_utils_sp.nn_interpolate(target_points.contiguous(), query_points.contiguous(),
+                                                 query_feats.contiguous())
+    dist, idx = pointnet2_utils_sp.three_nn(target_points, query_points)
+    dist_recip = 1.0 / (dist + 1e-8)
+    norm = torch.sum(dist_recip, dim=1, keepdim=True)
+    weight = dist_recip / norm
+    return pointnet2_utils_sp.three_interpolate(query_feats, idx, weight)
+
+
+class Ops_GetPointFeat_spconv(nn.Module):
+    def __init__(self, scale_lists=[2, 4, 8, 16], unit_voxel_extent=np.array([0.015, 0.015, 0.015]),
+                 voxel_num_limit=np.array([64, 64, 64])):
+        super().__init__()
+        self.scale_lists = scale_lists
+        self.unit_voxel_extent = np.asarray(unit_voxel_extent)
+        self.voxel_num_limit = np.asarray(voxel_num_limit)
+        self.offset = -0.5 * self.unit_voxel_extent * self.voxel_num_limit
+
+    def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):
+        points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()
+        levels = [feats1, feats2, feats3, feats4]
+        fused = not (torch.is_grad_enabled() and any(f.features.requires_grad for f in levels))
+        if fused:
+            width = sum(f.features.shape[1] for f in levels)
+            out = torch.empty(points.shape[0], width, dtype=torch.float32, device=points.device)
+            col = 0
+            for scale, feats in zip(self.scale_lists, levels):
+                vx_feats, vx_points = Ops_tensor2points(feats, self.offset, self.unit_voxel_extent * scale)
+                pointnet2_utils_sp.nn_interpolate(points, vx_points.contiguous(), vx_feats.contiguous(), out, col)
+                col += vx_feats.shape[1]
+            return out
+        outs = []
+        for scale, feats in zip(self.scale_lists, levels):
+            vx_feats, vx_points = Ops_tensor2points(feats, self.offset, self.unit_voxel_extent * scale)
+            outs.append(Ops_nearest_neighbor_interpolate(points, vx_points, vx_feats))
+        return torch.cat(outs, dim=1)

@@ -1,0 +1,62 @@
+"""Drop-in for the reference's models/refiner.py and the stage-2 loop that drives it.
+
+    Refiner(cfg).forward({"input_features","conf","obj_idx"}) -> {"trans_pred","rot_pred"}   refiner.py:57-95
+    refine_poses(...)   the iteration of tools/test_YCBV_stage2.py:204-225 with the pose composition
+                        and re-canonicalisation fused into one kernel (dcl_pose_compose)
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .dcl_net import svd3_project
+from .modules import Head_MultiLayerPerceptron
+
+
+def ortho9d2matrix(x_raw, y_raw, z_raw):
+    return svd3_project(torch.cat((x_raw, y_raw, z_raw), dim=1), True)
+
+
+class Refiner(nn.Module):
+    def __init__(self, cfg=None) -> None:
+        super().__init__()
+        plain = ([False] * 3, [0.0] * 3)
+        self.MLP_share = Head_MultiLayerPerceptron([256 + 3, 512, 512, 1024], ["relu"] * 3, *plain)
+        self.regressor_rot2 = Head_MultiLayerPerceptron([1024, 512, 128, 9], ["relu", "relu", "none"], *plain)
+        self.regressor_trans2 = Head_MultiLayerPerceptron([1024, 512, 128, 3], ["relu", "relu", "none"], *plain)
+
+    def forward(self, input_dict):
+        input_features = input_dict["input_features"]
+        conf = input_dict["conf"]
+        conf_softmax = torch.softmax(conf.unsqueeze(1), dim=2)[:, :, :1024]
+        shared_feature = self.MLP_share(input_features)
+        shared_feature = (shared_feature * conf_softmax).sum(dim=2, keepdim=True)
+        ortho9d_pred2 = self.regressor_rot2(shared_feature).squeeze(-1)
+        delta_t = self.regressor_trans2(shared_feature).squeeze(-1)
+        delta_R = svd3_project(ortho9d_pred2, True)
+        return {"trans_pred": delta_t, "rot_pred": delta_R}
+
+
+def pose_compose_(R, t, dR, dt, points_in, out_cm):
+    """In place: t <- R dt + t, R <- R dR (skipped when dR is None); then writes the canonicalised cloud
+    (points_in - t) R channel-major into out_cm[:, :3, :] (out_cm is (B, >=3, N), contiguous)."""
+    B, N = points_in.shape[0], points_in.shape[1]
+    assert out_cm.is_contiguous() and out_cm.shape[0] == B and out_cm.shape[2] == N and out_cm.shape[1] >= 3
+    L.check(L.load().dcl_pose_compose(B, N, L.ptr(R), L.ptr(t), L.ptr(dR), L.ptr(dt), L.ptr(points_in),
+                                      L.ptr(out_cm), out_cm.shape[1] * N, L.stream_ptr()), "pose_compose")
+
+
+def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration=2):
+    """Stage-2 iterative refinement.  points_inp (B,N,3), rot_pred (B,3,3), trans_pred (B,3),
+    F_Xo_p (B,256,N), conf (B,2N) -> refined (rot, trans).  The refiner input buffer (B,259,N) is built
+    once; each iteration only rewrites its first three channels."""
+    B, N, _ = points_inp.shape
+    points_inp = points_inp.contiguous()
+    rot_cur, trans_cur = rot_pred.clone().contiguous(), trans_pred.clone().contiguous()
+    inp_refiner = torch.empty(B, 3 + F_Xo_p.shape[1], N, dtype=torch.float32, device=points_inp.device)
+    inp_refiner[:, 3:, :] = F_Xo_p
+    pose_compose_(rot_cur, trans_cur, None, None, points_inp, inp_refiner)
+    for _ in range(iteration):
+        out = refiner({"input_features": inp_refiner, "conf": conf, "obj_idx": None})
+        pose_compose_(rot_cur, trans_cur, out["rot_pred"].contiguous(), out["trans_pred"].contiguous(),
+                      points_inp, inp_refiner)
+    return rot_cur, trans_cur

@@ -1,0 +1,199 @@
+/*
+ * dcl_b200.h — C-ABI of the B200-native DCL-Net hot path (libdcl_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a
+ * `cudaStream_t` (passed as void*), never allocates or frees, keeps no state,
+ * launches asynchronously on the given stream and returns a `cudaError_t`
+ * as int (0 == cudaSuccess).  The reference instead prints and calls
+ * exit(-1) on a launch failure (libs/pointnet_lib/src/sampling_gpu.cu:248-252).
+ *
+ * Group 1 mirrors, one-to-one, the launchers the reference's pybind wrappers
+ * call (same argument order and meaning; only the name gets a dcl_lib_ /
+ * dcl_sp_ prefix because the two reference libraries define same-named
+ * symbols).  Group 2 has no reference counterpart at the C level: it replaces
+ * PyTorch library calls the reference makes from models/*.py.
+ *
+ * All tensors are dense, row-major, fp32 / int32, resident on the current
+ * device.
+ */
+#ifndef DCL_B200_H
+#define DCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ABI version of this header; bumped on any signature change. */
+#define DCL_B200_ABI_VERSION 1
+int dcl_b200_abi_version(void);
+/* Compiled-for architecture as an integer (100 for sm_100a). */
+int dcl_b200_arch(void);
+
+/* ------------------------------------------------------------------------- */
+/* Group 1a: libs/pointnet_lib (batched (B,N,3) clouds)                        */
+/* ------------------------------------------------------------------------- */
+
+/* replaces furthest_point_sampling_kernel_launcher
+ * (libs/pointnet_lib/src/sampling_gpu.h:26-27, sampling_gpu.cu:211-253).
+ * dataset (b,n,3); temp (b,n) pre-filled by the caller (reference: 1e10),
+ * left holding the final min-distances; idxs (b,m) int32, idxs[:,0] = 0.
+ * Tie-break identical to the reference's shared-memory tree reduction. */
+int dcl_lib_furthest_point_sampling_kernel_launcher(int b, int n, int m,
+    const float* dataset, float* temp, int* idxs, void* stream);
+
+/* replaces gather_points_kernel_launcher_fast (sampling_gpu.h:12-13).
+ * points (b,c,n), idx (b,npoints) -> out (b,c,npoints). */
+int dcl_lib_gather_points_kernel_launcher_fast(int b, int c, int n, int npoints,
+    const float* points, const int* idx, float* out, void* stream);
+
+/* replaces gather_points_grad_kernel_launcher_fast (sampling_gpu.h:19-20).
+ * grad_out (b,c,npoints), idx (b,npoints); accumulates into grad_points (b,c,n)
+ * (caller zeroes it, libs/pointnet_lib/pointnet2_utils.py:70). */
+int dcl_lib_gather_points_grad_kernel_launcher_fast(int b, int c, int n, int npoints,
+    const float* grad_out, const int* idx, float* grad_points, void* stream);
+
+/* replaces ball_query_kernel_launcher_fast (definition ball_query_gpu.cu:48-49;
+ * pointer order is (new_xyz, xyz) as in the definition, not the header).
+ * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample); rows without a hit are
+ * left untouched (caller zeroes idx, pointnet2_utils.py:261). */
+int dcl_lib_ball_query_kernel_launcher_fast(int b, int n, int m, float radius, int nsample,
+    const float* new_xyz, const float* xyz, int* idx, void* stream);
+
+/* replaces group_points_kernel_launcher_fast (group_points_gpu.h:13-14).
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
+int dcl_lib_group_points_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample,
+    const float* points, const int* idx, float* out, void* stream);
+
+/* replaces group_points_grad_kernel_launcher_fast (group_points_gpu.h:19-20). */
+int dcl_lib_group_points_grad_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample,
+    const float* grad_out, const int* idx, float* grad_points, void* stream);
+
+/* replaces three_nn_kernel_launcher_fast (libs/pointnet_lib/src/interpolate_gpu.h:16-17).
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) squared, idx (b,n,3). */
+int dcl_lib_three_nn_kernel_launcher_fast(int b, int n, int m,
+    const float* unknown, const float* known, float* dist2, int* idx, void* stream);
+
+/* replaces knn_kernel_launcher_fast (interpolate_gpu.h:22-23); 1 <= k <= 200. */
+int dcl_lib_knn_kernel_launcher_fast(int b, int n, int m, int k,
+    const float* unknown, const float* known, float* dist2, int* idx, void* stream);
+
+/* replaces three_interpolate_kernel_launcher_fast (interpolate_gpu.h:28-29).
+ * points (b,c,m), idx/weight (b,n,3) -> out (b,c,n). */
+int dcl_lib_three_interpolate_kernel_launcher_fast(int b, int c, int m, int n,
+    const float* points, const int* idx, const float* weight, float* out, void* stream);
+
+/* replaces three_interpolate_grad_kernel_launcher_fast (interpolate_gpu.h:33-34).
+ * grad_out (b,c,n) -> accumulates into grad_points (b,c,m). */
+int dcl_lib_three_interpolate_grad_kernel_launcher_fast(int b, int c, int n, int m,
+    const float* grad_out, const int* idx, const float* weight, float* grad_points, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Group 1b: libs/pointnet_sp (flat, batch id in column 0)                     */
+/* ------------------------------------------------------------------------- */
+
+/* replaces three_nn_kernel_launcher_fast (libs/pointnet_sp/src/interpolate_gpu.h:16-17).
+ * unknown (n,4) bxyz, known (m,4) bxyz -> dist2 (n,3), idx (n,3) into `known`.
+ * Same O(n*m) scan as the reference, tiled through shared memory. */
+int dcl_sp_three_nn_kernel_launcher_fast(int n, int m,
+    const float* unknown, const float* known, float* dist2, int* idx, void* stream);
+
+/* Segmented variant of the same op: known rows are bucketed by batch id into
+ * caller-provided scratch, each query scans only its own bucket.  Results are
+ * bit-identical to dcl_sp_three_nn_kernel_launcher_fast.  `workspace` must hold
+ * dcl_sp_three_nn_workspace_bytes(n,m) bytes.  Batch ids that are not integers
+ * in [0, DCL_SP_MAX_BATCH) make the call fall back (on device, no host sync) to
+ * the full scan. */
+#define DCL_SP_MAX_BATCH 65536
+size_t dcl_sp_three_nn_workspace_bytes(int n, int m);
+int dcl_sp_three_nn_segmented(int n, int m,
+    const float* unknown, const float* known, float* dist2, int* idx,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces three_interpolate_kernel_launcher_fast (pointnet_sp interpolate_gpu.h:22-23).
+ * points (m,c), idx/weight (n,3) -> out (n,c). */
+int dcl_sp_three_interpolate_kernel_launcher_fast(int c, int m, int n,
+    const float* points, const int* idx, const float* weight, float* out, void* stream);
+
+/* replaces three_interpolate_grad_kernel_launcher_fast (pointnet_sp interpolate_gpu.h:27-28).
+ * grad_out (n,c) -> accumulates into grad_points (m,c). */
+int dcl_sp_three_interpolate_grad_kernel_launcher_fast(int c, int n, int m,
+    const float* grad_out, const int* idx, const float* weight, float* grad_points, void* stream);
+
+/* Fusion of models/Modules.py:213-226 (Ops_nearest_neighbor_interpolate):
+ * three_nn -> sqrt -> w = (1/(d+1e-8))/sum -> three_interpolate, writing into a
+ * column slice of a wider (n, out_stride) row-major output (the torch.cat of
+ * models/Modules.py:250).  Uses the segmented search; same workspace. */
+int dcl_sp_nn_interpolate_fused(int n, int m, int c,
+    const float* unknown, const float* known, const float* feats,
+    float* out, int out_stride, int out_col0,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Group 2: FDA correspondence head and pose solve (replace torch library calls) */
+/* ------------------------------------------------------------------------- */
+
+/* Fused Aligner (models/Modules.py:166-169) + confidence product
+ * (models/DCL_Net.py:213,215), one direction:
+ *   A        = softmax over the m axis of  RI_2^T RI_1      (b, m, n), never stored
+ *   RE_embed = RE_2 A                                       (b, p, n)
+ *   RI_embed = RI_2 A                                       (b, c, n)
+ * RI_1 (b,c,n) queries, RI_2 (b,c,m) keys, RE_2 (b,p,m) values; fp32, channel-major
+ * exactly as the reference holds them.  c in {64,128}, p == 256, n and m multiples
+ * of 128 / 64.  The contraction runs on tcgen05 with bf16 hi/lo-split operands and
+ * fp32 TMEM accumulation.  `workspace` holds the packed operands:
+ * dcl_fda_workspace_bytes(b,c,p,n,m).  lse_out (b,n) optional (may be NULL):
+ * per-query log-sum-exp, enough to rebuild A. */
+size_t dcl_fda_workspace_bytes(int b, int c, int p, int n, int m);
+int dcl_fda_align_fwd(int b, int c, int p, int n, int m,
+    const float* RI_1, const float* RI_2, const float* RE_2,
+    float* RE_embed, float* RI_embed, float* lse_out,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Materialise the attention map A (b,m,n) of models/Modules.py:167 from the
+ * inputs and the lse of dcl_fda_align_fwd (train / inspection path only). */
+int dcl_fda_attention_map(int b, int c, int n, int m,
+    const float* RI_1, const float* RI_2, const float* lse, float* A, void* stream);
+
+/* replaces ortho9d2matrix's torch.svd + det + diag_embed + matmuls
+ * (models/DCL_Net.py:15-36, models/refiner.py:35-56).
+ * in9 (b,9): when normalize_columns != 0, rows are [x_raw | y_raw | z_raw] and each
+ * 3-vector is scaled by 1/(|v|+1e-8) (utils/transform3D.py:18-20) and used as a
+ * COLUMN of M; when 0, in9 is a row-major 3x3 M used as is.
+ * out R (b,3,3) = U diag(1,1,det(U V^T)) V^T. */
+int dcl_svd3_project(int b, const float* in9, int normalize_columns, float* R, void* stream);
+
+/* Confidence-weighted Kabsch (BASELINE.json north_star part 3; no reference
+ * counterpart — SURVEY.md D2/a15).  src,dst (b,n,3), w (b,n) ->
+ * R (b,3,3), t (b,3) minimising sum_i w_i |R src_i + t - dst_i|^2. */
+int dcl_weighted_kabsch(int b, int n, const float* src, const float* dst, const float* w,
+    float* R, float* t, void* stream);
+
+/* Stage-2 pose composition (tools/test_YCBV_stage2.py:210,222-225):
+ *   t' = R dt + t ;  R' = R dR ;  out[b, ch, i] = sum_r (points_in[b,i,r] - t'[r]) R'[r][ch]
+ * R (b,3,3) and t (b,3) are updated in place; dR/dt may both be NULL (no update: only
+ * canonicalise with the current pose, test_YCBV_stage2.py:210).  The canonicalised cloud
+ * is written CHANNEL-MAJOR, i.e. already transposed as the refiner input wants it
+ * (test_YCBV_stage2.py:212,225): channel ch of instance b starts at
+ * points_out_cm + b*out_batch_stride + ch*n, so it can be the first three channels of
+ * the (b, 3+256, n) refiner input.  points_in/points_out_cm may be NULL (pose update only). */
+int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, const float* dt,
+    const float* points_in, float* points_out_cm, int64_t out_batch_stride, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Bring-up / test hook                                                       */
+/* ------------------------------------------------------------------------- */
+/* D (128 x N) = A (128 x K) B^T (B is N x K), all row-major fp32, through exactly the
+ * operand packing, UMMA descriptors, hi/lo split product and TMEM read-back of
+ * dcl_fda_align_fwd, in a single CTA.  N % 32 == 0, N <= 256, K % 16 == 0.
+ * swap_lbo_sbo must be 0 (1 exchanges the descriptor stride fields; used once on
+ * hardware to pin the descriptor semantics). */
+int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D,
+    int swap_lbo_sbo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCL_B200_H */

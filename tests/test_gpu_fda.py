@@ -1,0 +1,119 @@
+"""GPU parity of the fused FDA kernel through the C-ABI.
+Oracle: fp32/fp64 PyTorch restatement of Aligner + the confidence product (oracle/torch_oracle.py),
+itself pinned bit-for-bit to the reference's Aligner / Network.forward (tests/golden/model_*.npz).
+Tolerance (north_star): soft correspondences within 1e-3 relative — asserted here at 2e-4 of the tensor
+scale AND 1e-3 element-wise (relative to max(|ref|, 1e-2*scale))."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as T
+from tests.util import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+from dcl_net_b200 import _lib as L                                    # noqa: E402
+from dcl_net_b200.modules import Aligner, fda_align, fda_attention_map  # noqa: E402
+
+
+def _check(got, want, what, tol_scale=2e-4, tol_elem=1e-3):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    scale = want.abs().max().item()
+    err = (got - want).abs()
+    assert err.max().item() <= tol_scale * scale, f"{what}: max abs err {err.max().item():.3e} vs scale {scale:.3e}"
+    elem = (err / want.abs().clamp_min(1e-2 * scale)).max().item()
+    assert elem <= tol_elem, f"{what}: element-wise relative error {elem:.3e}"
+
+
+@pytest.mark.parametrize("N,K", [(64, 64), (256, 64), (64, 128), (32, 16), (128, 256)])
+def test_umma_probe(cuda_dev, N, K):
+    """Pins the UMMA descriptor / TMEM conventions the FDA kernel relies on: one CTA, D = A B^T."""
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A, B = torch.randn(128, K, generator=g), torch.randn(N, K, generator=g)
+    D = torch.full((128, N), float("nan"), device=cuda_dev)
+    a, b = A.to(cuda_dev), B.to(cuda_dev)
+    L.check(L.load().dcl_debug_umma_gemm(N, K, L.ptr(a), L.ptr(b), L.ptr(D), 0, L.stream_ptr()), "umma probe")
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().T
+    assert rel_err(D, want) < 3e-5, f"UMMA probe rel err {rel_err(D, want):.3e}"
+
+
+def _inputs(seed, b, c, n, m, kind):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "relu":  # post-ReLU features as in the network (BN eval ~ identity)
+        ri1, ri2 = torch.randn(b, c, n, generator=g).relu(), torch.randn(b, c, m, generator=g).relu()
+    elif kind == "peaked":  # large logits => near one-hot softmax, exercises the rescale path
+        ri1, ri2 = 3.0 * torch.randn(b, c, n, generator=g), 3.0 * torch.randn(b, c, m, generator=g)
+    else:  # increasing key norms => the running max keeps growing
+        ri1 = torch.randn(b, c, n, generator=g).relu()
+        ri2 = torch.randn(b, c, m, generator=g).relu() * torch.linspace(0.2, 2.5, m)[None, None, :]
+    re2 = torch.randn(b, 256, m, generator=g)
+    return ri1, ri2, re2
+
+
+@pytest.mark.parametrize("kind", ["relu", "peaked", "growing"])
+@pytest.mark.parametrize("b,c,n,m", [(1, 64, 128, 64), (2, 64, 128, 128), (2, 64, 256, 192), (3, 64, 1024, 1024),
+                                     (2, 128, 128, 64), (2, 128, 1024, 1024), (1, 64, 128, 2048)])
+def test_fda_align(cuda_dev, kind, b, c, n, m):
+    ri1, ri2, re2 = _inputs(7 + n + m, b, c, n, m, kind)
+    re_e, ri_e, lse = fda_align(ri1.to(cuda_dev), ri2.to(cuda_dev), re2.to(cuda_dev), return_lse=True)
+    torch.cuda.synchronize()
+    want_re, want_ri, a = T.fda_direction(ri1.double(), ri2.double(), re2.double())
+    _check(re_e, want_re, f"RE_embed {kind}")
+    _check(ri_e, want_ri, f"RI_embed {kind}")
+    want_lse = torch.logsumexp(torch.bmm(ri2.double().transpose(1, 2), ri1.double()), dim=1)
+    assert (lse.double().cpu() - want_lse).abs().max().item() < 1e-3 * max(1.0, want_lse.abs().max().item())
+
+
+def test_fda_matches_fp32_reference_restatement(cuda_dev):
+    """Against the fp32 restatement run on the GPU (what the reference computes, TF32 off)."""
+    ri1, ri2, re2 = (t.to(cuda_dev) for t in _inputs(5, 4, 64, 1024, 1024, "relu"))
+    re_e, ri_e = fda_align(ri1, ri2, re2)
+    want_re, want_ri, _ = T.fda_direction(ri1, ri2, re2)
+    _check(re_e, want_re, "RE_embed vs fp32")
+    _check(ri_e, want_ri, "RI_embed vs fp32")
+
+
+def test_aligner_module_and_attention_map(cuda_dev):
+    ri1, ri2, re2 = _inputs(9, 2, 64, 256, 128, "relu")
+    re_e, a = Aligner()(ri1.to(cuda_dev), ri2.to(cuda_dev), re2.to(cuda_dev))
+    want_re, want_a = T.aligner(ri1.double(), ri2.double(), re2.double())
+    _check(re_e, want_re, "Aligner RE_embed")
+    assert a.shape == (2, 128, 256)
+    assert (a.double().cpu() - want_a).abs().max().item() < 1e-5
+    assert (a.sum(1) - 1).abs().max().item() < 1e-4  # column-stochastic over the m axis (Modules.py:167)
+
+
+def test_aligner_golden(cuda_dev):
+    """tests/golden/model_aligner.npz was produced by the reference's own Aligner (oracle/make_golden.py)."""
+    gold = np.load(f"{GOLDEN}/model_aligner.npz")
+    g = torch.Generator().manual_seed(int(gold["seed"]))
+    ri1, ri2, re2 = (torch.randn(2, 64, 128, generator=g).relu(), torch.randn(2, 64, 192, generator=g).relu(),
+                     torch.randn(2, 256, 192, generator=g))
+    re_e, a = Aligner()(ri1.to(cuda_dev), ri2.to(cuda_dev), re2.to(cuda_dev))
+    _check(re_e, torch.from_numpy(gold["RE_embed"]), "Aligner vs golden")
+    assert np.abs(a.cpu().numpy()[:, ::16, ::16] - gold["A_sample"]).max() < 1e-5
+
+
+def test_fda_rejects_bad_shapes(cuda_dev):
+    x = torch.zeros(1, 32, 128, device=cuda_dev)
+    with pytest.raises(ValueError):
+        fda_align(x, x, torch.zeros(1, 256, 128, device=cuda_dev))
+    y = torch.zeros(1, 64, 100, device=cuda_dev)
+    with pytest.raises(ValueError):
+        fda_align(y, y, torch.zeros(1, 256, 100, device=cuda_dev))
+
+
+def test_fda_linearity_in_values_full_size(cuda_dev):
+    """Size-independent property at the BASELINE shape (B=32, N=M=1024): the output is linear in the
+    value operand, and a constant value row comes back as that constant (softmax weights sum to 1)."""
+    b, c, n, m = 32, 64, 1024, 1024
+    g = torch.Generator().manual_seed(77)
+    ri1, ri2 = torch.randn(b, c, n, generator=g).relu().to(cuda_dev), torch.randn(b, c, m, generator=g).relu().to(cuda_dev)
+    v1, v2 = torch.randn(b, 256, m, generator=g).to(cuda_dev), torch.randn(b, 256, m, generator=g).to(cuda_dev)
+    o1, _ = fda_align(ri1, ri2, v1)
+    o2, _ = fda_align(ri1, ri2, v2)
+    o12, _ = fda_align(ri1, ri2, 2.0 * v1 - 3.0 * v2)
+    assert rel_err(o12, 2.0 * o1 - 3.0 * o2) < 1e-4
+    ones, _ = fda_align(ri1, ri2, torch.full((b, 256, m), 0.75, device=cuda_dev))
+    assert (ones - 0.75).abs().max().item() < 1e-5

@@ -1,0 +1,210 @@
+"""GPU parity of the pose solve (a13, a15), the refiner loop (a14), the point-feature glue (a10) and the whole
+stage-1 tail (a12) through the drop-in Network / Refiner.
+Tolerances (north_star): rotation within 0.01 deg, translation within 1e-5 m."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu_oracle, torch_oracle as T
+from tests.util import GOLDEN, levels_to, rel_err, synthetic_backbone_levels
+
+pytestmark = pytest.mark.gpu
+
+from dcl_net_b200.dcl_net import Network, ortho9d2matrix, svd3_project, weighted_kabsch  # noqa: E402
+from dcl_net_b200.modules import Ops_GetPointFeat_spconv                                # noqa: E402
+from dcl_net_b200.refiner import Refiner, refine_poses                                  # noqa: E402
+
+
+class Cfg:
+    def __init__(self, n):
+        self.n_inp = self.n_tmp = n
+        self.unit_voxel_extent = [0.006] * 3
+
+
+def test_ortho9d_golden(cuda_dev):
+    """Fixture produced by the reference's own ortho9d2matrix (models/DCL_Net.py:15-36)."""
+    gold = np.load(f"{GOLDEN}/model_ortho9d.npz")
+    raw = torch.from_numpy(gold["raw"]).to(cuda_dev)
+    R = ortho9d2matrix(raw[:, :3].contiguous(), raw[:, 3:6].contiguous(), raw[:, 6:].contiguous())
+    want = torch.from_numpy(gold["R"])
+    # exclude ill-conditioned inputs (both implementations are arbitrary there): sigma_2 ~ sigma_3 with det<0 etc.
+    m = torch.stack([T.normalize_vector(raw[:, i:i + 3].cpu()) for i in (0, 3, 6)], dim=2)
+    s = torch.linalg.svdvals(m.double())
+    ok = (s[:, 1] - s[:, 2] > 1e-2) & (s[:, 2] > 1e-3)
+    assert ok.sum() >= 55
+    ang = T.rotation_angle_deg(R.cpu(), want)
+    assert ang[ok].max().item() < 0.01, f"rotation error {ang[ok].max().item():.4f} deg"
+    eye = torch.eye(3, device=cuda_dev).expand_as(R)
+    assert (R @ R.transpose(1, 2) - eye).abs().max().item() < 1e-5
+    assert (torch.det(R) - 1).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 32, 4096])
+def test_ortho9d_vs_oracle_random(cuda_dev, B):
+    g = torch.Generator().manual_seed(B)
+    raw = torch.randn(B, 9, generator=g)
+    R = svd3_project(raw.to(cuda_dev), True)
+    want = T.ortho9d2matrix(raw[:, :3], raw[:, 3:6], raw[:, 6:])
+    m = torch.stack([T.normalize_vector(raw[:, i:i + 3]) for i in (0, 3, 6)], dim=2)
+    s = torch.linalg.svdvals(m.double())
+    ok = (s[:, 1] - s[:, 2] > 1e-2) & (s[:, 2] > 1e-3)
+    assert T.rotation_angle_deg(R.cpu(), want)[ok].max().item() < 0.01
+    # against the exact (fp64) projection the kernel should be far tighter than the fp32 reference itself
+    exact = T.project_so3(m)
+    assert T.rotation_angle_deg(R.cpu(), exact)[ok].max().item() < 2e-4
+
+
+def test_ortho9d_reflection_case(cuda_dev):
+    """det(M) < 0: the sign goes on the smallest singular direction and the result is still a rotation."""
+    raw = torch.tensor([[1.0, 0.1, 0.0, 0.0, 1.0, 0.2, 0.1, 0.0, -0.5]])
+    R = svd3_project(raw.to(cuda_dev), True)
+    want = T.ortho9d2matrix(raw[:, :3], raw[:, 3:6], raw[:, 6:])
+    assert T.rotation_angle_deg(R.cpu(), want).item() < 0.01
+    assert abs(torch.det(R).item() - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("B,N", [(4, 1024), (32, 1024), (3, 100)])
+def test_weighted_kabsch(cuda_dev, B, N):
+    """Recovers a known rigid motion under noise weights; matches the fp64 oracle (parity unpinned by the
+    reference: the op is not in it)."""
+    g = torch.Generator().manual_seed(B * N)
+    src = (torch.rand(B, N, 3, generator=g) - 0.5) * 0.2
+    q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    q = q * torch.det(q).sign().view(B, 1, 1)
+    t = (torch.rand(B, 3, generator=g) - 0.5) * 0.06
+    dst = src @ q.transpose(1, 2) + t.unsqueeze(1) + 1e-3 * torch.randn(B, N, 3, generator=g)
+    w = torch.rand(B, N, generator=g)
+    R, tt = weighted_kabsch(src.to(cuda_dev), dst.to(cuda_dev), w.to(cuda_dev))
+    R_o, t_o = T.weighted_kabsch(src, dst, w)
+    assert T.rotation_angle_deg(R.cpu(), R_o).max().item() < 0.01
+    assert (tt.cpu().double() - t_o).abs().max().item() < 1e-5
+    assert T.rotation_angle_deg(R.cpu(), q).max().item() < 0.5
+
+
+def test_point_feats_golden(cuda_dev):
+    """Fixture from the reference's Ops_GetPointFeat_spconv (models/Modules.py:227-251) over the C-oracle ops."""
+    import types
+    gold = np.load(f"{GOLDEN}/model_point_feats.npz")
+    g = torch.Generator().manual_seed(int(gold["seed"]))
+    bsz, npts = 3, 200
+    points = (torch.rand(bsz * npts, 3, generator=g) - 0.5) * 0.2
+    batch_ids = torch.arange(bsz).repeat_interleave(npts)
+    levels = []
+    for li, (scale, ch) in enumerate(zip([2, 4, 6, 8], [32, 64, 128, 256])):
+        mv = [90, 40, 20, 6][li] * bsz
+        ind = torch.cat([torch.randint(0, bsz, (mv, 1), generator=g),
+                         torch.randint(0, 64 // scale, (mv, 3), generator=g)], 1).int()
+        ind = torch.unique(ind, dim=0)
+        ind = ind[torch.randperm(ind.shape[0], generator=g)]
+        levels.append(types.SimpleNamespace(features=torch.randn(ind.shape[0], ch, generator=g), indices=ind))
+    getter = Ops_GetPointFeat_spconv(scale_lists=[2, 4, 6, 8], unit_voxel_extent=np.array([0.006] * 3),
+                                     voxel_num_limit=[64, 64, 64])
+    with torch.no_grad():
+        got = getter(points.to(cuda_dev), batch_ids.to(cuda_dev), *levels_to(levels, cuda_dev))
+    want = torch.from_numpy(gold["point_feats"])
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-6
+    # the autograd (unfused) path gives the same numbers
+    for l in levels:
+        l.features.requires_grad_(True)
+    lv = levels_to(levels, cuda_dev)
+    for l in lv:
+        l.features.requires_grad_(True)
+    got2 = getter(points.to(cuda_dev), batch_ids.to(cuda_dev), *lv)
+    assert torch.equal(got2.detach(), got)
+    got2.sum().backward()
+    assert all(l.features.grad is not None for l in lv)
+
+
+def _tail_pair(seed, n, mode, dev, c_m=64):
+    torch.manual_seed(seed)
+    oracle_net = T.TailNetwork(mode=mode, c_m=c_m).eval()
+    net = Network(Cfg(n), mode=mode, c_m=c_m).eval()
+    missing = net.load_state_dict(oracle_net.state_dict(), strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return oracle_net, net.to(dev)
+
+
+def test_tail_golden(cuda_dev):
+    """Fixture produced by exec'ing the reference's own Network.forward FDA section (DCL_Net.py:187-235)."""
+    gold = np.load(f"{GOLDEN}/model_tail_b2_n128.npz")
+    oracle_net, net = _tail_pair(int(gold["seed_weights"]), 128, "train", cuda_dev)
+    from oracle.make_golden import param_checksum
+    assert abs(param_checksum(oracle_net) - float(gold["param_checksum"])) < 1e-6 * abs(float(gold["param_checksum"]))
+    g = torch.Generator().manual_seed(int(gold["seed_inputs"]))
+    f_xc, f_yo = torch.randn(256, 480, generator=g), torch.randn(256, 480, generator=g)
+    with torch.no_grad():
+        out = net.forward_from_point_feats(f_xc.to(cuda_dev), f_yo.to(cuda_dev), 2)
+    for k in ("F_Xo_p", "Xo_pred", "Yc_pred", "conf"):
+        assert rel_err(out[k], torch.from_numpy(gold[k])) < 1e-3, k
+    for k in ("F_Yc_p", "F_Xo_m", "F_Yc_m"):
+        assert rel_err(out["_debug"][k], torch.from_numpy(gold[k])) < 1e-3, k
+    ang = T.rotation_angle_deg(out["rot_pred"].cpu(), torch.from_numpy(gold["rot_pred"])).max().item()
+    dt = np.abs(out["trans_pred"].cpu().numpy() - gold["trans_pred"]).max()
+    assert ang < 0.01 and dt < 1e-5, (ang, dt)
+
+
+@pytest.mark.parametrize("b,n,c_m", [(4, 1024, 64), (2, 1024, 128), (32, 1024, 64)])
+def test_tail_vs_oracle(cuda_dev, b, n, c_m):
+    oracle_net, net = _tail_pair(3, n, "test", cuda_dev, c_m)
+    g = torch.Generator().manual_seed(b)
+    f_xc, f_yo = torch.randn(b * n, 480, generator=g), torch.randn(b * n, 480, generator=g)
+    with torch.no_grad():
+        want = oracle_net.to(cuda_dev)(f_xc.to(cuda_dev), f_yo.to(cuda_dev), b, n, n)  # fp32, TF32 off
+        got = net.forward_from_point_feats(f_xc.to(cuda_dev), f_yo.to(cuda_dev), b)
+    assert rel_err(got["F_Xo_p"], want["F_Xo_p"]) < 1e-3
+    assert rel_err(got["conf"], want["conf"]) < 1e-3
+    ang = T.rotation_angle_deg(got["rot_pred"].cpu(), want["rot_pred"].cpu()).max().item()
+    dt = (got["trans_pred"] - want["trans_pred"]).abs().max().item()
+    assert ang < 0.01 and dt < 1e-5, (ang, dt)
+
+
+def test_stage1_from_backbone_vs_oracle(cuda_dev):
+    """Point-feature interpolation -> FDA -> pose on a synthetic voxel pyramid (SURVEY.md §8d config 3, B=4)."""
+    b, n = 4, 1024
+    g = torch.Generator().manual_seed(12)
+    pts_inp = (torch.rand(b * n, 3, generator=g) - 0.5) * 0.16
+    pts_tmp = (torch.rand(b * n, 3, generator=g) - 0.5) * 0.16
+    lv_inp, lv_tmp = synthetic_backbone_levels(1, pts_inp, b), synthetic_backbone_levels(2, pts_tmp, b)
+    oracle_net, net = _tail_pair(4, n, "test", cuda_dev)
+    ids = torch.arange(b).repeat_interleave(n)
+    c_nn = lambda u, k: tuple(map(torch.from_numpy, cpu_oracle.sp_three_nn(u.numpy(), k.numpy())))
+    f_xc = T.get_point_feats(pts_inp, ids, [(l.features, l.indices) for l in lv_inp], [0.006] * 3, three_nn=c_nn)
+    f_yo = T.get_point_feats(pts_tmp, ids, [(l.features, l.indices) for l in lv_tmp], [0.006] * 3, three_nn=c_nn)
+    with torch.no_grad():
+        want = oracle_net(f_xc, f_yo, b, n, n)
+        got = net.forward_from_backbone(levels_to(lv_inp, cuda_dev), levels_to(lv_tmp, cuda_dev),
+                                        pts_inp.to(cuda_dev), pts_tmp.to(cuda_dev), b)
+    ang = T.rotation_angle_deg(got["rot_pred"].cpu(), want["rot_pred"]).max().item()
+    dt = (got["trans_pred"].cpu() - want["trans_pred"]).abs().max().item()
+    assert ang < 0.01 and dt < 1e-5, (ang, dt)
+
+
+def test_refiner_golden_and_loop(cuda_dev):
+    gold = np.load(f"{GOLDEN}/model_refiner.npz")
+    torch.manual_seed(int(gold["seed_weights"]))
+    oracle_ref = T.RefinerNet().eval()
+    ref = Refiner().eval()
+    ref.load_state_dict(oracle_ref.state_dict())
+    ref = ref.to(cuda_dev)
+    g = torch.Generator().manual_seed(int(gold["seed_inputs"]))
+    inp = {"input_features": torch.randn(2, 259, 1024, generator=g).to(cuda_dev),
+           "conf": torch.rand(2, 2048, generator=g).to(cuda_dev), "obj_idx": None}
+    with torch.no_grad():
+        out = ref(inp)
+    assert T.rotation_angle_deg(out["rot_pred"].cpu(), torch.from_numpy(gold["rot_pred"])).max().item() < 0.01
+    assert np.abs(out["trans_pred"].cpu().numpy() - gold["trans_pred"]).max() < 1e-5
+    # stage-2 loop (tools/test_YCBV_stage2.py:204-225), 2 iterations, vs the restated loop
+    B, N = 6, 1024
+    pts = (torch.rand(B, N, 3, generator=g) - 0.5) * 0.2
+    q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    rot = (q * torch.det(q).sign().view(B, 1, 1)).contiguous()
+    trans = (torch.rand(B, 3, generator=g) - 0.5) * 0.1
+    f = torch.randn(B, 256, N, generator=g)
+    conf = torch.rand(B, 2 * N, generator=g)
+    with torch.no_grad():
+        r_o, t_o = T.stage2_refine(oracle_ref, pts, rot, trans, f, conf, 2)
+        r_g, t_g = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), f.to(cuda_dev),
+                                conf.to(cuda_dev), 2)
+    assert T.rotation_angle_deg(r_g.cpu(), r_o).max().item() < 0.01
+    assert (t_g.cpu() - t_o).abs().max().item() < 1e-5

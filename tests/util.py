@@ -1,0 +1,74 @@
+"""Seeded synthetic inputs shared by the CPU and GPU tests."""
+import types
+
+import numpy as np
+import torch
+
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+
+
+def uniform_cloud(seed, b, n):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(b, n, 3, generator=g)
+
+
+def cad_like_cloud(seed, b, n, n_unique=None):
+    """Non-uniform surface-like cloud in metres, resampled WITH replacement => duplicated points => ties
+    (the dataloader does this when a crop has too few points, YCBV/dataloader_train_YCBV.py:195-198)."""
+    g = torch.Generator().manual_seed(seed)
+    n_unique = n_unique or max(8, n // 3)
+    u = torch.rand(b, n_unique, 2, generator=g)
+    theta, z = u[..., 0] * 6.2831853, (u[..., 1] - 0.5) * 0.2
+    base = torch.stack([0.05 * torch.cos(theta), 0.05 * torch.sin(theta), z], -1)
+    base = (base * 512).round() / 512  # coarse grid => exact distance ties between distinct points too
+    pick = torch.randint(0, n_unique, (b, n), generator=g)
+    return torch.gather(base, 1, pick.unsqueeze(-1).expand(b, n, 3)).contiguous()
+
+
+def flat_bxyz(seed, b, n_per, shuffle=True, scale=0.2):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.arange(b).repeat_interleave(n_per).float().unsqueeze(1)
+    pts = (torch.rand(b * n_per, 3, generator=g) - 0.5) * scale
+    rows = torch.cat([ids, pts], 1)
+    if shuffle:
+        rows = rows[torch.randperm(rows.shape[0], generator=g)]
+    return rows.contiguous()
+
+
+def synthetic_backbone_levels(seed, points, b, unit=0.006, scales=(2, 4, 6, 8), channels=(32, 64, 128, 256),
+                              shuffle=True):
+    """Voxel pyramid a sparse-conv backbone would output for `points` (b*n,3): per level, the occupied
+    voxels at that scale dilated by a 3x3x3 stencil, random features, rows shuffled across batches
+    (spconv does not keep them batch-sorted).  Offset/extent as models/Modules.py:234, DCL_Net.py:54."""
+    g = torch.Generator().manual_seed(seed)
+    n_per = points.shape[0] // b
+    ids = torch.arange(b).repeat_interleave(n_per)
+    offset = -0.5 * unit * 64
+    stencil = torch.stack(torch.meshgrid(*([torch.arange(-1, 2)] * 3), indexing="ij"), -1).reshape(-1, 3)
+    levels = []
+    for scale, ch in zip(scales, channels):
+        ext = unit * scale
+        lim = 64 // scale + (1 if 64 % scale else 0)
+        vox = torch.floor((points - offset) / ext).long().clamp(0, lim - 1)
+        vox = (vox[:, None, :] + stencil[None]).reshape(-1, 3)
+        bid = ids[:, None].expand(-1, 27).reshape(-1, 1)
+        keep = ((vox >= 0) & (vox < lim)).all(1)
+        ind = torch.unique(torch.cat([bid, vox], 1)[keep], dim=0).int()
+        if shuffle:
+            ind = ind[torch.randperm(ind.shape[0], generator=g)]
+        feats = torch.randn(ind.shape[0], ch, generator=g)
+        levels.append(types.SimpleNamespace(features=feats, indices=ind.contiguous()))
+    return levels
+
+
+def levels_to(levels, dev):
+    return [types.SimpleNamespace(features=l.features.to(dev), indices=l.indices.to(dev)) for l in levels]
+
+
+def rel_err(got, want):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def np_t(x):
+    return x.detach().cpu().numpy()
