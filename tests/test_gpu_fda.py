@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import torch_oracle as T
-from tests.util import GOLDEN, rel_err
+from dcl_testutil import GOLDEN, rel_err
 
 pytestmark = pytest.mark.gpu
 

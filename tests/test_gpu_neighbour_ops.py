@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import cpu_oracle, ref_kernels
-from tests.util import cad_like_cloud, flat_bxyz, np_t, rel_err, uniform_cloud
+from dcl_testutil import cad_like_cloud, flat_bxyz, np_t, rel_err, uniform_cloud
 
 pytestmark = pytest.mark.gpu
 

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import cpu_oracle, torch_oracle as T
-from tests.util import GOLDEN, levels_to, rel_err, synthetic_backbone_levels
+from dcl_testutil import GOLDEN, levels_to, rel_err, synthetic_backbone_levels
 
 pytestmark = pytest.mark.gpu
 

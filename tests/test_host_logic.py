@@ -1,0 +1,66 @@
+"""CPU: host-side logic — instance sharding, flat-tensor re-basing, and the N>1 pose gather over gloo (world 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dcl_net_b200 import sharding
+from dcl_testutil import flat_bxyz
+
+
+def test_instance_range_partitions():
+    for total in (0, 1, 7, 32, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.instance_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_flat_rebases_batch_ids():
+    rows = flat_bxyz(0, 8, 10)
+    parts = []
+    for r in range(4):
+        lo, hi = sharding.instance_range(8, r, 4)
+        part, keep = sharding.shard_flat(rows, lo, hi)
+        assert part[:, 0].min() >= 0 and part[:, 0].max() < hi - lo
+        assert torch.equal(part[:, 1:], rows[keep][:, 1:])
+        parts.append(int(keep.sum()))
+    assert sum(parts) == rows.shape[0]
+
+
+def test_gather_poses_single_process_is_identity():
+    r, t = torch.eye(3).repeat(5, 1, 1), torch.zeros(5, 3)
+    r2, t2 = sharding.gather_poses(r, t)
+    assert r2 is r and t2 is t
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = sharding.instance_range(total, rank, world)
+        ids = torch.arange(lo, hi, dtype=torch.float32)
+        rot = ids.view(-1, 1, 1) * torch.ones(1, 3, 3)
+        trans = ids.view(-1, 1) + torch.tensor([0.1, 0.2, 0.3])
+        r, t = sharding.gather_poses(rot, trans)
+        assert r.shape == (total, 3, 3) and t.shape == (total, 3)
+        assert torch.equal(r[:, 0, 0], torch.arange(total, dtype=torch.float32))
+        assert torch.allclose(t[:, 2], torch.arange(total, dtype=torch.float32) + 0.3)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 7])
+def test_gather_poses_world2_gloo(total):
+    mp.spawn(_worker, args=(2, _free_port(), total), nprocs=2, join=True)

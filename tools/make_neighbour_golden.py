@@ -10,8 +10,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import ref_kernels as R  # noqa: E402
-from tests.util import cad_like_cloud, flat_bxyz, uniform_cloud  # noqa: E402
+from dcl_testutil import cad_like_cloud, flat_bxyz, uniform_cloud  # noqa: E402
 
 
 def cases():
