@@ -14,6 +14,7 @@ _I, _F, _P, _SZ, _I64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_
 SIGNATURES = {
     "dcl_b200_abi_version": (_I, []),
     "dcl_b200_arch": (_I, []),
+    "dcl_b200_launch_count": (ctypes.c_ulonglong, []),
     "dcl_lib_furthest_point_sampling_kernel_launcher": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "dcl_lib_gather_points_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "dcl_lib_gather_points_grad_kernel_launcher_fast": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
@@ -32,6 +33,8 @@ SIGNATURES = {
     "dcl_sp_nn_interpolate_fused": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_fda_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "dcl_fda_align_fwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_pack": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_fwd_packed": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_attention_map": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
     "dcl_weighted_kabsch": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),

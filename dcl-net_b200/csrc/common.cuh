@@ -16,7 +16,16 @@
         if (!(cond)) return (int)cudaErrorInvalidValue; \
     } while (0)
 
-static inline int dcl_launch_status() { return (int)cudaGetLastError(); }
+// Diagnostic only: number of kernels this library has launched in the process
+// (dcl_b200_launch_count()).  Not used by any computation.
+extern unsigned long long g_dcl_kernel_launches;
+#define DCL_COUNT_LAUNCHES(n) (g_dcl_kernel_launches += (unsigned long long)(n))
+
+// Called after an entry point has issued `n_kernels` launches.
+static inline int dcl_launch_status(int n_kernels = 1) {
+    DCL_COUNT_LAUNCHES(n_kernels);
+    return (int)cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------
 // Reference arithmetic.  nvcc (-O2, default -fmad=true) contracts the

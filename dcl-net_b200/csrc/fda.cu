@@ -391,28 +391,30 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
                 m_ref = mx;
                 need = true;
             }
-            float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const float p = exp2f(__fmaf_rn(__uint_as_float(sv[i]), LOG2E, -m_ref));
-                sum += p;
-                sv[i] = __float_as_uint(p);
-            }
-            l = __fmaf_rn(l, alpha, sum);
+            for (int i = 0; i < 64; ++i)
+                sv[i] = __float_as_uint(exp2f(__fmaf_rn(__uint_as_float(sv[i]), LOG2E, -m_ref)));
 
             if (Cfg::NP == 1 && j >= 1) dcl_mbar_wait(o_done, (uint32_t)((j - 1) & 1));
             {
                 unsigned char* pd = p_row_base + (j % Cfg::NP) * Cfg::P_BYTES;
+                // The row sum is taken over the weights the tensor core will actually see (hi + lo), so that
+                // numerator and denominator of the softmax carry the same rounding.
+                float sum = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < KB / 8; ++kc) {
                     __nv_bfloat16 h[8], lw[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split_bf16(__uint_as_float(sv[kc * 8 + i]), h[i], lw[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        split_bf16(__uint_as_float(sv[kc * 8 + i]), h[i], lw[i]);
+                        sum += __bfloat162float(h[i]) + __bfloat162float(lw[i]);
+                    }
                     *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) =
                         make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
                     *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) =
                         make_uint4(pack2(lw[0], lw[1]), pack2(lw[2], lw[3]), pack2(lw[4], lw[5]), pack2(lw[6], lw[7]));
                 }
+                l = __fmaf_rn(l, alpha, sum);
             }
             if (j >= 1) {
                 if (Cfg::NP != 1) dcl_mbar_wait(o_done, (uint32_t)((j - 1) & 1));
@@ -587,30 +589,47 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int K, const 
 }
 
 template <int C>
-int fda_launch(int b, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2, float* RE_embed,
-               float* RI_embed, float* lse_out, void* workspace, cudaStream_t st) {
-    using Cfg = FdaCfg<C>;
-    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-    const size_t q_bytes = (size_t)b * (n / QT) * Cfg::Q_BYTES;
-    const size_t k_bytes = (size_t)b * (m / KB) * Cfg::K_BYTES;
-    __nv_bfloat16* Qp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* Kp = reinterpret_cast<__nv_bfloat16*>(ws + q_bytes);
-    __nv_bfloat16* Vp = reinterpret_cast<__nv_bfloat16*>(ws + q_bytes + k_bytes);
-    {
-        const int work_q = n * (C / 8), work_k = m * (C / 8), work_v = Cfg::VROWS * (m / 8);
-        int work = work_q > work_k ? work_q : work_k;
-        if (work_v > work) work = work_v;
-        dim3 grid(DCL_DIVUP(work, 256), b, 3);
-        fda_pack_kernel<C><<<grid, 256, 0, st>>>(n, m, RI_1, RI_2, RE_2, Qp, Kp, Vp);
-        int e = dcl_launch_status();
-        if (e) return e;
+struct FdaWs {
+    __nv_bfloat16 *Qp, *Kp, *Vp;
+    FdaWs(void* workspace, int b, int n, int m) {
+        using Cfg = FdaCfg<C>;
+        unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+        const size_t q_bytes = (size_t)b * (n / QT) * Cfg::Q_BYTES;
+        const size_t k_bytes = (size_t)b * (m / KB) * Cfg::K_BYTES;
+        Qp = reinterpret_cast<__nv_bfloat16*>(ws);
+        Kp = reinterpret_cast<__nv_bfloat16*>(ws + q_bytes);
+        Vp = reinterpret_cast<__nv_bfloat16*>(ws + q_bytes + k_bytes);
     }
+};
+
+template <int C>
+int fda_pack_launch(int b, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2, void* workspace,
+                    cudaStream_t st) {
+    using Cfg = FdaCfg<C>;
+    FdaWs<C> w(workspace, b, n, m);
+    const int work_q = n * (C / 8), work_k = m * (C / 8), work_v = Cfg::VROWS * (m / 8);
+    int work = work_q > work_k ? work_q : work_k;
+    if (work_v > work) work = work_v;
+    dim3 grid(DCL_DIVUP(work, 256), b, 3);
+    fda_pack_kernel<C><<<grid, 256, 0, st>>>(n, m, RI_1, RI_2, RE_2, w.Qp, w.Kp, w.Vp);
+    return dcl_launch_status();
+}
+
+template <int C>
+int fda_main_launch(int b, int n, int m, float* RE_embed, float* RI_embed, float* lse_out, void* workspace,
+                    cudaStream_t st) {
+    using Cfg = FdaCfg<C>;
+    FdaWs<C> w(workspace, b, n, m);
     cudaError_t e = cudaFuncSetAttribute(fda_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(n / QT, b);
-    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, Qp, Kp, Vp, RE_embed, RI_embed, lse_out);
+    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, w.Qp, w.Kp, w.Vp, RE_embed, RI_embed, lse_out);
     return dcl_launch_status();
+}
+
+bool fda_shape_ok(int b, int c, int p, int n, int m) {
+    return b >= 0 && (c == 64 || c == 128) && p == FDA_P && n > 0 && m > 0 && n % QT == 0 && m % KB == 0;
 }
 
 }  // namespace
@@ -621,19 +640,35 @@ DCL_API size_t dcl_fda_workspace_bytes(int b, int c, int p, int n, int m) {
     return (size_t)b * ((size_t)n * c + (size_t)m * c + (size_t)m * (p + c)) * 4 + 1024;
 }
 
-DCL_API int dcl_fda_align_fwd(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2,
-                              const float* RE_2, float* RE_embed, float* RI_embed, float* lse_out, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-    DCL_RETURN_IF_BAD(b >= 0 && (c == 64 || c == 128) && p == FDA_P);
-    DCL_RETURN_IF_BAD(n > 0 && m > 0 && n % QT == 0 && m % KB == 0);
+DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
     DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 1023u) == 0);
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     DCL_RETURN_IF_BAD(((((uintptr_t)RE_2) | ((uintptr_t)RI_2)) & 15u) == 0);
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c == 64)
-        return fda_launch<64>(b, n, m, RI_1, RI_2, RE_2, RE_embed, RI_embed, lse_out, workspace, st);
-    return fda_launch<128>(b, n, m, RI_1, RI_2, RE_2, RE_embed, RI_embed, lse_out, workspace, st);
+    if (c == 64) return fda_pack_launch<64>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
+    return fda_pack_launch<128>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
+}
+
+DCL_API int dcl_fda_fwd_packed(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, float* lse_out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
+    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 1023u) == 0);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c == 64) return fda_main_launch<64>(b, n, m, RE_embed, RI_embed, lse_out, workspace, st);
+    return fda_main_launch<128>(b, n, m, RE_embed, RI_embed, lse_out, workspace, st);
+}
+
+DCL_API int dcl_fda_align_fwd(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2,
+                              const float* RE_2, float* RE_embed, float* RI_embed, float* lse_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    int e = dcl_fda_pack(b, c, p, n, m, RI_1, RI_2, RE_2, workspace, workspace_bytes, stream);
+    if (e) return e;
+    return dcl_fda_fwd_packed(b, c, p, n, m, RE_embed, RI_embed, lse_out, workspace, workspace_bytes, stream);
 }
 
 DCL_API int dcl_fda_attention_map(int b, int c, int n, int m, const float* RI_1, const float* RI_2,

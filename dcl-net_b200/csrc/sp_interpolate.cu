@@ -380,7 +380,7 @@ int build_buckets(int m, const float* known, int* ws, float4* sorted, cudaStream
     if (m > 0) sp_bucket_hist_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws);
     sp_bucket_scan_kernel<<<1, 1024, 0, st>>>(ws);
     if (m > 0) sp_bucket_scatter_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws, sorted);
-    return dcl_launch_status();
+    return dcl_launch_status(m > 0 ? 3 : 1);
 }
 
 }  // namespace

@@ -279,11 +279,16 @@ DCL_API int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, 
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int update = (dR != nullptr && dt != nullptr) ? 1 : 0;
+    int launched = 0;
     if (n > 0 && points_in != nullptr && points_out_cm != nullptr) {
+        ++launched;
         dim3 grid(DCL_DIVUP(n, 256), b);
         pose_compose_kernel<<<grid, 256, 0, st>>>(n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride,
                                                   update);
     }
-    if (update) pose_commit_kernel<<<DCL_DIVUP(b, 128), 128, 0, st>>>(b, R, t, dR, dt);
-    return dcl_launch_status();
+    if (update) {
+        ++launched;
+        pose_commit_kernel<<<DCL_DIVUP(b, 128), 128, 0, st>>>(b, R, t, dR, dt);
+    }
+    return dcl_launch_status(launched);
 }

@@ -1,0 +1,72 @@
+"""PoseEngine — the call a user of this path makes: a batch of instances on the HOST in, poses on the host out.
+
+    engine = PoseEngine(net, device, batch, refiner=None, iterations=0)
+    rot, trans = engine.infer(host_batch)
+
+`host_batch` is what a backbone provider would hand over (pinned host tensors):
+    {"points_inp": (B*N,3), "points_tmp": (B*M,3),
+     "inp": [(features (Mv,C_l), indices (Mv,4) int32 bxyz) x 4 levels], "tmp": [... x 4]}
+Device buffers are allocated once with a fixed row capacity per pyramid level; every call copies the batch into
+them (cudaMemcpyAsync from pinned memory) and pads unused rows with batch id == B, a bucket no query belongs to,
+so shapes stay static.  Multi-GPU: one engine per process / GPU over its own instance shard (sharding.py).
+"""
+import types
+
+import torch
+
+from . import _lib as L
+from .refiner import refine_poses
+
+
+class PoseEngine:
+    def __init__(self, net, device, batch, capacities, refiner=None, iterations=0):
+        """capacities: per level, the maximum number of voxel rows of a batch (both towers use the same)."""
+        self.net, self.refiner, self.iterations = net.eval(), refiner, iterations
+        self.device, self.b = device, batch
+        self.n_inp, self.n_tmp = net.n_inp, net.n_tmp
+        L.load()
+        f32, i32 = dict(dtype=torch.float32, device=device), dict(dtype=torch.int32, device=device)
+        self.points = {"inp": torch.empty(batch * self.n_inp, 3, **f32), "tmp": torch.empty(batch * self.n_tmp, 3, **f32)}
+        self.levels = {}
+        for side in ("inp", "tmp"):
+            self.levels[side] = [types.SimpleNamespace(features=torch.zeros(cap, ch, **f32),
+                                                       indices=torch.zeros(cap, 4, **i32))
+                                 for cap, ch in zip(capacities, (32, 64, 128, 256))]
+        self.out_host = torch.empty(batch, 12, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 0
+
+    def load(self, host_batch):
+        """Asynchronous host->device copy of one batch into the static buffers."""
+        nbytes = 0
+        for side in ("inp", "tmp"):
+            src = host_batch["points_" + side]
+            self.points[side].copy_(src, non_blocking=True)
+            nbytes += src.numel() * 4
+            for lvl, (feats, ind) in zip(self.levels[side], host_batch[side]):
+                m = feats.shape[0]
+                if m > lvl.features.shape[0]:
+                    raise ValueError("PoseEngine: batch exceeds the level capacity it was built with")
+                lvl.features[:m].copy_(feats, non_blocking=True)
+                lvl.indices[:m].copy_(ind, non_blocking=True)
+                lvl.indices[m:, 0] = self.b  # padding rows: a batch id no query has
+                nbytes += feats.numel() * 4 + ind.numel() * 4
+        self.h2d_bytes = nbytes
+
+    @torch.no_grad()
+    def run(self):
+        """Device-resident pass over the loaded batch -> (rot (B,3,3), trans (B,3)) on the device."""
+        pred = self.net.forward_from_backbone(self.levels["inp"], self.levels["tmp"], self.points["inp"],
+                                              self.points["tmp"], self.b)
+        rot, trans = pred["rot_pred"], pred["trans_pred"]
+        if self.refiner is not None and self.iterations > 0:
+            rot, trans = refine_poses(self.refiner, self.points["inp"].view(self.b, self.n_inp, 3), rot, trans,
+                                      pred["F_Xo_p"], pred["conf"], self.iterations)
+        return rot, trans
+
+    def infer(self, host_batch):
+        """Host in, host out: H2D copies + pass + D2H of the (B,12) poses; returns after the poses have landed."""
+        self.load(host_batch)
+        rot, trans = self.run()
+        self.out_host.copy_(torch.cat([rot.reshape(self.b, 9), trans], dim=1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.out_host[:, :9].view(self.b, 3, 3), self.out_host[:, 9:]

@@ -15,6 +15,8 @@ from . import _lib as L
 from .pointnet_sp import pointnet2_utils as pointnet2_utils_sp
 
 _fda_ws = {}
+# bench.py sets this to a list to collect (start, end) CUDA events around every launch of the fused kernel.
+FDA_KERNEL_EVENTS = None
 
 
 def _fda_workspace(nbytes, device):
@@ -50,9 +52,17 @@ def fda_align(RI_1, RI_2, RE_2, return_lse=False):
     RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=RI_1.device)
     RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=RI_1.device)
     lse = torch.empty(B, N, dtype=torch.float32, device=RI_1.device) if return_lse else None
-    L.check(lib.dcl_fda_align_fwd(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(RE_embed),
-                                  L.ptr(RI_embed), L.ptr(lse), L.ptr(ws), ws.numel(), L.stream_ptr()),
-            "fda_align")
+    st = L.stream_ptr()
+    L.check(lib.dcl_fda_pack(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), st),
+            "fda_align (pack)")
+    if FDA_KERNEL_EVENTS is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    L.check(lib.dcl_fda_fwd_packed(B, C, P, N, M, L.ptr(RE_embed), L.ptr(RI_embed), L.ptr(lse), L.ptr(ws),
+                                   ws.numel(), st), "fda_align")
+    if FDA_KERNEL_EVENTS is not None:
+        ev1.record()
+        FDA_KERNEL_EVENTS.append((ev0, ev1))
     return (RE_embed, RI_embed, lse) if return_lse else (RE_embed, RI_embed)
 
 

@@ -31,6 +31,8 @@ extern "C" {
 int dcl_b200_abi_version(void);
 /* Compiled-for architecture as an integer (100 for sm_100a). */
 int dcl_b200_arch(void);
+/* Diagnostic: number of kernels this library has launched so far in the process. */
+unsigned long long dcl_b200_launch_count(void);
 
 /* ------------------------------------------------------------------------- */
 /* Group 1a: libs/pointnet_lib (batched (B,N,3) clouds)                        */
@@ -149,6 +151,16 @@ int dcl_sp_nn_interpolate_fused(int n, int m, int c,
 size_t dcl_fda_workspace_bytes(int b, int c, int p, int n, int m);
 int dcl_fda_align_fwd(int b, int c, int p, int n, int m,
     const float* RI_1, const float* RI_2, const float* RE_2,
+    float* RE_embed, float* RI_embed, float* lse_out,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two halves of dcl_fda_align_fwd, for callers that want to time or reuse them:
+ * dcl_fda_pack converts the fp32 operands into the bf16 hi/lo tile images in `workspace`;
+ * dcl_fda_fwd_packed runs the fused tcgen05 kernel on a packed workspace. */
+int dcl_fda_pack(int b, int c, int p, int n, int m,
+    const float* RI_1, const float* RI_2, const float* RE_2,
+    void* workspace, size_t workspace_bytes, void* stream);
+int dcl_fda_fwd_packed(int b, int c, int p, int n, int m,
     float* RE_embed, float* RI_embed, float* lse_out,
     void* workspace, size_t workspace_bytes, void* stream);
 

@@ -35,34 +35,7 @@ def flat_bxyz(seed, b, n_per, shuffle=True, scale=0.2):
     return rows.contiguous()
 
 
-def synthetic_backbone_levels(seed, points, b, unit=0.006, scales=(2, 4, 6, 8), channels=(32, 64, 128, 256),
-                              shuffle=True):
-    """Voxel pyramid a sparse-conv backbone would output for `points` (b*n,3): per level, the occupied
-    voxels at that scale dilated by a 3x3x3 stencil, random features, rows shuffled across batches
-    (spconv does not keep them batch-sorted).  Offset/extent as models/Modules.py:234, DCL_Net.py:54."""
-    g = torch.Generator().manual_seed(seed)
-    n_per = points.shape[0] // b
-    ids = torch.arange(b).repeat_interleave(n_per)
-    offset = -0.5 * unit * 64
-    stencil = torch.stack(torch.meshgrid(*([torch.arange(-1, 2)] * 3), indexing="ij"), -1).reshape(-1, 3)
-    levels = []
-    for scale, ch in zip(scales, channels):
-        ext = unit * scale
-        lim = 64 // scale + (1 if 64 % scale else 0)
-        vox = torch.floor((points - offset) / ext).long().clamp(0, lim - 1)
-        vox = (vox[:, None, :] + stencil[None]).reshape(-1, 3)
-        bid = ids[:, None].expand(-1, 27).reshape(-1, 1)
-        keep = ((vox >= 0) & (vox < lim)).all(1)
-        ind = torch.unique(torch.cat([bid, vox], 1)[keep], dim=0).int()
-        if shuffle:
-            ind = ind[torch.randperm(ind.shape[0], generator=g)]
-        feats = torch.randn(ind.shape[0], ch, generator=g)
-        levels.append(types.SimpleNamespace(features=feats, indices=ind.contiguous()))
-    return levels
-
-
-def levels_to(levels, dev):
-    return [types.SimpleNamespace(features=l.features.to(dev), indices=l.indices.to(dev)) for l in levels]
+from dcl_net_b200.synthetic import backbone_levels as synthetic_backbone_levels, levels_to  # noqa: E402,F401
 
 
 def rel_err(got, want):

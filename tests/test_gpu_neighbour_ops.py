@@ -217,7 +217,10 @@ def test_sp_three_interpolate_fwd_bwd(cuda_dev, c):
 
 @pytest.mark.parametrize("b,n_per,m_per,c", [(4, 256, 300, 32), (8, 1024, 130, 128), (2, 100, 2, 64), (3, 50, 40, 7)])
 def test_sp_nn_interpolate_fused_equals_unfused(cuda_dev, b, n_per, m_per, c):
-    """Fused search+weights+interpolation == the three-step chain of models/Modules.py:213-226, bit for bit."""
+    """Fused search+weights+interpolation vs the three-step chain of models/Modules.py:213-226 (kernel ->
+    torch element-wise weights -> kernel).  Neighbours are identical; the weights go through torch's own
+    element-wise kernels in the chain and through explicit IEEE ops in the fused kernel, so values agree to
+    rounding (<= 1e-6 relative), not necessarily bit for bit."""
     unknown, known = _sp_case(111, b, n_per, m_per)
     feats = torch.randn(known.shape[0], c, generator=torch.Generator().manual_seed(3))
     u, k, f = unknown.to(cuda_dev), known.to(cuda_dev), feats.to(cuda_dev)
@@ -228,5 +231,5 @@ def test_sp_nn_interpolate_fused_equals_unfused(cuda_dev, b, n_per, m_per, c):
     out = torch.full((u.shape[0], c + 8), -1.0, device=cuda_dev)
     pu_sp.nn_interpolate(u, k, f, out, 4 if c % 4 == 0 else 1)
     col0 = 4 if c % 4 == 0 else 1
-    _eq(out[:, col0:col0 + c], want, "fused nn_interpolate")
+    assert rel_err(out[:, col0:col0 + c], want) < 1e-6, "fused nn_interpolate"
     assert float(out[:, :col0].min()) == -1.0 and float(out[:, col0 + c:].max()) == -1.0

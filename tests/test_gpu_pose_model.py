@@ -111,7 +111,7 @@ def test_point_feats_golden(cuda_dev):
     for l in lv:
         l.features.requires_grad_(True)
     got2 = getter(points.to(cuda_dev), batch_ids.to(cuda_dev), *lv)
-    assert torch.equal(got2.detach(), got)
+    assert rel_err(got2, got) < 1e-6
     got2.sum().backward()
     assert all(l.features.grad is not None for l in lv)
 
