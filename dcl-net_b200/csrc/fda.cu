@@ -137,8 +137,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;                // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE (0)
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 // hi/lo split product:  D (+)= Ahi*Bhi + Ahi*Blo + Alo*Bhi   (one UMMA K step, K = 16)
@@ -540,7 +541,22 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int K, const 
         *reinterpret_cast<uint4*>(d) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
         *reinterpret_cast<uint4*>(d + a_half) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
     }
-    for (int i = threadIdx.x; i < N * kch; i += 128) {
+    const bool b_mn = (swap_lbo_sbo & 2) != 0;
+    swap_lbo_sbo &= 1;
+    const int nch = N / 8;
+    if (b_mn) {
+        // B^T image: rows = k (the contraction index), 8-element chunks along n — the "point-major" image of a
+        // (K points x N channels) activation, consumed as an MN-major B operand.
+        for (int i = threadIdx.x; i < K * nch; i += 128) {
+            const int k = i % K, nc = i / K;
+            __nv_bfloat16 h[8], l[8];
+            for (int e = 0; e < 8; ++e) split_bf16(B[(size_t)(nc * 8 + e) * K + k], h[e], l[e]);
+            unsigned char* d = sB + ((k >> 3) * nch + nc) * 128 + (k & 7) * 16;
+            *reinterpret_cast<uint4*>(d) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+            *reinterpret_cast<uint4*>(d + b_half) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+        }
+    }
+    for (int i = threadIdx.x; i < (b_mn ? 0 : N * kch); i += 128) {
         const int r = i % N, kc = i / N;
         __nv_bfloat16 h[8], l[8];
         for (int e = 0; e < 8; ++e) split_bf16(B[(size_t)r * K + kc * 8 + e], h[e], l[e]);
@@ -561,12 +577,17 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int K, const 
     if (threadIdx.x == 0) {
         uint32_t lbo = 128, sbo = (uint32_t)kch * 128;
         if (swap_lbo_sbo) { const uint32_t t = lbo; lbo = sbo; sbo = t; }
-        const uint32_t idesc = umma_idesc_bf16(128, N);
+        const uint32_t idesc = umma_idesc_bf16(128, N, b_mn);
         const uint32_t a0 = dcl_smem_u32(sA), b0 = dcl_smem_u32(sB);
+        // MN-major B: LBO = stride between 8-row K groups, SBO = stride between 8-element chunks along N.
+        uint32_t b_lbo = b_mn ? (uint32_t)nch * 128 : lbo, b_sbo = b_mn ? 128u : sbo;
+        if (b_mn && swap_lbo_sbo) { const uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+        if (b_mn) { lbo = 128; sbo = (uint32_t)kch * 128; }
         for (int kk = 0; kk < K / 16; ++kk) {
             const uint32_t off = kk * 256;
-            mma_split3(tmem_base, a0 + off, a0 + a_half + off, b0 + off, b0 + b_half + off, lbo, sbo, lbo, sbo, idesc,
-                       kk == 0);
+            const uint32_t boff = b_mn ? kk * 2 * (uint32_t)nch * 128 : off;
+            mma_split3(tmem_base, a0 + off, a0 + a_half + off, b0 + boff, b0 + b_half + boff, lbo, sbo, b_lbo, b_sbo,
+                       idesc, kk == 0);
         }
         tc_commit(&bar);
     }
@@ -643,7 +664,7 @@ DCL_API size_t dcl_fda_workspace_bytes(int b, int c, int p, int n, int m) {
 DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2,
                          void* workspace, size_t workspace_bytes, void* stream) {
     DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
-    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 1023u) == 0);
+    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 127u) == 0);
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     DCL_RETURN_IF_BAD(((((uintptr_t)RE_2) | ((uintptr_t)RI_2)) & 15u) == 0);
     if (b == 0) return 0;
@@ -655,7 +676,7 @@ DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, c
 DCL_API int dcl_fda_fwd_packed(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, float* lse_out,
                                void* workspace, size_t workspace_bytes, void* stream) {
     DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
-    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 1023u) == 0);
+    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 127u) == 0);
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -682,7 +703,7 @@ DCL_API int dcl_fda_attention_map(int b, int c, int n, int m, const float* RI_1,
 
 DCL_API int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, int swap_lbo_sbo,
                                 void* stream) {
-    DCL_RETURN_IF_BAD(N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0);
+    DCL_RETURN_IF_BAD(N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0 && swap_lbo_sbo >= 0 && swap_lbo_sbo < 4);
     const size_t smem = (size_t)(128 + N) * K * 4;
     DCL_RETURN_IF_BAD(smem <= 200 * 1024);
     cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

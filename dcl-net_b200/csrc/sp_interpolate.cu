@@ -192,43 +192,53 @@ __global__ void sp_bucket_scatter_kernel(int m, const float* __restrict__ known,
     sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
 }
 
-// Per-lane 3-NN over the lane's own bucket; a warp walks the distinct batch ids
-// present among its lanes so that every candidate load is a warp-uniform broadcast.
-__device__ __forceinline__ void sp_segmented_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
-                                                    const float4* __restrict__ known4, int m, bool valid, float4 u,
-                                                    float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+// 3-NN of one query by a group of LPQ consecutive lanes: lane `sub` scans candidates sub, sub+LPQ, ... of the
+// query's bucket (coalesced 16-B loads), then the LPQ partial triples are merged by a shuffle butterfly.  The
+// lexicographic key (d, original index) makes the result independent of who saw which candidate in which order.
+// All 32 lanes of the warp must call this (full-mask shuffles); afterwards every lane of a group holds the result.
+constexpr int LPQ = 8;
+
+__device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
+                                                const float4* __restrict__ known4, int m, bool valid, float4 u,
+                                                int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
     b1 = b2 = b3 = CUDART_INF_F;
-    i1 = i2 = i3 = 0;
+    i1 = i2 = i3 = 0x7fffffff;  // sentinels lose every tie; mapped back to the reference's 0 at the end
     if (ws[WS_FLAG] != 0) {
-        // Some batch id is not a small non-negative integer: buckets are unusable, do the
-        // reference's full ascending scan (float equality on the id) straight from global.
-        for (int k = 0; k < m; ++k) {
-            const float4 c = __ldg(known4 + k);
-            if (c.x != u.x) continue;
-            const float d = dcl_dist2(u.y, u.z, u.w, c.y, c.z, c.w);
-            nn3_insert_strict(d, k, b1, b2, b3, i1, i2, i3);
-        }
-        return;
-    }
-    int my_b;
-    const int nb = ws[WS_NB];
-    const bool has_bucket = valid && batch_id_ok(u.x, my_b) && my_b < nb;
-    unsigned todo = __ballot_sync(0xffffffffu, has_bucket);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int bid = __shfl_sync(0xffffffffu, my_b, leader);
-        const bool mine = has_bucket && (my_b == bid);
-        const int beg = ws[WS_OFF + bid], end = ws[WS_OFF + bid + 1];
-#pragma unroll 4
-        for (int j = beg; j < end; ++j) {
-            const float4 c = __ldg(sorted + j);
-            if (mine) {
-                const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
-                nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+        // Some batch id is not a small non-negative integer: buckets are unusable, scan everything
+        // (float equality on the id, as the reference does).
+        if (valid) {
+            for (int k = sub; k < m; k += LPQ) {
+                const float4 c = __ldg(known4 + k);
+                if (c.x != u.x) continue;
+                const float d = dcl_dist2(u.y, u.z, u.w, c.y, c.z, c.w);
+                if (d < CUDART_INF_F) nn3_insert_lex(d, k, b1, b2, b3, i1, i2, i3);  // inf / NaN never enter
             }
         }
-        todo &= ~__ballot_sync(0xffffffffu, mine);
+    } else {
+        int my_b;
+        if (valid && batch_id_ok(u.x, my_b) && my_b < ws[WS_NB]) {
+            const int beg = ws[WS_OFF + my_b], end = ws[WS_OFF + my_b + 1];
+#pragma unroll 4
+            for (int j = beg + sub; j < end; j += LPQ) {
+                const float4 c = __ldg(sorted + j);
+                const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
+                if (d < CUDART_INF_F) nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+            }
+        }
     }
+#pragma unroll
+    for (int o = LPQ / 2; o > 0; o >>= 1) {
+        const float ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o),
+                    ob3 = __shfl_xor_sync(0xffffffffu, b3, o);
+        const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o),
+                  oi3 = __shfl_xor_sync(0xffffffffu, i3, o);
+        nn3_insert_lex(ob1, oi1, b1, b2, b3, i1, i2, i3);
+        nn3_insert_lex(ob2, oi2, b1, b2, b3, i1, i2, i3);
+        nn3_insert_lex(ob3, oi3, b1, b2, b3, i1, i2, i3);
+    }
+    if (i1 == 0x7fffffff) i1 = 0;  // unfilled slots: (inf, 0) like the reference
+    if (i2 == 0x7fffffff) i2 = 0;
+    if (i3 == 0x7fffffff) i3 = 0;
 }
 
 __global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int m, const float* __restrict__ unknown,
@@ -237,13 +247,14 @@ __global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int 
                                                                      const float4* __restrict__ sorted,
                                                                      float* __restrict__ dist2,
                                                                      int* __restrict__ idx) {
-    const int qi = blockIdx.x * SP_THREADS + threadIdx.x;
+    const int qi = blockIdx.x * (SP_THREADS / LPQ) + threadIdx.x / LPQ;
+    const int sub = threadIdx.x % LPQ;
     const bool valid = qi < n;
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     float b1, b2, b3;
     int i1, i2, i3;
-    sp_segmented_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, b1, b2, b3, i1, i2, i3);
-    if (valid) {
+    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, i1, i2, i3);
+    if (valid && sub == 0) {
         dist2[qi * 3 + 0] = b1;
         dist2[qi * 3 + 1] = b2;
         dist2[qi * 3 + 2] = b3;
@@ -320,9 +331,10 @@ __global__ void __launch_bounds__(256) sp_interp_grad_v1_kernel(int c, int n, co
 }
 
 // ------------------------------------------------ fused search + interpolation
-// Phase 1: lane = query, segmented 3-NN, weights as models/Modules.py:222-224:
-//   dist = sqrt(d2); r = 1/(dist+1e-8); w = r / ((r0+r1)+r2)
-// Phase 2: the warp walks its 32 queries; lanes spread over channels (float4 each).
+// A group of LPQ lanes owns one query: segmented 3-NN (above), then weights as models/Modules.py:222-224
+//   dist = sqrt(d2); r = 1/(dist+1e-8); w = r / sum(r)      (sum associated as torch's CUDA reduction does
+//                                                             for a row of three: (r0 + r2) + r1)
+// and the group's lanes spread over the channels of the output row (float4 each).
 __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, int m, int c,
                                                                         const float* __restrict__ unknown,
                                                                         const float* __restrict__ known,
@@ -331,45 +343,37 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, i
                                                                         const float* __restrict__ feats,
                                                                         float* __restrict__ out, int out_stride,
                                                                         int out_col0, int vec_ok) {
-    const int qi = blockIdx.x * SP_THREADS + threadIdx.x;
+    const int qi = blockIdx.x * (SP_THREADS / LPQ) + threadIdx.x / LPQ;
+    const int sub = threadIdx.x % LPQ;
     const bool valid = qi < n;
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     float b1, b2, b3;
-    int i1, i2, i3;
-    sp_segmented_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, b1, b2, b3, i1, i2, i3);
+    int j0, j1, j2;
+    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+    if (!valid) return;
     const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
     const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
     const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
-    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
-
-    const int lane = threadIdx.x & 31;
-    const int q_base = qi - lane;
-    for (int q = 0; q < 32; ++q) {
-        if (q_base + q >= n) break;
-        const int j0 = __shfl_sync(0xffffffffu, i1, q), j1 = __shfl_sync(0xffffffffu, i2, q),
-                  j2 = __shfl_sync(0xffffffffu, i3, q);
-        const float a0 = __shfl_sync(0xffffffffu, w0, q), a1 = __shfl_sync(0xffffffffu, w1, q),
-                    a2 = __shfl_sync(0xffffffffu, w2, q);
-        float* orow = out + (size_t)(q_base + q) * out_stride + out_col0;
-        if (vec_ok) {
-            const float4* f0 = reinterpret_cast<const float4*>(feats + (size_t)j0 * c);
-            const float4* f1 = reinterpret_cast<const float4*>(feats + (size_t)j1 * c);
-            const float4* f2 = reinterpret_cast<const float4*>(feats + (size_t)j2 * c);
-            for (int cc = lane; cc < (c >> 2); cc += 32) {
-                const float4 x0 = __ldg(f0 + cc), x1 = __ldg(f1 + cc), x2 = __ldg(f2 + cc);
-                float4 o;
-                o.x = dcl_interp3(a0, x0.x, a1, x1.x, a2, x2.x);
-                o.y = dcl_interp3(a0, x0.y, a1, x1.y, a2, x2.y);
-                o.z = dcl_interp3(a0, x0.z, a1, x1.z, a2, x2.z);
-                o.w = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
-                reinterpret_cast<float4*>(orow)[cc] = o;
-            }
-        } else {
-            for (int cc = lane; cc < c; cc += 32)
-                orow[cc] = dcl_interp3(a0, feats[(size_t)j0 * c + cc], a1, feats[(size_t)j1 * c + cc], a2,
-                                       feats[(size_t)j2 * c + cc]);
+    const float norm = __fadd_rn(__fadd_rn(r0, r2), r1);
+    const float a0 = __fdiv_rn(r0, norm), a1 = __fdiv_rn(r1, norm), a2 = __fdiv_rn(r2, norm);
+    float* orow = out + (size_t)qi * out_stride + out_col0;
+    if (vec_ok) {
+        const float4* f0 = reinterpret_cast<const float4*>(feats + (size_t)j0 * c);
+        const float4* f1 = reinterpret_cast<const float4*>(feats + (size_t)j1 * c);
+        const float4* f2 = reinterpret_cast<const float4*>(feats + (size_t)j2 * c);
+        for (int cc = sub; cc < (c >> 2); cc += LPQ) {
+            const float4 x0 = __ldg(f0 + cc), x1 = __ldg(f1 + cc), x2 = __ldg(f2 + cc);
+            float4 o;
+            o.x = dcl_interp3(a0, x0.x, a1, x1.x, a2, x2.x);
+            o.y = dcl_interp3(a0, x0.y, a1, x1.y, a2, x2.y);
+            o.z = dcl_interp3(a0, x0.z, a1, x1.z, a2, x2.z);
+            o.w = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
+            reinterpret_cast<float4*>(orow)[cc] = o;
         }
+    } else {
+        for (int cc = sub; cc < c; cc += LPQ)
+            orow[cc] = dcl_interp3(a0, feats[(size_t)j0 * c + cc], a1, feats[(size_t)j1 * c + cc], a2,
+                                   feats[(size_t)j2 * c + cc]);
     }
 }
 
@@ -412,7 +416,7 @@ DCL_API int dcl_sp_three_nn_segmented(int n, int m, const float* unknown, const 
     float4* sorted = (float4*)(ws + WS_HDR_INTS);
     int err = build_buckets(m, known, ws, sorted, st);
     if (err) return err;
-    const int grid = DCL_DIVUP(n, SP_THREADS);
+    const int grid = DCL_DIVUP(n, SP_THREADS / LPQ);
     sp_three_nn_seg_kernel<<<grid, SP_THREADS, 0, st>>>(n, m, unknown, known, ws, sorted, dist2, idx);
     return dcl_launch_status();
 }
@@ -469,7 +473,7 @@ DCL_API int dcl_sp_nn_interpolate_fused(int n, int m, int c, const float* unknow
     if (err) return err;
     const int vec_ok = ((c & 3) == 0) && ((out_stride & 3) == 0) && ((out_col0 & 3) == 0) &&
                        ((((uintptr_t)feats) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
-    sp_nn_interp_fused_kernel<<<DCL_DIVUP(n, SP_THREADS), SP_THREADS, 0, st>>>(
+    sp_nn_interp_fused_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
         n, m, c, unknown, known, ws, sorted, feats, out, out_stride, out_col0, vec_ok);
     return dcl_launch_status();
 }

@@ -33,7 +33,7 @@ def _check(got, want, what, tol_norm=5e-4, atol_rel=1e-4):
     assert excess <= 0, f"{what}: allclose(rtol=1e-3, atol={atol_rel:.0e}*scale) violated by {excess:.3e}"
 
 
-@pytest.mark.parametrize("N,K", [(64, 64), (256, 64), (64, 128), (32, 16), (128, 256)])
+@pytest.mark.parametrize("N,K", [(64, 64), (256, 64), (64, 128), (32, 16), (128, 128)])
 def test_umma_probe(cuda_dev, N, K):
     """Pins the UMMA descriptor / TMEM conventions the FDA kernel relies on: one CTA, D = A B^T."""
     g = torch.Generator().manual_seed(N * 1000 + K)

@@ -104,16 +104,14 @@ def test_point_feats_golden(cuda_dev):
     want = torch.from_numpy(gold["point_feats"])
     assert got.shape == want.shape
     assert rel_err(got, want) < 1e-6
-    # the autograd (unfused) path gives the same numbers
-    for l in levels:
-        l.features.requires_grad_(True)
+    # the autograd (unfused) path gives the same numbers and propagates gradients to the voxel features
     lv = levels_to(levels, cuda_dev)
     for l in lv:
         l.features.requires_grad_(True)
     got2 = getter(points.to(cuda_dev), batch_ids.to(cuda_dev), *lv)
     assert rel_err(got2, got) < 1e-6
     got2.sum().backward()
-    assert all(l.features.grad is not None for l in lv)
+    assert all(l.features.grad is not None and float(l.features.grad.abs().sum()) > 0 for l in lv)
 
 
 def _tail_pair(seed, n, mode, dev, c_m=64):
