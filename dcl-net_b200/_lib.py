@@ -39,8 +39,23 @@ SIGNATURES = {
     "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
     "dcl_weighted_kabsch": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "dcl_pose_compose": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "dcl_pm_gemm": (_I, [_I, _P, _I, _P]),
+    "dcl_pm_pack_rows": (_I, [_I, _I, _I, _P, _P, _P]),
+    "dcl_pm_pack_cm": (_I, [_I, _I, _I, _P, _P, _P]),
+    "dcl_pm_unpack": (_I, [_I, _I, _P, _P, _P]),
+    "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _I, _P]),
+    "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
+
+
+
+class PmGemmProblem(ctypes.Structure):
+    """Mirror of dcl_pm_gemm_problem (include/dcl_b200.h)."""
+    _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
+                ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
+                ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P)]
+
 
 _lib = None
 

@@ -1,0 +1,326 @@
+// Point-major tensor-core GEMM for the pointwise MLP stacks of the FDA section
+// (models/DCL_Net.py:56-151: the disengage Conv3d1x1+BN+ReLU stacks; models/Modules.py:173-201:
+//  Head_MultiLayerPerceptron = Conv1d(k=1) -> ReLU -> [BatchNorm1d]).  A 1x1 convolution over points is
+//      Y[r, o] = act( sum_i X[r, i] * W[o, i] + bias[o] )        r = point (row), i/o = channels
+// The reference runs them as fp32 cuDNN/cuBLAS SIMT kernels; they are ~95 % of the stage-1 step.
+//
+// Here they run on tcgen05 with the same bf16 hi/lo operand split as the FDA kernel (3 MMAs per product,
+// fp32 accumulation in TMEM => fp32-faithful results) and a fused epilogue
+//      bias -> ReLU -> optional per-channel affine (eval-mode BatchNorm after the ReLU)
+// that emits, as requested per problem:
+//   * the next layer's operand directly ("PM image", below) — activations never round-trip through fp32,
+//   * an fp32 channel-major (B, C, N) tensor (what the FDA kernel / the caller consume),
+//   * per-warp partial sums of  row_weight[r] * Y[r, :]  (the confidence-weighted pooling of
+//     models/DCL_Net.py:228), reduced later in a fixed order => deterministic.
+// Eval-mode BN *before* the ReLU (the disengage blocks) is folded into W and bias on the host.
+//
+// PM image of an (R x C) activation, R % 128 == 0, C % 32 == 0: blobs of (128 rows x 32 channels), each blob
+// = bf16 hi image (8 KB) then bf16 lo image (8 KB), each image in the UMMA K-major no-swizzle layout
+//   byte(r, c, half) = ((r/128)*(C/32) + c/32)*16384 + half*8192 + ((r%128)/8)*512 + ((c%32)/8)*128 + (r%8)*16 + (c%8)*2
+// so one blob is one pipeline stage of the A operand, moved by ONE TMA bulk copy (LBO 128 B, SBO 512 B).
+// Packed weights: per (n-tile of NT output channels, k-block of 32 input channels) one blob
+//   [hi (NT x 32) | lo (NT x 32)], same layout with NT rows — one bulk copy per stage.
+//
+// CTA = 128 rows x NT output channels; warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue.
+// Two CTAs are resident per SM (TMEM NT <= 256 columns each), so one CTA's epilogue overlaps the other's MMAs.
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/dcl_b200.h"
+
+namespace {
+
+constexpr int GM_BM = 128;
+constexpr int GM_BK = 32;
+constexpr int GM_THREADS = 192;
+constexpr int GM_A_BLOB = GM_BM * GM_BK * 4;  // 16384
+constexpr int GM_MAX_PROBLEMS = 8;
+
+struct PmGemmBatch {
+    dcl_pm_gemm_problem p[GM_MAX_PROBLEMS];
+};
+
+template <int NT, int STAGES>
+struct GmCfg {
+    static constexpr int B_BLOB = NT * GM_BK * 4;
+    static constexpr int STAGE_BYTES = GM_A_BLOB + B_BLOB;
+    static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 128;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch) {
+    using Cfg = GmCfg<NT, STAGES>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const dcl_pm_gemm_problem& pr = batch.p[blockIdx.z];
+    const int mt = blockIdx.x, nti = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = pr.kb_total;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            dcl_mbar_init(full + i, 1);
+            dcl_mbar_init(empty + i, 1);
+        }
+        dcl_mbar_init(acc_full, 1);
+        dcl_fence_barrier_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
+            const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
+                                      (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
+            const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((kb / STAGES) - 1) & 1));
+                unsigned char* dst = smem + s * Cfg::STAGE_BYTES;
+                dcl_mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * GM_A_BLOB
+                                                          : a1 + (size_t)(kb - pr.kb0) * GM_A_BLOB;
+                dcl_bulk_g2s(dst, asrc, GM_A_BLOB, full + s);
+                dcl_bulk_g2s(dst + GM_A_BLOB, w + (size_t)kb * Cfg::B_BLOB, Cfg::B_BLOB, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                dcl_mbar_wait(full + s, (uint32_t)((kb / STAGES) & 1));
+                tc_fence_after();
+                const uint32_t a = dcl_smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t b = a + GM_A_BLOB;
+#pragma unroll
+                for (int ks = 0; ks < GM_BK / 16; ++ks) {
+                    const uint32_t off = ks * 256;
+                    mma_split3(tmem_base, a + off, a + GM_A_BLOB / 2 + off, b + off, b + Cfg::B_BLOB / 2 + off, 128, 512,
+                               128, 512, idesc, kb == 0 && ks == 0);
+                }
+                tc_commit(empty + s);
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const size_t r_glob = (size_t)mt * GM_BM + row;
+        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+        const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
+        const int cout = pr.cout;
+        size_t cm_base = 0;
+        if (pr.out_cm != nullptr) {
+            const size_t inst = r_glob / pr.rows_per_inst, within = r_glob - inst * pr.rows_per_inst;
+            cm_base = inst * (size_t)cout * pr.rows_per_inst + within;
+        }
+        dcl_mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < NT / 32; ++cc) {
+            uint32_t v[32];
+            DCL_TMEM_LD32(tmem_base + t_lane + cc * 32, v);
+            tc_wait_ld();
+            const int col0 = nti * NT + cc * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float y = __uint_as_float(v[i]);
+                if (pr.bias != nullptr) y += __ldg(pr.bias + col0 + i);
+                if (pr.relu) y = fmaxf(y, 0.f);
+                if (pr.post_scale != nullptr) y = __fmaf_rn(y, __ldg(pr.post_scale + col0 + i), __ldg(pr.post_shift + col0 + i));
+                v[i] = __float_as_uint(y);
+            }
+            if (pr.out_pm != nullptr) {
+                unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
+                                      ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[ch * 8 + e]), h[e], l[e]);
+                    *reinterpret_cast<uint4*>(blob + ch * 128) =
+                        make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+                    *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) =
+                        make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+                }
+            }
+            if (pr.out_cm != nullptr) {
+                float* o = pr.out_cm + cm_base + (size_t)col0 * pr.rows_per_inst;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[(size_t)i * pr.rows_per_inst] = __uint_as_float(v[i]);
+            }
+            if (pr.pool_out != nullptr) {
+                float pv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pv[i] = __uint_as_float(v[i]) * rw;
+                // transpose-reduce: afterwards pv[0] on lane L = sum over the warp's 32 rows of column L
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const bool upper = (lane & s) != 0;
+#pragma unroll
+                    for (int i = 0; i < s; ++i) {
+                        const float send = upper ? pv[i] : pv[i + s];
+                        const float keep = upper ? pv[i + s] : pv[i];
+                        pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                    }
+                }
+                pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncwarp();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, NT);
+    }
+}
+
+// ------------------------------------------------------------------ packing helpers
+// fp32 row-major (rows x c, row stride `ld`) -> PM image.  Thread = (row, chunk of 8 channels).
+__global__ void __launch_bounds__(256) pm_pack_rows_kernel(int rows, int c, int ld, const float* __restrict__ src,
+                                                           unsigned char* __restrict__ dst) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    const int nchunk = c / 8;
+    if (g >= (long)rows * nchunk) return;
+    // consecutive threads -> consecutive rows of the same chunk: 8 lanes write one 128-B run
+    const int r = (int)(g % rows), ch = (int)(g / rows);
+    const float* s = src + (size_t)r * ld + ch * 8;
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(__ldg(s + e), h[e], l[e]);
+    unsigned char* d = dst + ((size_t)(r / 128) * (c / 32) + ch / 4) * GM_A_BLOB + ((r % 128) >> 3) * 512 + (ch & 3) * 128 +
+                       (r & 7) * 16;
+    *reinterpret_cast<uint4*>(d) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(d + GM_A_BLOB / 2) =
+        make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+// fp32 channel-major (b, c, n) -> PM image of the (b*n x c) activation.  Thread = (row, chunk); reads coalesce
+// along n for a fixed channel.
+__global__ void __launch_bounds__(256) pm_pack_cm_kernel(int b, int c, int n, const float* __restrict__ src,
+                                                         unsigned char* __restrict__ dst) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    const long rows = (long)b * n;
+    const int nchunk = c / 8;
+    if (g >= rows * nchunk) return;
+    const long r = g % rows;
+    const int ch = (int)(g / rows);
+    const int inst = (int)(r / n), within = (int)(r % n);
+    const float* s = src + ((size_t)inst * c + ch * 8) * n + within;
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(__ldg(s + (size_t)e * n), h[e], l[e]);
+    unsigned char* d = dst + ((size_t)(r / 128) * (c / 32) + ch / 4) * GM_A_BLOB + ((r % 128) >> 3) * 512 + (ch & 3) * 128 +
+                       (r & 7) * 16;
+    *reinterpret_cast<uint4*>(d) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(d + GM_A_BLOB / 2) =
+        make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+// PM image -> fp32 row-major (hi + lo); tests / inspection.
+__global__ void __launch_bounds__(256) pm_unpack_kernel(int rows, int c, const unsigned char* __restrict__ src,
+                                                        float* __restrict__ dst) {
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)rows * c) return;
+    const int r = (int)(g / c), ch = (int)(g % c);
+    const unsigned char* s = src + ((size_t)(r / 128) * (c / 32) + ch / 32) * GM_A_BLOB + ((r % 128) >> 3) * 512 +
+                             ((ch % 32) >> 3) * 128 + (r & 7) * 16 + (ch & 7) * 2;
+    const float hi = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(s));
+    const float lo = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(s + GM_A_BLOB / 2));
+    dst[g] = hi + lo;
+}
+
+// out[inst, col] = sum over the `parts` per-warp partials of an instance, in index order (deterministic);
+// accumulate != 0 adds to what is already there.
+__global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout, int parts,
+                                                             const float* __restrict__ partials,
+                                                             float* __restrict__ out, int accumulate) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= insts * cout) return;
+    const int inst = g / cout, col = g % cout;
+    float acc = accumulate ? out[g] : 0.f;
+    const float* p = partials + (size_t)inst * parts * cout + col;
+    for (int i = 0; i < parts; ++i) acc += p[(size_t)i * cout];
+    out[g] = acc;
+}
+
+template <int NT, int STAGES>
+int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
+    using Cfg = GmCfg<NT, STAGES>;
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(rows / GM_BM, cout / NT, nprob);
+    pm_gemm_kernel<NT, STAGES><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch);
+    return dcl_launch_status();
+}
+
+}  // namespace
+
+DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int rows, void* stream) {
+    DCL_RETURN_IF_BAD(nproblems >= 1 && nproblems <= GM_MAX_PROBLEMS && problems != nullptr);
+    DCL_RETURN_IF_BAD(rows > 0 && rows % GM_BM == 0);
+    PmGemmBatch batch;
+    const int cout = problems[0].cout, nt = problems[0].nt;
+    DCL_RETURN_IF_BAD((nt == 64 || nt == 128 || nt == 256) && cout % nt == 0);
+    for (int i = 0; i < nproblems; ++i) {
+        const dcl_pm_gemm_problem& p = problems[i];
+        DCL_RETURN_IF_BAD(p.cout == cout && p.nt == nt && p.kb_total >= 1 && p.kb0 >= 0 && p.kb0 <= p.kb_total);
+        DCL_RETURN_IF_BAD(p.a0 != nullptr && p.w != nullptr && (p.kb0 == p.kb_total || p.a1 != nullptr));
+        DCL_RETURN_IF_BAD((p.post_scale == nullptr) == (p.post_shift == nullptr));
+        DCL_RETURN_IF_BAD(p.out_cm == nullptr || (p.rows_per_inst > 0 && p.rows_per_inst % 32 == 0 && rows % p.rows_per_inst == 0));
+        DCL_RETURN_IF_BAD(p.pool_out == nullptr || p.pool_w != nullptr);
+        DCL_RETURN_IF_BAD(((((uintptr_t)p.a0) | ((uintptr_t)p.a1) | ((uintptr_t)p.w) | ((uintptr_t)p.out_pm)) & 15u) == 0);
+        batch.p[i] = p;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nt == 256) return launch_gemm<256, 2>(batch, nproblems, rows, cout, st);
+    if (nt == 128) return launch_gemm<128, 3>(batch, nproblems, rows, cout, st);
+    return launch_gemm<64, 4>(batch, nproblems, rows, cout, st);
+}
+
+DCL_API int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, void* stream) {
+    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0 && ld >= c);
+    DCL_RETURN_IF_BAD((((uintptr_t)dst_pm) & 15u) == 0);
+    const long total = (long)rows * (c / 8);
+    pm_pack_rows_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
+        rows, c, ld, src, reinterpret_cast<unsigned char*>(dst_pm));
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, void* stream) {
+    DCL_RETURN_IF_BAD(b > 0 && n > 0 && ((long)b * n) % 128 == 0 && c > 0 && c % 32 == 0);
+    DCL_RETURN_IF_BAD((((uintptr_t)dst_pm) & 15u) == 0);
+    const long total = (long)b * n * (c / 8);
+    pm_pack_cm_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
+        b, c, n, src, reinterpret_cast<unsigned char*>(dst_pm));
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void* stream) {
+    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0);
+    const long total = (long)rows * c;
+    pm_unpack_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
+        rows, c, reinterpret_cast<const unsigned char*>(src_pm), dst);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, float* out, int accumulate,
+                               void* stream) {
+    DCL_RETURN_IF_BAD(insts > 0 && cout > 0 && parts > 0);
+    pm_pool_reduce_kernel<<<DCL_DIVUP(insts * cout, 256), 256, 0, (cudaStream_t)stream>>>(insts, cout, parts, partials,
+                                                                                        out, accumulate);
+    return dcl_launch_status();
+}

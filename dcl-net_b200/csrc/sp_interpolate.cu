@@ -17,6 +17,7 @@
 // reference strides by C between lanes).
 #include "common.cuh"
 #include "tile_pipe.cuh"
+#include "umma.cuh"
 #include "../../include/dcl_b200.h"
 #include <math_constants.h>
 
@@ -377,6 +378,53 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, i
     }
 }
 
+// Same, writing a PM image (see pm_gemm.cu): each lane of the group produces chunks of 8 channels and stores their
+// bf16 hi / lo halves straight into the operand layout of the first disengage GEMM.
+__global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_pm_kernel(int n, int m, int c,
+                                                                           const float* __restrict__ unknown,
+                                                                           const float* __restrict__ known,
+                                                                           const int* __restrict__ ws,
+                                                                           const float4* __restrict__ sorted,
+                                                                           const float* __restrict__ feats,
+                                                                           unsigned char* __restrict__ out_pm,
+                                                                           int c_total, int out_col0) {
+    const int qi = blockIdx.x * (SP_THREADS / LPQ) + threadIdx.x / LPQ;
+    const int sub = threadIdx.x % LPQ;
+    const bool valid = qi < n;
+    const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
+    float b1, b2, b3;
+    int j0, j1, j2;
+    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+    if (!valid) return;
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r2), r1);
+    const float a0 = __fdiv_rn(r0, norm), a1 = __fdiv_rn(r1, norm), a2 = __fdiv_rn(r2, norm);
+    const float4* f0 = reinterpret_cast<const float4*>(feats + (size_t)j0 * c);
+    const float4* f1 = reinterpret_cast<const float4*>(feats + (size_t)j1 * c);
+    const float4* f2 = reinterpret_cast<const float4*>(feats + (size_t)j2 * c);
+    unsigned char* row_base = out_pm + (size_t)(qi / 128) * (c_total / 32) * 16384 + ((qi % 128) >> 3) * 512 + (qi & 7) * 16;
+    for (int c8 = sub; c8 < (c >> 3); c8 += LPQ) {
+        float o[8];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const float4 x0 = __ldg(f0 + c8 * 2 + hh), x1 = __ldg(f1 + c8 * 2 + hh), x2 = __ldg(f2 + c8 * 2 + hh);
+            o[hh * 4 + 0] = dcl_interp3(a0, x0.x, a1, x1.x, a2, x2.x);
+            o[hh * 4 + 1] = dcl_interp3(a0, x0.y, a1, x1.y, a2, x2.y);
+            o[hh * 4 + 2] = dcl_interp3(a0, x0.z, a1, x1.z, a2, x2.z);
+            o[hh * 4 + 3] = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
+        }
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(o[e], h[e], l[e]);
+        const int chunk = (out_col0 >> 3) + c8;
+        unsigned char* d = row_base + (size_t)(chunk >> 2) * 16384 + (chunk & 3) * 128;
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+        *reinterpret_cast<uint4*>(d + 8192) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+    }
+}
+
 int build_buckets(int m, const float* known, int* ws, float4* sorted, cudaStream_t st) {
     // only the header words that are read before being written need clearing
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(WS_OFF + DCL_SP_MAX_BATCH + 4) * sizeof(int), st);
@@ -475,5 +523,23 @@ DCL_API int dcl_sp_nn_interpolate_fused(int n, int m, int c, const float* unknow
                        ((((uintptr_t)feats) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
     sp_nn_interp_fused_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
         n, m, c, unknown, known, ws, sorted, feats, out, out_stride, out_col0, vec_ok);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c, const float* unknown, const float* known,
+                                           const float* feats, void* out_pm, int c_total, int out_col0,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(n > 0 && n % 128 == 0 && m >= 0 && c > 0 && c % 8 == 0 && out_col0 % 8 == 0);
+    DCL_RETURN_IF_BAD(c_total % 32 == 0 && c_total >= out_col0 + c && workspace != nullptr && out_pm != nullptr);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_three_nn_workspace_bytes(n, m));
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
+                      ((uintptr_t)known & 15u) == 0 && ((uintptr_t)feats & 15u) == 0 && ((uintptr_t)out_pm & 15u) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* ws = (int*)workspace;
+    float4* sorted = (float4*)(ws + WS_HDR_INTS);
+    int err = build_buckets(m, known, ws, sorted, st);
+    if (err) return err;
+    sp_nn_interp_fused_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
+        n, m, c, unknown, known, ws, sorted, feats, reinterpret_cast<unsigned char*>(out_pm), c_total, out_col0);
     return dcl_launch_status();
 }

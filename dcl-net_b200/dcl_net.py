@@ -72,6 +72,20 @@ class Network(nn.Module):
         self.neck_fuser_bi = Head_MultiLayerPerceptron([256 * 2, 512, 512, 1024], *fuse)
         self.regressor_rot = Head_MultiLayerPerceptron([1024, 512, 128, 9], *plain)
         self.regressor_trans = Head_MultiLayerPerceptron([1024, 512, 128, 3], *plain)
+        self.use_fused_tail = True   # inference: pointwise MLPs on tensor cores (fused_tail.py)
+        self._fused_tail = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fused_tail = None      # parameters moved / cast: packed copies are stale
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._fused_tail = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        self._fused_tail = None
+        return super().train(mode)
 
     # ---- entry points -----------------------------------------------------------------
     def forward(self, data):
@@ -87,17 +101,40 @@ class Network(nn.Module):
         data["labels"]["points_inp"] = points_inp.view(b, self.n_inp, -1)
         return pred
 
+    def _fused(self, b):
+        """The tensor-core inference path (fused_tail.FusedTail), or None when it does not apply (training,
+        autograd, train-mode outputs, unsupported widths)."""
+        from .fused_tail import FusedTail
+        if torch.is_grad_enabled() or not self.use_fused_tail or not FusedTail.supported(self, b):
+            return None
+        if self._fused_tail is None:
+            self._fused_tail = FusedTail(self)
+        return self._fused_tail
+
+    def invalidate_packed_weights(self):
+        """Call after changing parameters in place (load_state_dict, .to()): weights are re-packed lazily."""
+        self._fused_tail = None
+
     def forward_from_backbone(self, levels_inp, levels_tmp, points_inp, points_tmp, b):
         """Pyramid levels of both towers -> prediction dict (models/DCL_Net.py:182-255)."""
         dev = points_inp.device
         ids_inp = torch.arange(b, device=dev).repeat_interleave(points_inp.shape[0] // b)
         ids_tmp = torch.arange(b, device=dev).repeat_interleave(points_tmp.shape[0] // b)
+        fused = self._fused(b)
+        if fused is not None:
+            pm_xc = self.stage1_get_point_feats.forward_pm(points_inp, ids_inp, *levels_inp)
+            pm_yo = self.stage1_get_point_feats.forward_pm(points_tmp, ids_tmp, *levels_tmp)
+            return fused.forward(pm_xc, pm_yo, b)
         F_Xc = self.stage1_get_point_feats(points_inp, ids_inp, *levels_inp)
         F_Yo = self.stage1_get_point_feats(points_tmp, ids_tmp, *levels_tmp)
         return self.forward_from_point_feats(F_Xc, F_Yo, b)
 
     def forward_from_point_feats(self, F_Xc, F_Yo, b):
         """F_Xc (b*n_inp, 480), F_Yo (b*n_tmp, 480) -> prediction dict (models/DCL_Net.py:187-255)."""
+        fused = self._fused(b)
+        if fused is not None:
+            from .fused_tail import pm_pack_rows
+            return fused.forward(pm_pack_rows(F_Xc), pm_pack_rows(F_Yo), b)
         F_Xc = F_Xc.view(b, self.n_inp, -1).transpose(1, 2)[:, :, :, None, None]
         F_Yo = F_Yo.view(b, self.n_tmp, -1).transpose(1, 2)[:, :, :, None, None]
         sq = lambda t: t.squeeze(-1).squeeze(-1)

@@ -1,0 +1,244 @@
+"""Inference engine for everything of Network.forward after the backbone (models/DCL_Net.py:182-244), with the
+pointwise MLP stacks on tensor cores (csrc/pm_gemm.cu) instead of fp32 cuDNN/cuBLAS calls.
+
+Activations travel between layers as "PM images" (bf16 hi/lo operand images, include/dcl_b200.h) written by the
+producing kernel's epilogue; fp32 channel-major tensors exist only where the reference interface or the FDA kernel
+needs them.  Weights are packed once per Network (eval-mode BatchNorm before a ReLU is folded into the convolution;
+BatchNorm after a ReLU becomes the GEMM epilogue's per-channel affine).
+
+Dataflow (test mode), b instances of n points per side, R = b*n rows:
+   PM(F_Xc), PM(F_Yo)  (R x 480)      <- pointnet_sp fused 3-NN interpolation, or pack of an fp32 (R,480) matrix
+   8 x [480 -> 256]  ReLU             one launch, 8 problems
+   4 x [256 -> 256], 4 x [256 -> c_m] two launches; outputs PM and/or fp32 (b,C,n) as their consumers need
+   dual fused FDA (csrc/fda.cu)       F_Xo_p, F_Xo_m, F_Yc_p, F_Yc_m
+   confidence heads [2c_m -> 128 -> 128] on tensor cores, [128 -> 1] + sigmoid + softmax over 2n in torch
+   fusers [512 -> 512 -> 512 -> 1024] ReLU+BN, the last layer pooling rows with the confidence weights
+   regressors on the pooled (b,1024) feature (tiny, torch) -> 9-D -> svd3_project, 3-D translation
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from .modules import fda_align
+
+_EPS_NAMES = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
+
+
+def pm_bytes(rows, c):
+    return rows * c * 4
+
+
+def pm_empty(rows, c, device):
+    return torch.empty(pm_bytes(rows, c), dtype=torch.uint8, device=device)
+
+
+def pm_pack_rows(x):
+    """fp32 (R, C) row-major -> PM image (R % 128 == 0, C % 32 == 0)."""
+    x = x.contiguous()
+    rows, c = x.shape
+    out = pm_empty(rows, c, x.device)
+    L.check(L.load().dcl_pm_pack_rows(rows, c, c, L.ptr(x), L.ptr(out), L.stream_ptr()), "pm_pack_rows")
+    return out
+
+
+def pm_pack_cm(x):
+    """fp32 (B, C, N) channel-major -> PM image of the (B*N, C) activation."""
+    x = x.contiguous()
+    b, c, n = x.shape
+    out = pm_empty(b * n, c, x.device)
+    L.check(L.load().dcl_pm_pack_cm(b, c, n, L.ptr(x), L.ptr(out), L.stream_ptr()), "pm_pack_cm")
+    return out
+
+
+def pm_unpack(pm, rows, c):
+    out = torch.empty(rows, c, dtype=torch.float32, device=pm.device)
+    L.check(L.load().dcl_pm_unpack(rows, c, L.ptr(pm), L.ptr(out), L.stream_ptr()), "pm_unpack")
+    return out
+
+
+def pick_nt(cout):
+    for nt in (256, 128, 64):
+        if cout % nt == 0:
+            return nt
+    raise ValueError(f"pm_gemm: cout={cout} is not a multiple of 64")
+
+
+def pack_weight(w, nt):
+    """(cout, cin) fp32 -> packed bf16 hi/lo blobs, one per (n-tile, k-block of 32)."""
+    cout, cin = w.shape
+    assert cout % nt == 0 and cin % 32 == 0
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+
+    def img(x):  # (tile, rg, r, kb, ch, e) -> (tile, kb, rg, ch, r, e)
+        return x.view(cout // nt, nt // 8, 8, cin // 32, 4, 8).permute(0, 3, 1, 4, 2, 5)
+    packed = torch.stack([img(hi), img(lo)], dim=2).contiguous()  # (tile, kb, half, rg, ch, r, e)
+    return packed.view(torch.uint8).reshape(-1)
+
+
+class Layer:
+    """One packed GEMM layer: y = post(relu(x W^T + bias))."""
+
+    def __init__(self, w, bias, relu, post_scale=None, post_shift=None):
+        self.cout, self.cin = w.shape
+        self.nt = pick_nt(self.cout)
+        self.w = pack_weight(w.float().contiguous(), self.nt)
+        self.bias = None if bias is None else bias.float().contiguous()
+        self.relu = int(relu)
+        self.post_scale = None if post_scale is None else post_scale.float().contiguous()
+        self.post_shift = None if post_shift is None else post_shift.float().contiguous()
+
+
+def _bn_affine(bn):
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return s, bn.bias - bn.running_mean * s
+
+
+def layers_from_disengage(stack):
+    """nn.Sequential of two BasicBlock_3DCONV (Conv3d 1x1x1 no bias -> BN3d -> ReLU): BN folded into the conv."""
+    out = []
+    for block in stack:
+        conv, bn = block.layers[0], block.layers[1]
+        s, t = _bn_affine(bn)
+        w = conv.weight.reshape(conv.out_channels, conv.in_channels) * s[:, None]
+        out.append(Layer(w, t, relu=True))
+    return out
+
+
+def layers_from_head(head):
+    """Head_MultiLayerPerceptron: Conv1d(k=1) -> [ReLU] -> [BN]; returns (gemm layers, trailing torch convs).
+    Layers whose width is not a multiple of 64 (the final 1/3/9-wide ones) stay in torch."""
+    mods = list(head.layers)
+    gemm, rest, i = [], [], 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, torch.nn.Conv1d)
+        relu = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ReLU)
+        j = i + 1 + int(relu)
+        bn = mods[j] if j < len(mods) and isinstance(mods[j], torch.nn.BatchNorm1d) else None
+        j += int(bn is not None)
+        if conv.out_channels % 64 == 0 and conv.in_channels % 32 == 0 and not rest:
+            ps, pt = _bn_affine(bn) if bn is not None else (None, None)
+            gemm.append(Layer(conv.weight.reshape(conv.out_channels, conv.in_channels), conv.bias, relu, ps, pt))
+        else:
+            rest.append((conv, relu, bn))
+        i = j
+    return gemm, rest
+
+
+def run_gemm(problems, rows):
+    """problems: list of dicts with keys a0, [a1], layer, [out_pm], [out_cm], [rows_per_inst], [pool_w], [pool_out]."""
+    arr = (L.PmGemmProblem * len(problems))()
+    keep = []
+    for slot, p in zip(arr, problems):
+        lay = p["layer"]
+        a1 = p.get("a1")
+        kb_total = lay.cin // 32
+        c0 = p.get("c0", lay.cin if a1 is None else None)
+        slot.a0, slot.a1 = L.ptr(p["a0"]), L.ptr(a1)
+        slot.kb0, slot.kb_total = c0 // 32, kb_total
+        slot.w, slot.bias = L.ptr(lay.w), L.ptr(lay.bias)
+        slot.post_scale, slot.post_shift = L.ptr(lay.post_scale), L.ptr(lay.post_shift)
+        slot.relu, slot.cout, slot.nt = lay.relu, lay.cout, lay.nt
+        slot.out_pm, slot.out_cm = L.ptr(p.get("out_pm")), L.ptr(p.get("out_cm"))
+        slot.rows_per_inst = p.get("rows_per_inst", 0)
+        slot.pool_w, slot.pool_out = L.ptr(p.get("pool_w")), L.ptr(p.get("pool_out"))
+        keep.append(p)
+    L.check(L.load().dcl_pm_gemm(len(problems), ctypes.cast(arr, ctypes.c_void_p), rows, L.stream_ptr()), "pm_gemm")
+
+
+class FusedTail:
+    """Packed-weight inference path of a dcl_net.Network (eval mode, test mode, no autograd)."""
+
+    def __init__(self, net):
+        self.net = net
+        self.c_m = net.disengage_Xc_m1[1].layers[0].out_channels
+        with torch.no_grad():
+            self.dis = {name: layers_from_disengage(getattr(net, "disengage_" + name)) for name in _EPS_NAMES}
+            self.conf, self.conf_rest = layers_from_head(net.regressor_conf)
+            self.conf_bi, self.conf_bi_rest = layers_from_head(net.regressor_conf_bi)
+            self.fuser, rest_a = layers_from_head(net.neck_fuser)
+            self.fuser_bi, rest_b = layers_from_head(net.neck_fuser_bi)
+        assert not rest_a and not rest_b and len(self.fuser) == 3 and len(self.conf) == 2
+
+    @staticmethod
+    def supported(net, b):
+        c_m = net.disengage_Xc_m1[1].layers[0].out_channels
+        return (net.n_inp == net.n_tmp and net.n_inp % 128 == 0 and c_m in (64, 128) and not net.training
+                and net.mode == "test")
+
+    def _tail_convs(self, rest, x):
+        for conv, relu, bn in rest:
+            x = conv(x)
+            if relu:
+                x = F.relu(x)
+            if bn is not None:
+                x = bn(x)
+        return x
+
+    @torch.no_grad()
+    def forward(self, pm_xc, pm_yo, b):
+        net, c_m = self.net, self.c_m
+        n = net.n_inp
+        rows = b * n
+        dev = pm_xc.device
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- disengage layer 1: eight 480 -> 256 problems in one launch
+        h1 = {name: pm_empty(rows, 256, dev) for name in _EPS_NAMES}
+        run_gemm([{"a0": pm_xc if name.startswith("Xc") else pm_yo, "layer": self.dis[name][0], "out_pm": h1[name]}
+                  for name in _EPS_NAMES], rows)
+
+        # ---- disengage layer 2: outputs in the formats their consumers read
+        pm_out = {name: pm_empty(rows, 256 if "_p" in name else c_m, dev) for name in ("Xc_p1", "Yo_p2", "Xc_m1", "Yo_m2")}
+        cm_out = {name: torch.empty(b, 256 if "_p" in name else c_m, n, **f32)
+                  for name in ("Xc_p2", "Yo_p1", "Xc_m1", "Xc_m2", "Yo_m1", "Yo_m2")}
+        for group in (("Xc_p1", "Xc_p2", "Yo_p1", "Yo_p2"), ("Xc_m1", "Xc_m2", "Yo_m1", "Yo_m2")):
+            run_gemm([{"a0": h1[name], "layer": self.dis[name][1], "out_pm": pm_out.get(name),
+                       "out_cm": cm_out.get(name), "rows_per_inst": n} for name in group], rows)
+        del h1
+
+        # ---- dual FDA (both attention products of a direction in one fused kernel)
+        F_Xo_p, F_Xo_m = fda_align(cm_out["Xc_m1"], cm_out["Yo_m1"], cm_out["Yo_p1"])
+        F_Yc_p, F_Yc_m = fda_align(cm_out["Yo_m2"], cm_out["Xc_m2"], cm_out["Xc_p2"])
+        pm_Xo_p, pm_Xo_m, pm_Yc_p, pm_Yc_m = (pm_pack_cm(t) for t in (F_Xo_p, F_Xo_m, F_Yc_p, F_Yc_m))
+
+        # ---- confidence heads: cat([F_Xc_m1, F_Xo_m]) / cat([F_Yc_m, F_Yo_m2]) -> 128 -> 128 -> 1
+        c1 = [pm_empty(rows, 128, dev) for _ in range(2)]
+        run_gemm([{"a0": pm_out["Xc_m1"], "a1": pm_Xo_m, "c0": c_m, "layer": self.conf[0], "out_pm": c1[0]},
+                  {"a0": pm_Yc_m, "a1": pm_out["Yo_m2"], "c0": c_m, "layer": self.conf_bi[0], "out_pm": c1[1]}], rows)
+        c2 = [torch.empty(b, 128, n, **f32) for _ in range(2)]
+        run_gemm([{"a0": c1[0], "layer": self.conf[1], "out_cm": c2[0], "rows_per_inst": n},
+                  {"a0": c1[1], "layer": self.conf_bi[1], "out_cm": c2[1], "rows_per_inst": n}], rows)
+        conf_1 = self._tail_convs(self.conf_rest, c2[0])
+        conf_2 = self._tail_convs(self.conf_bi_rest, c2[1])
+        conf = torch.sigmoid(torch.cat([conf_1, conf_2], dim=2))
+        conf_softmax = torch.softmax(conf, dim=2)
+        w1 = conf_softmax[:, 0, :n].reshape(-1).contiguous()
+        w2 = conf_softmax[:, 0, n:].reshape(-1).contiguous()
+
+        # ---- fusers: cat([F_Xc_p1, F_Xo_p]) / cat([F_Yc_p, F_Yo_p2]) -> 512 -> 512 -> 1024, pooled with conf_softmax
+        f1 = [pm_empty(rows, 512, dev) for _ in range(2)]
+        run_gemm([{"a0": pm_out["Xc_p1"], "a1": pm_Xo_p, "c0": 256, "layer": self.fuser[0], "out_pm": f1[0]},
+                  {"a0": pm_Yc_p, "a1": pm_out["Yo_p2"], "c0": 256, "layer": self.fuser_bi[0], "out_pm": f1[1]}], rows)
+        f2 = [pm_empty(rows, 512, dev) for _ in range(2)]
+        run_gemm([{"a0": f1[0], "layer": self.fuser[1], "out_pm": f2[0]},
+                  {"a0": f1[1], "layer": self.fuser_bi[1], "out_pm": f2[1]}], rows)
+        parts = [torch.empty(rows // 32, 1024, **f32) for _ in range(2)]
+        run_gemm([{"a0": f2[0], "layer": self.fuser[2], "pool_w": w1, "pool_out": parts[0]},
+                  {"a0": f2[1], "layer": self.fuser_bi[2], "pool_w": w2, "pool_out": parts[1]}], rows)
+        pooled = torch.empty(b, 1024, **f32)
+        lib = L.load()
+        L.check(lib.dcl_pm_pool_reduce(b, 1024, n // 32, L.ptr(parts[0]), L.ptr(pooled), 0, L.stream_ptr()), "pool")
+        L.check(lib.dcl_pm_pool_reduce(b, 1024, n // 32, L.ptr(parts[1]), L.ptr(pooled), 1, L.stream_ptr()), "pool")
+        F_p_wei = pooled.unsqueeze(-1)
+
+        # ---- pose regressors on the pooled feature (b x 1024: tiny) and the SO(3) projection
+        from .dcl_net import svd3_project
+        ortho9d = net.regressor_rot(F_p_wei).squeeze(-1)
+        rot = svd3_project(ortho9d, True)
+        trans = net.regressor_trans(F_p_wei).squeeze(-1)
+        return {"trans_pred": trans, "rot_pred": rot, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p,
+                "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}

@@ -167,6 +167,20 @@ class Ops_GetPointFeat_spconv(nn.Module):
         self.voxel_num_limit = np.asarray(voxel_num_limit)
         self.offset = -0.5 * self.unit_voxel_extent * self.voxel_num_limit
 
+    def forward_pm(self, points, batch_ids, feats1, feats2, feats3, feats4):
+        """Inference only: the concatenated (n, 480) point features as a PM image (operand of the tensor-core
+        disengage GEMMs) instead of an fp32 matrix."""
+        points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()
+        levels = [feats1, feats2, feats3, feats4]
+        width = sum(f.features.shape[1] for f in levels)
+        out = torch.empty(points.shape[0] * width * 4, dtype=torch.uint8, device=points.device)
+        col = 0
+        for scale, feats in zip(self.scale_lists, levels):
+            vx_feats, vx_points = Ops_tensor2points(feats, self.offset, self.unit_voxel_extent * scale)
+            pointnet2_utils_sp.nn_interpolate_pm(points, vx_points.contiguous(), vx_feats.contiguous(), out, width, col)
+            col += vx_feats.shape[1]
+        return out
+
     def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):
         points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()
         levels = [feats1, feats2, feats3, feats4]

@@ -112,3 +112,16 @@ def nn_interpolate(target_points, query_points, query_feats, out=None, out_col0=
                                             L.ptr(out), out.size(1), out_col0, L.ptr(ws), ws.numel(),
                                             L.stream_ptr()), "pointnet_sp.nn_interpolate")
     return out
+
+
+def nn_interpolate_pm(target_points, query_points, query_feats, out_pm, c_total, out_col0):
+    """nn_interpolate writing columns [out_col0, out_col0+C) of a PM image (operand format of the tensor-core
+    MLP kernels, include/dcl_b200.h) with c_total channels; n must be a multiple of 128."""
+    assert target_points.is_contiguous() and query_points.is_contiguous() and query_feats.is_contiguous()
+    n, m, c = target_points.size(0), query_points.size(0), query_feats.size(1)
+    lib = L.load()
+    ws = _workspace(lib.dcl_sp_three_nn_workspace_bytes(n, m), target_points.device)
+    L.check(lib.dcl_sp_nn_interpolate_fused_pm(n, m, c, L.ptr(target_points), L.ptr(query_points), L.ptr(query_feats),
+                                               L.ptr(out_pm), c_total, out_col0, L.ptr(ws), ws.numel(),
+                                               L.stream_ptr()), "pointnet_sp.nn_interpolate_pm")
+    return out_pm

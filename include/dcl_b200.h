@@ -195,6 +195,60 @@ int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, const fl
     const float* points_in, float* points_out_cm, int64_t out_batch_stride, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Group 3: pointwise MLP stacks on tensor cores (replace cuDNN/cuBLAS calls)     */
+/* ------------------------------------------------------------------------- */
+
+/* "PM image" of an (R x C) activation (R % 128 == 0, C % 32 == 0; 4*R*C bytes): blobs of 128 rows x 32
+ * channels, each blob = bf16 hi image (8 KB) then bf16 lo image (8 KB), value = hi + lo:
+ *   byte(r,c,half) = ((r/128)*(C/32) + c/32)*16384 + half*8192 + ((r%128)/8)*512 + ((c%32)/8)*128 + (r%8)*16 + (c%8)*2
+ * Packed weights of a (cout x cin) layer, n-tile width nt in {64,128,256} (cout % nt == 0, cin % 32 == 0):
+ *   byte(o,i,half) = ((o/nt)*(cin/32) + i/32)*(nt*128) + half*(nt*64) + ((o%nt)/8)*512 + ((i%32)/8)*128 + (o%8)*16 + (i%8)*2
+ *
+ * One problem:  Y = act(X W^T + bias) with X = [a0 | a1] concatenated along channels (a0 contributes kb0
+ * k-blocks of 32 channels and must be exactly that wide; a1 the remaining kb_total - kb0), i.e. the
+ * Conv3d/Conv1d 1x1 (+folded BatchNorm) + ReLU layers of models/DCL_Net.py:56-151 and the
+ * Conv1d -> ReLU -> BatchNorm layers of models/Modules.py:173-201 (post_scale/post_shift = eval-mode BN
+ * applied after the activation).  Outputs, each optional: out_pm (PM image of Y), out_cm (fp32, (R/rows_per_inst,
+ * cout, rows_per_inst) channel-major as the reference holds activations), pool_out ((R/32) x cout partial sums over
+ * each 32-row group of pool_w[r] * Y[r,:], for the confidence-weighted pooling of models/DCL_Net.py:228). */
+typedef struct dcl_pm_gemm_problem {
+    const void* a0;
+    const void* a1;
+    int kb0;
+    int kb_total;
+    const void* w;
+    const float* bias;
+    const float* post_scale;
+    const float* post_shift;
+    int relu;
+    int cout;
+    int nt;
+    void* out_pm;
+    float* out_cm;
+    int rows_per_inst;
+    const float* pool_w;
+    float* pool_out;
+} dcl_pm_gemm_problem;
+
+/* Up to 8 problems with equal (cout, nt) over the same number of rows in ONE launch (grid.z = problem). */
+int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int rows, void* stream);
+/* fp32 row-major (rows x c, leading dimension ld) -> PM image. */
+int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, void* stream);
+/* fp32 channel-major (b, c, n) -> PM image of the (b*n x c) activation. */
+int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, void* stream);
+/* PM image -> fp32 row-major (rows x c). */
+int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void* stream);
+/* out[inst, :] (+)= sum of `parts` consecutive partial rows per instance, in index order. */
+int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, float* out, int accumulate,
+    void* stream);
+/* dcl_sp_nn_interpolate_fused writing columns [out_col0, out_col0+c) of a PM image with c_total channels
+ * (n % 128 == 0, c % 8 == 0, out_col0 % 8 == 0) instead of an fp32 matrix. */
+int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c,
+    const float* unknown, const float* known, const float* feats,
+    void* out_pm, int c_total, int out_col0,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Bring-up / test hook                                                       */
 /* ------------------------------------------------------------------------- */
 /* D (128 x N) = A (128 x K) B^T (B is N x K), all row-major fp32, through exactly the

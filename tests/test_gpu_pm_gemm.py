@@ -1,0 +1,142 @@
+"""GPU parity of the tensor-core pointwise-MLP path (csrc/pm_gemm.cu, fused_tail.py) — SURVEY.md §8 a12 (the MLP
+stacks of the FDA section) and a10 (point features written as operand images).
+Oracle: fp64 matmul / the fp32 PyTorch layers of the reference (oracle/torch_oracle.py).  The bf16 hi/lo split keeps
+~2^-17 per product with fp32 accumulation: asserted at 2e-5 of the output scale per layer."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as T
+from dcl_testutil import flat_bxyz, rel_err
+
+pytestmark = pytest.mark.gpu
+
+from dcl_net_b200 import _lib as L                                  # noqa: E402
+from dcl_net_b200 import fused_tail as FT                            # noqa: E402
+from dcl_net_b200.dcl_net import Network                             # noqa: E402
+from dcl_net_b200.pointnet_sp import pointnet2_utils as pu_sp        # noqa: E402
+
+
+@pytest.mark.parametrize("rows,c", [(128, 32), (256, 480), (1024, 64)])
+def test_pm_pack_roundtrip(cuda_dev, rows, c):
+    x = torch.randn(rows, c, generator=torch.Generator().manual_seed(rows + c)).to(cuda_dev)
+    pm = FT.pm_pack_rows(x)
+    back = FT.pm_unpack(pm, rows, c)
+    assert (back - x).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
+    # channel-major packing gives the same image
+    b = rows // 128
+    x_cm = x.view(b, 128, c).transpose(1, 2).contiguous()
+    assert torch.equal(FT.pm_pack_cm(x_cm), pm)
+
+
+def _ref_layer(x, w, bias, relu, ps, pt):
+    y = x.double() @ w.double().T
+    if bias is not None:
+        y = y + bias.double()
+    if relu:
+        y = y.clamp_min(0)
+    if ps is not None:
+        y = y * ps.double() + pt.double()
+    return y
+
+
+@pytest.mark.parametrize("rows,cin,cout,relu,post,split", [
+    (256, 480, 256, True, False, 0), (128, 256, 64, True, False, 0), (384, 256, 128, False, False, 0),
+    (256, 512, 512, True, True, 256), (128, 128, 1024, True, True, 0), (256, 256, 128, True, False, 128),
+    (128, 32, 64, False, False, 0)])
+def test_pm_gemm_layer(cuda_dev, rows, cin, cout, relu, post, split):
+    g = torch.Generator().manual_seed(rows + cin + cout)
+    x = torch.randn(rows, cin, generator=g).to(cuda_dev)
+    w = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(cuda_dev)
+    bias = torch.randn(cout, generator=g).to(cuda_dev)
+    ps = (torch.rand(cout, generator=g) + 0.5).to(cuda_dev) if post else None
+    pt = torch.randn(cout, generator=g).to(cuda_dev) if post else None
+    lay = FT.Layer(w, bias, relu, ps, pt)
+    n_inst = 128
+    out_pm = FT.pm_empty(rows, cout, cuda_dev)
+    out_cm = torch.full((rows // n_inst, cout, n_inst), float("nan"), device=cuda_dev)
+    pool_w = torch.rand(rows, generator=g).to(cuda_dev)
+    pool_out = torch.full((rows // 32, cout), float("nan"), device=cuda_dev)
+    prob = {"layer": lay, "out_pm": out_pm, "out_cm": out_cm, "rows_per_inst": n_inst, "pool_w": pool_w, "pool_out": pool_out}
+    if split:
+        prob.update(a0=FT.pm_pack_rows(x[:, :split]), a1=FT.pm_pack_rows(x[:, split:]), c0=split)
+    else:
+        prob.update(a0=FT.pm_pack_rows(x))
+    FT.run_gemm([prob], rows)
+    torch.cuda.synchronize()
+    want = _ref_layer(x, w, bias, relu, ps, pt)
+    scale = want.abs().max().item()
+    got_pm = FT.pm_unpack(out_pm, rows, cout)
+    assert (got_pm.double() - want).abs().max().item() <= 3e-5 * scale
+    got_cm = out_cm.transpose(1, 2).reshape(rows, cout)
+    assert (got_cm.double() - want).abs().max().item() <= 2e-5 * scale
+    want_pool = (want * pool_w.double()[:, None]).view(rows // 32, 32, cout).sum(1)
+    assert (pool_out.double() - want_pool).abs().max().item() <= 2e-5 * want_pool.abs().max().item()
+    pooled = torch.empty(rows // n_inst, cout, device=cuda_dev)
+    L.check(L.load().dcl_pm_pool_reduce(rows // n_inst, cout, n_inst // 32, L.ptr(pool_out), L.ptr(pooled), 0,
+                                        L.stream_ptr()), "pool")
+    assert rel_err(pooled, want_pool.view(rows // n_inst, n_inst // 32, cout).sum(1)) < 2e-5
+
+
+def test_pm_gemm_batched_problems(cuda_dev):
+    """Several problems (different inputs and weights) in one launch."""
+    g = torch.Generator().manual_seed(3)
+    rows, cin, cout = 256, 64, 256
+    xs = [torch.randn(rows, cin, generator=g).to(cuda_dev) for _ in range(3)]
+    ws = [(torch.randn(cout, cin, generator=g) / 8).to(cuda_dev) for _ in range(5)]
+    outs = [FT.pm_empty(rows, cout, cuda_dev) for _ in range(5)]
+    FT.run_gemm([{"a0": FT.pm_pack_rows(xs[i % 3]), "layer": FT.Layer(ws[i], None, i % 2 == 0), "out_pm": outs[i]}
+                 for i in range(5)], rows)
+    for i in range(5):
+        want = _ref_layer(xs[i % 3], ws[i], None, i % 2 == 0, None, None)
+        assert (FT.pm_unpack(outs[i], rows, cout).double() - want).abs().max().item() <= 3e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("b,n_per,m_per,c,col0,ctot", [(2, 128, 90, 32, 0, 480), (4, 256, 40, 128, 96, 480), (1, 128, 7, 256, 224, 480)])
+def test_nn_interpolate_pm_equals_fp32(cuda_dev, b, n_per, m_per, c, col0, ctot):
+    unknown = flat_bxyz(5, b, n_per, shuffle=False).to(cuda_dev)
+    known = flat_bxyz(6, b, m_per).to(cuda_dev)
+    feats = torch.randn(known.shape[0], c, generator=torch.Generator().manual_seed(7)).to(cuda_dev)
+    want = pu_sp.nn_interpolate(unknown, known, feats)
+    pm = torch.zeros(FT.pm_bytes(b * n_per, ctot), dtype=torch.uint8, device=cuda_dev)
+    pu_sp.nn_interpolate_pm(unknown, known, feats, pm, ctot, col0)
+    got = FT.pm_unpack(pm, b * n_per, ctot)
+    assert (got[:, col0:col0 + c] - want).abs().max().item() <= 2.0 ** -16 * want.abs().max().item()
+    assert float(got[:, :col0].abs().sum()) == 0 and float(got[:, col0 + c:].abs().sum()) == 0
+
+
+class Cfg:
+    def __init__(self, n):
+        self.n_inp = self.n_tmp = n
+        self.unit_voxel_extent = [0.006] * 3
+
+
+@pytest.mark.parametrize("b,n,c_m", [(2, 128, 64), (4, 1024, 64), (2, 1024, 128)])
+def test_fused_tail_equals_unfused_and_oracle(cuda_dev, b, n, c_m):
+    torch.manual_seed(11)
+    oracle_net = T.TailNetwork(mode="test", c_m=c_m).eval()
+    # non-trivial BatchNorm statistics so that folding / the post-ReLU affine are really exercised
+    gg = torch.Generator().manual_seed(12)
+    for mod in oracle_net.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm3d)):
+            mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=gg))
+            mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=gg))
+            mod.weight.data.copy_(0.5 + torch.rand(mod.num_features, generator=gg))
+            mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=gg))
+    net = Network(Cfg(n), mode="test", c_m=c_m).eval()
+    net.load_state_dict(oracle_net.state_dict(), strict=False)
+    net = net.to(cuda_dev)
+    g = torch.Generator().manual_seed(b * n)
+    f_xc, f_yo = torch.randn(b * n, 480, generator=g).to(cuda_dev), torch.randn(b * n, 480, generator=g).to(cuda_dev)
+    with torch.no_grad():
+        got = net.forward_from_point_feats(f_xc, f_yo, b)
+        assert net._fused_tail is not None, "the tensor-core path did not run"
+        net.use_fused_tail = False
+        unfused = net.forward_from_point_feats(f_xc, f_yo, b)
+        want = oracle_net.to(cuda_dev)(f_xc, f_yo, b, n, n)
+    for ref, name in ((unfused, "unfused"), (want, "oracle")):
+        assert rel_err(got["F_Xo_p"], ref["F_Xo_p"]) < 1e-3, name
+        assert rel_err(got["conf"], ref["conf"]) < 1e-3, name
+        ang = T.rotation_angle_deg(got["rot_pred"].cpu(), ref["rot_pred"].cpu()).max().item()
+        dt = (got["trans_pred"] - ref["trans_pred"]).abs().max().item()
+        assert ang < 0.01 and dt < 1e-5, (name, ang, dt)
