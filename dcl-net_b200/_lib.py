@@ -45,6 +45,7 @@ SIGNATURES = {
     "dcl_pm_unpack": (_I, [_I, _I, _P, _P, _P]),
     "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _I, _P]),
     "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
 
@@ -54,7 +55,7 @@ class PmGemmProblem(ctypes.Structure):
     """Mirror of dcl_pm_gemm_problem (include/dcl_b200.h)."""
     _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
-                ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P)]
+                ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P)]
 
 
 _lib = None
@@ -72,7 +73,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if lib.dcl_b200_abi_version() != 1:
+        if lib.dcl_b200_abi_version() != 2:
             raise RuntimeError("libdcl_b200.so ABI version mismatch with dcl_net_b200/_lib.py")
         _lib = lib
     return _lib

@@ -11,7 +11,8 @@
 //   * the next layer's operand directly ("PM image", below) — activations never round-trip through fp32,
 //   * an fp32 channel-major (B, C, N) tensor (what the FDA kernel / the caller consume),
 //   * per-warp partial sums of  row_weight[r] * Y[r, :]  (the confidence-weighted pooling of
-//     models/DCL_Net.py:228), reduced later in a fixed order => deterministic.
+//     models/DCL_Net.py:228), reduced later in a fixed order => deterministic,
+//   * a per-row dot product  sum_o Y[r,o] * dot_w[o]  (the final 128 -> 1 layer of the confidence heads).
 // Eval-mode BN *before* the ReLU (the disengage blocks) is folded into W and bias on the host.
 //
 // PM image of an (R x C) activation, R % 128 == 0, C % 32 == 0: blobs of (128 rows x 32 channels), each blob
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
             const size_t inst = r_glob / pr.rows_per_inst, within = r_glob - inst * pr.rows_per_inst;
             cm_base = inst * (size_t)cout * pr.rows_per_inst + within;
         }
+        float dot = 0.f;
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -139,6 +141,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
                 if (pr.relu) y = fmaxf(y, 0.f);
                 if (pr.post_scale != nullptr) y = __fmaf_rn(y, __ldg(pr.post_scale + col0 + i), __ldg(pr.post_shift + col0 + i));
                 v[i] = __float_as_uint(y);
+            }
+            if (pr.dot_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dot = __fmaf_rn(__uint_as_float(v[i]), __ldg(pr.dot_w + col0 + i), dot);
             }
             if (pr.out_pm != nullptr) {
                 unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
@@ -177,6 +183,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
                 pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
             }
         }
+        if (pr.dot_out != nullptr) pr.dot_out[r_glob] = dot;
         tc_fence_before();
     }
     __syncwarp();
@@ -282,6 +289,7 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
         DCL_RETURN_IF_BAD((p.post_scale == nullptr) == (p.post_shift == nullptr));
         DCL_RETURN_IF_BAD(p.out_cm == nullptr || (p.rows_per_inst > 0 && p.rows_per_inst % 32 == 0 && rows % p.rows_per_inst == 0));
         DCL_RETURN_IF_BAD(p.pool_out == nullptr || p.pool_w != nullptr);
+        DCL_RETURN_IF_BAD(p.dot_out == nullptr || (p.dot_w != nullptr && cout == nt));
         DCL_RETURN_IF_BAD(((((uintptr_t)p.a0) | ((uintptr_t)p.a1) | ((uintptr_t)p.w) | ((uintptr_t)p.out_pm)) & 15u) == 0);
         batch.p[i] = p;
     }

@@ -127,16 +127,45 @@ __device__ __forceinline__ bool batch_id_ok(float b, int& ib) {
     return (b == (float)ib) && ib >= 0 && ib < DCL_SP_MAX_BATCH;
 }
 
-__global__ void sp_bucket_hist_kernel(int m, const float* __restrict__ known, int* __restrict__ ws) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    int ib;
-    if (batch_id_ok(known[k * 4], ib)) {
-        atomicAdd(ws + WS_OFF + ib, 1);
-        atomicMax(ws + WS_NB, ib + 1);
-    } else {
-        atomicOr(ws + WS_FLAG, 1);
+// How the m known rows are handed over: (m,4) float bxyz rows, or — fusing Ops_tensor2points
+// (models/Modules.py:204-211) — (m,4) int voxel indices (b,ix,iy,iz) whose centres are
+//   ((float(i) * ext) + offset) + 0.5*ext      evaluated in fp32 in exactly that order, as torch does.
+struct KnownRows {
+    const float* rows;
+    const int* vox;
+    float ext[3], off[3], half[3];
+    __device__ __forceinline__ float4 get(int k) const {
+        if (rows != nullptr) return __ldg(reinterpret_cast<const float4*>(rows) + k);
+        const int4 v = __ldg(reinterpret_cast<const int4*>(vox) + k);
+        return make_float4((float)v.x, __fadd_rn(__fadd_rn(__fmul_rn((float)v.y, ext[0]), off[0]), half[0]),
+                           __fadd_rn(__fadd_rn(__fmul_rn((float)v.z, ext[1]), off[1]), half[1]),
+                           __fadd_rn(__fadd_rn(__fmul_rn((float)v.w, ext[2]), off[2]), half[2]));
     }
+};
+
+constexpr int SP_SBINS = 1024;  // batch ids below this are aggregated per block in shared memory
+
+__global__ void __launch_bounds__(256) sp_bucket_hist_kernel(int m, KnownRows kr, int* __restrict__ ws) {
+    __shared__ int s_cnt[SP_SBINS];
+    __shared__ int s_max;
+    for (int i = threadIdx.x; i < SP_SBINS; i += 256) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < m) {
+        int ib;
+        if (batch_id_ok(kr.get(k).x, ib)) {
+            if (ib < SP_SBINS) atomicAdd(s_cnt + ib, 1);
+            else atomicAdd(ws + WS_OFF + ib, 1);
+            atomicMax(&s_max, ib + 1);
+        } else {
+            atomicOr(ws + WS_FLAG, 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SP_SBINS; i += 256)
+        if (s_cnt[i] != 0) atomicAdd(ws + WS_OFF + i, s_cnt[i]);
+    if (threadIdx.x == 0 && s_max != 0) atomicMax(ws + WS_NB, s_max);
 }
 
 // Single CTA: exclusive scan of the bucket counts in place; off[nb] = total.
@@ -182,15 +211,28 @@ __global__ void __launch_bounds__(1024) sp_bucket_scan_kernel(int* __restrict__ 
     if (threadIdx.x == 0) off[nb] = s_carry;
 }
 
-__global__ void sp_bucket_scatter_kernel(int m, const float* __restrict__ known, int* __restrict__ ws,
-                                         float4* __restrict__ sorted) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    const float4 r = reinterpret_cast<const float4*>(known)[k];
-    int ib;
-    if (!batch_id_ok(r.x, ib)) return;
-    const int pos = ws[WS_OFF + ib] + atomicAdd(ws + WS_CUR + ib, 1);
-    sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
+__global__ void __launch_bounds__(256) sp_bucket_scatter_kernel(int m, KnownRows kr, int* __restrict__ ws,
+                                                                float4* __restrict__ sorted) {
+    __shared__ int s_cnt[SP_SBINS];  // per-block count, then the block's base inside the bucket
+    for (int i = threadIdx.x; i < SP_SBINS; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ib = -1, local = 0;
+    if (k < m) {
+        r = kr.get(k);
+        if (!batch_id_ok(r.x, ib)) ib = -1;
+        else if (ib < SP_SBINS) local = atomicAdd(s_cnt + ib, 1);
+        else local = atomicAdd(ws + WS_CUR + ib, 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SP_SBINS; i += 256)
+        if (s_cnt[i] != 0) s_cnt[i] = atomicAdd(ws + WS_CUR + i, s_cnt[i]);
+    __syncthreads();
+    if (ib >= 0) {
+        const int pos = ws[WS_OFF + ib] + local + (ib < SP_SBINS ? s_cnt[ib] : 0);
+        sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
+    }
 }
 
 // 3-NN of one query by a group of LPQ consecutive lanes: lane `sub` scans candidates sub, sub+LPQ, ... of the
@@ -200,7 +242,7 @@ __global__ void sp_bucket_scatter_kernel(int m, const float* __restrict__ known,
 constexpr int LPQ = 8;
 
 __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
-                                                const float4* __restrict__ known4, int m, bool valid, float4 u,
+                                                const KnownRows& kr, int m, bool valid, float4 u,
                                                 int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
     b1 = b2 = b3 = CUDART_INF_F;
     i1 = i2 = i3 = 0x7fffffff;  // sentinels lose every tie; mapped back to the reference's 0 at the end
@@ -209,7 +251,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         // (float equality on the id, as the reference does).
         if (valid) {
             for (int k = sub; k < m; k += LPQ) {
-                const float4 c = __ldg(known4 + k);
+                const float4 c = kr.get(k);
                 if (c.x != u.x) continue;
                 const float d = dcl_dist2(u.y, u.z, u.w, c.y, c.z, c.w);
                 if (d < CUDART_INF_F) nn3_insert_lex(d, k, b1, b2, b3, i1, i2, i3);  // inf / NaN never enter
@@ -219,11 +261,12 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         int my_b;
         if (valid && batch_id_ok(u.x, my_b) && my_b < ws[WS_NB]) {
             const int beg = ws[WS_OFF + my_b], end = ws[WS_OFF + my_b + 1];
-#pragma unroll 4
+#pragma unroll 8
             for (int j = beg + sub; j < end; j += LPQ) {
                 const float4 c = __ldg(sorted + j);
                 const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
-                if (d < CUDART_INF_F) nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+                // one compare rejects almost every candidate; ties (d == b3) and the first three go the slow way
+                if (!(d > b3) && d < CUDART_INF_F) nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
             }
         }
     }
@@ -243,7 +286,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
 }
 
 __global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int m, const float* __restrict__ unknown,
-                                                                     const float* __restrict__ known,
+                                                                     KnownRows kr,
                                                                      const int* __restrict__ ws,
                                                                      const float4* __restrict__ sorted,
                                                                      float* __restrict__ dist2,
@@ -254,7 +297,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int 
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     float b1, b2, b3;
     int i1, i2, i3;
-    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, i1, i2, i3);
+    sp_group_search(ws, sorted, kr, m, valid, u, sub, b1, b2, b3, i1, i2, i3);
     if (valid && sub == 0) {
         dist2[qi * 3 + 0] = b1;
         dist2[qi * 3 + 1] = b2;
@@ -338,7 +381,7 @@ __global__ void __launch_bounds__(256) sp_interp_grad_v1_kernel(int c, int n, co
 // and the group's lanes spread over the channels of the output row (float4 each).
 __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, int m, int c,
                                                                         const float* __restrict__ unknown,
-                                                                        const float* __restrict__ known,
+                                                                        KnownRows kr,
                                                                         const int* __restrict__ ws,
                                                                         const float4* __restrict__ sorted,
                                                                         const float* __restrict__ feats,
@@ -350,7 +393,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, i
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     float b1, b2, b3;
     int j0, j1, j2;
-    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+    sp_group_search(ws, sorted, kr, m, valid, u, sub, b1, b2, b3, j0, j1, j2);
     if (!valid) return;
     const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
     const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
@@ -382,7 +425,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_kernel(int n, i
 // bf16 hi / lo halves straight into the operand layout of the first disengage GEMM.
 __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_pm_kernel(int n, int m, int c,
                                                                            const float* __restrict__ unknown,
-                                                                           const float* __restrict__ known,
+                                                                           KnownRows kr,
                                                                            const int* __restrict__ ws,
                                                                            const float4* __restrict__ sorted,
                                                                            const float* __restrict__ feats,
@@ -394,7 +437,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_pm_kernel(int n
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     float b1, b2, b3;
     int j0, j1, j2;
-    sp_group_search(ws, sorted, reinterpret_cast<const float4*>(known), m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+    sp_group_search(ws, sorted, kr, m, valid, u, sub, b1, b2, b3, j0, j1, j2);
     if (!valid) return;
     const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
     const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
@@ -425,13 +468,30 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_fused_pm_kernel(int n
     }
 }
 
-int build_buckets(int m, const float* known, int* ws, float4* sorted, cudaStream_t st) {
+KnownRows rows_from_float(const float* known) {
+    KnownRows kr = {};
+    kr.rows = known;
+    return kr;
+}
+
+KnownRows rows_from_voxels(const int* vox, const float* ext3, const float* off3) {
+    KnownRows kr = {};
+    kr.vox = vox;
+    for (int i = 0; i < 3; ++i) {
+        kr.ext[i] = ext3[i];
+        kr.off[i] = off3[i];
+        kr.half[i] = 0.5f * ext3[i];
+    }
+    return kr;
+}
+
+int build_buckets(int m, const KnownRows& kr, int* ws, float4* sorted, cudaStream_t st) {
     // only the header words that are read before being written need clearing
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(WS_OFF + DCL_SP_MAX_BATCH + 4) * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    if (m > 0) sp_bucket_hist_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws);
+    if (m > 0) sp_bucket_hist_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, kr, ws);
     sp_bucket_scan_kernel<<<1, 1024, 0, st>>>(ws);
-    if (m > 0) sp_bucket_scatter_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, known, ws, sorted);
+    if (m > 0) sp_bucket_scatter_kernel<<<DCL_DIVUP(m, 256), 256, 0, st>>>(m, kr, ws, sorted);
     return dcl_launch_status(m > 0 ? 3 : 1);
 }
 
@@ -462,10 +522,11 @@ DCL_API int dcl_sp_three_nn_segmented(int n, int m, const float* unknown, const 
     cudaStream_t st = (cudaStream_t)stream;
     int* ws = (int*)workspace;
     float4* sorted = (float4*)(ws + WS_HDR_INTS);
-    int err = build_buckets(m, known, ws, sorted, st);
+    const KnownRows kr = rows_from_float(known);
+    int err = build_buckets(m, kr, ws, sorted, st);
     if (err) return err;
     const int grid = DCL_DIVUP(n, SP_THREADS / LPQ);
-    sp_three_nn_seg_kernel<<<grid, SP_THREADS, 0, st>>>(n, m, unknown, known, ws, sorted, dist2, idx);
+    sp_three_nn_seg_kernel<<<grid, SP_THREADS, 0, st>>>(n, m, unknown, kr, ws, sorted, dist2, idx);
     return dcl_launch_status();
 }
 
@@ -517,12 +578,13 @@ DCL_API int dcl_sp_nn_interpolate_fused(int n, int m, int c, const float* unknow
     cudaStream_t st = (cudaStream_t)stream;
     int* ws = (int*)workspace;
     float4* sorted = (float4*)(ws + WS_HDR_INTS);
-    int err = build_buckets(m, known, ws, sorted, st);
+    const KnownRows kr = rows_from_float(known);
+    int err = build_buckets(m, kr, ws, sorted, st);
     if (err) return err;
     const int vec_ok = ((c & 3) == 0) && ((out_stride & 3) == 0) && ((out_col0 & 3) == 0) &&
                        ((((uintptr_t)feats) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
     sp_nn_interp_fused_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
-        n, m, c, unknown, known, ws, sorted, feats, out, out_stride, out_col0, vec_ok);
+        n, m, c, unknown, kr, ws, sorted, feats, out, out_stride, out_col0, vec_ok);
     return dcl_launch_status();
 }
 
@@ -537,9 +599,32 @@ DCL_API int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c, const float* unk
     cudaStream_t st = (cudaStream_t)stream;
     int* ws = (int*)workspace;
     float4* sorted = (float4*)(ws + WS_HDR_INTS);
-    int err = build_buckets(m, known, ws, sorted, st);
+    const KnownRows kr = rows_from_float(known);
+    int err = build_buckets(m, kr, ws, sorted, st);
     if (err) return err;
     sp_nn_interp_fused_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
-        n, m, c, unknown, known, ws, sorted, feats, reinterpret_cast<unsigned char*>(out_pm), c_total, out_col0);
+        n, m, c, unknown, kr, ws, sorted, feats, reinterpret_cast<unsigned char*>(out_pm), c_total, out_col0);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c, const float* unknown, const int* vox_indices,
+                                         const float* voxel_extent3, const float* offset3, const float* feats,
+                                         void* out_pm, int c_total, int out_col0, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(n > 0 && n % 128 == 0 && m >= 0 && c > 0 && c % 8 == 0 && out_col0 % 8 == 0);
+    DCL_RETURN_IF_BAD(c_total % 32 == 0 && c_total >= out_col0 + c && workspace != nullptr && out_pm != nullptr);
+    DCL_RETURN_IF_BAD(voxel_extent3 != nullptr && offset3 != nullptr);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_three_nn_workspace_bytes(n, m));
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
+                      ((uintptr_t)vox_indices & 15u) == 0 && ((uintptr_t)feats & 15u) == 0 &&
+                      ((uintptr_t)out_pm & 15u) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* ws = (int*)workspace;
+    float4* sorted = (float4*)(ws + WS_HDR_INTS);
+    const KnownRows kr = rows_from_voxels(vox_indices, voxel_extent3, offset3);
+    int err = build_buckets(m, kr, ws, sorted, st);
+    if (err) return err;
+    sp_nn_interp_fused_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
+        n, m, c, unknown, kr, ws, sorted, feats, reinterpret_cast<unsigned char*>(out_pm), c_total, out_col0);
     return dcl_launch_status();
 }

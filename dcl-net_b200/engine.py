@@ -34,6 +34,8 @@ class PoseEngine:
                                  for cap, ch in zip(capacities, (32, 64, 128, 256))]
         self.out_host = torch.empty(batch, 12, dtype=torch.float32).pin_memory()
         self.h2d_bytes = 0
+        self._graph = None
+        self._static = None
 
     def load(self, host_batch):
         """Asynchronous host->device copy of one batch into the static buffers."""
@@ -52,9 +54,31 @@ class PoseEngine:
                 nbytes += feats.numel() * 4 + ind.numel() * 4
         self.h2d_bytes = nbytes
 
-    @torch.no_grad()
+    def capture(self, warmup=2):
+        """Capture the whole pass into a CUDA graph (shapes are static): one launch per step instead of a few
+        hundred.  The loaded batch must be valid; later load() calls just refill the same buffers."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._run_eager()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._static = self._run_eager()
+        self._graph = graph
+        return self
+
     def run(self):
         """Device-resident pass over the loaded batch -> (rot (B,3,3), trans (B,3)) on the device."""
+        if self._graph is not None:
+            self._graph.replay()
+            return self._static
+        return self._run_eager()
+
+    @torch.no_grad()
+    def _run_eager(self):
         pred = self.net.forward_from_backbone(self.levels["inp"], self.levels["tmp"], self.points["inp"],
                                               self.points["tmp"], self.b)
         rot, trans = pred["rot_pred"], pred["trans_pred"]

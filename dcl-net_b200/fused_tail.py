@@ -145,6 +145,7 @@ def run_gemm(problems, rows):
         slot.out_pm, slot.out_cm = L.ptr(p.get("out_pm")), L.ptr(p.get("out_cm"))
         slot.rows_per_inst = p.get("rows_per_inst", 0)
         slot.pool_w, slot.pool_out = L.ptr(p.get("pool_w")), L.ptr(p.get("pool_out"))
+        slot.dot_w, slot.dot_out = L.ptr(p.get("dot_w")), L.ptr(p.get("dot_out"))
         keep.append(p)
     L.check(L.load().dcl_pm_gemm(len(problems), ctypes.cast(arr, ctypes.c_void_p), rows, L.stream_ptr()), "pm_gemm")
 
@@ -162,6 +163,12 @@ class FusedTail:
             self.fuser, rest_a = layers_from_head(net.neck_fuser)
             self.fuser_bi, rest_b = layers_from_head(net.neck_fuser_bi)
         assert not rest_a and not rest_b and len(self.fuser) == 3 and len(self.conf) == 2
+        self.conf_dot, self.conf_dot_bias = [], []
+        for rest in (self.conf_rest, self.conf_bi_rest):
+            (conv, relu, bn), = rest
+            assert conv.out_channels == 1 and not relu and bn is None
+            self.conf_dot.append(conv.weight.detach().reshape(-1).float().contiguous())
+            self.conf_dot_bias.append(conv.bias.detach().float().reshape(1, 1).clone())
 
     @staticmethod
     def supported(net, b):
@@ -209,11 +216,12 @@ class FusedTail:
         c1 = [pm_empty(rows, 128, dev) for _ in range(2)]
         run_gemm([{"a0": pm_out["Xc_m1"], "a1": pm_Xo_m, "c0": c_m, "layer": self.conf[0], "out_pm": c1[0]},
                   {"a0": pm_Yc_m, "a1": pm_out["Yo_m2"], "c0": c_m, "layer": self.conf_bi[0], "out_pm": c1[1]}], rows)
-        c2 = [torch.empty(b, 128, n, **f32) for _ in range(2)]
-        run_gemm([{"a0": c1[0], "layer": self.conf[1], "out_cm": c2[0], "rows_per_inst": n},
-                  {"a0": c1[1], "layer": self.conf_bi[1], "out_cm": c2[1], "rows_per_inst": n}], rows)
-        conf_1 = self._tail_convs(self.conf_rest, c2[0])
-        conf_2 = self._tail_convs(self.conf_bi_rest, c2[1])
+        # the trailing 128 -> 1 convolution is a per-row dot product in the epilogue of the second layer
+        logits = torch.empty(2, b, n, **f32)
+        run_gemm([{"a0": c1[0], "layer": self.conf[1], "dot_w": self.conf_dot[0], "dot_out": logits[0]},
+                  {"a0": c1[1], "layer": self.conf_bi[1], "dot_w": self.conf_dot[1], "dot_out": logits[1]}], rows)
+        conf_1 = (logits[0] + self.conf_dot_bias[0]).unsqueeze(1)
+        conf_2 = (logits[1] + self.conf_dot_bias[1]).unsqueeze(1)
         conf = torch.sigmoid(torch.cat([conf_1, conf_2], dim=2))
         conf_softmax = torch.softmax(conf, dim=2)
         w1 = conf_softmax[:, 0, :n].reshape(-1).contiguous()

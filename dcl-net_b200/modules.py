@@ -176,9 +176,13 @@ class Ops_GetPointFeat_spconv(nn.Module):
         out = torch.empty(points.shape[0] * width * 4, dtype=torch.uint8, device=points.device)
         col = 0
         for scale, feats in zip(self.scale_lists, levels):
-            vx_feats, vx_points = Ops_tensor2points(feats, self.offset, self.unit_voxel_extent * scale)
-            pointnet2_utils_sp.nn_interpolate_pm(points, vx_points.contiguous(), vx_feats.contiguous(), out, width, col)
-            col += vx_feats.shape[1]
+            # Ops_tensor2points is fused into the kernels: they take the int voxel indices and form the centres
+            # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.
+            ext = torch.as_tensor(np.asarray(self.unit_voxel_extent * scale), dtype=torch.float32).tolist()
+            off = torch.as_tensor(np.asarray(self.offset), dtype=torch.float32).tolist()
+            pointnet2_utils_sp.nn_interpolate_vox_pm(points, feats.indices.contiguous(), ext, off,
+                                                     feats.features.contiguous(), out, width, col)
+            col += feats.features.shape[1]
         return out
 
     def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):

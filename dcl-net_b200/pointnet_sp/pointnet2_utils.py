@@ -125,3 +125,21 @@ def nn_interpolate_pm(target_points, query_points, query_feats, out_pm, c_total,
                                                L.ptr(out_pm), c_total, out_col0, L.ptr(ws), ws.numel(),
                                                L.stream_ptr()), "pointnet_sp.nn_interpolate_pm")
     return out_pm
+
+
+def nn_interpolate_vox_pm(target_points, vox_indices, voxel_extent, offset, query_feats, out_pm, c_total, out_col0):
+    """nn_interpolate_pm taking the sparse tensor's int32 (m,4) voxel indices (b,ix,iy,iz) plus the level's voxel
+    extent / offset (3 floats each) instead of precomputed centres (Ops_tensor2points fused into the kernels)."""
+    import ctypes
+    assert target_points.is_contiguous() and vox_indices.is_contiguous() and query_feats.is_contiguous()
+    L.require(vox_indices, torch.int32, "vox_indices")
+    n, m, c = target_points.size(0), vox_indices.size(0), query_feats.size(1)
+    lib = L.load()
+    ws = _workspace(lib.dcl_sp_three_nn_workspace_bytes(n, m), target_points.device)
+    ext = (ctypes.c_float * 3)(*[float(v) for v in voxel_extent])
+    off = (ctypes.c_float * 3)(*[float(v) for v in offset])
+    L.check(lib.dcl_sp_nn_interpolate_vox_pm(n, m, c, L.ptr(target_points), L.ptr(vox_indices),
+                                             ctypes.cast(ext, ctypes.c_void_p), ctypes.cast(off, ctypes.c_void_p),
+                                             L.ptr(query_feats), L.ptr(out_pm), c_total, out_col0, L.ptr(ws),
+                                             ws.numel(), L.stream_ptr()), "pointnet_sp.nn_interpolate_vox_pm")
+    return out_pm

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header; bumped on any signature change. */
-#define DCL_B200_ABI_VERSION 1
+#define DCL_B200_ABI_VERSION 2
 int dcl_b200_abi_version(void);
 /* Compiled-for architecture as an integer (100 for sm_100a). */
 int dcl_b200_arch(void);
@@ -228,6 +228,8 @@ typedef struct dcl_pm_gemm_problem {
     int rows_per_inst;
     const float* pool_w;
     float* pool_out;
+    const float* dot_w;   /* [cout]; needs cout == nt */
+    float* dot_out;       /* [R]: sum_o Y[r,o] * dot_w[o] — a trailing cout -> 1 layer without its bias */
 } dcl_pm_gemm_problem;
 
 /* Up to 8 problems with equal (cout, nt) over the same number of rows in ONE launch (grid.z = problem). */
@@ -246,6 +248,14 @@ int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, fl
 int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c,
     const float* unknown, const float* known, const float* feats,
     void* out_pm, int c_total, int out_col0,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* dcl_sp_nn_interpolate_fused_pm with Ops_tensor2points (models/Modules.py:204-211) fused in: the known rows are the
+ * sparse tensor's int32 (m,4) indices (b,ix,iy,iz); their centres ((float(i)*ext)+offset)+0.5*ext are formed in the
+ * kernels in exactly torch's fp32 evaluation order.  voxel_extent3 / offset3 are HOST pointers to 3 floats. */
+int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c,
+    const float* unknown, const int* vox_indices, const float* voxel_extent3, const float* offset3,
+    const float* feats, void* out_pm, int c_total, int out_col0,
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */

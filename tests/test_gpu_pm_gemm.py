@@ -140,3 +140,25 @@ def test_fused_tail_equals_unfused_and_oracle(cuda_dev, b, n, c_m):
         ang = T.rotation_angle_deg(got["rot_pred"].cpu(), ref["rot_pred"].cpu()).max().item()
         dt = (got["trans_pred"] - ref["trans_pred"]).abs().max().item()
         assert ang < 0.01 and dt < 1e-5, (name, ang, dt)
+
+
+def test_nn_interpolate_vox_pm_equals_tensor2points_path(cuda_dev):
+    """Voxel centres formed inside the kernels == Ops_tensor2points followed by the float-row kernels, bit for bit."""
+    import types
+    from dcl_net_b200.modules import Ops_tensor2points
+    g = torch.Generator().manual_seed(21)
+    b, n_per, c = 3, 128, 64
+    unknown = flat_bxyz(22, b, n_per, shuffle=False, scale=0.3).to(cuda_dev)
+    ind = torch.cat([torch.randint(0, b, (500, 1), generator=g), torch.randint(0, 16, (500, 3), generator=g)], 1).int()
+    ind = torch.unique(ind, dim=0)
+    ind = ind[torch.randperm(ind.shape[0], generator=g)].contiguous().to(cuda_dev)
+    feats = torch.randn(ind.shape[0], c, generator=g).to(cuda_dev)
+    ext, off = np.array([0.024, 0.024, 0.024]), np.array([-0.192, -0.192, -0.192])
+    _, centres = Ops_tensor2points(types.SimpleNamespace(features=feats, indices=ind), off, ext)
+    pm_a = torch.zeros(FT.pm_bytes(b * n_per, 64), dtype=torch.uint8, device=cuda_dev)
+    pm_b = torch.zeros_like(pm_a)
+    pu_sp.nn_interpolate_pm(unknown, centres.contiguous(), feats, pm_a, 64, 0)
+    e32 = torch.as_tensor(ext, dtype=torch.float32).tolist()
+    o32 = torch.as_tensor(off, dtype=torch.float32).tolist()
+    pu_sp.nn_interpolate_vox_pm(unknown, ind, e32, o32, feats, pm_b, 64, 0)
+    assert torch.equal(pm_a, pm_b)
