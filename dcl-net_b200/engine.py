@@ -94,3 +94,74 @@ class PoseEngine:
         self.out_host.copy_(torch.cat([rot.reshape(self.b, 9), trans], dim=1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self.out_host[:, :9].view(self.b, 3, 3), self.out_host[:, 9:]
+
+
+class PipelinedPoseEngine:
+    """Host-in / host-out inference over a stream of batches with the copies overlapped with compute:
+    `depth` PoseEngines (each with its own static buffers and CUDA graph) are used round-robin; batch i+1 is
+    copied to the device on a copy stream while batch i computes, and each batch's (B,12) poses are read back
+    to pinned host memory right after its pass.  Every batch still pays its own H2D and D2H."""
+
+    def __init__(self, net, device, batch, capacities, depth=2, refiner=None, iterations=0, use_graph=True):
+        self.engines = [PoseEngine(net, device, batch, capacities, refiner, iterations) for _ in range(depth)]
+        self.device, self.use_graph = device, use_graph
+        self.copy_stream = torch.cuda.Stream(device)
+        self._captured = False
+        self.h2d_bytes = 0
+
+    def _ensure_graphs(self, first_batch):
+        if self.use_graph and not self._captured:
+            for eng in self.engines:
+                eng.load(first_batch)
+                torch.cuda.synchronize(self.device)
+                eng.capture()
+        self._captured = True
+
+    def infer_many(self, host_batches):
+        """Yields (rot (B,3,3), trans (B,3)) host tensors, in order, one per input batch.  The yielded tensors
+        alias a per-engine pinned buffer: consume them before `depth` more batches have been requested."""
+        host_batches = iter(host_batches)
+        try:
+            first = next(host_batches)
+        except StopIteration:
+            return
+        self._ensure_graphs(first)
+        main = torch.cuda.current_stream(self.device)
+        depth = len(self.engines)
+        loaded = [torch.cuda.Event() for _ in range(depth)]
+        done = [torch.cuda.Event() for _ in range(depth)]
+        pending = []   # engine slots whose results have not been yielded yet
+
+        def stage(slot, batch):
+            eng = self.engines[slot]
+            self.copy_stream.wait_event(done[slot])          # the slot's previous pass has consumed its buffers
+            with torch.cuda.stream(self.copy_stream):
+                eng.load(batch)
+                loaded[slot].record(self.copy_stream)
+            self.h2d_bytes = eng.h2d_bytes
+
+        for ev in done:
+            ev.record(main)
+        stage(0, first)
+        i = 0
+        nxt = next(host_batches, None)
+        while True:
+            slot = i % depth
+            eng = self.engines[slot]
+            if nxt is not None:
+                stage((i + 1) % depth, nxt)                   # overlaps with the pass launched below
+            main.wait_event(loaded[slot])
+            rot, trans = eng.run()
+            eng.out_host.copy_(torch.cat([rot.reshape(eng.b, 9), trans], dim=1), non_blocking=True)
+            done[slot].record(main)
+            pending.append(slot)
+            if len(pending) == depth or nxt is None:
+                while pending and (len(pending) == depth or nxt is None):
+                    s = pending.pop(0)
+                    done[s].synchronize()
+                    e = self.engines[s]
+                    yield e.out_host[:, :9].view(e.b, 3, 3), e.out_host[:, 9:]
+            if nxt is None:
+                break
+            i += 1
+            nxt = next(host_batches, None)
