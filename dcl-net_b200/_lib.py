@@ -46,6 +46,7 @@ SIGNATURES = {
     "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _I, _P]),
     "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
 
@@ -56,6 +57,12 @@ class PmGemmProblem(ctypes.Structure):
     _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
                 ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P)]
+
+
+class PoseHeadMlp(ctypes.Structure):
+    """Mirror of dcl_pose_head_mlp (include/dcl_b200.h)."""
+    _fields_ = [("w1", _P), ("b1", _P), ("w2", _P), ("b2", _P), ("w3", _P), ("b3", _P),
+                ("d_in", _I), ("d_h1", _I), ("d_h2", _I), ("d_out", _I)]
 
 
 _lib = None

@@ -48,21 +48,24 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
         const int tc = pipe.acquire(t) / 3;
         const float* tile = pipe.tile(t);
         const int kbase = t * BQ_TILE_PTS;
-        if (!done) {
-            for (int j = 0; j < tc; ++j) {
+        // No `break` inside the scan: with independent thread scheduling a divergent exit keeps the lanes of a
+        // warp apart for the rest of the loop (measured: ~8x the instructions).  Lanes that are full just stop
+        // recording; the warp leaves a chunk early only when all of its lanes are done (a uniform branch).
+        for (int j0 = 0; j0 < tc; j0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const int jend = min(tc, j0 + 32);
+            for (int j = j0; j < jend; ++j) {
                 const float d2 = dcl_dist2(cx, cy, cz, tile[j * 3 + 0], tile[j * 3 + 1], tile[j * 3 + 2]);
-                if (d2 < radius2) {
+                if (!done && d2 < radius2) {
                     const int k = kbase + j;
                     if (cnt == 0) {
                         for (int l = 0; l < nsample; ++l) my_row[l * row_stride] = k;
                     }
                     my_row[cnt * row_stride] = k;
                     ++cnt;
-                    if (cnt >= nsample) {
-                        done = true;
-                        break;
-                    }
+                    done = cnt >= nsample;
                 }
+                __syncwarp();
             }
         }
         const int all_done = __syncthreads_and(done ? 1 : 0);

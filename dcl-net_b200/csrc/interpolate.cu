@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(NN_THREADS) knn_reg_kernel(int n, int m, int k
 #pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
             const float d = dcl_dist2(ux, uy, uz, tile[j * 3 + 0], tile[j * 3 + 1], tile[j * 3 + 2]);
+            // Insertions are rare once the list has warmed up: make the branch warp-uniform so that the
+            // (fully unrolled, ~6*KMAX instruction) bubble is skipped instead of executed predicated-off.
+            if (!__any_sync(0xffffffffu, d < best[KMAX - 1])) continue;
             if (d < best[KMAX - 1]) {
                 best[KMAX - 1] = d;
                 besti[KMAX - 1] = kbase + j;

@@ -16,7 +16,10 @@
 // (ordered(d2), ~bitrev(t)) with an integer max, which selects the same point.
 #include "common.cuh"
 #include "../../include/dcl_b200.h"
+#include <cooperative_groups.h>
 #include <math.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -197,6 +200,136 @@ __global__ void __launch_bounds__(1024, 1) fps_streaming_kernel(int n, int m, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster version (n >= 1024, i.e. the reference's T = 1024): CS CTAs of 1024 threads share one cloud, so
+// CS times as many SMs work on the serial chain of m-1 rounds.  Thread `tid` of CTA `rank` owns the points
+// k = tid + 1024*(rank + CS*i): every k it owns is in the reference thread's residue class (k mod 1024 = tid)
+// and ascending in i, so the per-thread "first maximum" is the reference's.  Points and running distances
+// live in registers.  Per round: sweep -> warp argmax (2 redux) -> one __syncthreads -> CTA argmax ->
+// the CTA winner (key + coordinates, 20 B) is written into every CTA's mailbox through distributed shared
+// memory -> cluster barrier -> every thread picks the cluster winner.  Key = (ordered(d2), T - bitrev(tid),
+// ~k): maximal d2, then the reference tree's slot preference, then — for equal slots in different CTAs —
+// the lowest k.
+struct FpsMail {
+    uint32_t u, lo;
+    float x, y, z;
+    uint32_t pad[3];
+};
+
+template <int PPT, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1)
+    fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, float* __restrict__ temp,
+                       int* __restrict__ idxs) {
+    __shared__ FpsMail s_warp[2][32];
+    __shared__ FpsMail s_mail[2][CS];
+    if (m <= 0) return;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    dataset += (size_t)cloud * n * 3;
+    temp += (size_t)cloud * n;
+    idxs += (size_t)cloud * m;
+
+    float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + 1024 * (rank + CS * i);
+        const bool ok = k < n;
+        px[i] = ok ? dataset[k * 3 + 0] : 0.f;
+        py[i] = ok ? dataset[k * 3 + 1] : 0.f;
+        pz[i] = ok ? dataset[k * 3 + 2] : 0.f;
+        td[i] = ok ? temp[k] : -1.f;  // a padded slot can never beat best = -1 (strict '>')
+    }
+    const uint32_t tie_rank = fps_tie_rank(tid, 1024);  // [1, 1024]
+    if (rank == 0 && tid == 0) idxs[0] = 0;
+    float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];
+
+    for (int j = 1; j < m; ++j) {
+        const int par = j & 1;
+        float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bestk = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const float d = dcl_dist2(px[i], py[i], pz[i], x1, y1, z1);
+            const float d2 = fminf(d, td[i]);
+            td[i] = d2;
+            if (d2 > best) {
+                best = d2;
+                bestk = tid + 1024 * (rank + CS * i);
+                bx = px[i];
+                by = py[i];
+                bz = pz[i];
+            }
+        }
+        // warp level
+        const uint32_t u = ordered_bits(best);
+        const uint32_t umax = __reduce_max_sync(0xffffffffu, u);
+        const uint32_t lo = (u == umax) ? ((tie_rank << 21) | (0x1FFFFFu - (uint32_t)bestk)) : 0u;
+        const uint32_t lomax = __reduce_max_sync(0xffffffffu, lo);
+        if (lo == lomax && lo != 0u) {
+            FpsMail& e = s_warp[par][warp];
+            e.u = umax;
+            e.lo = lomax;
+            e.x = bx;
+            e.y = by;
+            e.z = bz;
+        }
+        __syncthreads();
+        // CTA level (every warp redundantly; only warp 0 publishes)
+        const FpsMail we = s_warp[par][lane];
+        const uint32_t gu = __reduce_max_sync(0xffffffffu, we.u);
+        const uint32_t wl = (we.u == gu) ? we.lo : 0u;
+        const uint32_t gl = __reduce_max_sync(0xffffffffu, wl);
+        if (warp == 0) {
+            const int src = __ffs(__ballot_sync(0xffffffffu, wl == gl && wl != 0u)) - 1;
+            const float wx = __shfl_sync(0xffffffffu, we.x, src), wy = __shfl_sync(0xffffffffu, we.y, src),
+                        wz = __shfl_sync(0xffffffffu, we.z, src);
+            if (lane < CS) {
+                FpsMail* remote = cluster.map_shared_rank(&s_mail[par][rank], lane);
+                remote->u = gu;
+                remote->lo = gl;
+                remote->x = wx;
+                remote->y = wy;
+                remote->z = wz;
+            }
+        }
+        cluster.sync();
+        // cluster level: CS entries, identical in every CTA
+        uint32_t bu = 0u, bl = 0u;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+            const FpsMail e = s_mail[par][r];
+            if (e.u > bu || (e.u == bu && e.lo > bl)) {
+                bu = e.u;
+                bl = e.lo;
+                x1 = e.x;
+                y1 = e.y;
+                z1 = e.z;
+            }
+        }
+        if (rank == 0 && tid == 0) idxs[j] = (int)(0x1FFFFFu - (bl & 0x1FFFFFu));
+    }
+    if (m > 1) {
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = tid + 1024 * (rank + CS * i);
+            if (k < n) temp[k] = td[i];
+        }
+    }
+    cluster.sync();  // no CTA may exit while a peer can still write into its mailbox
+}
+
+template <int CS>
+int launch_cluster(int b, int n, int m, const float* dataset, float* temp, int* idxs, cudaStream_t st) {
+    const int ppt = DCL_DIVUP(n, 1024 * CS);
+    if (ppt <= 1) fps_cluster_kernel<1, CS><<<b * CS, 1024, 0, st>>>(n, m, dataset, temp, idxs);
+    else if (ppt <= 2) fps_cluster_kernel<2, CS><<<b * CS, 1024, 0, st>>>(n, m, dataset, temp, idxs);
+    else if (ppt <= 4) fps_cluster_kernel<4, CS><<<b * CS, 1024, 0, st>>>(n, m, dataset, temp, idxs);
+    else fps_cluster_kernel<8, CS><<<b * CS, 1024, 0, st>>>(n, m, dataset, temp, idxs);
+    return dcl_launch_status();
+}
+
 template <int PPT, int MODE>
 int launch_resident(int b, int n, int m, int T, int threads, const float* dataset, float* temp, int* idxs,
                     cudaStream_t st) {
@@ -217,6 +350,13 @@ DCL_API int dcl_lib_furthest_point_sampling_kernel_launcher(int b, int n, int m,
     const int T = ref_opt_n_threads(n);
     const int threads = T < 32 ? 32 : T;
     const int ppt = DCL_DIVUP(n, T);
+    // Clouds of >= 2048 points: a thread-block cluster per cloud (4 CTAs; 8 when the batch alone cannot fill
+    // the SMs or the cloud is too large for 4), points in registers.
+    if (T == 1024 && n >= 2048 && n <= 1024 * 8 * 8) {
+        const bool use8 = (n > 1024 * 4 * 8) || (b * 4 < 96);
+        return use8 ? launch_cluster<8>(b, n, m, dataset, temp, idxs, st)
+                    : launch_cluster<4>(b, n, m, dataset, temp, idxs, st);
+    }
     if (ppt <= 1) return launch_resident<1, 0>(b, n, m, T, threads, dataset, temp, idxs, st);
     if (ppt <= 2) return launch_resident<2, 0>(b, n, m, T, threads, dataset, temp, idxs, st);
     if (ppt <= 4) return launch_resident<4, 0>(b, n, m, T, threads, dataset, temp, idxs, st);

@@ -27,6 +27,45 @@ def svd3_project(m9, normalize_columns):
     return R
 
 
+def _head_struct(head, keep):
+    """dcl_pose_head_mlp for a Head_MultiLayerPerceptron [d_in -> d_h1 -> d_h2 -> d_out] (Conv1d, ReLU, Conv1d,
+    ReLU, Conv1d); returns None when the module does not have that shape."""
+    convs = [m for m in head.layers if isinstance(m, nn.Conv1d)]
+    others = [m for m in head.layers if not isinstance(m, (nn.Conv1d, nn.ReLU))]
+    if len(convs) != 3 or others or len(list(head.layers)) != 5:
+        return None
+    s = L.PoseHeadMlp()
+    tensors = []
+    for conv in convs:
+        tensors += [conv.weight.detach().reshape(conv.out_channels, conv.in_channels).contiguous(),
+                    conv.bias.detach().contiguous()]
+    if any(t.dtype != torch.float32 for t in tensors) or max(c.in_channels for c in convs) > 1024:
+        return None
+    keep += tensors
+    s.w1, s.b1, s.w2, s.b2, s.w3, s.b3 = (L.ptr(t) for t in tensors)
+    s.d_in, s.d_h1, s.d_h2, s.d_out = convs[0].in_channels, convs[1].in_channels, convs[2].in_channels, convs[2].out_channels
+    return s
+
+
+def pose_heads(pooled, rot_head, trans_head):
+    """regressor_rot / regressor_trans (or the refiner's *_2 pair) on the pooled (B, d_in) feature in ONE kernel
+    (csrc/pose_head.cu) -> (ortho9d (B,9), trans (B,3)).  Inference only."""
+    import ctypes
+    keep = []
+    hs, ht = _head_struct(rot_head, keep), _head_struct(trans_head, keep)
+    pooled = pooled.contiguous()
+    if hs is None or ht is None or pooled.dtype != torch.float32:
+        x = pooled.unsqueeze(-1)
+        return rot_head(x).squeeze(-1), trans_head(x).squeeze(-1)
+    B = pooled.shape[0]
+    o9 = torch.empty(B, hs.d_out, dtype=torch.float32, device=pooled.device)
+    t3 = torch.empty(B, ht.d_out, dtype=torch.float32, device=pooled.device)
+    L.check(L.load().dcl_pose_head(B, L.ptr(pooled), ctypes.cast(ctypes.pointer(hs), ctypes.c_void_p),
+                                   ctypes.cast(ctypes.pointer(ht), ctypes.c_void_p), L.ptr(o9), L.ptr(t3),
+                                   L.stream_ptr()), "pose_head")
+    return o9, t3
+
+
 def ortho9d2matrix(x_raw, y_raw, z_raw):
     """Rotation from three raw 3-vectors: columns normalised by (|v| + 1e-8), then the SO(3) projection
     U diag(1,1,det(UV^T)) V^T.  Inference path (no autograd through the kernel)."""

@@ -244,9 +244,8 @@ class FusedTail:
         F_p_wei = pooled.unsqueeze(-1)
 
         # ---- pose regressors on the pooled feature (b x 1024: tiny) and the SO(3) projection
-        from .dcl_net import svd3_project
-        ortho9d = net.regressor_rot(F_p_wei).squeeze(-1)
+        from .dcl_net import pose_heads, svd3_project
+        ortho9d, trans = pose_heads(pooled, net.regressor_rot, net.regressor_trans)
         rot = svd3_project(ortho9d, True)
-        trans = net.regressor_trans(F_p_wei).squeeze(-1)
         return {"trans_pred": trans, "rot_pred": rot, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p,
                 "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}

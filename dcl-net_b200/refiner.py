@@ -30,8 +30,12 @@ class Refiner(nn.Module):
         conf_softmax = torch.softmax(conf.unsqueeze(1), dim=2)[:, :, :1024]
         shared_feature = self.MLP_share(input_features)
         shared_feature = (shared_feature * conf_softmax).sum(dim=2, keepdim=True)
-        ortho9d_pred2 = self.regressor_rot2(shared_feature).squeeze(-1)
-        delta_t = self.regressor_trans2(shared_feature).squeeze(-1)
+        if torch.is_grad_enabled():
+            ortho9d_pred2 = self.regressor_rot2(shared_feature).squeeze(-1)
+            delta_t = self.regressor_trans2(shared_feature).squeeze(-1)
+        else:
+            from .dcl_net import pose_heads
+            ortho9d_pred2, delta_t = pose_heads(shared_feature.squeeze(-1), self.regressor_rot2, self.regressor_trans2)
         delta_R = svd3_project(ortho9d_pred2, True)
         return {"trans_pred": delta_t, "rot_pred": delta_R}
 

@@ -250,6 +250,19 @@ int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c,
     void* out_pm, int c_total, int out_col0,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two pose regressors (models/DCL_Net.py:139-151,230-235; models/refiner.py:66-77) on the pooled feature
+ * (b, d_in): per head three dense layers d_in -> d_h1 -> d_h2 -> d_out with ReLU after the first two
+ * (Conv1d(k=1) on a (b, d_in, 1) tensor).  Weights are the Conv1d tensors as they are, fp32 row-major
+ * (d_out x d_in); every width <= 1024.  out_rot (b, rot_head->d_out), out_trans (b, trans_head->d_out). */
+typedef struct dcl_pose_head_mlp {
+    const float* w1; const float* b1;
+    const float* w2; const float* b2;
+    const float* w3; const float* b3;
+    int d_in, d_h1, d_h2, d_out;
+} dcl_pose_head_mlp;
+int dcl_pose_head(int b, const float* pooled, const dcl_pose_head_mlp* rot_head,
+    const dcl_pose_head_mlp* trans_head, float* out_rot, float* out_trans, void* stream);
+
 /* dcl_sp_nn_interpolate_fused_pm with Ops_tensor2points (models/Modules.py:204-211) fused in: the known rows are the
  * sparse tensor's int32 (m,4) indices (b,ix,iy,iz); their centres ((float(i)*ext)+offset)+0.5*ext are formed in the
  * kernels in exactly torch's fp32 evaluation order.  voxel_extent3 / offset3 are HOST pointers to 3 floats. */

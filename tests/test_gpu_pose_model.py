@@ -206,3 +206,21 @@ def test_refiner_golden_and_loop(cuda_dev):
                                 conf.to(cuda_dev), 2)
     assert T.rotation_angle_deg(r_g.cpu(), r_o).max().item() < 0.01
     assert (t_g.cpu() - t_o).abs().max().item() < 1e-5
+
+
+def test_pose_heads_kernel_vs_torch(cuda_dev):
+    """csrc/pose_head.cu against the reference's own module class semantics (Conv1d+ReLU stacks, Modules.py:173-201)."""
+    from dcl_net_b200.dcl_net import pose_heads
+    from dcl_net_b200.modules import Head_MultiLayerPerceptron
+    torch.manual_seed(5)
+    plain = (["relu", "relu", "none"], [False] * 3, [0.0] * 3)
+    rot = Head_MultiLayerPerceptron([1024, 512, 128, 9], *plain).to(cuda_dev).eval()
+    trans = Head_MultiLayerPerceptron([1024, 512, 128, 3], *plain).to(cuda_dev).eval()
+    for B in (1, 32, 130):
+        x = torch.randn(B, 1024, device=cuda_dev)
+        with torch.no_grad():
+            o9, t3 = pose_heads(x, rot, trans)
+            want9 = rot(x.double().unsqueeze(-1).float()).squeeze(-1)
+            want3 = trans(x.unsqueeze(-1)).squeeze(-1)
+        assert o9.shape == (B, 9) and t3.shape == (B, 3)
+        assert rel_err(o9, want9) < 1e-5 and rel_err(t3, want3) < 1e-5
