@@ -68,7 +68,17 @@ def pose_heads(pooled, rot_head, trans_head):
 
 def ortho9d2matrix(x_raw, y_raw, z_raw):
     """Rotation from three raw 3-vectors: columns normalised by (|v| + 1e-8), then the SO(3) projection
-    U diag(1,1,det(UV^T)) V^T.  Inference path (no autograd through the kernel)."""
+    U diag(1,1,det(UV^T)) V^T.  Runs the dcl_svd3_project kernel; when autograd is recording a gradient through
+    it (training) the same formula is evaluated with torch's differentiable SVD, as the reference does
+    (models/DCL_Net.py:22-35)."""
+    if torch.is_grad_enabled() and (x_raw.requires_grad or y_raw.requires_grad or z_raw.requires_grad):
+        def unit(v):
+            return v / (torch.sqrt(v.pow(2).sum(1, keepdim=True)) + 1e-8)
+        m = torch.stack((unit(x_raw), unit(y_raw), unit(z_raw)), dim=2)
+        u, _, v = torch.svd(m)
+        sigma = torch.ones(m.shape[0], 3, dtype=m.dtype, device=m.device)
+        sigma[:, -1] = torch.bmm(u, v.transpose(1, 2)).det()
+        return u @ torch.diag_embed(sigma) @ v.transpose(1, 2)
     return svd3_project(torch.cat((x_raw, y_raw, z_raw), dim=1), True)
 
 
@@ -198,7 +208,7 @@ class Network(nn.Module):
         F_p_wei = torch.sum(torch.cat([F_p1, F_p2], dim=2) * conf_softmax, dim=2, keepdim=True)
 
         ortho9d_pred = self.regressor_rot(F_p_wei).squeeze(-1)
-        rot_pred = svd3_project(ortho9d_pred, True)
+        rot_pred = ortho9d2matrix(ortho9d_pred[:, :3], ortho9d_pred[:, 3:6], ortho9d_pred[:, 6:])
         trans_pred = self.regressor_trans(F_p_wei).squeeze(-1)
 
         prediction = {"trans_pred": trans_pred, "rot_pred": rot_pred, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p}

@@ -28,14 +28,49 @@ def _fda_workspace(nbytes, device):
     return ws
 
 
+class FdaAlignFunction(torch.autograd.Function):
+    """Autograd wrapper of the fused kernel (training path).  Forward = the fused tcgen05 kernel, saving only the
+    inputs and the per-query log-sum-exp; backward rebuilds A = exp(S - lse) with dcl_fda_attention_map (the
+    reference keeps A alive instead, models/Modules.py:167-169) and forms the five gradient products with library
+    GEMMs:  dA = RE_2^T gE + RI_2^T gI;  dS = A o (dA - sum_m A o dA);
+            dRE_2 = gE A^T;  dRI_2 = gI A^T + RI_1 dS^T;  dRI_1 = RI_2 dS."""
+
+    @staticmethod
+    def forward(ctx, RI_1, RI_2, RE_2):
+        RE_embed, RI_embed, lse = _fda_align_kernel(RI_1, RI_2, RE_2, True)
+        ctx.save_for_backward(RI_1, RI_2, RE_2, lse)
+        ctx.mark_non_differentiable(lse)
+        return RE_embed, RI_embed, lse
+
+    @staticmethod
+    def backward(ctx, gE, gI, _g_lse):
+        RI_1, RI_2, RE_2, lse = ctx.saved_tensors
+        A = fda_attention_map(RI_1, RI_2, lse)                       # (B, M, N)
+        gE = torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
+        gI = torch.zeros_like(RI_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gI is None else gI
+        dA = torch.bmm(RE_2.transpose(1, 2), gE) + torch.bmm(RI_2.transpose(1, 2), gI)
+        dS = A * (dA - (A * dA).sum(dim=1, keepdim=True))
+        d_RE_2 = torch.bmm(gE, A.transpose(1, 2))
+        d_RI_2 = torch.bmm(gI, A.transpose(1, 2)) + torch.bmm(RI_1, dS.transpose(1, 2))
+        d_RI_1 = torch.bmm(RI_2, dS)
+        return d_RI_1, d_RI_2, d_RE_2
+
+
 def fda_align(RI_1, RI_2, RE_2, return_lse=False):
     """One FDA direction, fused:  A = softmax_m(RI_2^T RI_1) is never materialised.
 
     RI_1 (B,C,N) queries, RI_2 (B,C,M) keys, RE_2 (B,P,M) values, fp32, C in {64,128}, P=256,
     N % 128 == 0, M % 64 == 0.  Returns RE_embed = RE_2 A (B,P,N) and RI_embed = RI_2 A (B,C,N)
     (models/Modules.py:167-168 and models/DCL_Net.py:213/215), optionally the per-query
-    log-sum-exp (B,N).  Inference path: no autograd graph is recorded.
+    log-sum-exp (B,N).  Differentiable (FdaAlignFunction) when autograd is recording.
     """
+    if torch.is_grad_enabled() and (RI_1.requires_grad or RI_2.requires_grad or RE_2.requires_grad):
+        out = FdaAlignFunction.apply(RI_1.contiguous(), RI_2.contiguous(), RE_2.contiguous())
+        return out if return_lse else out[:2]
+    return _fda_align_kernel(RI_1, RI_2, RE_2, return_lse)
+
+
+def _fda_align_kernel(RI_1, RI_2, RE_2, return_lse=False):
     RI_1 = L.require(RI_1.contiguous(), torch.float32, "RI_1")
     RI_2 = L.require(RI_2.contiguous(), torch.float32, "RI_2")
     RE_2 = L.require(RE_2.contiguous(), torch.float32, "RE_2")

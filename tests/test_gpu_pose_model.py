@@ -224,3 +224,73 @@ def test_pose_heads_kernel_vs_torch(cuda_dev):
             want3 = trans(x.unsqueeze(-1)).squeeze(-1)
         assert o9.shape == (B, 9) and t3.shape == (B, 3)
         assert rel_err(o9, want9) < 1e-5 and rel_err(t3, want3) < 1e-5
+
+
+def test_training_step_gradients_match_oracle(cuda_dev):
+    """Train mode (autograd on): the drop-in Network — fused FDA forward + FdaAlignFunction backward, torch-SVD pose
+    — against the restated reference graph (bmm/softmax/svd autograd), same weights, same loss.  SURVEY.md config #5
+    (forward + backward through a11-a13 with the pose / correspondence losses of models/DCL_Net.py:265-303)."""
+    b, n = 2, 256
+    torch.manual_seed(21)
+    oracle_net = T.TailNetwork(mode="train").train()
+    net = Network(Cfg(n), mode="train").train()
+    net.load_state_dict(oracle_net.state_dict(), strict=False)
+    oracle_net, net = oracle_net.to(cuda_dev), net.to(cuda_dev)
+    g = torch.Generator().manual_seed(22)
+    f_xc, f_yo = torch.randn(b * n, 480, generator=g).to(cuda_dev), torch.randn(b * n, 480, generator=g).to(cuda_dev)
+    pts_tmp = ((torch.rand(b, n, 3, generator=g) - 0.5) * 0.2).to(cuda_dev)
+    q, _ = torch.linalg.qr(torch.randn(b, 3, 3, generator=g))
+    rot_gt = (q * torch.det(q).sign().view(b, 1, 1)).to(cuda_dev)
+    trans_gt = ((torch.rand(b, 3, generator=g) - 0.5) * 0.1).to(cuda_dev)
+
+    def loss_fn(out):
+        # L2 pose loss + correspondence losses + confidence regulariser (non-symmetric branch of DCL_Net.py:279-296)
+        posed = torch.bmm(pts_tmp, out["rot_pred"].transpose(1, 2)) + out["trans_pred"].unsqueeze(1)
+        posed_gt = torch.bmm(pts_tmp, rot_gt.transpose(1, 2)) + trans_gt.unsqueeze(1)
+        l_pose = torch.norm(posed - posed_gt, dim=2).mean()
+        l_xo = torch.norm(out["Xo_pred"] - pts_tmp, dim=2)
+        l_yc = torch.norm(out["Yc_pred"] - posed_gt, dim=2)
+        conf = out["conf"]
+        l_conf = torch.mean(torch.cat([l_xo, l_yc], dim=1).detach() * conf - 0.01 * torch.log(conf))
+        return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
+
+    a = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
+    bb = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
+    loss_mine = loss_fn(net.forward_from_point_feats(a[0], a[1], b))
+    loss_ref = loss_fn(oracle_net(bb[0], bb[1], b, n, n))
+    assert abs(loss_mine.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+    loss_mine.backward()
+    loss_ref.backward()
+    for mine, ref in zip(a, bb):
+        assert rel_err(mine.grad, ref.grad) < 2e-3
+    ref_params = dict(oracle_net.named_parameters())
+    checked = 0
+    for name, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        rg = ref_params[name].grad
+        assert rg is not None, name
+        if rg.abs().max() > 0:
+            assert rel_err(p.grad, rg) < 5e-3, name
+            checked += 1
+    assert checked > 40
+
+
+def test_fda_align_function_gradcheck_like(cuda_dev):
+    """FdaAlignFunction backward against autograd through the unfused bmm/softmax graph."""
+    from dcl_net_b200.modules import fda_align
+    g = torch.Generator().manual_seed(31)
+    ri1 = torch.randn(2, 64, 128, generator=g).relu().to(cuda_dev).requires_grad_(True)
+    ri2 = torch.randn(2, 64, 192, generator=g).relu().to(cuda_dev).requires_grad_(True)
+    re2 = torch.randn(2, 256, 192, generator=g).to(cuda_dev).requires_grad_(True)
+    ge, gi = torch.randn(2, 256, 128, generator=g).to(cuda_dev), torch.randn(2, 64, 128, generator=g).to(cuda_dev)
+    e, m = fda_align(ri1, ri2, re2)
+    (e * ge).sum().backward(retain_graph=True)
+    (m * gi).sum().backward()
+    got = [t.grad.clone() for t in (ri1, ri2, re2)]
+    for t in (ri1, ri2, re2):
+        t.grad = None
+    e_o, m_o, _ = T.fda_direction(ri1, ri2, re2)
+    ((e_o * ge).sum() + (m_o * gi).sum()).backward()
+    for gg, t in zip(got, (ri1, ri2, re2)):
+        assert rel_err(gg, t.grad) < 1e-3
