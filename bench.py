@@ -220,7 +220,7 @@ def run_b200_arm(args, rank, world, local_rank):
     def step_resident(i):
         rot, trans = engines[i % ROTATE].run()
         if world > 1:
-            rot, trans = sharding.gather_poses(rot, trans)
+            rot, trans = sharding.gather_poses(rot, trans, equal_shards=True)
         return rot, trans
 
     def barrier():

@@ -24,13 +24,19 @@ def shard_flat(rows, lo, hi):
     return out, keep
 
 
-def gather_poses(rot, trans, total=None):
+def gather_poses(rot, trans, total=None, equal_shards=False):
     """all_gather of per-rank (b_r,3,3)/(b_r,3) poses into (B,3,3)/(B,3) on every rank.  Works with
-    ragged shards.  No-op without an initialised process group."""
+    ragged shards (the shard sizes are exchanged first, which costs a host sync); pass equal_shards=True when
+    every rank holds the same number of instances to get a single asynchronous all_gather.
+    No-op without an initialised process group."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return rot, trans
     world = dist.get_world_size()
     packed = torch.cat([rot.reshape(rot.shape[0], 9), trans], dim=1).contiguous()
+    if equal_shards:
+        full = packed.new_empty(world * packed.shape[0], 12)
+        dist.all_gather_into_tensor(full, packed)
+        return full[:, :9].reshape(-1, 3, 3), full[:, 9:]
     counts = [torch.zeros(1, dtype=torch.int64, device=packed.device) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([packed.shape[0]], dtype=torch.int64, device=packed.device))
     counts = [int(c.item()) for c in counts]

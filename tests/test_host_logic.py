@@ -55,6 +55,9 @@ def _worker(rank, world, port, total):
         trans = ids.view(-1, 1) + torch.tensor([0.1, 0.2, 0.3])
         r, t = sharding.gather_poses(rot, trans)
         assert r.shape == (total, 3, 3) and t.shape == (total, 3)
+        if total % world == 0:  # equal shards: the single asynchronous all_gather gives the same answer
+            r2, t2 = sharding.gather_poses(rot, trans, equal_shards=True)
+            assert torch.equal(r2, r) and torch.equal(t2, t)
         assert torch.equal(r[:, 0, 0], torch.arange(total, dtype=torch.float32))
         assert torch.allclose(t[:, 2], torch.arange(total, dtype=torch.float32) + 0.3)
     finally:
