@@ -46,7 +46,8 @@ SIGNATURES = {
     "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _I, _P]),
     "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
-    "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    "dcl_pose_head_workspace_bytes": (_SZ, [_I, _P, _P]),
+    "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
 

@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
     uint64_t* acc_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-    const dcl_pm_gemm_problem& pr = batch.p[blockIdx.z];
-    const int mt = blockIdx.x, nti = blockIdx.y;
+    // grid = (problems, n-tiles, m-tiles): CTAs that read the same A blobs (same m-tile: the other n-tiles of a
+    // layer, the other problems sharing the input) are launched next to each other, so each blob comes from DRAM
+    // once and is an L2 hit for the rest (with the m-tile fastest, ncu showed 3x the unique bytes read from DRAM).
+    const dcl_pm_gemm_problem& pr = batch.p[blockIdx.x];
+    const int mt = blockIdx.z, nti = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = pr.kb_total;
 
@@ -269,7 +272,7 @@ int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStr
     cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid(rows / GM_BM, cout / NT, nprob);
+    dim3 grid(nprob, cout / NT, rows / GM_BM);
     pm_gemm_kernel<NT, STAGES><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch);
     return dcl_launch_status();
 }
@@ -278,7 +281,7 @@ int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStr
 
 DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int rows, void* stream) {
     DCL_RETURN_IF_BAD(nproblems >= 1 && nproblems <= GM_MAX_PROBLEMS && problems != nullptr);
-    DCL_RETURN_IF_BAD(rows > 0 && rows % GM_BM == 0);
+    DCL_RETURN_IF_BAD(rows > 0 && rows % GM_BM == 0 && rows / GM_BM <= 65535);
     PmGemmBatch batch;
     const int cout = problems[0].cout, nt = problems[0].nt;
     DCL_RETURN_IF_BAD((nt == 64 || nt == 128 || nt == 256) && cout % nt == 0);

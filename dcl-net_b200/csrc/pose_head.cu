@@ -1,61 +1,80 @@
 // Pose regressors on the pooled feature: regressor_rot / regressor_trans of models/DCL_Net.py:139-151,230-235
 // (and regressor_rot2 / regressor_trans2 of models/refiner.py:66-77): Head_MultiLayerPerceptron
-// [d_in -> d_h1 -> d_h2 -> d_out], Conv1d(k=1) + ReLU on a (b, d_in, 1) tensor, i.e. three tiny dense layers per
-// instance.  The reference runs each as a cuDNN convolution with a single output position (~50 us apiece on B200);
-// here one CTA per (instance, head) keeps the activations in shared memory and streams the fp32 weights once:
-// warp per output row, lanes stride the input with 128-bit loads, shuffle reduction.  fp32 FMA throughout.
+// [d_in -> d_h1 -> d_h2 -> d_out], Conv1d(k=1) + ReLU on a (b, d_in, 1) tensor, i.e. three small dense layers
+// applied to every instance of the batch.  The reference runs each as a cuDNN convolution with a single output
+// position (~50 us apiece on B200).  Here each layer of BOTH heads is one launch of a small-batch dense kernel:
+// a CTA stages up to 32 instances' input vectors in shared memory once, each warp owns one output row whose
+// fp32 weights it streams exactly once with 128-bit loads and applies to all staged instances (one accumulator
+// per instance), finishing with a shuffle reduction.  Weights are read once per layer instead of once per
+// instance.  fp32 FMA throughout.
 #include "common.cuh"
 #include "../../include/dcl_b200.h"
 
 namespace {
 
 constexpr int PH_THREADS = 256;
+constexpr int PH_ROWS = PH_THREADS / 32;  // output rows per CTA
+constexpr int PH_INST = 32;               // instances per CTA
 constexpr int PH_MAX_IN = 1024;
 
-__device__ __forceinline__ float warp_dot(const float* __restrict__ w, const float* x, int n, int lane) {
-    float acc = 0.f;
-    if ((n & 127) == 0) {
-        const float4* w4 = reinterpret_cast<const float4*>(w);
-        const float4* x4 = reinterpret_cast<const float4*>(x);
-        for (int i = lane; i < (n >> 2); i += 32) {
-            const float4 a = __ldg(w4 + i), b = x4[i];
-            acc = __fmaf_rn(a.x, b.x, acc);
-            acc = __fmaf_rn(a.y, b.y, acc);
-            acc = __fmaf_rn(a.z, b.z, acc);
-            acc = __fmaf_rn(a.w, b.w, acc);
+struct DenseJob {
+    const float* x;     // (b, k) input of this head
+    const float* w;     // (o, k)
+    const float* bias;  // (o)
+    float* y;           // (b, o)
+    int k, o, relu;
+};
+
+// grid = (row chunks, heads, instance chunks)
+__global__ void __launch_bounds__(PH_THREADS) dense_small_batch_kernel(DenseJob j0, DenseJob j1, int b) {
+    extern __shared__ __align__(16) float s_x[];  // PH_INST x k
+    const DenseJob& j = blockIdx.y == 0 ? j0 : j1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * PH_ROWS + warp;
+    const int i0 = blockIdx.z * PH_INST;
+    const int ni = min(PH_INST, b - i0);
+    if (blockIdx.x * PH_ROWS >= j.o) return;  // this head has fewer rows than the other one
+    const int k = j.k;
+    for (int idx = threadIdx.x; idx < ni * k; idx += PH_THREADS) s_x[idx] = j.x[(size_t)i0 * k + idx];
+    __syncthreads();
+    if (row >= j.o) return;
+    float acc[PH_INST];
+#pragma unroll
+    for (int i = 0; i < PH_INST; ++i) acc[i] = 0.f;
+    const float* wr = j.w + (size_t)row * k;
+    if ((k & 127) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        for (int c = lane; c < (k >> 2); c += 32) {
+            const float4 a = __ldg(w4 + c);
+#pragma unroll
+            for (int i = 0; i < PH_INST; ++i) {
+                if (i < ni) {
+                    const float4 xv = reinterpret_cast<const float4*>(s_x + (size_t)i * k)[c];
+                    acc[i] = __fmaf_rn(a.x, xv.x, acc[i]);
+                    acc[i] = __fmaf_rn(a.y, xv.y, acc[i]);
+                    acc[i] = __fmaf_rn(a.z, xv.z, acc[i]);
+                    acc[i] = __fmaf_rn(a.w, xv.w, acc[i]);
+                }
+            }
         }
     } else {
-        for (int i = lane; i < n; i += 32) acc = __fmaf_rn(__ldg(w + i), x[i], acc);
-    }
+        for (int c = lane; c < k; c += 32) {
+            const float a = __ldg(wr + c);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    return acc;
-}
-
-__global__ void __launch_bounds__(PH_THREADS) pose_head_kernel(dcl_pose_head_mlp h0, dcl_pose_head_mlp h1,
-                                                               const float* __restrict__ pooled,
-                                                               float* __restrict__ out0, float* __restrict__ out1) {
-    __shared__ __align__(16) float s_x[PH_MAX_IN];
-    __shared__ __align__(16) float s_a[PH_MAX_IN];
-    __shared__ __align__(16) float s_b[PH_MAX_IN];
-    const dcl_pose_head_mlp& h = blockIdx.y == 0 ? h0 : h1;
-    float* out = blockIdx.y == 0 ? out0 : out1;
-    const int inst = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < h.d_in; i += PH_THREADS) s_x[i] = pooled[(size_t)inst * h.d_in + i];
-    __syncthreads();
-    for (int o = warp; o < h.d_h1; o += PH_THREADS / 32) {
-        const float v = warp_dot(h.w1 + (size_t)o * h.d_in, s_x, h.d_in, lane);
-        if (lane == 0) s_a[o] = fmaxf(v + h.b1[o], 0.f);
+            for (int i = 0; i < PH_INST; ++i)
+                if (i < ni) acc[i] = __fmaf_rn(a, s_x[(size_t)i * k + c], acc[i]);
+        }
     }
-    __syncthreads();
-    for (int o = warp; o < h.d_h2; o += PH_THREADS / 32) {
-        const float v = warp_dot(h.w2 + (size_t)o * h.d_h1, s_a, h.d_h1, lane);
-        if (lane == 0) s_b[o] = fmaxf(v + h.b2[o], 0.f);
-    }
-    __syncthreads();
-    for (int o = warp; o < h.d_out; o += PH_THREADS / 32) {
-        const float v = warp_dot(h.w3 + (size_t)o * h.d_h2, s_b, h.d_h2, lane);
-        if (lane == 0) out[(size_t)inst * h.d_out + o] = v + h.b3[o];
+    const float bias = j.bias[row];
+#pragma unroll
+    for (int i = 0; i < PH_INST; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && i < ni) {
+            v += bias;
+            j.y[(size_t)(i0 + i) * j.o + row] = j.relu ? fmaxf(v, 0.f) : v;
+        }
     }
 }
 
@@ -64,15 +83,44 @@ bool head_ok(const dcl_pose_head_mlp& h) {
            h.d_h1 <= PH_MAX_IN && h.d_h2 > 0 && h.d_h2 <= PH_MAX_IN && h.d_out > 0;
 }
 
+int launch_layer(const DenseJob& a, const DenseJob& c, int b, cudaStream_t st) {
+    const int kmax = a.k > c.k ? a.k : c.k, omax = a.o > c.o ? a.o : c.o;
+    const size_t smem = (size_t)PH_INST * kmax * sizeof(float);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(dense_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(DCL_DIVUP(omax, PH_ROWS), 2, DCL_DIVUP(b, PH_INST));
+    dense_small_batch_kernel<<<grid, PH_THREADS, smem, st>>>(a, c, b);
+    return dcl_launch_status();
+}
+
 }  // namespace
 
+DCL_API size_t dcl_pose_head_workspace_bytes(int b, const dcl_pose_head_mlp* rot_head,
+                                             const dcl_pose_head_mlp* trans_head) {
+    if (b < 0 || rot_head == nullptr || trans_head == nullptr) return 0;
+    return (size_t)b * (rot_head->d_h1 + rot_head->d_h2 + trans_head->d_h1 + trans_head->d_h2) * sizeof(float) + 64;
+}
+
 DCL_API int dcl_pose_head(int b, const float* pooled, const dcl_pose_head_mlp* rot_head,
-                          const dcl_pose_head_mlp* trans_head, float* out_rot, float* out_trans, void* stream) {
+                          const dcl_pose_head_mlp* trans_head, float* out_rot, float* out_trans, void* workspace,
+                          size_t workspace_bytes, void* stream) {
     DCL_RETURN_IF_BAD(b >= 0 && pooled != nullptr && rot_head != nullptr && trans_head != nullptr);
     DCL_RETURN_IF_BAD(head_ok(*rot_head) && head_ok(*trans_head) && rot_head->d_in == trans_head->d_in);
     DCL_RETURN_IF_BAD(out_rot != nullptr && out_trans != nullptr && (((uintptr_t)pooled) & 15u) == 0);
+    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 15u) == 0 &&
+                      workspace_bytes >= dcl_pose_head_workspace_bytes(b, rot_head, trans_head));
     if (b == 0) return 0;
-    dim3 grid(b, 2);
-    pose_head_kernel<<<grid, PH_THREADS, 0, (cudaStream_t)stream>>>(*rot_head, *trans_head, pooled, out_rot, out_trans);
-    return dcl_launch_status();
+    cudaStream_t st = (cudaStream_t)stream;
+    const dcl_pose_head_mlp& r = *rot_head;
+    const dcl_pose_head_mlp& t = *trans_head;
+    float* r1 = reinterpret_cast<float*>(workspace);
+    float* r2 = r1 + (size_t)b * r.d_h1;
+    float* t1 = r2 + (size_t)b * r.d_h2;
+    float* t2 = t1 + (size_t)b * t.d_h1;
+    int e = launch_layer({pooled, r.w1, r.b1, r1, r.d_in, r.d_h1, 1}, {pooled, t.w1, t.b1, t1, t.d_in, t.d_h1, 1}, b, st);
+    if (e) return e;
+    e = launch_layer({r1, r.w2, r.b2, r2, r.d_h1, r.d_h2, 1}, {t1, t.w2, t.b2, t2, t.d_h1, t.d_h2, 1}, b, st);
+    if (e) return e;
+    return launch_layer({r2, r.w3, r.b3, out_rot, r.d_h2, r.d_out, 0}, {t2, t.w3, t.b3, out_trans, t.d_h2, t.d_out, 0}, b,
+                        st);
 }

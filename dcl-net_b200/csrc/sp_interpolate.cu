@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(256) sp_bucket_scatter_kernel(int m, KnownRows
 // lexicographic key (d, original index) makes the result independent of who saw which candidate in which order.
 // All 32 lanes of the warp must call this (full-mask shuffles); afterwards every lane of a group holds the result.
 constexpr int LPQ = 8;
+constexpr int SP_SEG_TILE_FLOATS = 512 * 4;  // 512 bucket entries (8 KB) per stage
 
 __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
                                                 const KnownRows& kr, int m, bool valid, float4 u,
@@ -258,8 +259,38 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
             }
         }
     } else {
-        int my_b;
-        if (valid && batch_id_ok(u.x, my_b) && my_b < ws[WS_NB]) {
+        int my_b = -1;
+        const bool has_bucket = valid && batch_id_ok(u.x, my_b) && my_b < ws[WS_NB];
+        // Common case: every query of the CTA belongs to the same batch item (clouds are stored batch-major).
+        // Then the bucket is streamed ONCE per CTA through shared memory by TMA bulk copies (2-stage ring) and
+        // all 16 query groups scan it there; ncu showed the per-group global loads stalled on the long
+        // scoreboard two thirds of the time.  Mixed CTAs take the per-group global path below.
+        __shared__ __align__(16) float s_tile[2 * SP_SEG_TILE_FLOATS];
+        __shared__ uint64_t s_bar[2];
+        __shared__ int s_b0;
+        if (threadIdx.x == 0) s_b0 = has_bucket ? my_b : -1;
+        __syncthreads();
+        const int b0 = s_b0;
+        const bool uniform = __syncthreads_and((!valid || (has_bucket && my_b == b0)) ? 1 : 0) && b0 >= 0;
+        if (uniform) {
+            const int beg = ws[WS_OFF + b0], end = ws[WS_OFF + b0 + 1];
+            DclTilePipe<SP_SEG_TILE_FLOATS> pipe;
+            pipe.init(s_tile, s_bar, reinterpret_cast<const float*>(sorted + beg), (end - beg) * 4);
+            for (int t = 0; t < pipe.ntiles; ++t) {
+                const int cnt = pipe.acquire(t) / 4;
+                const float4* tile = reinterpret_cast<const float4*>(pipe.tile(t));
+                if (valid) {
+#pragma unroll 4
+                    for (int j = sub; j < cnt; j += LPQ) {
+                        const float4 c = tile[j];
+                        const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
+                        if (!(d > b3) && d < CUDART_INF_F)
+                            nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+                    }
+                }
+                pipe.release(t);
+            }
+        } else if (has_bucket) {
             const int beg = ws[WS_OFF + my_b], end = ws[WS_OFF + my_b + 1];
 #pragma unroll 8
             for (int j = beg + sub; j < end; j += LPQ) {

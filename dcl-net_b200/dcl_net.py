@@ -60,9 +60,11 @@ def pose_heads(pooled, rot_head, trans_head):
     B = pooled.shape[0]
     o9 = torch.empty(B, hs.d_out, dtype=torch.float32, device=pooled.device)
     t3 = torch.empty(B, ht.d_out, dtype=torch.float32, device=pooled.device)
-    L.check(L.load().dcl_pose_head(B, L.ptr(pooled), ctypes.cast(ctypes.pointer(hs), ctypes.c_void_p),
-                                   ctypes.cast(ctypes.pointer(ht), ctypes.c_void_p), L.ptr(o9), L.ptr(t3),
-                                   L.stream_ptr()), "pose_head")
+    lib = L.load()
+    ps, pt = ctypes.cast(ctypes.pointer(hs), ctypes.c_void_p), ctypes.cast(ctypes.pointer(ht), ctypes.c_void_p)
+    ws = torch.empty(lib.dcl_pose_head_workspace_bytes(B, ps, pt), dtype=torch.uint8, device=pooled.device)
+    L.check(lib.dcl_pose_head(B, L.ptr(pooled), ps, pt, L.ptr(o9), L.ptr(t3), L.ptr(ws), ws.numel(), L.stream_ptr()),
+            "pose_head")
     return o9, t3
 
 

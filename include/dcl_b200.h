@@ -260,8 +260,10 @@ typedef struct dcl_pose_head_mlp {
     const float* w3; const float* b3;
     int d_in, d_h1, d_h2, d_out;
 } dcl_pose_head_mlp;
+size_t dcl_pose_head_workspace_bytes(int b, const dcl_pose_head_mlp* rot_head, const dcl_pose_head_mlp* trans_head);
 int dcl_pose_head(int b, const float* pooled, const dcl_pose_head_mlp* rot_head,
-    const dcl_pose_head_mlp* trans_head, float* out_rot, float* out_trans, void* stream);
+    const dcl_pose_head_mlp* trans_head, float* out_rot, float* out_trans,
+    void* workspace, size_t workspace_bytes, void* stream);
 
 /* dcl_sp_nn_interpolate_fused_pm with Ops_tensor2points (models/Modules.py:204-211) fused in: the known rows are the
  * sparse tensor's int32 (m,4) indices (b,ix,iy,iz); their centres ((float(i)*ext)+offset)+0.5*ext are formed in the
