@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/dcl_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -47,6 +48,80 @@ struct GmCfg {
     static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 128;
 };
+
+// Epilogue of one (128 x NT) tile: TMEM accumulator -> bias / ReLU / affine -> requested outputs.
+// Called by the four epilogue warps (quad = warp & 3 selects the TMEM lane quarter) after the accumulator is complete.
+template <int NT>
+__device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr, int mt, int nti, uint32_t tmem_acc,
+                                                 int quad, int lane) {
+    const int row = quad * 32 + lane;
+    const size_t r_glob = (size_t)mt * GM_BM + row;
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
+    const int cout = pr.cout;
+    size_t cm_base = 0;
+    if (pr.out_cm != nullptr) {
+        const size_t inst = r_glob / pr.rows_per_inst, within = r_glob - inst * pr.rows_per_inst;
+        cm_base = inst * (size_t)cout * pr.rows_per_inst + within;
+    }
+    float dot = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < NT / 32; ++cc) {
+        uint32_t v[32];
+        DCL_TMEM_LD32(tmem_acc + t_lane + cc * 32, v);
+        tc_wait_ld();
+        const int col0 = nti * NT + cc * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float y = __uint_as_float(v[i]);
+            if (pr.bias != nullptr) y += __ldg(pr.bias + col0 + i);
+            if (pr.relu) y = fmaxf(y, 0.f);
+            if (pr.post_scale != nullptr) y = __fmaf_rn(y, __ldg(pr.post_scale + col0 + i), __ldg(pr.post_shift + col0 + i));
+            v[i] = __float_as_uint(y);
+        }
+        if (pr.dot_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dot = __fmaf_rn(__uint_as_float(v[i]), __ldg(pr.dot_w + col0 + i), dot);
+        }
+        if (pr.out_pm != nullptr) {
+            unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
+                                  ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                __nv_bfloat16 h[8], l[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[ch * 8 + e]), h[e], l[e]);
+                *reinterpret_cast<uint4*>(blob + ch * 128) =
+                    make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+                *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) =
+                    make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+            }
+        }
+        if (pr.out_cm != nullptr) {
+            float* o = pr.out_cm + cm_base + (size_t)col0 * pr.rows_per_inst;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[(size_t)i * pr.rows_per_inst] = __uint_as_float(v[i]);
+        }
+        if (pr.pool_out != nullptr) {
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = __uint_as_float(v[i]) * rw;
+            // transpose-reduce: afterwards pv[0] on lane L = sum over the warp's 32 rows of column L
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const bool upper = (lane & s) != 0;
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    const float send = upper ? pv[i] : pv[i + s];
+                    const float keep = upper ? pv[i + s] : pv[i];
+                    pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
+        }
+    }
+    if (pr.dot_out != nullptr) pr.dot_out[r_glob] = dot;
+}
 
 template <int NT, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch) {
@@ -117,76 +192,9 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
         }
     } else {
         // ===================== epilogue =====================
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const size_t r_glob = (size_t)mt * GM_BM + row;
-        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-        const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
-        const int cout = pr.cout;
-        size_t cm_base = 0;
-        if (pr.out_cm != nullptr) {
-            const size_t inst = r_glob / pr.rows_per_inst, within = r_glob - inst * pr.rows_per_inst;
-            cm_base = inst * (size_t)cout * pr.rows_per_inst + within;
-        }
-        float dot = 0.f;
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < NT / 32; ++cc) {
-            uint32_t v[32];
-            DCL_TMEM_LD32(tmem_base + t_lane + cc * 32, v);
-            tc_wait_ld();
-            const int col0 = nti * NT + cc * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float y = __uint_as_float(v[i]);
-                if (pr.bias != nullptr) y += __ldg(pr.bias + col0 + i);
-                if (pr.relu) y = fmaxf(y, 0.f);
-                if (pr.post_scale != nullptr) y = __fmaf_rn(y, __ldg(pr.post_scale + col0 + i), __ldg(pr.post_shift + col0 + i));
-                v[i] = __float_as_uint(y);
-            }
-            if (pr.dot_out != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) dot = __fmaf_rn(__uint_as_float(v[i]), __ldg(pr.dot_w + col0 + i), dot);
-            }
-            if (pr.out_pm != nullptr) {
-                unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
-                                      ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[ch * 8 + e]), h[e], l[e]);
-                    *reinterpret_cast<uint4*>(blob + ch * 128) =
-                        make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-                    *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) =
-                        make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-                }
-            }
-            if (pr.out_cm != nullptr) {
-                float* o = pr.out_cm + cm_base + (size_t)col0 * pr.rows_per_inst;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[(size_t)i * pr.rows_per_inst] = __uint_as_float(v[i]);
-            }
-            if (pr.pool_out != nullptr) {
-                float pv[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pv[i] = __uint_as_float(v[i]) * rw;
-                // transpose-reduce: afterwards pv[0] on lane L = sum over the warp's 32 rows of column L
-#pragma unroll
-                for (int s = 16; s >= 1; s >>= 1) {
-                    const bool upper = (lane & s) != 0;
-#pragma unroll
-                    for (int i = 0; i < s; ++i) {
-                        const float send = upper ? pv[i] : pv[i + s];
-                        const float keep = upper ? pv[i + s] : pv[i];
-                        pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                    }
-                }
-                pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
-            }
-        }
-        if (pr.dot_out != nullptr) pr.dot_out[r_glob] = dot;
+        gm_epilogue_tile<NT>(pr, mt, nti, tmem_base, warp & 3, lane);
         tc_fence_before();
     }
     __syncwarp();
@@ -195,6 +203,177 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
         tc_fence_after();
         tc_dealloc(tmem_base, NT);
     }
+}
+
+// ------------------------------------------------------------------ persistent, cluster-of-2 variant
+// Same math and epilogue; what changes is how the tensor pipe is kept fed (ncu on the kernel above: tensor pipe
+// active ~45 %; a 2-stage ring per CTA cannot cover the L2 latency and 62 B/clk/SM of operand traffic is at the
+// limit of what L2 delivers):
+//   * one persistent CTA per SM walks a static list of tiles; a deep ring (192 KB of stages) runs ahead across
+//     tile boundaries; two TMEM accumulators alternate so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * CTAs are paired in a cluster: the pair works on two m-tiles of the same (problem, n-tile), so both need the
+//     same weight blobs at the same time — CTA 0 fetches the hi half, CTA 1 the lo half, each MULTICASTS its half
+//     into both CTAs' shared memory (cp.async.bulk ... .multicast::cluster).  Operand traffic per SM drops from
+//     48 to 32 KB per k-block.  A stage is refilled only after BOTH CTAs' MMAs released it: tcgen05.commit is
+//     multicast to the pair's `empty` barriers (2 arrivals per phase).
+__device__ __forceinline__ void dcl_bulk_g2s_mcast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(dcl_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(dcl_smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(dcl_smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t dcl_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void dcl_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NT, int STAGES>
+struct GmPCfg {
+    static constexpr int B_BLOB = NT * GM_BK * 4;
+    static constexpr int STAGE_BYTES = GM_A_BLOB + B_BLOB;
+    static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(2 * NT <= 512, "TMEM budget");
+};
+
+template <int NT, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+    pm_gemm_cluster_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
+    using Cfg = GmPCfg<NT, STAGES>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = dcl_cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int total_units = npairs_m * ntiles_n * nprob;   // unit = (m-tile pair, n-tile, problem); problem fastest
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            dcl_mbar_init(full + i, 1);
+            dcl_mbar_init(empty + i, 2);
+        }
+        for (int i = 0; i < 2; ++i) {
+            dcl_mbar_init(acc_full + i, 1);
+            dcl_mbar_init(acc_empty + i, 128);
+        }
+        dcl_fence_barrier_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, 2 * NT);
+    tc_fence_before();
+    __syncthreads();
+    dcl_cluster_sync();  // the peer's barriers are initialised before anything is multicast at them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int u = cluster_id; u < total_units; u += nclusters) {
+                const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+                const dcl_pm_gemm_problem& pr = batch.p[prob];
+                const int KB = pr.kb_total;
+                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
+                const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
+                                          (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
+                const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB +
+                                         rank * (Cfg::B_BLOB / 2);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    if (it >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((it / STAGES) - 1) & 1));
+                    unsigned char* dst = smem + s * Cfg::STAGE_BYTES;
+                    dcl_mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                    const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * GM_A_BLOB
+                                                              : a1 + (size_t)(kb - pr.kb0) * GM_A_BLOB;
+                    dcl_bulk_g2s(dst, asrc, GM_A_BLOB, full + s);
+                    dcl_bulk_g2s_mcast(dst + GM_A_BLOB + rank * (Cfg::B_BLOB / 2), w + (size_t)kb * Cfg::B_BLOB,
+                                       Cfg::B_BLOB / 2, full + s, (uint16_t)0x3);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
+            int it = 0, tl = 0;
+            for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
+                const int KB = batch.p[u % nprob].kb_total;
+                const int acc = tl & 1;
+                if (tl >= 2) dcl_mbar_wait(acc_empty + acc, (uint32_t)(((tl >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * NT;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    dcl_mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t a = dcl_smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint32_t b = a + GM_A_BLOB;
+#pragma unroll
+                    for (int ks = 0; ks < GM_BK / 16; ++ks) {
+                        const uint32_t off = ks * 256;
+                        mma_split3(tacc, a + off, a + GM_A_BLOB / 2 + off, b + off, b + Cfg::B_BLOB / 2 + off, 128, 512,
+                                   128, 512, idesc, kb == 0 && ks == 0);
+                    }
+                    tc_commit_mcast(empty + s, (uint16_t)0x3);
+                }
+                tc_commit(acc_full + acc);
+            }
+        }
+    } else {
+        int tl = 0;
+        for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
+            const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+            const int acc = tl & 1;
+            dcl_mbar_wait(acc_full + acc, (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            gm_epilogue_tile<NT>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp & 3, lane);
+            tc_fence_before();
+            dcl_mbar_arrive(acc_empty + acc);
+        }
+    }
+    __syncwarp();
+    __syncthreads();
+    dcl_cluster_sync();  // no CTA leaves while its peer may still multicast into it
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, 2 * NT);
+    }
+}
+
+template <int NT, int STAGES>
+int launch_gemm_cluster(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
+    using Cfg = GmPCfg<NT, STAGES>;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_cluster_kernel<NT, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const int ntiles_n = cout / NT, npairs_m = rows / (2 * GM_BM);
+    const int units = npairs_m * ntiles_n * nprob;
+    int clusters = num_sms / 2;
+    if (clusters > units) clusters = units;
+    pm_gemm_cluster_kernel<NT, STAGES><<<2 * clusters, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n,
+                                                                                        npairs_m);
+    return dcl_launch_status();
 }
 
 // ------------------------------------------------------------------ packing helpers
@@ -297,6 +476,13 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
         batch.p[i] = p;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // Persistent cluster-of-2 kernel when the m-tiles pair up; DCL_PM_GEMM_SIMPLE=1 forces the simple kernel (A/B).
+    static const bool force_simple = getenv("DCL_PM_GEMM_SIMPLE") != nullptr;
+    if (!force_simple && (rows / GM_BM) % 2 == 0) {
+        if (nt == 256) return launch_gemm_cluster<256, 4>(batch, nproblems, rows, cout, st);
+        if (nt == 128) return launch_gemm_cluster<128, 6>(batch, nproblems, rows, cout, st);
+        return launch_gemm_cluster<64, 8>(batch, nproblems, rows, cout, st);
+    }
     if (nt == 256) return launch_gemm<256, 2>(batch, nproblems, rows, cout, st);
     if (nt == 128) return launch_gemm<128, 3>(batch, nproblems, rows, cout, st);
     return launch_gemm<64, 4>(batch, nproblems, rows, cout, st);

@@ -162,3 +162,24 @@ def test_nn_interpolate_vox_pm_equals_tensor2points_path(cuda_dev):
     o32 = torch.as_tensor(off, dtype=torch.float32).tolist()
     pu_sp.nn_interpolate_vox_pm(unknown, ind, e32, o32, feats, pm_b, 64, 0)
     assert torch.equal(pm_a, pm_b)
+
+
+@pytest.mark.parametrize("rows,cin,cout,nprob", [(2048, 96, 512, 5), (4096, 160, 256, 3), (1024, 480, 128, 8), (2048, 64, 64, 2)])
+def test_pm_gemm_persistent_many_tiles(cuda_dev, rows, cin, cout, nprob):
+    """More work units than CTA pairs and k-block counts that are not multiples of the ring depth: exercises the
+    persistent tile loop, the ring wrap-around across tiles, the TMEM accumulator ping-pong and the multicast pairing."""
+    g = torch.Generator().manual_seed(rows + cin + cout + nprob)
+    xs = [torch.randn(rows, cin, generator=g).to(cuda_dev) for _ in range(2)]
+    pms = [FT.pm_pack_rows(x) for x in xs]
+    ws = [(torch.randn(cout, cin, generator=g) / cin ** 0.5).to(cuda_dev) for _ in range(nprob)]
+    bs = [torch.randn(cout, generator=g).to(cuda_dev) for _ in range(nprob)]
+    outs = [FT.pm_empty(rows, cout, cuda_dev) for _ in range(nprob)]
+    cms = [torch.empty(rows // 128, cout, 128, device=cuda_dev) for _ in range(nprob)]
+    FT.run_gemm([{"a0": pms[i % 2], "layer": FT.Layer(ws[i], bs[i], True), "out_pm": outs[i], "out_cm": cms[i],
+                  "rows_per_inst": 128} for i in range(nprob)], rows)
+    torch.cuda.synchronize()
+    for i in range(nprob):
+        want = _ref_layer(xs[i % 2], ws[i], bs[i], True, None, None)
+        scale = want.abs().max().item()
+        assert (FT.pm_unpack(outs[i], rows, cout).double() - want).abs().max().item() <= 3e-5 * scale, i
+        assert (cms[i].transpose(1, 2).reshape(rows, cout).double() - want).abs().max().item() <= 2e-5 * scale, i

@@ -254,26 +254,41 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         l_conf = torch.mean(torch.cat([l_xo, l_yc], dim=1).detach() * conf - 0.01 * torch.log(conf))
         return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
 
+    # Three runs of the same step: this implementation, the fp32 reference graph, and the reference graph in fp64.
+    # Train-mode BatchNorm and the SVD backward amplify rounding, so "parity" for gradients is defined against
+    # the fp64 result: this implementation must be as close to it as the fp32 reference graph itself is.
+    import copy
+    oracle64 = copy.deepcopy(oracle_net).double()
     a = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
     bb = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
+    cc = f_xc.double().requires_grad_(True), f_yo.double().requires_grad_(True)
     loss_mine = loss_fn(net.forward_from_point_feats(a[0], a[1], b))
     loss_ref = loss_fn(oracle_net(bb[0], bb[1], b, n, n))
-    assert abs(loss_mine.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+    pts_tmp, rot_gt, trans_gt = pts_tmp.double(), rot_gt.double(), trans_gt.double()
+    loss_64 = loss_fn(oracle64(cc[0], cc[1], b, n, n))
+    assert abs(loss_mine.item() - loss_64.item()) < 1e-4 * abs(loss_64.item())
     loss_mine.backward()
     loss_ref.backward()
-    # train-mode BatchNorm and the SVD backward (1/(s_i^2 - s_j^2) factors) amplify the ~1e-5 forward differences
-    for mine, ref in zip(a, bb):
-        assert rel_err(mine.grad, ref.grad) < 3e-2
-    ref_params = dict(oracle_net.named_parameters())
+    loss_64.backward()
+
+    def check(mine, ref32, ref64, what):
+        scale = ref64.abs().max().item()
+        if scale == 0:
+            return
+        e_mine = (mine.double() - ref64).abs().max().item() / scale
+        e_ref = (ref32.double() - ref64).abs().max().item() / scale
+        assert e_mine <= max(4.0 * e_ref, 2e-3), f"{what}: {e_mine:.3e} vs fp32 reference graph {e_ref:.3e}"
+
+    for mine, r32, r64 in zip(a, bb, cc):
+        check(mine.grad, r32.grad, r64.grad, "input grad")
+    p32, p64 = dict(oracle_net.named_parameters()), dict(oracle64.named_parameters())
     checked = 0
     for name, p in net.named_parameters():
         if p.grad is None:
             continue
-        rg = ref_params[name].grad
-        assert rg is not None, name
-        if rg.abs().max() > 0:
-            assert rel_err(p.grad, rg) < 3e-2, name
-            checked += 1
+        assert p32[name].grad is not None, name
+        check(p.grad, p32[name].grad, p64[name].grad, name)
+        checked += 1
     assert checked > 40
 
 
