@@ -50,15 +50,49 @@ struct GmCfg {
 };
 
 // Epilogue of one (128 x NT) tile: TMEM accumulator -> bias / ReLU / affine -> requested outputs.
-// Called by the four epilogue warps (quad = warp & 3 selects the TMEM lane quarter) after the accumulator is complete.
+// Called by the four epilogue warps (128 threads; quad = warp & 3 selects the TMEM lane quarter) after the
+// accumulator is complete.  ncu on the first version showed ~40 instructions per output column and warp (per-element
+// null checks, constant-bank loads with a dynamic problem index, scalar bf16 conversions) — the epilogue, not the
+// MMAs, paced the kernel.  Now: the problem descriptor is copied to registers once, the per-column parameters
+// (bias, post-scale, post-shift, dot vector; neutral values when absent) are staged in shared memory by the epilogue
+// warps and read back with 128-bit broadcast loads, the per-element math is branch-free (FADD, FMNMX, FFMA) and the
+// hi/lo split converts two values per instruction.
+struct GmColParams {           // per output column of the tile, in shared memory
+    float bias[256], scale[256], shift[256], dotw[256];
+};
+
+__device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// two fp32 -> packed bf16x2 hi and lo parts (x = hi + lo)
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 template <int NT>
-__device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr, int mt, int nti, uint32_t tmem_acc,
-                                                 int quad, int lane) {
+__device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_in, int mt, int nti, uint32_t tmem_acc,
+                                                 int quad, int lane, GmColParams& cp) {
+    const dcl_pm_gemm_problem pr = pr_in;  // registers, not repeated constant-bank loads with a dynamic index
     const int row = quad * 32 + lane;
+    const int tid = row;
     const size_t r_glob = (size_t)mt * GM_BM + row;
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-    const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
     const int cout = pr.cout;
+    // stage the tile's column parameters (previous tile's readers are past this point: barrier first)
+    gm_epi_barrier();
+    for (int c = tid; c < NT; c += 128) {
+        const int col = nti * NT + c;
+        cp.bias[c] = pr.bias != nullptr ? __ldg(pr.bias + col) : 0.f;
+        cp.scale[c] = pr.post_scale != nullptr ? __ldg(pr.post_scale + col) : 1.f;
+        cp.shift[c] = pr.post_shift != nullptr ? __ldg(pr.post_shift + col) : 0.f;
+        cp.dotw[c] = pr.dot_w != nullptr ? __ldg(pr.dot_w + col) : 0.f;
+    }
+    gm_epi_barrier();
+    const float relu_floor = pr.relu ? 0.f : -3.402823466e+38f;
+    const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
     size_t cm_base = 0;
     if (pr.out_cm != nullptr) {
         const size_t inst = r_glob / pr.rows_per_inst, within = r_glob - inst * pr.rows_per_inst;
@@ -71,50 +105,57 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr, 
         DCL_TMEM_LD32(tmem_acc + t_lane + cc * 32, v);
         tc_wait_ld();
         const int col0 = nti * NT + cc * 32;
+        float y[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float y = __uint_as_float(v[i]);
-            if (pr.bias != nullptr) y += __ldg(pr.bias + col0 + i);
-            if (pr.relu) y = fmaxf(y, 0.f);
-            if (pr.post_scale != nullptr) y = __fmaf_rn(y, __ldg(pr.post_scale + col0 + i), __ldg(pr.post_shift + col0 + i));
-            v[i] = __float_as_uint(y);
+        for (int q = 0; q < 8; ++q) {
+            const float4 bb = reinterpret_cast<const float4*>(cp.bias + cc * 32)[q];
+            const float4 sc = reinterpret_cast<const float4*>(cp.scale + cc * 32)[q];
+            const float4 sh = reinterpret_cast<const float4*>(cp.shift + cc * 32)[q];
+            y[q * 4 + 0] = __fmaf_rn(fmaxf(__uint_as_float(v[q * 4 + 0]) + bb.x, relu_floor), sc.x, sh.x);
+            y[q * 4 + 1] = __fmaf_rn(fmaxf(__uint_as_float(v[q * 4 + 1]) + bb.y, relu_floor), sc.y, sh.y);
+            y[q * 4 + 2] = __fmaf_rn(fmaxf(__uint_as_float(v[q * 4 + 2]) + bb.z, relu_floor), sc.z, sh.z);
+            y[q * 4 + 3] = __fmaf_rn(fmaxf(__uint_as_float(v[q * 4 + 3]) + bb.w, relu_floor), sc.w, sh.w);
         }
         if (pr.dot_out != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dot = __fmaf_rn(__uint_as_float(v[i]), __ldg(pr.dot_w + col0 + i), dot);
+            for (int q = 0; q < 8; ++q) {
+                const float4 dw = reinterpret_cast<const float4*>(cp.dotw + cc * 32)[q];
+                dot = __fmaf_rn(y[q * 4 + 0], dw.x, dot);
+                dot = __fmaf_rn(y[q * 4 + 1], dw.y, dot);
+                dot = __fmaf_rn(y[q * 4 + 2], dw.z, dot);
+                dot = __fmaf_rn(y[q * 4 + 3], dw.w, dot);
+            }
         }
         if (pr.out_pm != nullptr) {
             unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
                                   ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-                __nv_bfloat16 h[8], l[8];
+                uint32_t h[4], l[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[ch * 8 + e]), h[e], l[e]);
-                *reinterpret_cast<uint4*>(blob + ch * 128) =
-                    make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-                *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) =
-                    make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+                for (int e = 0; e < 4; ++e) split2_bf16(y[ch * 8 + 2 * e], y[ch * 8 + 2 * e + 1], h[e], l[e]);
+                *reinterpret_cast<uint4*>(blob + ch * 128) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) = make_uint4(l[0], l[1], l[2], l[3]);
             }
         }
         if (pr.out_cm != nullptr) {
             float* o = pr.out_cm + cm_base + (size_t)col0 * pr.rows_per_inst;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[(size_t)i * pr.rows_per_inst] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) o[(size_t)i * pr.rows_per_inst] = y[i];
         }
         if (pr.pool_out != nullptr) {
             float pv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = __uint_as_float(v[i]) * rw;
+            for (int i = 0; i < 32; ++i) pv[i] = y[i] * rw;
             // transpose-reduce: afterwards pv[0] on lane L = sum over the warp's 32 rows of column L
 #pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-                const bool upper = (lane & s) != 0;
+            for (int st = 16; st >= 1; st >>= 1) {
+                const bool upper = (lane & st) != 0;
 #pragma unroll
-                for (int i = 0; i < s; ++i) {
-                    const float send = upper ? pv[i] : pv[i + s];
-                    const float keep = upper ? pv[i + s] : pv[i];
-                    pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                for (int i = 0; i < st; ++i) {
+                    const float send = upper ? pv[i] : pv[i + st];
+                    const float keep = upper ? pv[i + st] : pv[i];
+                    pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, st);
                 }
             }
             pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
@@ -127,6 +168,7 @@ template <int NT, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch) {
     using Cfg = GmCfg<NT, STAGES>;
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(16) GmColParams s_colp;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;
@@ -194,7 +236,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
         // ===================== epilogue =====================
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
-        gm_epilogue_tile<NT>(pr, mt, nti, tmem_base, warp & 3, lane);
+        gm_epilogue_tile<NT>(pr, mt, nti, tmem_base, warp & 3, lane, s_colp);
         tc_fence_before();
     }
     __syncwarp();
@@ -253,6 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
     pm_gemm_cluster_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
     using Cfg = GmPCfg<NT, STAGES>;
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(16) GmColParams s_colp;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;   // [2]
@@ -341,7 +384,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
             const int acc = tl & 1;
             dcl_mbar_wait(acc_full + acc, (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
-            gm_epilogue_tile<NT>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp & 3, lane);
+            gm_epilogue_tile<NT>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp & 3, lane, s_colp);
             tc_fence_before();
             dcl_mbar_arrive(acc_empty + acc);
         }
