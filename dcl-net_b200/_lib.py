@@ -49,6 +49,7 @@ SIGNATURES = {
     "dcl_pose_head_workspace_bytes": (_SZ, [_I, _P, _P]),
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
+    "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
 
 

@@ -50,8 +50,9 @@ constexpr float RESCALE_TH = 8.0f;  // lazy rescale threshold (log2 units)
 template <int C>
 struct FdaCfg {
     static constexpr int VROWS = FDA_P + C;           // value rows: RE_2 then RI_2
+    static constexpr int NK = (C == 64) ? 2 : 1;      // K block ring depth
     static constexpr int NV = (C == 64) ? 4 : 2;      // V chunk ring depth
-    static constexpr int NP = (C == 64) ? 2 : 1;      // P buffers
+    static constexpr int NP = 2;                      // P buffers (the o_done pairing below assumes 2)
     static constexpr int Q_HALF = QT * C * 2;         // bytes of the hi (or lo) image
     static constexpr int K_HALF = KB * C * 2;
     static constexpr int V_HALF = VROWS * KS * 2;
@@ -59,7 +60,7 @@ struct FdaCfg {
     static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = 2 * V_HALF, P_BYTES = 2 * P_HALF;
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = OFF_Q + Q_BYTES;
-    static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+    static constexpr int OFF_V = OFF_K + NK * K_BYTES;
     static constexpr int OFF_P = OFF_V + NV * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
@@ -148,11 +149,11 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
     uint64_t* k_empty = bars + 3;  // [2]
     uint64_t* s_full = bars + 5;   // [2]
     uint64_t* s_empty = bars + 7;  // [2]
-    uint64_t* o_done = bars + 9;
-    uint64_t* p_full = bars + 10;  // [NP] (<= 2)
-    uint64_t* v_full = bars + 12;  // [NV] (<= 4)
-    uint64_t* v_empty = bars + 16; // [NV]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* o_done = bars + 9;   // [2]: PV(j) commits to o_done[j & 1], so a waiter is never more than one phase behind
+    uint64_t* p_full = bars + 11;  // [NP] (<= 2)
+    uint64_t* v_full = bars + 13;  // [NV] (<= 4)
+    uint64_t* v_empty = bars + 17; // [NV]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, bs = blockIdx.y;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             dcl_mbar_init(s_empty + i, 128);
         }
         dcl_mbar_init(o_done, 1);
+        dcl_mbar_init(o_done + 1, 1);
         for (int i = 0; i < Cfg::NP; ++i) dcl_mbar_init(p_full + i, 128);
         for (int i = 0; i < Cfg::NV; ++i) {
             dcl_mbar_init(v_full + i, 1);
@@ -196,16 +198,18 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             dcl_mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
             dcl_bulk_g2s(smem + Cfg::OFF_Q, gQ, Cfg::Q_BYTES, q_full);
             auto load_k = [&](int j) {
-                const int s = j & 1;
-                if (j >= 2) dcl_mbar_wait(k_empty + s, (uint32_t)(((j >> 1) - 1) & 1));
+                const int s = j % Cfg::NK;
+                if (j >= Cfg::NK) dcl_mbar_wait(k_empty + s, (uint32_t)((j / Cfg::NK - 1) & 1));
                 dcl_mbar_arrive_expect_tx(k_full + s, Cfg::K_BYTES);
                 dcl_bulk_g2s(smem + Cfg::OFF_K + s * Cfg::K_BYTES, gK + (size_t)j * Cfg::K_BYTES, Cfg::K_BYTES,
                              k_full + s);
             };
-            load_k(0);
-            if (NB > 1) load_k(1);
+            for (int j = 0; j < Cfg::NK && j < NB; ++j) load_k(j);
             int vi = 0;  // running V chunk counter
             for (int j = 0; j < NB; ++j) {
+                // K block j+NK reuses the slot of block j, free once S(j) has completed; S(j) is issued ahead of
+                // PV(j-1), so this wait never depends on the V chunks issued below.
+                if (j + Cfg::NK < NB) load_k(j + Cfg::NK);
                 for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
                     const int s = vi % Cfg::NV;
                     const int use = vi / Cfg::NV;
@@ -214,7 +218,6 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
                     dcl_bulk_g2s(smem + Cfg::OFF_V + s * Cfg::V_BYTES, gV + (size_t)vi * Cfg::V_BYTES, Cfg::V_BYTES,
                                  v_full + s);
                 }
-                if (j + 2 < NB) load_k(j + 2);
             }
         }
     } else if (warp == 1) {
@@ -224,20 +227,28 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             constexpr uint32_t idesc_o1 = umma_idesc_bf16(QT, 256);
             constexpr uint32_t idesc_o2 = umma_idesc_bf16(QT, C);
             const uint32_t tO = tmem_base;
+            // Descriptors differ only in their 14-bit start-address field: build one per operand image and bump it.
+            const uint64_t dQh = umma_desc(sQ, Cfg::QK_LBO, Cfg::QK_SBO);
+            const uint64_t dQl = umma_desc(sQ + Cfg::Q_HALF, Cfg::QK_LBO, Cfg::QK_SBO);
+            const uint64_t dK0 = umma_desc(sK, Cfg::QK_LBO, Cfg::QK_SBO);
+            const uint64_t dV0 = umma_desc(sV, Cfg::V_LBO, Cfg::V_SBO);
+            const uint64_t dP0 = umma_desc(sP, Cfg::P_LBO, Cfg::P_SBO);
             auto issue_s = [&](int j) {
-                const int s = j & 1;
-                dcl_mbar_wait(k_full + s, (uint32_t)((j >> 1) & 1));
-                if (j >= 2) dcl_mbar_wait(s_empty + s, (uint32_t)(((j >> 1) - 1) & 1));
+                const int s = j % Cfg::NK;
+                dcl_mbar_wait(k_full + s, (uint32_t)((j / Cfg::NK) & 1));
+                if (j >= 2) dcl_mbar_wait(s_empty + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
                 tc_fence_after();
-                const uint32_t kb = sK + s * Cfg::K_BYTES;
-                const uint32_t tS = tmem_base + Cfg::S_COL + s * KB;
+                const uint64_t dKh = dK0 + (uint64_t)((s * Cfg::K_BYTES) >> 4);
+                const uint64_t dKl = dKh + (uint64_t)(Cfg::K_HALF >> 4);
+                const uint32_t tS = tmem_base + Cfg::S_COL + (j & 1) * KB;
 #pragma unroll
                 for (int kk = 0; kk < C / 16; ++kk) {
-                    const uint32_t off = kk * 2 * Cfg::QK_LBO;  // two K chunks per UMMA
-                    mma_split3(tS, sQ + off, sQ + Cfg::Q_HALF + off, kb + off, kb + Cfg::K_HALF + off, Cfg::QK_LBO,
-                               Cfg::QK_SBO, Cfg::QK_LBO, Cfg::QK_SBO, idesc_s, kk == 0);
+                    const uint64_t off = (uint64_t)((kk * 2 * Cfg::QK_LBO) >> 4);  // two K chunks per UMMA
+                    tc_mma_bf16(tS, dQh + off, dKh + off, idesc_s, kk == 0 ? 0u : 1u);
+                    tc_mma_bf16(tS, dQh + off, dKl + off, idesc_s, 1u);
+                    tc_mma_bf16(tS, dQl + off, dKh + off, idesc_s, 1u);
                 }
-                tc_commit(s_full + s);
+                tc_commit(s_full + (j & 1));
                 tc_commit(k_empty + s);
             };
             dcl_mbar_wait(q_full, 0);
@@ -248,24 +259,29 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
                 const int ps = j % Cfg::NP;
                 dcl_mbar_wait(p_full + ps, (uint32_t)((j / Cfg::NP) & 1));
                 tc_fence_after();
-                const uint32_t pb = sP + ps * Cfg::P_BYTES;
+                const uint64_t dPh = dP0 + (uint64_t)((ps * Cfg::P_BYTES) >> 4);
+#pragma unroll
                 for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
                     const int s = vi % Cfg::NV;
                     dcl_mbar_wait(v_full + s, (uint32_t)((vi / Cfg::NV) & 1));
                     tc_fence_after();
-                    const uint32_t vb = sV + s * Cfg::V_BYTES;
-                    const uint32_t pa = pb + ks * 2 * Cfg::P_LBO;
-                    const bool first = (j == 0 && ks == 0);
+                    const uint64_t dVh = dV0 + (uint64_t)((s * Cfg::V_BYTES) >> 4);
+                    const uint64_t dVl = dVh + (uint64_t)(Cfg::V_HALF >> 4);
+                    const uint64_t dAh = dPh + (uint64_t)((ks * 2 * Cfg::P_LBO) >> 4);
+                    const uint64_t dAl = dAh + (uint64_t)(Cfg::P_HALF >> 4);
+                    const uint32_t acc = (j == 0 && ks == 0) ? 0u : 1u;
                     // value rows [0,256) -> O columns [0,256)
-                    mma_split3(tO, pa, pa + Cfg::P_HALF, vb, vb + Cfg::V_HALF, Cfg::P_LBO, Cfg::P_SBO, Cfg::V_LBO,
-                               Cfg::V_SBO, idesc_o1, first);
+                    tc_mma_bf16(tO, dAh, dVh, idesc_o1, acc);
+                    tc_mma_bf16(tO, dAh, dVl, idesc_o1, 1u);
+                    tc_mma_bf16(tO, dAl, dVh, idesc_o1, 1u);
                     // value rows [256,256+C) -> O columns [256,256+C)
-                    const uint32_t vb2 = vb + (256 / 8) * Cfg::V_SBO;
-                    mma_split3(tO + 256, pa, pa + Cfg::P_HALF, vb2, vb2 + Cfg::V_HALF, Cfg::P_LBO, Cfg::P_SBO,
-                               Cfg::V_LBO, Cfg::V_SBO, idesc_o2, first);
+                    constexpr uint64_t v2 = (uint64_t)(((256 / 8) * Cfg::V_SBO) >> 4);
+                    tc_mma_bf16(tO + 256, dAh, dVh + v2, idesc_o2, acc);
+                    tc_mma_bf16(tO + 256, dAh, dVl + v2, idesc_o2, 1u);
+                    tc_mma_bf16(tO + 256, dAl, dVh + v2, idesc_o2, 1u);
                     tc_commit(v_empty + s);
                 }
-                tc_commit(o_done);
+                tc_commit(o_done + (j & 1));
             }
         }
     } else {
@@ -291,47 +307,50 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             tc_fence_before();
             dcl_mbar_arrive(s_empty + sb);
 
-            float mx = __uint_as_float(sv[0]);
+            float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
 #pragma unroll
-            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-            mx *= LOG2E;
+            for (int i = 2; i < 64; i += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+                mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+            }
+            const float mx = fmaxf(mx0, mx1) * LOG2E;
             float alpha = 1.f;
             bool need = false;
             if (j == 0) {
                 m_ref = mx;
             } else if (mx > m_ref + RESCALE_TH) {
-                alpha = exp2f(m_ref - mx);
+                alpha = ex2_approx(m_ref - mx);
                 m_ref = mx;
                 need = true;
             }
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-                sv[i] = __float_as_uint(exp2f(__fmaf_rn(__uint_as_float(sv[i]), LOG2E, -m_ref)));
-
-            if (Cfg::NP == 1 && j >= 1) dcl_mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+            // P buffer j%NP was last read by PV(j-NP)
+            if (j >= 2) dcl_mbar_wait(o_done + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
             {
                 unsigned char* pd = p_row_base + (j % Cfg::NP) * Cfg::P_BYTES;
                 // The row sum is taken over the weights the tensor core will actually see (hi + lo), so that
                 // numerator and denominator of the softmax carry the same rounding.
-                float sum = 0.f;
+                float sum0 = 0.f, sum1 = 0.f;
+                const float neg_m = -m_ref;
 #pragma unroll
                 for (int kc = 0; kc < KB / 8; ++kc) {
-                    __nv_bfloat16 h[8], lw[8];
+                    uint32_t h[4], lw[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        split_bf16(__uint_as_float(sv[kc * 8 + i]), h[i], lw[i]);
-                        sum += __bfloat162float(h[i]) + __bfloat162float(lw[i]);
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e]), LOG2E, neg_m));
+                        const float p1 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e + 1]), LOG2E, neg_m));
+                        split2_bf16(p0, p1, h[e], lw[e]);
+                        sum0 += __uint_as_float(h[e] << 16) + __uint_as_float(lw[e] << 16);
+                        sum1 += __uint_as_float(h[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
                     }
-                    *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) =
-                        make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-                    *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) =
-                        make_uint4(pack2(lw[0], lw[1]), pack2(lw[2], lw[3]), pack2(lw[4], lw[5]), pack2(lw[6], lw[7]));
+                    *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
-                l = __fmaf_rn(l, alpha, sum);
+                l = __fmaf_rn(l, alpha, sum0 + sum1);
             }
             if (j >= 1) {
-                if (Cfg::NP != 1) dcl_mbar_wait(o_done, (uint32_t)((j - 1) & 1));
                 if (__any_sync(0xffffffffu, need)) {
+                    // O is rescaled between PV(j-1) and PV(j)
+                    dcl_mbar_wait(o_done + ((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
                     tc_fence_after();
 #pragma unroll 1
                     for (int cc = 0; cc < Cfg::VROWS / 32; ++cc) {
@@ -351,7 +370,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             dcl_mbar_arrive(p_full + (j % Cfg::NP));
         }
         // ---- epilogue: O / l -> global (channel-major, consecutive lanes = consecutive queries)
-        dcl_mbar_wait(o_done, (uint32_t)((NB - 1) & 1));
+        dcl_mbar_wait(o_done + ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const int qglob = qt * QT + row;
@@ -521,6 +540,97 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int K, const 
     }
 }
 
+// ------------------------------------------------------------------ CTA-pair UMMA probe (tests / bring-up)
+// D (256 x N) = A (256 x K) * B (N x K)^T issued once by the leader CTA of a 2-CTA cluster with cta_group::2:
+// CTA r holds A rows [128r, 128r+128) and B rows [r N/2, (r+1) N/2) in its own shared memory, and finds rows
+// [128r, 128r+128) of D (all N columns) in its own TMEM.  mode 0: the pair meets at a cluster barrier before the
+// MMA; mode 1: the peer instead announces its operands with a remote mbarrier arrive on the leader's barrier (the
+// hand-off a pipelined kernel uses).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    umma_pair_probe_kernel(int N, int K, const float* __restrict__ A, const float* __restrict__ B,
+                           float* __restrict__ D, int mode) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar_done, bar_ready;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t rank = dcl_cluster_ctarank();
+    const int nh = N / 2;
+    const int a_half = 128 * K * 2, b_half = nh * K * 2;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 2 * a_half;
+    const int kch = K / 8;
+    const float* Ar = A + (size_t)rank * 128 * K;
+    const float* Br = B + (size_t)rank * nh * K;
+    for (int i = threadIdx.x; i < 128 * kch; i += 128) {
+        const int r = i % 128, kc = i / 128;
+        uint32_t h[4], l[4];
+        for (int e = 0; e < 4; ++e)
+            split2_bf16(Ar[(size_t)r * K + kc * 8 + 2 * e], Ar[(size_t)r * K + kc * 8 + 2 * e + 1], h[e], l[e]);
+        unsigned char* d = sA + ((r >> 3) * kch + kc) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + a_half) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    for (int i = threadIdx.x; i < nh * kch; i += 128) {
+        const int r = i % nh, kc = i / nh;
+        uint32_t h[4], l[4];
+        for (int e = 0; e < 4; ++e)
+            split2_bf16(Br[(size_t)r * K + kc * 8 + 2 * e], Br[(size_t)r * K + kc * 8 + 2 * e + 1], h[e], l[e]);
+        unsigned char* d = sB + ((r >> 3) * kch + kc) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(d + b_half) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    if (threadIdx.x == 0) {
+        dcl_mbar_init(&bar_done, 1);
+        dcl_mbar_init(&bar_ready, 1);
+        dcl_fence_barrier_init();
+    }
+    dcl_fence_proxy_async();
+    __syncthreads();
+    dcl_cluster_sync();  // barriers of both CTAs exist before anything is signalled at them
+    if ((threadIdx.x >> 5) == 0) tc2_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (mode == 0) {
+        dcl_cluster_sync();
+    } else if (rank == 1 && threadIdx.x == 0) {
+        dcl_mbar_arrive_remote(&bar_ready, 0);
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        if (mode != 0) dcl_mbar_wait_cluster(&bar_ready, 0);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(256, N);
+        const uint64_t dAh = umma_desc(dcl_smem_u32(sA), 128, (uint32_t)kch * 128);
+        const uint64_t dAl = dAh + (uint64_t)(a_half >> 4);
+        const uint64_t dBh = umma_desc(dcl_smem_u32(sB), 128, (uint32_t)kch * 128);
+        const uint64_t dBl = dBh + (uint64_t)(b_half >> 4);
+        for (int kk = 0; kk < K / 16; ++kk) {
+            const uint64_t off = (uint64_t)(kk * 256) >> 4;
+            tc2_mma_bf16(tmem_base, dAh + off, dBh + off, idesc, kk == 0 ? 0u : 1u);
+            tc2_mma_bf16(tmem_base, dAh + off, dBl + off, idesc, 1u);
+            tc2_mma_bf16(tmem_base, dAl + off, dBh + off, idesc, 1u);
+        }
+        tc2_commit_mcast(&bar_done, (uint16_t)0x3);
+    }
+    dcl_mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int quad = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = quad * 32 + lane;
+    for (int cc = 0; cc < N / 32; ++cc) {
+        uint32_t ov[32];
+        DCL_TMEM_LD32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc * 32, ov);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) D[((size_t)rank * 128 + row) * N + cc * 32 + i] = __uint_as_float(ov[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    dcl_cluster_sync();
+    if ((threadIdx.x >> 5) == 0) {
+        tc_fence_after();
+        tc2_dealloc(tmem_base, 256);
+    }
+}
+
 template <int C>
 struct FdaWs {
     __nv_bfloat16 *Qp, *Kp, *Vp;
@@ -621,5 +731,16 @@ DCL_API int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, fl
     cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D, swap_lbo_sbo);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* B, float* D, int mode, void* stream) {
+    DCL_RETURN_IF_BAD(N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0 && mode >= 0 && mode < 2);
+    const size_t smem = (size_t)(128 + N / 2) * K * 4;
+    DCL_RETURN_IF_BAD(smem <= 200 * 1024);
+    cudaError_t e =
+        cudaFuncSetAttribute(umma_pair_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    umma_pair_probe_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D, mode);
     return dcl_launch_status();
 }

@@ -63,15 +63,6 @@ struct GmColParams {           // per output column of the tile, in shared memor
 
 __device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// two fp32 -> packed bf16x2 hi and lo parts (x = hi + lo)
-__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 template <int NT>
 __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_in, int mt, int nti, uint32_t tmem_acc,
                                                  int quad, int lane, GmColParams& cp) {
@@ -258,27 +249,6 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
 //     into both CTAs' shared memory (cp.async.bulk ... .multicast::cluster).  Operand traffic per SM drops from
 //     48 to 32 KB per k-block.  A stage is refilled only after BOTH CTAs' MMAs released it: tcgen05.commit is
 //     multicast to the pair's `empty` barriers (2 arrivals per phase).
-__device__ __forceinline__ void dcl_bulk_g2s_mcast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                                   uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-        ::"r"(dcl_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(dcl_smem_u32(bar)), "h"(cta_mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(dcl_smem_u32(bar)), "h"(cta_mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t dcl_cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void dcl_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 template <int NT, int STAGES>
 struct GmPCfg {

@@ -46,7 +46,10 @@ class FdaAlignFunction(torch.autograd.Function):
     def backward(ctx, gE, gI, _g_lse):
         RI_1, RI_2, RE_2, lse = ctx.saved_tensors
         A = fda_attention_map(RI_1, RI_2, lse)                       # (B, M, N)
-        gE = torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
+        # The forward's lse comes out of the split-bf16 logits; the fp32 logits recomputed here differ from those by
+        # ~|S| 2^-17, a common factor per query column that the renormalisation removes exactly.
+        A = A / A.sum(dim=1, keepdim=True)
+        gE =torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
         gI = torch.zeros_like(RI_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gI is None else gI
         dA = torch.bmm(RE_2.transpose(1, 2), gE) + torch.bmm(RI_2.transpose(1, 2), gI)
         dS = A * (dA - (A * dA).sum(dim=1, keepdim=True))

@@ -284,6 +284,13 @@ int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c,
 int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D,
     int swap_lbo_sbo, void* stream);
 
+/* D (256 x N) = A (256 x K) B^T issued by the leader of a 2-CTA cluster as one M=256
+ * tcgen05.mma.cta_group::2 per K step: CTA r holds A rows [128r,128r+128) and B rows
+ * [rN/2,(r+1)N/2).  mode 0: cluster barrier before the MMA; mode 1: the peer hands its
+ * operands over with a remote mbarrier arrive.  Pins the CTA-pair conventions. */
+int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* B, float* D,
+    int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,20 @@ def test_umma_probe(cuda_dev, N, K):
     assert rel_err(D, want) < 3e-5, f"UMMA probe rel err {rel_err(D, want):.3e}"
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("N,K", [(64, 64), (256, 64), (128, 128), (32, 16)])
+def test_umma_pair_probe(cuda_dev, N, K, mode):
+    """Pins the CTA-pair (cta_group::2, M=256) conventions: B split by rows over the pair, D rows per CTA."""
+    g = torch.Generator().manual_seed(N * 1000 + K + mode)
+    A, B = torch.randn(256, K, generator=g), torch.randn(N, K, generator=g)
+    D = torch.full((256, N), float("nan"), device=cuda_dev)
+    a, b = A.to(cuda_dev), B.to(cuda_dev)
+    L.check(L.load().dcl_debug_umma_pair_gemm(N, K, L.ptr(a), L.ptr(b), L.ptr(D), mode, L.stream_ptr()), "pair probe")
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().T
+    assert rel_err(D, want) < 3e-5, f"UMMA pair probe rel err {rel_err(D, want):.3e}"
+
+
 def _inputs(seed, b, c, n, m, kind):
     g = torch.Generator().manual_seed(seed)
     if kind == "relu":  # post-ReLU features as in the network (BN eval ~ identity)

@@ -254,14 +254,19 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         l_conf = torch.mean(torch.cat([l_xo, l_yc], dim=1).detach() * conf - 0.01 * torch.log(conf))
         return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
 
-    # Three runs of the same step: this implementation, the fp32 reference graph, and the reference graph in fp64.
-    # Train-mode BatchNorm and the SVD backward amplify rounding, so "parity" for gradients is defined against
-    # the fp64 result: this implementation must be as close to it as the fp32 reference graph itself is.
+    # Four runs of the same step: this implementation, the fp32 reference graph, the reference graph in fp64, and the
+    # fp64 graph with its FDA outputs perturbed by 1e-5 (relative to their max; 100x below the 1e-3 forward bar).
+    # The step is badly conditioned — train-mode BatchNorm and ReLU gates near zero make some weight gradients jump
+    # by percents under a 1e-6 perturbation (tools/diag_train_grad.py) — so gradient parity is defined against the
+    # fp64 result with that perturbation response as the floor: this implementation must be as close to fp64 as the
+    # fp32 reference graph is, or within 3x of what a 1e-5 forward perturbation does.  The FDA gradients on their
+    # own are checked at 5e-5 in test_fda_align_function_gradcheck_like below.
     import copy
     oracle64 = copy.deepcopy(oracle_net).double()
     a = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
     bb = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
     cc = f_xc.double().requires_grad_(True), f_yo.double().requires_grad_(True)
+    dd = f_xc.double().requires_grad_(True), f_yo.double().requires_grad_(True)
     loss_mine = loss_fn(net.forward_from_point_feats(a[0], a[1], b))
     loss_ref = loss_fn(oracle_net(bb[0], bb[1], b, n, n))
     pts_tmp, rot_gt, trans_gt = pts_tmp.double(), rot_gt.double(), trans_gt.double()
@@ -270,24 +275,43 @@ def test_training_step_gradients_match_oracle(cuda_dev):
     loss_mine.backward()
     loss_ref.backward()
     loss_64.backward()
+    g64 = {name: p.grad.clone() for name, p in oracle64.named_parameters() if p.grad is not None}
+    oracle64.zero_grad()
+    exact_direction = T.fda_direction
+    noise = torch.Generator(device=cuda_dev).manual_seed(23)
 
-    def check(mine, ref32, ref64, what):
+    def perturbed_direction(ri_1, ri_2, re_2):
+        e, m, att = exact_direction(ri_1, ri_2, re_2)
+        e = e + 1e-5 * e.abs().max().detach() * torch.randn(e.shape, generator=noise, device=e.device, dtype=e.dtype)
+        m = m + 1e-5 * m.abs().max().detach() * torch.randn(m.shape, generator=noise, device=m.device, dtype=m.dtype)
+        return e, m, att
+
+    T.fda_direction = perturbed_direction
+    try:
+        loss_fn(oracle64(dd[0], dd[1], b, n, n)).backward()
+    finally:
+        T.fda_direction = exact_direction
+    gpert = {name: p.grad for name, p in oracle64.named_parameters() if p.grad is not None}
+
+    def check(mine, ref32, ref64, pert64, what):
         scale = ref64.abs().max().item()
         if scale == 0:
             return
         e_mine = (mine.double() - ref64).abs().max().item() / scale
         e_ref = (ref32.double() - ref64).abs().max().item() / scale
-        assert e_mine <= max(4.0 * e_ref, 2e-3), f"{what}: {e_mine:.3e} vs fp32 reference graph {e_ref:.3e}"
+        e_floor = (pert64 - ref64).abs().max().item() / scale
+        assert e_mine <= max(4.0 * e_ref, 3.0 * e_floor, 1e-4), \
+            f"{what}: {e_mine:.3e} vs fp32 reference graph {e_ref:.3e}, 1e-5 perturbation response {e_floor:.3e}"
 
-    for mine, r32, r64 in zip(a, bb, cc):
-        check(mine.grad, r32.grad, r64.grad, "input grad")
-    p32, p64 = dict(oracle_net.named_parameters()), dict(oracle64.named_parameters())
+    for mine, r32, r64, rp in zip(a, bb, cc, dd):
+        check(mine.grad, r32.grad, r64.grad, rp.grad, "input grad")
+    p32 = dict(oracle_net.named_parameters())
     checked = 0
     for name, p in net.named_parameters():
         if p.grad is None:
             continue
         assert p32[name].grad is not None, name
-        check(p.grad, p32[name].grad, p64[name].grad, name)
+        check(p.grad, p32[name].grad, g64[name], gpert[name], name)
         checked += 1
     assert checked > 40
 
@@ -309,4 +333,4 @@ def test_fda_align_function_gradcheck_like(cuda_dev):
     e_o, m_o, _ = T.fda_direction(ri1, ri2, re2)
     ((e_o * ge).sum() + (m_o * gi).sum()).backward()
     for gg, t in zip(got, (ri1, ri2, re2)):
-        assert rel_err(gg, t.grad) < 1e-3
+        assert rel_err(gg, t.grad) < 5e-5
