@@ -35,6 +35,7 @@ SIGNATURES = {
     "dcl_fda_align_fwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_pack": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_fwd_packed": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_fwd_packed_pm": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_attention_map": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
     "dcl_weighted_kabsch": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
+    "dcl_debug_fda_set_trace": (_I, [_P]),
 }
 
 

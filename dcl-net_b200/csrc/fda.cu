@@ -29,20 +29,21 @@
 //               SBO = byte distance between core matrices adjacent in the row direction
 // (cute::UMMA::make_umma_desc<Major::K>, INTERLEAVE: ((8,n),2):((1,SBO),LBO) in uint128).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-5 = softmax / correction / epilogue (one thread per query row; warp w touches
-// TMEM lanes 32*(w%4)..+31).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (in the CTA-pair kernel the
+// peer's warp 1 relays its load completions to the leader), warps 2-9 = softmax / correction / epilogue, two
+// threads per query row (warps w and w+4 touch TMEM lanes 32*(w%4)..+31 and split the columns).
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/dcl_b200.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace {
 
 constexpr int QT = 128;  // queries per CTA (UMMA M)
 constexpr int KB = 64;   // keys per block (UMMA N of the S product, K of the O product)
 constexpr int KS = 16;   // keys per V chunk = one UMMA K step
-constexpr int FDA_THREADS = 192;
+constexpr int FDA_THREADS = 320;  // TMA warp, MMA warp, eight softmax warps
 constexpr int FDA_P = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_TH = 8.0f;  // lazy rescale threshold (log2 units)
@@ -63,7 +64,8 @@ struct FdaCfg {
     static constexpr int OFF_V = OFF_K + NK * K_BYTES;
     static constexpr int OFF_P = OFF_V + NV * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int OFF_XCH = OFF_BAR + 256;      // 6 x 128 floats exchanged between the two threads of a row
+    static constexpr int SMEM_BYTES = OFF_XCH + 6 * QT * 4;
     static constexpr int S_COL = VROWS;               // TMEM: O at [0,VROWS), S ping-pong after it
     static constexpr int TMEM_COLS = 512;
     static_assert(VROWS + 2 * KB <= 512, "TMEM budget");
@@ -133,14 +135,211 @@ __global__ void __launch_bounds__(256) fda_pack_kernel(int n, int m, const float
     }
 }
 
+// ------------------------------------------------------------------ timeline trace (bring-up / profiling)
+// When a trace buffer is installed (dcl_debug_fda_set_trace), CTA (0,0) of the FDA kernels stamps clock64() at the
+// hand-off points of its three roles: trace[role * 1024 + block * 8 + event].
+__device__ long long* g_fda_trace = nullptr;
+__device__ __forceinline__ long long fda_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// life-cycle stamps (globaltimer, ns) of CTA (0,0) [slot 0] and of the last leader CTA of the grid [slot 1]:
+// trace[3 * 1024 + slot * 8 + event], events 0 entry, 1 set-up done, 2 main loop done, 3 epilogue done, 4 exit.
+__device__ __forceinline__ long long* fda_life_slot() {
+    long long* g = g_fda_trace;
+    if (g == nullptr) return nullptr;
+    if (blockIdx.x == 0 && blockIdx.y == 0) return g + 3 * 1024;
+    if (blockIdx.x == ((gridDim.x - 1) & ~1u) && blockIdx.y == gridDim.y - 1) return g + 3 * 1024 + 8;
+    return nullptr;
+}
+__device__ __forceinline__ void fda_life(long long* slot, int ev) {
+    if (slot != nullptr) slot[ev] = fda_globaltimer();
+}
+__device__ __forceinline__ void fda_stamp(long long* tr, int role, int j, int ev) {
+    if (tr != nullptr && j < 128) tr[role * 1024 + j * 8 + ev] = clock64();
+}
+
+// Where a launch delivers its two results.  Each of RE_embed (256 channels) and RI_embed (C channels) can go out
+// as the reference's fp32 channel-major tensor, as a point-major bf16 hi/lo image (dcl_pm_gemm's activation format,
+// pm_gemm.cu) ready to be the next layer's A operand, or both; null pointers are skipped.
+struct FdaOut {
+    float* re_cm;
+    float* ri_cm;
+    unsigned char* re_pm;
+    unsigned char* ri_pm;
+    float* lse;
+};
+
+// ------------------------------------------------------------------ softmax / correction / epilogue warps
+// PAIR: the barriers the MMA issuer waits on live in the leader CTA of the pair; every warp announces itself there
+// with one cluster-scope arrive (local or remote).  Otherwise every thread arrives on its own CTA's barrier.
+template <bool PAIR>
+__device__ __forceinline__ void fda_arrive(uint64_t* bar, int lane) {
+    if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) dcl_mbar_arrive_remote(bar, 0);
+    } else {
+        dcl_mbar_arrive(bar);
+    }
+}
+
+// Eight warps, two threads per query row: warps w and w+4 own the same TMEM lane quadrant and split the 64 keys of a
+// block (and the O columns in the rescale / epilogue) in halves, so every scheduler holds two softmax warps and the
+// S -> P latency, which paces the tensor pipe, halves.  The two threads of a row agree on the running maximum through
+// a double-buffered shared-memory slot and a 64-thread named barrier; their partial row sums meet in the epilogue.
+template <class Cfg, bool PAIR>
+__device__ __forceinline__ void fda_softmax_warps(unsigned char* smem, uint32_t tmem_base, int warp, int lane, int qt,
+                                                  int bs, int n, int NB, uint64_t* s_full, uint64_t* s_empty,
+                                                  uint64_t* o_done, uint64_t* p_full, const FdaOut& out) {
+    constexpr int C = Cfg::VROWS - FDA_P;
+    constexpr int HK = KB / 2;                   // keys per thread and block
+    constexpr int OC = Cfg::VROWS / 32;          // 32-column chunks of O
+    long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) ? g_fda_trace : nullptr;
+    long long* life = (warp == 2 && lane == 0) ? fda_life_slot() : nullptr;
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);  // [parity][half][row] partial maxima, then [half][row] sums
+    const uint32_t pair_bar = 1u + (uint32_t)quad;
+    float m_ref = -CUDART_INF_F, l = 0.f;
+    unsigned char* p_row_base = smem + Cfg::OFF_P + (row >> 3) * Cfg::P_SBO + (row & 7) * 16 + half * (HK / 8) * Cfg::P_LBO;
+    for (int j = 0; j < NB; ++j) {
+        const int sb = j & 1;
+        fda_stamp(tr, 1, j, 0);
+        dcl_mbar_wait(s_full + sb, (uint32_t)((j >> 1) & 1));
+        fda_stamp(tr, 1, j, 1);
+        tc_fence_after();
+        uint32_t sv[HK];
+        DCL_TMEM_LD32(tmem_base + t_lane + Cfg::S_COL + sb * KB + half * HK, sv);
+        tc_wait_ld();
+        tc_fence_before();
+        fda_arrive<PAIR>(s_empty + sb, lane);
+        fda_stamp(tr, 1, j, 2);
+
+        float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
+#pragma unroll
+        for (int i = 2; i < HK; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+        }
+        float mx = fmaxf(mx0, mx1);
+        xch[(sb * 2 + half) * QT + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, xch[(sb * 2 + (half ^ 1)) * QT + row]) * LOG2E;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+            m_ref = mx;
+        } else if (mx > m_ref + RESCALE_TH) {
+            alpha = ex2_approx(m_ref - mx);
+            m_ref = mx;
+            need = true;
+        }
+        // P buffer j%NP was last read by PV(j-NP)
+        fda_stamp(tr, 1, j, 3);
+        if (j >= 2) dcl_mbar_wait(o_done + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
+        fda_stamp(tr, 1, j, 4);
+        {
+            unsigned char* pd = p_row_base + (j % Cfg::NP) * Cfg::P_BYTES;
+            // The row sum is taken over the weights the tensor core will actually see (hi + lo), so that
+            // numerator and denominator of the softmax carry the same rounding.
+            float sum0 = 0.f, sum1 = 0.f;
+            const float neg_m = -m_ref;
+#pragma unroll
+            for (int kc = 0; kc < HK / 8; ++kc) {
+                uint32_t h[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e]), LOG2E, neg_m));
+                    const float p1 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e + 1]), LOG2E, neg_m));
+                    split2_bf16(p0, p1, h[e], lw[e]);
+                    sum0 += __uint_as_float(h[e] << 16) + __uint_as_float(lw[e] << 16);
+                    sum1 += __uint_as_float(h[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
+                *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            l = __fmaf_rn(l, alpha, sum0 + sum1);
+        }
+        if (j >= 1) {
+            if (__any_sync(0xffffffffu, need)) {
+                // O is rescaled between PV(j-1) and PV(j); this thread takes its half of the columns
+                dcl_mbar_wait(o_done + ((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = half * (OC / 2); cc < (half + 1) * (OC / 2); ++cc) {
+                    uint32_t ov[32];
+                    const uint32_t ta = tmem_base + t_lane + cc * 32;
+                    DCL_TMEM_LD32(ta, ov);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                    DCL_TMEM_ST32(ta, ov);
+                }
+                tc_wait_st();
+            }
+        }
+        dcl_fence_proxy_async();
+        tc_fence_before();
+        fda_arrive<PAIR>(p_full + (j % Cfg::NP), lane);
+        fda_stamp(tr, 1, j, 5);
+    }
+    fda_life(life, 2);
+    // ---- epilogue: O / l -> global; the two threads of a row first add up their partial sums
+    float* lx = xch + 4 * QT;
+    lx[half * QT + row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    l += lx[(half ^ 1) * QT + row];
+    dcl_mbar_wait(o_done + ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qglob = qt * QT + row;
+    const size_t tile = (size_t)bs * (n / QT) + qt;  // 128-row tile of the (b*n)-row point-major images
+    const uint32_t pm_row = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 16u;
+#pragma unroll 1
+    for (int cc = half * (OC / 2); cc < (half + 1) * (OC / 2); ++cc) {
+        uint32_t ov[32];
+        DCL_TMEM_LD32(tmem_base + t_lane + cc * 32, ov);
+        tc_wait_ld();
+        const bool is_re = cc < FDA_P / 32;
+        const int kb = is_re ? cc : cc - FDA_P / 32;  // 32-channel block within its tensor
+        float y[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(ov[i]) * inv_l;
+        float* cm = is_re ? out.re_cm : out.ri_cm;
+        if (cm != nullptr) {
+            // channel-major: consecutive lanes = consecutive queries, 512 contiguous bytes per channel and CTA
+            float* o = cm + ((size_t)bs * (is_re ? FDA_P : C) + kb * 32) * n + qglob;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[(size_t)i * n] = y[i];
+        }
+        unsigned char* pm = is_re ? out.re_pm : out.ri_pm;
+        if (pm != nullptr) {
+            // one whole 16 KB blob (128 rows x 32 channels, hi | lo) per CTA and iteration
+            unsigned char* blob = pm + (tile * ((is_re ? FDA_P : C) / 32) + kb) * 16384 + pm_row;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t h[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_bf16(y[ch * 8 + 2 * e], y[ch * 8 + 2 * e + 1], h[e], lw[e]);
+                *reinterpret_cast<uint4*>(blob + ch * 128) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(blob + 8192 + ch * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
+    }
+    if (half == 0 && out.lse != nullptr) out.lse[(size_t)bs * n + qglob] = m_ref * (1.0f / LOG2E) + logf(l);
+    tc_fence_before();
+    fda_life(life, 3);
+}
+
 // ------------------------------------------------------------------ main kernel
 template <int C>
 __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, const __nv_bfloat16* __restrict__ Qp,
                                                                  const __nv_bfloat16* __restrict__ Kp,
                                                                  const __nv_bfloat16* __restrict__ Vp,
-                                                                 float* __restrict__ RE_embed,
-                                                                 float* __restrict__ RI_embed,
-                                                                 float* __restrict__ lse_out) {
+                                                                 const FdaOut out) {
     using Cfg = FdaCfg<C>;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -158,6 +357,8 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, bs = blockIdx.y;
     const int NB = m / KB;  // key blocks
+    long long* life0 = threadIdx.x == 0 ? fda_life_slot() : nullptr;
+    fda_life(life0, 0);
 
     if (threadIdx.x == 0) {
         dcl_mbar_init(q_full, 1);
@@ -165,11 +366,11 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             dcl_mbar_init(k_full + i, 1);
             dcl_mbar_init(k_empty + i, 1);
             dcl_mbar_init(s_full + i, 1);
-            dcl_mbar_init(s_empty + i, 128);
+            dcl_mbar_init(s_empty + i, 256);
         }
         dcl_mbar_init(o_done, 1);
         dcl_mbar_init(o_done + 1, 1);
-        for (int i = 0; i < Cfg::NP; ++i) dcl_mbar_init(p_full + i, 128);
+        for (int i = 0; i < Cfg::NP; ++i) dcl_mbar_init(p_full + i, 256);
         for (int i = 0; i < Cfg::NV; ++i) {
             dcl_mbar_init(v_full + i, 1);
             dcl_mbar_init(v_empty + i, 1);
@@ -181,6 +382,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    fda_life(life0, 1);
 
     const uint32_t sQ = dcl_smem_u32(smem + Cfg::OFF_Q);
     const uint32_t sK = dcl_smem_u32(smem + Cfg::OFF_K);
@@ -189,12 +391,13 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (dcl_elect_one()) {
             const unsigned char* gQ =
                 reinterpret_cast<const unsigned char*>(Qp) + ((size_t)bs * (n / QT) + qt) * Cfg::Q_BYTES;
             const unsigned char* gK = reinterpret_cast<const unsigned char*>(Kp) + (size_t)bs * NB * Cfg::K_BYTES;
             const unsigned char* gV =
                 reinterpret_cast<const unsigned char*>(Vp) + (size_t)bs * (m / KS) * Cfg::V_BYTES;
+            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
             dcl_mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
             dcl_bulk_g2s(smem + Cfg::OFF_Q, gQ, Cfg::Q_BYTES, q_full);
             auto load_k = [&](int j) {
@@ -213,7 +416,10 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
                 for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
                     const int s = vi % Cfg::NV;
                     const int use = vi / Cfg::NV;
+                    if (ks == 0) fda_stamp(trp, 2, j, 0);
                     if (use >= 1) dcl_mbar_wait(v_empty + s, (uint32_t)((use - 1) & 1));
+                    if (ks == 0) fda_stamp(trp, 2, j, 1);
+                    if (ks == 3) fda_stamp(trp, 2, j, 2);
                     dcl_mbar_arrive_expect_tx(v_full + s, Cfg::V_BYTES);
                     dcl_bulk_g2s(smem + Cfg::OFF_V + s * Cfg::V_BYTES, gV + (size_t)vi * Cfg::V_BYTES, Cfg::V_BYTES,
                                  v_full + s);
@@ -222,7 +428,8 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (dcl_elect_one()) {
+            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KB);
             constexpr uint32_t idesc_o1 = umma_idesc_bf16(QT, 256);
             constexpr uint32_t idesc_o2 = umma_idesc_bf16(QT, C);
@@ -235,8 +442,11 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             const uint64_t dP0 = umma_desc(sP, Cfg::P_LBO, Cfg::P_SBO);
             auto issue_s = [&](int j) {
                 const int s = j % Cfg::NK;
+                fda_stamp(tr, 0, j, 0);
                 dcl_mbar_wait(k_full + s, (uint32_t)((j / Cfg::NK) & 1));
+                fda_stamp(tr, 0, j, 1);
                 if (j >= 2) dcl_mbar_wait(s_empty + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
+                fda_stamp(tr, 0, j, 2);
                 tc_fence_after();
                 const uint64_t dKh = dK0 + (uint64_t)((s * Cfg::K_BYTES) >> 4);
                 const uint64_t dKl = dKh + (uint64_t)(Cfg::K_HALF >> 4);
@@ -257,13 +467,17 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             for (int j = 0; j < NB; ++j) {
                 if (j + 1 < NB) issue_s(j + 1);
                 const int ps = j % Cfg::NP;
+                fda_stamp(tr, 0, j, 3);
                 dcl_mbar_wait(p_full + ps, (uint32_t)((j / Cfg::NP) & 1));
+                fda_stamp(tr, 0, j, 4);
                 tc_fence_after();
                 const uint64_t dPh = dP0 + (uint64_t)((ps * Cfg::P_BYTES) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
                     const int s = vi % Cfg::NV;
                     dcl_mbar_wait(v_full + s, (uint32_t)((vi / Cfg::NV) & 1));
+                    if (ks == 0) fda_stamp(tr, 0, j, 6);
+                    if (ks == 3) fda_stamp(tr, 0, j, 7);
                     tc_fence_after();
                     const uint64_t dVh = dV0 + (uint64_t)((s * Cfg::V_BYTES) >> 4);
                     const uint64_t dVl = dVh + (uint64_t)(Cfg::V_HALF >> 4);
@@ -282,115 +496,11 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
                     tc_commit(v_empty + s);
                 }
                 tc_commit(o_done + (j & 1));
+                fda_stamp(tr, 0, j, 5);
             }
         }
     } else {
-        // ===================== softmax / correction / epilogue =====================
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
-        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-        float m_ref = -CUDART_INF_F, l = 0.f;
-        unsigned char* p_row_base = smem + Cfg::OFF_P + (row >> 3) * Cfg::P_SBO + (row & 7) * 16;
-        for (int j = 0; j < NB; ++j) {
-            const int sb = j & 1;
-            dcl_mbar_wait(s_full + sb, (uint32_t)((j >> 1) & 1));
-            tc_fence_after();
-            uint32_t sv[64];
-            {
-                const uint32_t ta = tmem_base + t_lane + Cfg::S_COL + sb * KB;
-                uint32_t* lo = sv;
-                uint32_t* hi = sv + 32;
-                DCL_TMEM_LD32(ta, lo);
-                DCL_TMEM_LD32(ta + 32, hi);
-                tc_wait_ld();
-            }
-            tc_fence_before();
-            dcl_mbar_arrive(s_empty + sb);
-
-            float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
-#pragma unroll
-            for (int i = 2; i < 64; i += 2) {
-                mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-                mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-            }
-            const float mx = fmaxf(mx0, mx1) * LOG2E;
-            float alpha = 1.f;
-            bool need = false;
-            if (j == 0) {
-                m_ref = mx;
-            } else if (mx > m_ref + RESCALE_TH) {
-                alpha = ex2_approx(m_ref - mx);
-                m_ref = mx;
-                need = true;
-            }
-            // P buffer j%NP was last read by PV(j-NP)
-            if (j >= 2) dcl_mbar_wait(o_done + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
-            {
-                unsigned char* pd = p_row_base + (j % Cfg::NP) * Cfg::P_BYTES;
-                // The row sum is taken over the weights the tensor core will actually see (hi + lo), so that
-                // numerator and denominator of the softmax carry the same rounding.
-                float sum0 = 0.f, sum1 = 0.f;
-                const float neg_m = -m_ref;
-#pragma unroll
-                for (int kc = 0; kc < KB / 8; ++kc) {
-                    uint32_t h[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p0 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e]), LOG2E, neg_m));
-                        const float p1 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e + 1]), LOG2E, neg_m));
-                        split2_bf16(p0, p1, h[e], lw[e]);
-                        sum0 += __uint_as_float(h[e] << 16) + __uint_as_float(lw[e] << 16);
-                        sum1 += __uint_as_float(h[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-                    }
-                    *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                }
-                l = __fmaf_rn(l, alpha, sum0 + sum1);
-            }
-            if (j >= 1) {
-                if (__any_sync(0xffffffffu, need)) {
-                    // O is rescaled between PV(j-1) and PV(j)
-                    dcl_mbar_wait(o_done + ((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
-                    tc_fence_after();
-#pragma unroll 1
-                    for (int cc = 0; cc < Cfg::VROWS / 32; ++cc) {
-                        uint32_t ov[32];
-                        const uint32_t ta = tmem_base + t_lane + cc * 32;
-                        DCL_TMEM_LD32(ta, ov);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                        DCL_TMEM_ST32(ta, ov);
-                    }
-                    tc_wait_st();
-                }
-            }
-            dcl_fence_proxy_async();
-            tc_fence_before();
-            dcl_mbar_arrive(p_full + (j % Cfg::NP));
-        }
-        // ---- epilogue: O / l -> global (channel-major, consecutive lanes = consecutive queries)
-        dcl_mbar_wait(o_done + ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
-        tc_fence_after();
-        const float inv_l = 1.0f / l;
-        const int qglob = qt * QT + row;
-        float* re = RE_embed + (size_t)bs * FDA_P * n + qglob;
-        float* ri = RI_embed + (size_t)bs * C * n + qglob;
-#pragma unroll 1
-        for (int cc = 0; cc < Cfg::VROWS / 32; ++cc) {
-            uint32_t ov[32];
-            DCL_TMEM_LD32(tmem_base + t_lane + cc * 32, ov);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = cc * 32 + i;
-                const float v = __uint_as_float(ov[i]) * inv_l;
-                if (col < FDA_P) dcl_st_stream_f1(re + (size_t)col * n, v);
-                else dcl_st_stream_f1(ri + (size_t)(col - FDA_P) * n, v);
-            }
-        }
-        if (lse_out != nullptr) lse_out[(size_t)bs * n + qglob] = m_ref * (1.0f / LOG2E) + logf(l);
-        tc_fence_before();
+        fda_softmax_warps<Cfg, false>(smem, tmem_base, warp, lane, qt, bs, n, NB, s_full, s_empty, o_done, p_full, out);
     }
     __syncwarp();
     __syncthreads();
@@ -398,6 +508,253 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
         tc_fence_after();
         tc_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+    fda_life(life0, 4);
+}
+
+// ------------------------------------------------------------------ CTA-pair kernel
+// Two query tiles of one instance share every K block and V chunk: the pair runs each product as ONE M=256
+// tcgen05.mma.cta_group::2 issued by the leader (cluster rank 0); CTA r stages only its half of the B operand —
+// keys [32r, 32r+32) of a block, value rows [128r, 128r+128) and [256 + rC/2, 256 + (r+1)C/2) of a chunk — so the
+// L2 -> shared-memory traffic per SM halves (the single-CTA kernel is bound by it: 2.1 MB per CTA against ~43 B/clk/SM
+// of L2 bandwidth) and the freed shared memory deepens the V ring.  Conventions pinned by dcl_debug_umma_pair_gemm.
+//   * Operand loads are issued by each CTA for its own half; the peer's MMA warp relays "my half landed"
+//     to the leader's full barriers (count 2 there) in the order the leader consumes them.
+//   * tcgen05.commit multicasts every completion (S ready, K/V slot free, PV done) to both CTAs.
+//   * Softmax warps of both CTAs announce "S read" / "P written" with one cluster-scope arrive per warp on the
+//     leader's barriers (count 8).
+template <int C>
+struct FdaPairCfg {
+    static constexpr int VROWS = FDA_P + C;
+    static constexpr int VH = VROWS / 2;               // value rows staged per CTA
+    static constexpr int NK = 2;
+    static constexpr int NV = (C == 64) ? 8 : 5;
+    static constexpr int NP = 2;
+    static constexpr int Q_HALF = QT * C * 2;
+    static constexpr int K_HALF = (KB / 2) * C * 2;    // hi (or lo) image of this CTA's 32 keys
+    static constexpr int V_HALF = VH * KS * 2;         // hi (or lo) image of this CTA's value rows, one chunk
+    static constexpr int V_PART_A = 128 * KS * 2;      // rows of the N=256 product come first, then the N=C product's
+    static constexpr int P_HALF = QT * KB * 2;
+    static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = 2 * V_HALF, P_BYTES = 2 * P_HALF;
+    static constexpr int G_K_HALF = KB * C * 2, G_K_BYTES = 2 * G_K_HALF;         // images written by fda_pack_kernel
+    static constexpr int G_V_HALF = VROWS * KS * 2, G_V_BYTES = 2 * G_V_HALF;
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = OFF_Q + Q_BYTES;
+    static constexpr int OFF_V = OFF_K + NK * K_BYTES;
+    static constexpr int OFF_P = OFF_V + NV * V_BYTES;
+    static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+    static constexpr int OFF_XCH = OFF_BAR + 512;
+    static constexpr int SMEM_BYTES = OFF_XCH + 6 * QT * 4;
+    static constexpr int S_COL = VROWS;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static constexpr int QK_LBO = 128, QK_SBO = (C / 8) * 128;
+    static constexpr int V_LBO = 128, V_SBO = 256;
+    static constexpr int P_LBO = 128, P_SBO = (KB / 8) * 128;
+};
+
+template <int C>
+__global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m, const __nv_bfloat16* __restrict__ Qp,
+                                                                  const __nv_bfloat16* __restrict__ Kp,
+                                                                  const __nv_bfloat16* __restrict__ Vp,
+                                                                  const FdaOut out) {
+    using Cfg = FdaPairCfg<C>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;    // [2]
+    uint64_t* s_empty = bars + 7;   // [2]
+    uint64_t* o_done = bars + 9;    // [2]
+    uint64_t* p_full = bars + 11;   // [2]
+    uint64_t* v_full = bars + 13;   // [NV] (<= 8)
+    uint64_t* v_empty = bars + 21;  // [NV]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = dcl_cluster_ctarank();
+    const bool leader = rank == 0;
+    const int qt = blockIdx.x, bs = blockIdx.y;  // cluster = blocks (2i, 2i+1) along x
+    const int NB = m / KB;
+    long long* life0 = threadIdx.x == 0 ? fda_life_slot() : nullptr;
+    fda_life(life0, 0);
+
+    if (threadIdx.x == 0) {
+        const uint32_t both = leader ? 2u : 1u;  // leader: own producer + the peer's relay
+        dcl_mbar_init(q_full, both);
+        for (int i = 0; i < 2; ++i) {
+            dcl_mbar_init(k_full + i, both);
+            dcl_mbar_init(k_empty + i, 1);
+            dcl_mbar_init(s_full + i, 1);
+            dcl_mbar_init(s_empty + i, 16);
+            dcl_mbar_init(o_done + i, 1);
+            dcl_mbar_init(p_full + i, 16);
+        }
+        for (int i = 0; i < Cfg::NV; ++i) {
+            dcl_mbar_init(v_full + i, both);
+            dcl_mbar_init(v_empty + i, 1);
+        }
+        dcl_fence_barrier_init();
+    }
+    __syncthreads();
+    dcl_cluster_sync();  // both CTAs' barriers exist before anything is signalled at them
+    if (warp == 1) tc2_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    fda_life(life0, 1);
+
+    const uint32_t sQ = dcl_smem_u32(smem + Cfg::OFF_Q);
+    const uint32_t sK = dcl_smem_u32(smem + Cfg::OFF_K);
+    const uint32_t sV = dcl_smem_u32(smem + Cfg::OFF_V);
+    const uint32_t sP = dcl_smem_u32(smem + Cfg::OFF_P);
+
+    if (warp == 0) {
+        // ===================== TMA producer (each CTA: its Q tile, its halves of K and V) =====================
+        if (dcl_elect_one()) {
+            const unsigned char* gQ =
+                reinterpret_cast<const unsigned char*>(Qp) + ((size_t)bs * (n / QT) + qt) * Cfg::Q_BYTES;
+            const unsigned char* gK = reinterpret_cast<const unsigned char*>(Kp) + (size_t)bs * NB * Cfg::G_K_BYTES +
+                                      rank * Cfg::K_HALF;
+            const unsigned char* gV =
+                reinterpret_cast<const unsigned char*>(Vp) + (size_t)bs * (m / KS) * Cfg::G_V_BYTES;
+            const unsigned char* gVa = gV + (size_t)rank * Cfg::V_PART_A;                       // rows [128r, +128)
+            const unsigned char* gVb = gV + (size_t)(256 + rank * (C / 2)) * (KS * 2);           // rows [256 + rC/2, ..)
+            constexpr uint32_t V_PART_B = Cfg::V_HALF - Cfg::V_PART_A;
+            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            dcl_mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+            dcl_bulk_g2s(smem + Cfg::OFF_Q, gQ, Cfg::Q_BYTES, q_full);
+            auto load_k = [&](int j) {
+                const int s = j % Cfg::NK;
+                if (j >= Cfg::NK) dcl_mbar_wait(k_empty + s, (uint32_t)((j / Cfg::NK - 1) & 1));
+                dcl_mbar_arrive_expect_tx(k_full + s, Cfg::K_BYTES);
+                unsigned char* dst = smem + Cfg::OFF_K + s * Cfg::K_BYTES;
+                const unsigned char* src = gK + (size_t)j * Cfg::G_K_BYTES;
+                dcl_bulk_g2s(dst, src, Cfg::K_HALF, k_full + s);
+                dcl_bulk_g2s(dst + Cfg::K_HALF, src + Cfg::G_K_HALF, Cfg::K_HALF, k_full + s);
+            };
+            for (int j = 0; j < Cfg::NK && j < NB; ++j) load_k(j);
+            int vi = 0;
+            for (int j = 0; j < NB; ++j) {
+                if (j + Cfg::NK < NB) load_k(j + Cfg::NK);
+                for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
+                    const int s = vi % Cfg::NV;
+                    const int use = vi / Cfg::NV;
+                    if (ks == 0) fda_stamp(trp, 2, j, 0);
+                    if (use >= 1) dcl_mbar_wait(v_empty + s, (uint32_t)((use - 1) & 1));
+                    if (ks == 0) fda_stamp(trp, 2, j, 1);
+                    if (ks == 3) fda_stamp(trp, 2, j, 2);
+                    dcl_mbar_arrive_expect_tx(v_full + s, Cfg::V_BYTES);
+                    unsigned char* dst = smem + Cfg::OFF_V + s * Cfg::V_BYTES;
+                    const size_t g = (size_t)vi * Cfg::G_V_BYTES;
+                    dcl_bulk_g2s(dst, gVa + g, Cfg::V_PART_A, v_full + s);
+                    dcl_bulk_g2s(dst + Cfg::V_PART_A, gVb + g, V_PART_B, v_full + s);
+                    dcl_bulk_g2s(dst + Cfg::V_HALF, gVa + g + Cfg::G_V_HALF, Cfg::V_PART_A, v_full + s);
+                    dcl_bulk_g2s(dst + Cfg::V_HALF + Cfg::V_PART_A, gVb + g + Cfg::G_V_HALF, V_PART_B, v_full + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && dcl_elect_one()) {
+            // ===================== MMA issuer (leader only) =====================
+            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            constexpr uint32_t idesc_s = umma_idesc_bf16(2 * QT, KB);
+            constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256);
+            constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C);
+            const uint32_t tO = tmem_base;
+            const uint64_t dQh = umma_desc(sQ, Cfg::QK_LBO, Cfg::QK_SBO);
+            const uint64_t dQl = dQh + (uint64_t)(Cfg::Q_HALF >> 4);
+            const uint64_t dK0 = umma_desc(sK, Cfg::QK_LBO, Cfg::QK_SBO);
+            const uint64_t dV0 = umma_desc(sV, Cfg::V_LBO, Cfg::V_SBO);
+            const uint64_t dP0 = umma_desc(sP, Cfg::P_LBO, Cfg::P_SBO);
+            auto issue_s = [&](int j) {
+                const int s = j % Cfg::NK;
+                fda_stamp(tr, 0, j, 0);
+                dcl_mbar_wait_cluster(k_full + s, (uint32_t)((j / Cfg::NK) & 1));
+                fda_stamp(tr, 0, j, 1);
+                if (j >= 2) dcl_mbar_wait_cluster(s_empty + (j & 1), (uint32_t)(((j >> 1) - 1) & 1));
+                fda_stamp(tr, 0, j, 2);
+                tc_fence_after();
+                const uint64_t dKh = dK0 + (uint64_t)((s * Cfg::K_BYTES) >> 4);
+                const uint64_t dKl = dKh + (uint64_t)(Cfg::K_HALF >> 4);
+                const uint32_t tS = tmem_base + Cfg::S_COL + (j & 1) * KB;
+#pragma unroll
+                for (int kk = 0; kk < C / 16; ++kk) {
+                    const uint64_t off = (uint64_t)((kk * 2 * Cfg::QK_LBO) >> 4);
+                    tc2_mma_bf16(tS, dQh + off, dKh + off, idesc_s, kk == 0 ? 0u : 1u);
+                    tc2_mma_bf16(tS, dQh + off, dKl + off, idesc_s, 1u);
+                    tc2_mma_bf16(tS, dQl + off, dKh + off, idesc_s, 1u);
+                }
+                tc2_commit_mcast(s_full + (j & 1), (uint16_t)0x3);
+                tc2_commit_mcast(k_empty + s, (uint16_t)0x3);
+            };
+            dcl_mbar_wait_cluster(q_full, 0);
+            issue_s(0);
+            int vi = 0;
+            for (int j = 0; j < NB; ++j) {
+                if (j + 1 < NB) issue_s(j + 1);
+                const int ps = j & 1;
+                fda_stamp(tr, 0, j, 3);
+                dcl_mbar_wait_cluster(p_full + ps, (uint32_t)((j >> 1) & 1));
+                fda_stamp(tr, 0, j, 4);
+                tc_fence_after();
+                const uint64_t dPh = dP0 + (uint64_t)((ps * Cfg::P_BYTES) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
+                    const int s = vi % Cfg::NV;
+                    dcl_mbar_wait_cluster(v_full + s, (uint32_t)((vi / Cfg::NV) & 1));
+                    if (ks == 0) fda_stamp(tr, 0, j, 6);
+                    if (ks == 3) fda_stamp(tr, 0, j, 7);
+                    tc_fence_after();
+                    const uint64_t dVh = dV0 + (uint64_t)((s * Cfg::V_BYTES) >> 4);
+                    const uint64_t dVl = dVh + (uint64_t)(Cfg::V_HALF >> 4);
+                    const uint64_t dAh = dPh + (uint64_t)((ks * 2 * Cfg::P_LBO) >> 4);
+                    const uint64_t dAl = dAh + (uint64_t)(Cfg::P_HALF >> 4);
+                    const uint32_t acc = (j == 0 && ks == 0) ? 0u : 1u;
+                    tc2_mma_bf16(tO, dAh, dVh, idesc_o1, acc);
+                    tc2_mma_bf16(tO, dAh, dVl, idesc_o1, 1u);
+                    tc2_mma_bf16(tO, dAl, dVh, idesc_o1, 1u);
+                    constexpr uint64_t v2 = (uint64_t)(Cfg::V_PART_A >> 4);
+                    tc2_mma_bf16(tO + 256, dAh, dVh + v2, idesc_o2, acc);
+                    tc2_mma_bf16(tO + 256, dAh, dVl + v2, idesc_o2, 1u);
+                    tc2_mma_bf16(tO + 256, dAl, dVh + v2, idesc_o2, 1u);
+                    tc2_commit_mcast(v_empty + s, (uint16_t)0x3);
+                }
+                tc2_commit_mcast(o_done + (j & 1), (uint16_t)0x3);
+                fda_stamp(tr, 0, j, 5);
+            }
+        } else if (!leader && dcl_elect_one()) {
+            // ===================== relay (peer): "my half landed", in the leader's consumption order =====================
+            dcl_mbar_wait(q_full, 0);
+            dcl_mbar_arrive_remote(q_full, 0);
+            auto relay_k = [&](int j) {
+                const int s = j % Cfg::NK;
+                dcl_mbar_wait(k_full + s, (uint32_t)((j / Cfg::NK) & 1));
+                dcl_mbar_arrive_remote(k_full + s, 0);
+            };
+            relay_k(0);
+            int vi = 0;
+            for (int j = 0; j < NB; ++j) {
+                if (j + 1 < NB) relay_k(j + 1);
+                for (int ks = 0; ks < KB / KS; ++ks, ++vi) {
+                    const int s = vi % Cfg::NV;
+                    dcl_mbar_wait(v_full + s, (uint32_t)((vi / Cfg::NV) & 1));
+                    dcl_mbar_arrive_remote(v_full + s, 0);
+                }
+            }
+        }
+    } else {
+        fda_softmax_warps<Cfg, true>(smem, tmem_base, warp, lane, qt, bs, n, NB, s_full, s_empty, o_done, p_full, out);
+    }
+    __syncwarp();
+    __syncthreads();
+    dcl_cluster_sync();  // the leader's MMAs read the peer's shared memory until the last commit
+    if (warp == 1) {
+        tc_fence_after();
+        tc2_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+    fda_life(life0, 4);
 }
 
 // ------------------------------------------------------------------ attention map (train / inspection)
@@ -659,16 +1016,46 @@ int fda_pack_launch(int b, int n, int m, const float* RI_1, const float* RI_2, c
 }
 
 template <int C>
-int fda_main_launch(int b, int n, int m, float* RE_embed, float* RI_embed, float* lse_out, void* workspace,
-                    cudaStream_t st) {
+int fda_main_launch(int b, int n, int m, const FdaOut& out, void* workspace, cudaStream_t st) {
     using Cfg = FdaCfg<C>;
     FdaWs<C> w(workspace, b, n, m);
     cudaError_t e = cudaFuncSetAttribute(fda_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(n / QT, b);
-    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, w.Qp, w.Kp, w.Vp, RE_embed, RI_embed, lse_out);
+    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, w.Qp, w.Kp, w.Vp, out);
     return dcl_launch_status();
+}
+
+// CTA-pair variant: needs an even number of query tiles per instance.
+template <int C>
+int fda_pair_launch(int b, int n, int m, const FdaOut& out, void* workspace, cudaStream_t st) {
+    using Cfg = FdaPairCfg<C>;
+    FdaWs<C> w(workspace, b, n, m);
+    cudaError_t e = cudaFuncSetAttribute(fda_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n / QT, b);
+    cfg.blockDim = dim3(FDA_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const __nv_bfloat16 *q = w.Qp, *k = w.Kp, *v = w.Vp;
+    e = cudaLaunchKernelEx(&cfg, fda_pair_kernel<C>, n, m, q, k, v, out);
+    if (e != cudaSuccess) return (int)e;
+    return dcl_launch_status();
+}
+
+bool fda_use_pair(int n) {
+    static const bool forced_single = getenv("DCL_FDA_SINGLE") != nullptr;  // A/B switch for benchmarking
+    return !forced_single && (n / QT) % 2 == 0;
 }
 
 bool fda_shape_ok(int b, int c, int p, int n, int m) {
@@ -695,15 +1082,30 @@ DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, c
     return fda_pack_launch<128>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
 }
 
-DCL_API int dcl_fda_fwd_packed(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, float* lse_out,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+DCL_API int dcl_fda_fwd_packed_pm(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, void* RE_pm,
+                                  void* RI_pm, float* lse_out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
     DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
+    DCL_RETURN_IF_BAD((((uintptr_t)RE_pm) & 15u) == 0 && (((uintptr_t)RI_pm) & 15u) == 0);
+    const FdaOut out = {RE_embed, RI_embed, reinterpret_cast<unsigned char*>(RE_pm),
+                        reinterpret_cast<unsigned char*>(RI_pm), lse_out};
     DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 127u) == 0);
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c == 64) return fda_main_launch<64>(b, n, m, RE_embed, RI_embed, lse_out, workspace, st);
-    return fda_main_launch<128>(b, n, m, RE_embed, RI_embed, lse_out, workspace, st);
+    if (fda_use_pair(n)) {
+        if (c == 64) return fda_pair_launch<64>(b, n, m, out, workspace, st);
+        return fda_pair_launch<128>(b, n, m, out, workspace, st);
+    }
+    if (c == 64) return fda_main_launch<64>(b, n, m, out, workspace, st);
+    return fda_main_launch<128>(b, n, m, out, workspace, st);
+}
+
+DCL_API int dcl_fda_fwd_packed(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, float* lse_out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(RE_embed != nullptr && RI_embed != nullptr);
+    return dcl_fda_fwd_packed_pm(b, c, p, n, m, RE_embed, RI_embed, nullptr, nullptr, lse_out, workspace,
+                                 workspace_bytes, stream);
 }
 
 DCL_API int dcl_fda_align_fwd(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2,
@@ -743,4 +1145,9 @@ DCL_API int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* 
     if (e != cudaSuccess) return (int)e;
     umma_pair_probe_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D, mode);
     return dcl_launch_status();
+}
+
+DCL_API int dcl_debug_fda_set_trace(long long* device_buffer) {
+    cudaError_t e = cudaMemcpyToSymbol(g_fda_trace, &device_buffer, sizeof(device_buffer));
+    return (int)e;
 }

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (dcl_elect_one()) {
             const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
             const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
                                       (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (dcl_elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % STAGES;
@@ -296,7 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (dcl_elect_one()) {
             int it = 0;
             for (int u = cluster_id; u < total_units; u += nclusters) {
                 const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
@@ -321,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (dcl_elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
             int it = 0, tl = 0;
             for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {

@@ -58,6 +58,15 @@ __device__ __forceinline__ void dcl_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// One lane of a converged warp; unlike `lane == 0` the compiler knows a single thread is active and emits the
+// uniform-datapath instructions behind it (UTCHMMA, UBLKCP, ...) back to back instead of wrapping each one in an
+// elect / vote loop (~7 instructions and ~50 cycles per MMA in the issuing thread).
+__device__ __forceinline__ bool dcl_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- CTA-pair (cta_group::2) forms: both CTAs of the pair allocate / free together, the leader (cluster rank 0)
 // issues the MMA with M = 256 (its own 128 rows and the peer's), each CTA holding N/2 rows of the B operand at the
 // same shared-memory offset, and commits to the barrier at the same offset in both CTAs.
@@ -85,28 +94,21 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t a_desc, u
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrive (release, cluster scope) on the barrier at the same offset as `bar` in CTA `cta_rank` of the cluster
+// arrive on the barrier at the same offset as `bar` in CTA `cta_rank` of the cluster.  Default semantics
+// (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive does: a cluster-scope release costs a
+// MEMBAR.ALL.GPU + ERRBAR in front of every arrive (~1000 cycles on the softmax -> MMA critical path).  The data
+// handed over here is either already complete (tcgen05.ld results in registers) or made visible to the async proxy
+// by the fence.proxy.async each writer executes before the arrive.
 __device__ __forceinline__ void dcl_mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(dcl_smem_u32(bar)), "r"(cta_rank)
         : "memory");
 }
-// wait with cluster-scope acquire (pairs with dcl_mbar_arrive_remote)
-__device__ __forceinline__ void dcl_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(dcl_smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
+// wait on a barrier that also receives remote arrives (default acquire, like ClusterBarrier::wait)
+__device__ __forceinline__ void dcl_mbar_wait_cluster(uint64_t* bar, uint32_t parity) { dcl_mbar_wait(bar, parity); }
 
 #define DCL_TMEM_LD32(taddr, r)                                                                                  \
     asm volatile(                                                                                                \

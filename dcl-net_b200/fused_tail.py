@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .modules import fda_align
+from .modules import fda_align_formats
 
 _EPS_NAMES = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
 
@@ -153,6 +153,8 @@ def run_gemm(problems, rows):
 class FusedTail:
     """Packed-weight inference path of a dcl_net.Network (eval mode, test mode, no autograd)."""
 
+    keep_debug = False  # True: also materialise F_Xo_m / F_Yc_p / F_Yc_m in the reference layout (tests)
+
     def __init__(self, net):
         self.net = net
         self.c_m = net.disengage_Xc_m1[1].layers[0].out_channels
@@ -207,10 +209,13 @@ class FusedTail:
                        "out_cm": cm_out.get(name), "rows_per_inst": n} for name in group], rows)
         del h1
 
-        # ---- dual FDA (both attention products of a direction in one fused kernel)
-        F_Xo_p, F_Xo_m = fda_align(cm_out["Xc_m1"], cm_out["Yo_m1"], cm_out["Yo_p1"])
-        F_Yc_p, F_Yc_m = fda_align(cm_out["Yo_m2"], cm_out["Xc_m2"], cm_out["Xc_p2"])
-        pm_Xo_p, pm_Xo_m, pm_Yc_p, pm_Yc_m = (pm_pack_cm(t) for t in (F_Xo_p, F_Xo_m, F_Yc_p, F_Yc_m))
+        # ---- dual FDA (both attention products of a direction in one fused kernel); the aligned features leave the
+        # kernel as point-major images for the MLPs below, F_Xo_p also in the reference's layout (stage 2 reads it)
+        dbg = self.keep_debug
+        F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _ = fda_align_formats(
+            cm_out["Xc_m1"], cm_out["Yo_m1"], cm_out["Yo_p1"], re_cm=True, ri_cm=dbg, re_pm=True, ri_pm=True)
+        F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _ = fda_align_formats(
+            cm_out["Yo_m2"], cm_out["Xc_m2"], cm_out["Xc_p2"], re_cm=dbg, ri_cm=dbg, re_pm=True, ri_pm=True)
 
         # ---- confidence heads: cat([F_Xc_m1, F_Xo_m]) / cat([F_Yc_m, F_Yo_m2]) -> 128 -> 128 -> 1
         c1 = [pm_empty(rows, 128, dev) for _ in range(2)]

@@ -49,7 +49,7 @@ class FdaAlignFunction(torch.autograd.Function):
         # The forward's lse comes out of the split-bf16 logits; the fp32 logits recomputed here differ from those by
         # ~|S| 2^-17, a common factor per query column that the renormalisation removes exactly.
         A = A / A.sum(dim=1, keepdim=True)
-        gE =torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
+        gE = torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
         gI = torch.zeros_like(RI_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gI is None else gI
         dA = torch.bmm(RE_2.transpose(1, 2), gE) + torch.bmm(RI_2.transpose(1, 2), gI)
         dS = A * (dA - (A * dA).sum(dim=1, keepdim=True))
@@ -74,6 +74,15 @@ def fda_align(RI_1, RI_2, RE_2, return_lse=False):
 
 
 def _fda_align_kernel(RI_1, RI_2, RE_2, return_lse=False):
+    RE_embed, RI_embed, _, _, lse = fda_align_formats(RI_1, RI_2, RE_2, return_lse=return_lse)
+    return (RE_embed, RI_embed, lse) if return_lse else (RE_embed, RI_embed)
+
+
+def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False):
+    """fda_align (inference only) with a choice of output formats: `*_cm` = the reference's fp32 (B,ch,N) tensors,
+    `*_pm` = point-major bf16 hi/lo images over the B*N query rows (fused_tail.pm_unpack restores (B*N, ch)), which
+    the tensor-core MLPs that consume the aligned features (models/DCL_Net.py:216-228) read without a repack.
+    Returns (RE_cm, RI_cm, RE_pm, RI_pm, lse) with None for the formats not requested."""
     RI_1 = L.require(RI_1.contiguous(), torch.float32, "RI_1")
     RI_2 = L.require(RI_2.contiguous(), torch.float32, "RI_2")
     RE_2 = L.require(RE_2.contiguous(), torch.float32, "RE_2")
@@ -87,21 +96,24 @@ def _fda_align_kernel(RI_1, RI_2, RE_2, return_lse=False):
         raise ValueError(f"fda_align: unsupported shape C={C} P={P} N={N} M={M} "
                          "(need C in {64,128}, P=256, N%128==0, M%64==0)")
     ws = _fda_workspace(nbytes, RI_1.device)
-    RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=RI_1.device)
-    RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=RI_1.device)
-    lse = torch.empty(B, N, dtype=torch.float32, device=RI_1.device) if return_lse else None
+    dev = RI_1.device
+    RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=dev) if re_cm else None
+    RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=dev) if ri_cm else None
+    RE_img = torch.empty(B * N * P * 4, dtype=torch.uint8, device=dev) if re_pm else None
+    RI_img = torch.empty(B * N * C * 4, dtype=torch.uint8, device=dev) if ri_pm else None
+    lse = torch.empty(B, N, dtype=torch.float32, device=dev) if return_lse else None
     st = L.stream_ptr()
     L.check(lib.dcl_fda_pack(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), st),
             "fda_align (pack)")
     if FDA_KERNEL_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.check(lib.dcl_fda_fwd_packed(B, C, P, N, M, L.ptr(RE_embed), L.ptr(RI_embed), L.ptr(lse), L.ptr(ws),
-                                   ws.numel(), st), "fda_align")
+    L.check(lib.dcl_fda_fwd_packed_pm(B, C, P, N, M, L.ptr(RE_embed), L.ptr(RI_embed), L.ptr(RE_img), L.ptr(RI_img),
+                                      L.ptr(lse), L.ptr(ws), ws.numel(), st), "fda_align")
     if FDA_KERNEL_EVENTS is not None:
         ev1.record()
         FDA_KERNEL_EVENTS.append((ev0, ev1))
-    return (RE_embed, RI_embed, lse) if return_lse else (RE_embed, RI_embed)
+    return RE_embed, RI_embed, RE_img, RI_img, lse
 
 
 def fda_attention_map(RI_1, RI_2, lse):

@@ -164,6 +164,16 @@ int dcl_fda_fwd_packed(int b, int c, int p, int n, int m,
     float* RE_embed, float* RI_embed, float* lse_out,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* dcl_fda_fwd_packed with a choice of output formats: each of RE_embed / RI_embed goes out
+ * as the reference's fp32 channel-major tensor (RE_embed, RI_embed), as a point-major
+ * bf16 hi/lo image over the b*n query rows (RE_pm: 256 channels, RI_pm: c channels — the
+ * activation format of dcl_pm_gemm, so the fuser / confidence MLPs of
+ * models/DCL_Net.py:216-228 read the aligned features without a repack), or both.
+ * NULL outputs are skipped. */
+int dcl_fda_fwd_packed_pm(int b, int c, int p, int n, int m,
+    float* RE_embed, float* RI_embed, void* RE_pm, void* RI_pm, float* lse_out,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 /* Materialise the attention map A (b,m,n) of models/Modules.py:167 from the
  * inputs and the lse of dcl_fda_align_fwd (train / inspection path only). */
 int dcl_fda_attention_map(int b, int c, int n, int m,
@@ -290,6 +300,12 @@ int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D,
  * operands over with a remote mbarrier arrive.  Pins the CTA-pair conventions. */
 int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* B, float* D,
     int mode, void* stream);
+
+/* Installs (or, with NULL, removes) a device buffer of 4*1024 int64 into which CTA (0,0) of
+ * the FDA kernels stamps clock64() at its role hand-offs: [role*1024 + key_block*8 + event],
+ * roles 0 = MMA issuer, 1 = softmax warp 2, 2 = TMA producer; [3*1024 + slot*8 + event] holds
+ * globaltimer life-cycle stamps of the first and the last CTA (tools/trace_fda.py). */
+int dcl_debug_fda_set_trace(long long* device_buffer);
 
 #ifdef __cplusplus
 }

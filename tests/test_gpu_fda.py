@@ -118,6 +118,23 @@ def test_aligner_golden(cuda_dev):
     assert np.abs(a.cpu().numpy()[:, ::16, ::16] - gold["A_sample"]).max() < 1e-4 * gold["A_sample"].max()
 
 
+@pytest.mark.parametrize("b,c,n,m", [(2, 64, 128, 128), (2, 128, 256, 192), (3, 128, 1024, 1024)])
+def test_fda_point_major_outputs(cuda_dev, b, c, n, m):
+    """The point-major bf16 hi/lo images the fused tail consumes hold the same numbers as the fp32 outputs
+    (hi + lo carries 16 mantissa bits), alone or next to them."""
+    from dcl_net_b200.modules import fda_align_formats
+    from dcl_net_b200.fused_tail import pm_unpack
+    ri1, ri2, re2 = (x.to(cuda_dev) for x in _inputs(3 + n, b, c, n, m, "relu"))
+    re_cm, ri_cm, re_pm, ri_pm, _ = fda_align_formats(ri1, ri2, re2, re_pm=True, ri_pm=True)
+    only = fda_align_formats(ri1, ri2, re2, re_cm=False, ri_cm=False, re_pm=True, ri_pm=True)
+    assert only[0] is None and only[1] is None
+    assert torch.equal(only[2], re_pm) and torch.equal(only[3], ri_pm)
+    for cm, pm, ch in ((re_cm, re_pm, 256), (ri_cm, ri_pm, c)):
+        rows = pm_unpack(pm, b * n, ch)                       # (b*n, ch)
+        want = cm.transpose(1, 2).reshape(b * n, ch)
+        assert (rows - want).abs().max().item() <= 2.0 ** -16 * want.abs().max().item()
+
+
 def test_fda_rejects_bad_shapes(cuda_dev):
     x = torch.zeros(1, 32, 128, device=cuda_dev)
     with pytest.raises(ValueError):

@@ -255,7 +255,7 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
 
     # Four runs of the same step: this implementation, the fp32 reference graph, the reference graph in fp64, and the
-    # fp64 graph with its FDA outputs perturbed by 1e-5 (relative to their max; 100x below the 1e-3 forward bar).
+    # fp64 graph with its aligned features (Aligner outputs) perturbed by 1e-5 (relative to their max; 100x below the 1e-3 forward bar).
     # The step is badly conditioned — train-mode BatchNorm and ReLU gates near zero make some weight gradients jump
     # by percents under a 1e-6 perturbation (tools/diag_train_grad.py) — so gradient parity is defined against the
     # fp64 result with that perturbation response as the floor: this implementation must be as close to fp64 as the
@@ -277,20 +277,19 @@ def test_training_step_gradients_match_oracle(cuda_dev):
     loss_64.backward()
     g64 = {name: p.grad.clone() for name, p in oracle64.named_parameters() if p.grad is not None}
     oracle64.zero_grad()
-    exact_direction = T.fda_direction
+    exact_aligner = T.aligner
     noise = torch.Generator(device=cuda_dev).manual_seed(23)
 
-    def perturbed_direction(ri_1, ri_2, re_2):
-        e, m, att = exact_direction(ri_1, ri_2, re_2)
+    def perturbed_aligner(ri_1, ri_2, re_2):
+        e, att = exact_aligner(ri_1, ri_2, re_2)
         e = e + 1e-5 * e.abs().max().detach() * torch.randn(e.shape, generator=noise, device=e.device, dtype=e.dtype)
-        m = m + 1e-5 * m.abs().max().detach() * torch.randn(m.shape, generator=noise, device=m.device, dtype=m.dtype)
-        return e, m, att
+        return e, att
 
-    T.fda_direction = perturbed_direction
+    T.aligner = perturbed_aligner
     try:
         loss_fn(oracle64(dd[0], dd[1], b, n, n)).backward()
     finally:
-        T.fda_direction = exact_direction
+        T.aligner = exact_aligner
     gpert = {name: p.grad for name, p in oracle64.named_parameters() if p.grad is not None}
 
     def check(mine, ref32, ref64, pert64, what):
