@@ -193,7 +193,7 @@ def cpu_baseline(args):
 def run_b200_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from dcl_net_b200 import _lib, modules, sharding
+    from dcl_net_b200 import _lib, fused_tail, modules, sharding
     from dcl_net_b200.dcl_net import Network
     from dcl_net_b200.engine import PipelinedPoseEngine, PoseEngine
 
@@ -241,6 +241,7 @@ def run_b200_arm(args, rank, world, local_rank):
         # ---- timed region 0 (eager launches): per-launch CUDA events around the fused FDA kernel, and the
         #      count of this library's kernel launches per step
         modules.FDA_KERNEL_EVENTS = []
+        fused_tail.GEMM_EVENTS = []
         launches0 = lib.dcl_b200_launch_count()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,6 +254,8 @@ def run_b200_arm(args, rank, world, local_rank):
         launches = lib.dcl_b200_launch_count() - launches0
         fda_events, modules.FDA_KERNEL_EVENTS = modules.FDA_KERNEL_EVENTS, None
         fda_ms = [a.elapsed_time(bb) for a, bb in fda_events]
+        gemm_events, fused_tail.GEMM_EVENTS = fused_tail.GEMM_EVENTS, None
+        gemm = [(a.elapsed_time(bb), fl) for a, bb, fl, nt in gemm_events if nt == 256]   # the 256-wide-tile kernel
         # ---- timed region 1: device-resident, the step replayed as a CUDA graph (same kernels, one launch)
         use_graph = not args.no_graph
         if use_graph:
@@ -300,18 +303,30 @@ def run_b200_arm(args, rank, world, local_rank):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"
+    # Dominant kernel: the persistent cluster GEMM with 256-wide tiles (disengage and fuser layers; 5 launches/step).
+    gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(fl for _, fl in gemm)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm else float("nan")
+    split_note = ("every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful, so the algorithmic "
+                  "fraction is bounded by 1/3; tensor-pipe occupancy is ~3x the algorithmic fraction")
+    roofline = {"kernel": "pm_gemm_cluster_kernel<256,4>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": gemm_ms / len(gemm) if gemm else None, "launches_timed": len(gemm),
+                "algorithmic_flops_per_step": gemm_flops / args.steps,
+                "executed_mma_flops_per_step": 3 * gemm_flops / args.steps,
+                "executed_frac": 3 * achieved / peak_tf,
+                "share_of_step": gemm_ms / ms_eager if gemm else None,
+                "timed_in": "eager pass of the same K steps (the graph-replayed pass launches the identical kernels)",
+                "note": split_note}
     flops_per_launch = b * 2.0 * N_PTS * N_PTS * (args.c_m + P_DIM + args.c_m)
     fda_avg_ms = statistics.mean(fda_ms) if fda_ms else float("nan")
-    achieved = flops_per_launch / (fda_avg_ms * 1e-3) / 1e12
-    roofline = {"kernel": f"fda_fwd_kernel<{args.c_m}>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": fda_avg_ms, "launches_timed": len(fda_ms),
-                "algorithmic_flops_per_launch": flops_per_launch,
-                "executed_mma_flops_per_launch": 3 * flops_per_launch,
-                "share_of_step": (sum(fda_ms) / ms_eager) if fda_ms else None,
-                "timed_in": "eager pass of the same K steps (the graph-replayed pass launches the identical kernels)",
-                "note": "every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful; "
-                        "tensor-pipe occupancy is ~3x the algorithmic fraction"}
+    fda_achieved = flops_per_launch / (fda_avg_ms * 1e-3) / 1e12
+    fda_kernel = ("fda_pair_kernel" if (N_PTS // 128) % 2 == 0 and not os.environ.get("DCL_FDA_SINGLE")
+                  else "fda_fwd_kernel")
+    roofline_fda = {"kernel": f"{fda_kernel}<{args.c_m}>", "bound": "tensor", "achieved": fda_achieved,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": fda_achieved / peak_tf,
+                    "executed_frac": 3 * fda_achieved / peak_tf, "avg_launch_ms": fda_avg_ms,
+                    "launches_timed": len(fda_ms), "algorithmic_flops_per_launch": flops_per_launch,
+                    "share_of_step": (sum(fda_ms) / ms_eager) if fda_ms else None}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -320,7 +335,8 @@ def run_b200_arm(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": b * 12 * 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph" if use_graph else "eager",
-                "ms_per_step_eager": ms_eager / args.steps, "clocks": clocks, "roofline": roofline}
+                "ms_per_step_eager": ms_eager / args.steps, "clocks": clocks, "roofline": roofline,
+                "roofline_fda": roofline_fda}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)

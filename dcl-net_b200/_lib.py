@@ -49,6 +49,8 @@ SIGNATURES = {
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_pose_head_workspace_bytes": (_SZ, [_I, _P, _P]),
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_sp_levels_workspace_bytes": (_SZ, [_I, _P]),
+    "dcl_sp_nn_interpolate_levels_pm": (_I, [_I, _P, _I, _P, _P, _I, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_fda_set_trace": (_I, [_P]),
@@ -61,6 +63,12 @@ class PmGemmProblem(ctypes.Structure):
     _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
                 ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P)]
+
+
+class SpLevel(ctypes.Structure):
+    """Mirror of dcl_sp_level (include/dcl_b200.h)."""
+    _fields_ = [("m", _I), ("c", _I), ("out_col0", _I), ("vox_indices", _P), ("voxel_extent", ctypes.c_float * 3),
+                ("offset", ctypes.c_float * 3), ("feats", _P)]
 
 
 class PoseHeadMlp(ctypes.Structure):

@@ -526,6 +526,194 @@ int build_buckets(int m, const KnownRows& kr, int* ws, float4* sorted, cudaStrea
     return dcl_launch_status(m > 0 ? 3 : 1);
 }
 
+// ------------------------------------------------ all pyramid levels of one tower in two launches
+// Ops_GetPointFeat_spconv (models/Modules.py:227-251) interpolates the same query points from four voxel levels.
+// One launch builds all the levels' buckets — a cluster of 8 CTAs per level, whose per-CTA histograms meet through
+// distributed shared memory, so there is no global header to clear and no separate scan / scatter pass — and one
+// launch runs search + interpolation for every level (a CTA keeps its 16 queries and walks the levels).
+constexpr int SPL_MAX_LEVELS = 8;
+constexpr int SPB_THREADS = 512, SPB_CLUSTER = 8;
+constexpr int SPL_HDR_INTS = WS_OFF + SP_SBINS + 4;  // flag, nb, offsets[SP_SBINS + 1]; multiple of 4
+
+struct SpLevelDev {
+    int m, c, out_col0;
+    KnownRows kr;
+    int* ws;
+    float4* sorted;
+    const float* feats;
+};
+struct SpLevelBatch {
+    int nlevels;
+    SpLevelDev lv[SPL_MAX_LEVELS];
+};
+
+__global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREADS)
+    sp_bucket_build_cluster_kernel(const __grid_constant__ SpLevelBatch batch) {
+    __shared__ int s_cnt[SP_SBINS];   // this CTA's histogram; the other CTAs of the cluster read it through DSMEM
+    __shared__ int s_base[SP_SBINS];  // where this CTA's entries of bucket b start in sorted[]
+    __shared__ int s_cur[SP_SBINS];   // bucket totals, then scatter cursors
+    __shared__ int s_meta[2];         // [0] a batch id that is no integer in [0, SP_SBINS), [1] max id + 1
+    __shared__ int s_warp[SPB_THREADS / 32];
+    const SpLevelDev& lv = batch.lv[blockIdx.y];
+    const uint32_t rank = dcl_cluster_ctarank();
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < SP_SBINS; i += SPB_THREADS) s_cnt[i] = 0;
+    if (tid < 2) s_meta[tid] = 0;
+    __syncthreads();
+    const int m = lv.m;
+    const int slice = DCL_DIVUP(m, SPB_CLUSTER);
+    const int k0 = (int)rank * slice, k1 = min(m, k0 + slice);
+    // pass 1: histogram of this CTA's slice; lanes with the same bucket (the usual case: clouds are stored
+    // batch-major) elect one lane to add their count
+    for (int kb = k0; kb < k1; kb += SPB_THREADS) {
+        const int k = kb + tid;
+        int ib = -1;
+        if (k < k1) {
+            if (!batch_id_ok(lv.kr.get(k).x, ib) || ib >= SP_SBINS) {
+                ib = -1;
+                s_meta[0] = 1;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, ib);
+        if (ib >= 0 && lane == __ffs(peers) - 1) {
+            atomicAdd(s_cnt + ib, __popc(peers));
+            atomicMax(&s_meta[1], ib + 1);
+        }
+    }
+    __syncthreads();
+    dcl_cluster_sync();
+    // combine: bucket totals and the number of entries the lower-ranked CTAs put into each bucket
+    for (int b = tid; b < SP_SBINS; b += SPB_THREADS) {
+        int total = 0, before = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
+            const int cnt = dcl_ld_dsmem_s32(s_cnt + b, r);
+            total += cnt;
+            before += (r < rank) ? cnt : 0;
+        }
+        s_cur[b] = total;
+        s_base[b] = before;
+    }
+    int flag = 0, nb = 0;
+    if (tid == 0) {
+        for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
+            flag |= dcl_ld_dsmem_s32(&s_meta[0], r);
+            nb = max(nb, dcl_ld_dsmem_s32(&s_meta[1], r));
+        }
+    }
+    __syncthreads();
+    dcl_cluster_sync();  // nobody reads a peer's shared memory after this point
+    // exclusive scan of the totals (two buckets per thread)
+    {
+        const int a = s_cur[2 * tid], bsum = s_cur[2 * tid + 1];
+        int x = a + bsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[tid >> 5] = x;
+        __syncthreads();
+        if (tid < 32) {
+            int w = (tid < SPB_THREADS / 32) ? s_warp[tid] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (tid >= o) w += y;
+            }
+            if (tid < SPB_THREADS / 32) s_warp[tid] = w;
+        }
+        __syncthreads();
+        const int excl = x - (a + bsum) + ((tid >= 32) ? s_warp[(tid >> 5) - 1] : 0);
+        s_base[2 * tid] += excl;
+        s_base[2 * tid + 1] += excl + a;
+        if (rank == 0) {
+            lv.ws[WS_OFF + 2 * tid] = excl;
+            lv.ws[WS_OFF + 2 * tid + 1] = excl + a;
+            if (tid == SPB_THREADS - 1) lv.ws[WS_OFF + SP_SBINS] = excl + a + bsum;
+            if (tid == 0) {
+                lv.ws[WS_FLAG] = flag;
+                lv.ws[WS_NB] = nb;
+            }
+        }
+        __syncthreads();
+        s_cur[2 * tid] = 0;
+        s_cur[2 * tid + 1] = 0;
+        __syncthreads();
+    }
+    // pass 2: scatter this CTA's slice
+    for (int kb = k0; kb < k1; kb += SPB_THREADS) {
+        const int k = kb + tid;
+        int ib = -1;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < k1) {
+            r = lv.kr.get(k);
+            if (!batch_id_ok(r.x, ib) || ib >= SP_SBINS) ib = -1;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, ib);
+        const int leader = __ffs(peers) - 1;
+        int first = 0;
+        if (ib >= 0 && lane == leader) first = atomicAdd(s_cur + ib, __popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (ib >= 0) {
+            const int pos = s_base[ib] + first + __popc(peers & ((1u << lane) - 1u));
+            lv.sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int n, const float* __restrict__ unknown,
+                                                                            const __grid_constant__ SpLevelBatch batch,
+                                                                            unsigned char* __restrict__ out_pm,
+                                                                            int c_total) {
+    const int qi = blockIdx.x * (SP_THREADS / LPQ) + threadIdx.x / LPQ;
+    const int sub = threadIdx.x % LPQ;
+    const bool valid = qi < n;
+    const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
+    unsigned char* row_base =
+        out_pm + (size_t)(qi / 128) * (c_total / 32) * 16384 + ((qi % 128) >> 3) * 512 + (qi & 7) * 16;
+    for (int li = 0; li < batch.nlevels; ++li) {
+        const SpLevelDev& lv = batch.lv[li];
+        if (lv.m == 0) continue;  // nothing to interpolate from (the reference would gather row 0 of an empty tensor)
+        float b1, b2, b3;
+        int j0, j1, j2;
+        sp_group_search(lv.ws, lv.sorted, lv.kr, lv.m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+        if (valid) {
+            const int c = lv.c;
+            const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+            const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+            const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+            const float norm = __fadd_rn(__fadd_rn(r0, r2), r1);
+            const float a0 = __fdiv_rn(r0, norm), a1 = __fdiv_rn(r1, norm), a2 = __fdiv_rn(r2, norm);
+            const float4* f0 = reinterpret_cast<const float4*>(lv.feats + (size_t)j0 * c);
+            const float4* f1 = reinterpret_cast<const float4*>(lv.feats + (size_t)j1 * c);
+            const float4* f2 = reinterpret_cast<const float4*>(lv.feats + (size_t)j2 * c);
+            for (int c8 = sub; c8 < (c >> 3); c8 += LPQ) {
+                float o[8];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float4 x0 = __ldg(f0 + c8 * 2 + hh), x1 = __ldg(f1 + c8 * 2 + hh), x2 = __ldg(f2 + c8 * 2 + hh);
+                    o[hh * 4 + 0] = dcl_interp3(a0, x0.x, a1, x1.x, a2, x2.x);
+                    o[hh * 4 + 1] = dcl_interp3(a0, x0.y, a1, x1.y, a2, x2.y);
+                    o[hh * 4 + 2] = dcl_interp3(a0, x0.z, a1, x1.z, a2, x2.z);
+                    o[hh * 4 + 3] = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
+                }
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_bf16(o[2 * e], o[2 * e + 1], h[e], l[e]);
+                const int chunk = (lv.out_col0 >> 3) + c8;
+                unsigned char* d = row_base + (size_t)(chunk >> 2) * 16384 + (chunk & 3) * 128;
+                *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(d + 8192) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    }
+}
+
+size_t sp_level_ws_bytes(int m) {
+    return (size_t)SPL_HDR_INTS * sizeof(int) + (size_t)(m > 0 ? m : 0) * sizeof(float4) + 16;
+}
+
 }  // namespace
 
 DCL_API int dcl_sp_three_nn_kernel_launcher_fast(int n, int m, const float* unknown, const float* known,
@@ -658,4 +846,45 @@ DCL_API int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c, const float* unkno
     sp_nn_interp_fused_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
         n, m, c, unknown, kr, ws, sorted, feats, reinterpret_cast<unsigned char*>(out_pm), c_total, out_col0);
     return dcl_launch_status();
+}
+
+DCL_API size_t dcl_sp_levels_workspace_bytes(int nlevels, const dcl_sp_level* levels) {
+    if (nlevels < 0 || nlevels > SPL_MAX_LEVELS || (nlevels > 0 && levels == nullptr)) return 0;
+    size_t total = 0;
+    for (int i = 0; i < nlevels; ++i) total += sp_level_ws_bytes(levels[i].m);
+    return total;
+}
+
+DCL_API int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nlevels, const dcl_sp_level* levels,
+                                            void* out_pm, int c_total, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+    DCL_RETURN_IF_BAD(n > 0 && n % 128 == 0 && nlevels >= 1 && nlevels <= SPL_MAX_LEVELS && levels != nullptr);
+    DCL_RETURN_IF_BAD(c_total % 32 == 0 && workspace != nullptr && out_pm != nullptr);
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
+                      ((uintptr_t)out_pm & 15u) == 0);
+    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_levels_workspace_bytes(nlevels, levels));
+    SpLevelBatch batch = {};
+    batch.nlevels = nlevels;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    for (int i = 0; i < nlevels; ++i) {
+        const dcl_sp_level& in = levels[i];
+        DCL_RETURN_IF_BAD(in.m >= 0 && in.c > 0 && in.c % 8 == 0 && in.out_col0 >= 0 && in.out_col0 % 8 == 0 &&
+                          c_total >= in.out_col0 + in.c);
+        DCL_RETURN_IF_BAD(in.m == 0 || (in.vox_indices != nullptr && in.feats != nullptr));
+        DCL_RETURN_IF_BAD(((uintptr_t)in.vox_indices & 15u) == 0 && ((uintptr_t)in.feats & 15u) == 0);
+        SpLevelDev& lv = batch.lv[i];
+        lv.m = in.m;
+        lv.c = in.c;
+        lv.out_col0 = in.out_col0;
+        lv.kr = rows_from_voxels(in.vox_indices, in.voxel_extent, in.offset);
+        lv.ws = reinterpret_cast<int*>(w);
+        lv.sorted = reinterpret_cast<float4*>(w + (size_t)SPL_HDR_INTS * sizeof(int));
+        lv.feats = in.feats;
+        w += sp_level_ws_bytes(in.m);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    sp_bucket_build_cluster_kernel<<<dim3(SPB_CLUSTER, nlevels), SPB_THREADS, 0, st>>>(batch);
+    sp_nn_interp_levels_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
+        n, unknown, batch, reinterpret_cast<unsigned char*>(out_pm), c_total);
+    return dcl_launch_status(2);
 }

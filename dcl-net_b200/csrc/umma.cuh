@@ -58,6 +58,19 @@ __device__ __forceinline__ void dcl_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// load an int from the shared memory of CTA `cta_rank` of the cluster, at the same offset as `p` here (DSMEM)
+__device__ __forceinline__ int dcl_ld_dsmem_s32(const int* p, uint32_t cta_rank) {
+    int v;
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+        "ld.shared::cluster.s32 %0, [ra];\n\t}"
+        : "=r"(v)
+        : "r"(dcl_smem_u32(p)), "r"(cta_rank)
+        : "memory");
+    return v;
+}
+
 // One lane of a converged warp; unlike `lane == 0` the compiler knows a single thread is active and emits the
 // uniform-datapath instructions behind it (UTCHMMA, UBLKCP, ...) back to back instead of wrapping each one in an
 // elect / vote loop (~7 instructions and ~50 cycles per MMA in the issuing thread).

@@ -128,6 +128,10 @@ def layers_from_head(head):
     return gemm, rest
 
 
+# bench.py sets this to a list to collect (start, end, algorithmic flops, tile width) around every dcl_pm_gemm launch.
+GEMM_EVENTS = None
+
+
 def run_gemm(problems, rows):
     """problems: list of dicts with keys a0, [a1], layer, [out_pm], [out_cm], [rows_per_inst], [pool_w], [pool_out]."""
     arr = (L.PmGemmProblem * len(problems))()
@@ -147,7 +151,14 @@ def run_gemm(problems, rows):
         slot.pool_w, slot.pool_out = L.ptr(p.get("pool_w")), L.ptr(p.get("pool_out"))
         slot.dot_w, slot.dot_out = L.ptr(p.get("dot_w")), L.ptr(p.get("dot_out"))
         keep.append(p)
+    if GEMM_EVENTS is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     L.check(L.load().dcl_pm_gemm(len(problems), ctypes.cast(arr, ctypes.c_void_p), rows, L.stream_ptr()), "pm_gemm")
+    if GEMM_EVENTS is not None:
+        ev1.record()
+        flops = sum(2.0 * rows * p["layer"].cin * p["layer"].cout for p in problems)
+        GEMM_EVENTS.append((ev0, ev1, flops, problems[0]["layer"].nt))
 
 
 class FusedTail:

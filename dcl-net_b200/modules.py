@@ -224,15 +224,16 @@ class Ops_GetPointFeat_spconv(nn.Module):
         levels = [feats1, feats2, feats3, feats4]
         width = sum(f.features.shape[1] for f in levels)
         out = torch.empty(points.shape[0] * width * 4, dtype=torch.uint8, device=points.device)
-        col = 0
+        # Ops_tensor2points is fused into the kernels: they take the int voxel indices and form the centres
+        # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.  All four levels go in one call
+        # (one bucket-build launch, one search + interpolation launch).
+        off = torch.as_tensor(np.asarray(self.offset), dtype=torch.float32).tolist()
+        specs, col = [], 0
         for scale, feats in zip(self.scale_lists, levels):
-            # Ops_tensor2points is fused into the kernels: they take the int voxel indices and form the centres
-            # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.
             ext = torch.as_tensor(np.asarray(self.unit_voxel_extent * scale), dtype=torch.float32).tolist()
-            off = torch.as_tensor(np.asarray(self.offset), dtype=torch.float32).tolist()
-            pointnet2_utils_sp.nn_interpolate_vox_pm(points, feats.indices.contiguous(), ext, off,
-                                                     feats.features.contiguous(), out, width, col)
+            specs.append((feats.indices.contiguous(), ext, off, feats.features.contiguous(), col))
             col += feats.features.shape[1]
+        pointnet2_utils_sp.nn_interpolate_vox_levels_pm(points, specs, out, width)
         return out
 
     def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):

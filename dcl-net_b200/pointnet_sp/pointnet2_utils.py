@@ -143,3 +143,30 @@ def nn_interpolate_vox_pm(target_points, vox_indices, voxel_extent, offset, quer
                                              L.ptr(query_feats), L.ptr(out_pm), c_total, out_col0, L.ptr(ws),
                                              ws.numel(), L.stream_ptr()), "pointnet_sp.nn_interpolate_vox_pm")
     return out_pm
+
+
+def nn_interpolate_vox_levels_pm(target_points, levels, out_pm, c_total):
+    """All pyramid levels of one tower in two launches (one bucket build, one search + interpolation), bit-identical
+    to calling nn_interpolate_vox_pm per level.  `levels`: list of (vox_indices (m,4) int32, voxel_extent[3],
+    offset[3], feats (m,c) fp32, out_col0)."""
+    import ctypes
+    assert target_points.is_contiguous()
+    n = target_points.size(0)
+    arr = (L.SpLevel * len(levels))()
+    keep = []
+    for slot, (vox, ext, off, feats, col0) in zip(arr, levels):
+        assert vox.is_contiguous() and feats.is_contiguous()
+        L.require(vox, torch.int32, "vox_indices")
+        L.require(feats, torch.float32, "feats")
+        slot.m, slot.c, slot.out_col0 = vox.size(0), feats.size(1), col0
+        slot.vox_indices, slot.feats = L.ptr(vox), L.ptr(feats)
+        slot.voxel_extent = (ctypes.c_float * 3)(*[float(v) for v in ext])
+        slot.offset = (ctypes.c_float * 3)(*[float(v) for v in off])
+        keep.append((vox, feats))
+    lib = L.load()
+    arr_p = ctypes.cast(arr, ctypes.c_void_p)
+    ws = _workspace(lib.dcl_sp_levels_workspace_bytes(len(levels), arr_p), target_points.device)
+    L.check(lib.dcl_sp_nn_interpolate_levels_pm(n, L.ptr(target_points), len(levels), arr_p, L.ptr(out_pm), c_total,
+                                                L.ptr(ws), ws.numel(), L.stream_ptr()),
+            "pointnet_sp.nn_interpolate_vox_levels_pm")
+    return out_pm

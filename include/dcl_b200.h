@@ -283,6 +283,26 @@ int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c,
     const float* feats, void* out_pm, int c_total, int out_col0,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* All pyramid levels of one tower at once (Ops_GetPointFeat_spconv.forward,
+ * models/Modules.py:227-251, calls Ops_nearest_neighbor_interpolate once per level with the
+ * same query points): one launch builds every level's batch buckets, one launch searches
+ * and interpolates every level into its column range of the same point-major image.
+ * Same results, bit for bit, as nlevels calls of dcl_sp_nn_interpolate_vox_pm.
+ * voxel_extent / offset are host values; vox_indices (m,4) int32 and feats (m,c) fp32 are
+ * device pointers.  nlevels <= 8.  Batch ids >= 1024 take the full-scan fallback; a level
+ * with m == 0 leaves its columns untouched. */
+typedef struct dcl_sp_level {
+    int m, c, out_col0;
+    const int* vox_indices;
+    float voxel_extent[3];
+    float offset[3];
+    const float* feats;
+} dcl_sp_level;
+size_t dcl_sp_levels_workspace_bytes(int nlevels, const dcl_sp_level* levels);
+int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nlevels,
+    const dcl_sp_level* levels, void* out_pm, int c_total,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Bring-up / test hook                                                       */
 /* ------------------------------------------------------------------------- */

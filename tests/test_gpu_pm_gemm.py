@@ -164,6 +164,45 @@ def test_nn_interpolate_vox_pm_equals_tensor2points_path(cuda_dev):
     assert torch.equal(pm_a, pm_b)
 
 
+@pytest.mark.parametrize("b,n_per,sizes", [(3, 128, (500, 200, 60, 9)), (32, 256, (30000, 9000, 2500, 700)),
+                                          (2, 128, (300, 0, 5, 1)), (1, 128, (4000,))])
+def test_nn_interpolate_levels_equals_per_level_calls(cuda_dev, b, n_per, sizes):
+    """The two-launch multi-level path (cluster bucket build + one search/interpolation launch) writes the same
+    point-major image, bit for bit, as one nn_interpolate_vox_pm call per level — including an empty level, levels
+    with fewer than three voxels per instance and shuffled voxel order."""
+    g = torch.Generator().manual_seed(sum(sizes) + b)
+    unknown = flat_bxyz(23, b, n_per, shuffle=False, scale=0.3).to(cuda_dev)
+    widths = (32, 64, 128, 256)[:len(sizes)]
+    total = sum(widths)
+    specs, col = [], 0
+    pm_a = torch.zeros(FT.pm_bytes(b * n_per, total), dtype=torch.uint8, device=cuda_dev)
+    pm_b = torch.zeros_like(pm_a)
+    for li, (m, c) in enumerate(zip(sizes, widths)):
+        side = 64 >> li
+        ind = torch.cat([torch.randint(0, b, (m, 1), generator=g), torch.randint(0, side, (m, 3), generator=g)], 1).int()
+        if m:
+            ind = torch.unique(ind, dim=0)
+            ind = ind[torch.randperm(ind.shape[0], generator=g)]
+        ind = ind.contiguous().to(cuda_dev)
+        feats = torch.randn(ind.shape[0], c, generator=g).to(cuda_dev)
+        ext = [0.6 / side] * 3
+        off = [-0.3] * 3
+        specs.append((ind, ext, off, feats, col))
+        if ind.shape[0]:
+            pu_sp.nn_interpolate_vox_pm(unknown, ind, ext, off, feats, pm_a, total, col)
+        col += c
+    pu_sp.nn_interpolate_vox_levels_pm(unknown, specs, pm_b, total)
+    if 0 in [s[0].shape[0] for s in specs]:
+        # an empty level: every query gets (inf, 0) neighbours -> weights NaN -> skip that column range
+        rows_a, rows_b = FT.pm_unpack(pm_a, b * n_per, total), FT.pm_unpack(pm_b, b * n_per, total)
+        c0 = 0
+        for (ind, _, _, _, col0), c in zip(specs, widths):
+            if ind.shape[0]:
+                assert torch.equal(rows_a[:, col0:col0 + c], rows_b[:, col0:col0 + c])
+    else:
+        assert torch.equal(pm_a, pm_b)
+
+
 @pytest.mark.parametrize("rows,cin,cout,nprob", [(2048, 96, 512, 5), (4096, 160, 256, 3), (1024, 480, 128, 8), (2048, 64, 64, 2)])
 def test_pm_gemm_persistent_many_tiles(cuda_dev, rows, cin, cout, nprob):
     """More work units than CTA pairs and k-block counts that are not multiples of the ring depth: exercises the
