@@ -44,11 +44,12 @@ SIGNATURES = {
     "dcl_pm_pack_rows": (_I, [_I, _I, _I, _P, _P, _P]),
     "dcl_pm_pack_cm": (_I, [_I, _I, _I, _P, _P, _P]),
     "dcl_pm_unpack": (_I, [_I, _I, _P, _P, _P]),
-    "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _I, _P]),
+    "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _P, _I, _P]),
     "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_pose_head_workspace_bytes": (_SZ, [_I, _P, _P]),
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_conf_weights": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcl_sp_levels_workspace_bytes": (_SZ, [_I, _P]),
     "dcl_sp_nn_interpolate_levels_pm": (_I, [_I, _P, _I, _P, _P, _I, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
@@ -92,7 +93,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if lib.dcl_b200_abi_version() != 2:
+        if lib.dcl_b200_abi_version() != 3:
             raise RuntimeError("libdcl_b200.so ABI version mismatch with dcl_net_b200/_lib.py")
         _lib = lib
     return _lib

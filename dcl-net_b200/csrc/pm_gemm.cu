@@ -444,10 +444,12 @@ __global__ void __launch_bounds__(256) pm_unpack_kernel(int rows, int c, const u
     dst[g] = hi + lo;
 }
 
-// out[inst, col] = sum over the `parts` per-warp partials of an instance, in index order (deterministic);
-// accumulate != 0 adds to what is already there.
+// out[inst, col] = sum over the `parts` per-warp partials of an instance, in index order (deterministic), then —
+// when a second set of partials is given — over that set, continuing the same running sum (so one launch equals
+// two accumulating launches bit for bit); accumulate != 0 starts from what is already there.
 __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout, int parts,
                                                              const float* __restrict__ partials,
+                                                             const float* __restrict__ partials2,
                                                              float* __restrict__ out, int accumulate) {
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= insts * cout) return;
@@ -455,6 +457,10 @@ __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout
     float acc = accumulate ? out[g] : 0.f;
     const float* p = partials + (size_t)inst * parts * cout + col;
     for (int i = 0; i < parts; ++i) acc += p[(size_t)i * cout];
+    if (partials2 != nullptr) {
+        const float* q = partials2 + (size_t)inst * parts * cout + col;
+        for (int i = 0; i < parts; ++i) acc += q[(size_t)i * cout];
+    }
     out[g] = acc;
 }
 
@@ -527,10 +533,10 @@ DCL_API int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void*
     return dcl_launch_status();
 }
 
-DCL_API int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, float* out, int accumulate,
-                               void* stream) {
-    DCL_RETURN_IF_BAD(insts > 0 && cout > 0 && parts > 0);
+DCL_API int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, const float* partials2,
+                               float* out, int accumulate, void* stream) {
+    DCL_RETURN_IF_BAD(insts > 0 && cout > 0 && parts > 0 && partials != nullptr && out != nullptr);
     pm_pool_reduce_kernel<<<DCL_DIVUP(insts * cout, 256), 256, 0, (cudaStream_t)stream>>>(insts, cout, parts, partials,
-                                                                                        out, accumulate);
+                                                                                        partials2, out, accumulate);
     return dcl_launch_status();
 }

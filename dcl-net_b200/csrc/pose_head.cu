@@ -9,6 +9,7 @@
 // instance.  fp32 FMA throughout.
 #include "common.cuh"
 #include "../../include/dcl_b200.h"
+#include <math_constants.h>
 
 namespace {
 
@@ -35,25 +36,53 @@ __global__ void __launch_bounds__(PH_THREADS) dense_small_batch_kernel(DenseJob 
     const int ni = min(PH_INST, b - i0);
     if (blockIdx.x * PH_ROWS >= j.o) return;  // this head has fewer rows than the other one
     const int k = j.k;
-    for (int idx = threadIdx.x; idx < ni * k; idx += PH_THREADS) s_x[idx] = j.x[(size_t)i0 * k + idx];
-    __syncthreads();
+    // Stage the instances' input vectors: they are contiguous, so one bulk copy (TMA) brings all of them; a
+    // per-thread load loop pays one L2 round trip per few elements (it was 3/4 of this kernel's time).
+    __shared__ uint64_t s_bar;
+    const float* xsrc = j.x + (size_t)i0 * k;
+    const uint32_t xbytes = (uint32_t)ni * (uint32_t)k * 4u;
+    const bool bulk = ((((uintptr_t)xsrc) & 15u) == 0) && ((xbytes & 15u) == 0) && xbytes < (1u << 20);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            dcl_mbar_init(&s_bar, 1);
+            dcl_fence_barrier_init();
+            dcl_mbar_arrive_expect_tx(&s_bar, xbytes);
+            dcl_bulk_g2s(s_x, xsrc, xbytes, &s_bar);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < ni * k; idx += PH_THREADS) s_x[idx] = xsrc[idx];
+    }
+    // the weight row does not depend on the staged inputs: fetch it while they land
+    const float* wr = j.w + (size_t)min(row, j.o - 1) * k;
+    const bool vec = (k & 127) == 0 && k <= PH_MAX_IN;
+    float4 wreg[PH_MAX_IN / 128];
+    if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll
+        for (int t = 0; t < PH_MAX_IN / 128; ++t)
+            wreg[t] = (t < (k >> 7)) ? __ldg(w4 + t * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();  // s_bar initialised / cooperative staging complete
+    if (bulk) dcl_mbar_wait(&s_bar, 0);
     if (row >= j.o) return;
     float acc[PH_INST];
 #pragma unroll
     for (int i = 0; i < PH_INST; ++i) acc[i] = 0.f;
-    const float* wr = j.w + (size_t)row * k;
-    if ((k & 127) == 0) {
-        const float4* w4 = reinterpret_cast<const float4*>(wr);
-        for (int c = lane; c < (k >> 2); c += 32) {
-            const float4 a = __ldg(w4 + c);
+    if (vec) {
 #pragma unroll
-            for (int i = 0; i < PH_INST; ++i) {
-                if (i < ni) {
-                    const float4 xv = reinterpret_cast<const float4*>(s_x + (size_t)i * k)[c];
-                    acc[i] = __fmaf_rn(a.x, xv.x, acc[i]);
-                    acc[i] = __fmaf_rn(a.y, xv.y, acc[i]);
-                    acc[i] = __fmaf_rn(a.z, xv.z, acc[i]);
-                    acc[i] = __fmaf_rn(a.w, xv.w, acc[i]);
+        for (int t = 0; t < PH_MAX_IN / 128; ++t) {
+            if (t < (k >> 7)) {
+                const float4 a = wreg[t];
+                const int c = t * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < PH_INST; ++i) {
+                    if (i < ni) {
+                        const float4 xv = reinterpret_cast<const float4*>(s_x + (size_t)i * k)[c];
+                        acc[i] = __fmaf_rn(a.x, xv.x, acc[i]);
+                        acc[i] = __fmaf_rn(a.y, xv.y, acc[i]);
+                        acc[i] = __fmaf_rn(a.z, xv.z, acc[i]);
+                        acc[i] = __fmaf_rn(a.w, xv.w, acc[i]);
+                    }
                 }
             }
         }
@@ -75,6 +104,65 @@ __global__ void __launch_bounds__(PH_THREADS) dense_small_batch_kernel(DenseJob 
             v += bias;
             j.y[(size_t)(i0 + i) * j.o + row] = j.relu ? fmaxf(v, 0.f) : v;
         }
+    }
+}
+
+// Confidence weights (models/DCL_Net.py:219-220): conf = sigmoid(cat([conf_1, conf_2], dim=2)), conf_softmax =
+// softmax(conf, dim=2) over the 2n correspondences of an instance.  One CTA per instance; the logits come from the
+// per-row dot epilogue of dcl_pm_gemm without their bias, which is added here.  Outputs: conf (b, 2n) and the two
+// halves of conf_softmax as flat per-row weights (b*n each), the layout the pooled fuser epilogue reads.
+constexpr int CW_THREADS = 256;
+__global__ void __launch_bounds__(CW_THREADS) conf_weights_kernel(int n, const float* __restrict__ logit_1,
+                                                                  const float* __restrict__ logit_2,
+                                                                  const float* __restrict__ bias_1,
+                                                                  const float* __restrict__ bias_2,
+                                                                  float* __restrict__ conf, float* __restrict__ w1,
+                                                                  float* __restrict__ w2) {
+    __shared__ float s_red[CW_THREADS / 32];
+    __shared__ float s_bcast;
+    const int bi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float b1 = bias_1[0], b2 = bias_2[0];
+    const float* l1 = logit_1 + (size_t)bi * n;
+    const float* l2 = logit_2 + (size_t)bi * n;
+    float* crow = conf + (size_t)bi * 2 * n;
+    // pass 1: sigmoid, row maximum
+    float mx = -CUDART_INF_F;
+    for (int i = tid; i < 2 * n; i += CW_THREADS) {
+        const float x = (i < n) ? __fadd_rn(l1[i], b1) : __fadd_rn(l2[i - n], b2);
+        const float c = 1.0f / (1.0f + expf(-x));
+        crow[i] = c;
+        mx = fmaxf(mx, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float m = s_red[0];
+        for (int w = 1; w < CW_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+        s_bcast = m;
+    }
+    __syncthreads();
+    mx = s_bcast;
+    // pass 2: sum of exp(c - max) (each thread re-reads what it wrote)
+    float sum = 0.f;
+    for (int i = tid; i < 2 * n; i += CW_THREADS) sum += expf(crow[i] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < CW_THREADS / 32; ++w) t += s_red[w];
+        s_bcast = t;
+    }
+    __syncthreads();
+    const float total = s_bcast;
+    for (int i = tid; i < 2 * n; i += CW_THREADS) {
+        const float w = expf(crow[i] - mx) / total;
+        if (i < n) w1[(size_t)bi * n + i] = w;
+        else w2[(size_t)bi * n + i - n] = w;
     }
 }
 
@@ -123,4 +211,12 @@ DCL_API int dcl_pose_head(int b, const float* pooled, const dcl_pose_head_mlp* r
     if (e) return e;
     return launch_layer({r2, r.w3, r.b3, out_rot, r.d_h2, r.d_out, 0}, {t2, t.w3, t.b3, out_trans, t.d_h2, t.d_out, 0}, b,
                         st);
+}
+
+DCL_API int dcl_conf_weights(int b, int n, const float* logit_1, const float* logit_2, const float* bias_1,
+                             const float* bias_2, float* conf, float* w1, float* w2, void* stream) {
+    DCL_RETURN_IF_BAD(b >= 0 && n > 0 && logit_1 && logit_2 && bias_1 && bias_2 && conf && w1 && w2);
+    if (b == 0) return 0;
+    conf_weights_kernel<<<b, CW_THREADS, 0, (cudaStream_t)stream>>>(n, logit_1, logit_2, bias_1, bias_2, conf, w1, w2);
+    return dcl_launch_status();
 }

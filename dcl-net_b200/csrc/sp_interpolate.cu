@@ -532,7 +532,7 @@ int build_buckets(int m, const KnownRows& kr, int* ws, float4* sorted, cudaStrea
 // distributed shared memory, so there is no global header to clear and no separate scan / scatter pass — and one
 // launch runs search + interpolation for every level (a CTA keeps its 16 queries and walks the levels).
 constexpr int SPL_MAX_LEVELS = 8;
-constexpr int SPB_THREADS = 512, SPB_CLUSTER = 8;
+constexpr int SPB_THREADS = 512, SPB_CLUSTER = 8, SPB_ITEMS = 10;
 constexpr int SPL_HDR_INTS = WS_OFF + SP_SBINS + 4;  // flag, nb, offsets[SP_SBINS + 1]; multiple of 4
 
 struct SpLevelDev {
@@ -563,21 +563,45 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
     const int m = lv.m;
     const int slice = DCL_DIVUP(m, SPB_CLUSTER);
     const int k0 = (int)rank * slice, k1 = min(m, k0 + slice);
+    // Slices of up to SPB_ITEMS points per thread (m <= 40960 per level) stay in registers between the two passes
+    // and all their loads are in flight at once; longer slices are re-read in pass 2.
+    const bool in_regs = (k1 - k0) <= SPB_THREADS * SPB_ITEMS;
+    float4 held[SPB_ITEMS];
+    int held_b[SPB_ITEMS];
+    if (in_regs) {
+#pragma unroll
+        for (int t = 0; t < SPB_ITEMS; ++t) {
+            const int k = k0 + t * SPB_THREADS + tid;
+            held[t] = (k < k1) ? lv.kr.get(k) : make_float4(-1.f, 0.f, 0.f, 0.f);
+        }
+    }
     // pass 1: histogram of this CTA's slice; lanes with the same bucket (the usual case: clouds are stored
     // batch-major) elect one lane to add their count
-    for (int kb = k0; kb < k1; kb += SPB_THREADS) {
-        const int k = kb + tid;
+    auto classify = [&](float bf, bool live) {
         int ib = -1;
-        if (k < k1) {
-            if (!batch_id_ok(lv.kr.get(k).x, ib) || ib >= SP_SBINS) {
-                ib = -1;
-                s_meta[0] = 1;
-            }
+        if (live && (!batch_id_ok(bf, ib) || ib >= SP_SBINS)) {
+            ib = -1;
+            s_meta[0] = 1;
         }
+        return ib;
+    };
+    auto count_one = [&](int ib) {
         const unsigned peers = __match_any_sync(0xffffffffu, ib);
         if (ib >= 0 && lane == __ffs(peers) - 1) {
             atomicAdd(s_cnt + ib, __popc(peers));
             atomicMax(&s_meta[1], ib + 1);
+        }
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int t = 0; t < SPB_ITEMS; ++t) {
+            held_b[t] = classify(held[t].x, k0 + t * SPB_THREADS + tid < k1);
+            count_one(held_b[t]);
+        }
+    } else {
+        for (int kb = k0; kb < k1; kb += SPB_THREADS) {
+            const int k = kb + tid;
+            count_one(classify(k < k1 ? lv.kr.get(k).x : 0.f, k < k1));
         }
     }
     __syncthreads();
@@ -642,14 +666,7 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
         __syncthreads();
     }
     // pass 2: scatter this CTA's slice
-    for (int kb = k0; kb < k1; kb += SPB_THREADS) {
-        const int k = kb + tid;
-        int ib = -1;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < k1) {
-            r = lv.kr.get(k);
-            if (!batch_id_ok(r.x, ib) || ib >= SP_SBINS) ib = -1;
-        }
+    auto place_one = [&](const float4& r, int ib, int k) {
         const unsigned peers = __match_any_sync(0xffffffffu, ib);
         const int leader = __ffs(peers) - 1;
         int first = 0;
@@ -658,6 +675,16 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
         if (ib >= 0) {
             const int pos = s_base[ib] + first + __popc(peers & ((1u << lane) - 1u));
             lv.sorted[pos] = make_float4(r.y, r.z, r.w, __int_as_float(k));
+        }
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int t = 0; t < SPB_ITEMS; ++t) place_one(held[t], held_b[t], k0 + t * SPB_THREADS + tid);
+    } else {
+        for (int kb = k0; kb < k1; kb += SPB_THREADS) {
+            const int k = kb + tid;
+            const float4 r = (k < k1) ? lv.kr.get(k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            place_one(r, classify(r.x, k < k1), k);
         }
     }
 }

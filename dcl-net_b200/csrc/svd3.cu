@@ -69,7 +69,9 @@ __device__ void project_so3(const double Min[3][3], float* __restrict__ R) {
             off += fabs(A[r][0] * A[r][1]) + fabs(A[r][0] * A[r][2]) + fabs(A[r][1] * A[r][2]);
             diag += A[r][0] * A[r][0] + A[r][1] * A[r][1] + A[r][2] * A[r][2];
         }
-        if (off <= 1e-30 * diag) break;
+        // columns orthogonal to fp64 round-off: further sweeps only churn the last bit (convergence is quadratic,
+        // 4-6 sweeps in practice; the old 1e-30 test never fired and every matrix paid all 12)
+        if (off <= 1e-15 * diag) break;
     }
     double nrm[3];
 #pragma unroll

@@ -236,12 +236,12 @@ class FusedTail:
         logits = torch.empty(2, b, n, **f32)
         run_gemm([{"a0": c1[0], "layer": self.conf[1], "dot_w": self.conf_dot[0], "dot_out": logits[0]},
                   {"a0": c1[1], "layer": self.conf_bi[1], "dot_w": self.conf_dot[1], "dot_out": logits[1]}], rows)
-        conf_1 = (logits[0] + self.conf_dot_bias[0]).unsqueeze(1)
-        conf_2 = (logits[1] + self.conf_dot_bias[1]).unsqueeze(1)
-        conf = torch.sigmoid(torch.cat([conf_1, conf_2], dim=2))
-        conf_softmax = torch.softmax(conf, dim=2)
-        w1 = conf_softmax[:, 0, :n].reshape(-1).contiguous()
-        w2 = conf_softmax[:, 0, n:].reshape(-1).contiguous()
+        # sigmoid + softmax over the 2n correspondences (DCL_Net.py:219-220), bias of the dot layer added inside
+        conf = torch.empty(b, 2 * n, **f32)
+        w1, w2 = torch.empty(rows, **f32), torch.empty(rows, **f32)
+        L.check(L.load().dcl_conf_weights(b, n, L.ptr(logits[0]), L.ptr(logits[1]), L.ptr(self.conf_dot_bias[0]),
+                                          L.ptr(self.conf_dot_bias[1]), L.ptr(conf), L.ptr(w1), L.ptr(w2),
+                                          L.stream_ptr()), "conf_weights")
 
         # ---- fusers: cat([F_Xc_p1, F_Xo_p]) / cat([F_Yc_p, F_Yo_p2]) -> 512 -> 512 -> 1024, pooled with conf_softmax
         f1 = [pm_empty(rows, 512, dev) for _ in range(2)]
@@ -255,13 +255,13 @@ class FusedTail:
                   {"a0": f2[1], "layer": self.fuser_bi[2], "pool_w": w2, "pool_out": parts[1]}], rows)
         pooled = torch.empty(b, 1024, **f32)
         lib = L.load()
-        L.check(lib.dcl_pm_pool_reduce(b, 1024, n // 32, L.ptr(parts[0]), L.ptr(pooled), 0, L.stream_ptr()), "pool")
-        L.check(lib.dcl_pm_pool_reduce(b, 1024, n // 32, L.ptr(parts[1]), L.ptr(pooled), 1, L.stream_ptr()), "pool")
+        L.check(lib.dcl_pm_pool_reduce(b, 1024, n // 32, L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(pooled), 0,
+                                       L.stream_ptr()), "pool")
         F_p_wei = pooled.unsqueeze(-1)
 
         # ---- pose regressors on the pooled feature (b x 1024: tiny) and the SO(3) projection
         from .dcl_net import pose_heads, svd3_project
         ortho9d, trans = pose_heads(pooled, net.regressor_rot, net.regressor_trans)
         rot = svd3_project(ortho9d, True)
-        return {"trans_pred": trans, "rot_pred": rot, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p,
+        return {"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p,
                 "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}

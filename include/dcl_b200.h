@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header; bumped on any signature change. */
-#define DCL_B200_ABI_VERSION 2
+#define DCL_B200_ABI_VERSION 3
 int dcl_b200_abi_version(void);
 /* Compiled-for architecture as an integer (100 for sm_100a). */
 int dcl_b200_arch(void);
@@ -250,9 +250,10 @@ int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, vo
 int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, void* stream);
 /* PM image -> fp32 row-major (rows x c). */
 int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void* stream);
-/* out[inst, :] (+)= sum of `parts` consecutive partial rows per instance, in index order. */
-int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, float* out, int accumulate,
-    void* stream);
+/* out[inst, :] (+)= sum of `parts` consecutive partial rows per instance, in index order, then
+ * (partials2 != NULL) of the second set's, continuing the same running sum. */
+int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, const float* partials2,
+    float* out, int accumulate, void* stream);
 /* dcl_sp_nn_interpolate_fused writing columns [out_col0, out_col0+c) of a PM image with c_total channels
  * (n % 128 == 0, c % 8 == 0, out_col0 % 8 == 0) instead of an fp32 matrix. */
 int dcl_sp_nn_interpolate_fused_pm(int n, int m, int c,
@@ -282,6 +283,13 @@ int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c,
     const float* unknown, const int* vox_indices, const float* voxel_extent3, const float* offset3,
     const float* feats, void* out_pm, int c_total, int out_col0,
     void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces models/DCL_Net.py:219-220: conf = sigmoid(cat([conf_1, conf_2], dim=2));
+ * conf_softmax = softmax(conf, dim=2).  logit_1 / logit_2 (b,n) are the outputs of the last
+ * regressor_conf / regressor_conf_bi layer WITHOUT its bias (bias_1 / bias_2: one device float
+ * each).  conf (b,2n); w1 / w2 (b*n) = conf_softmax[:, :n] / [:, n:]. */
+int dcl_conf_weights(int b, int n, const float* logit_1, const float* logit_2,
+    const float* bias_1, const float* bias_2, float* conf, float* w1, float* w2, void* stream);
 
 /* All pyramid levels of one tower at once (Ops_GetPointFeat_spconv.forward,
  * models/Modules.py:227-251, calls Ops_nearest_neighbor_interpolate once per level with the

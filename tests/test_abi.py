@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_arch():
     lib = _lib.load()
-    assert lib.dcl_b200_abi_version() == 2
+    assert lib.dcl_b200_abi_version() == 3
     assert lib.dcl_b200_arch() == 100
 
 
