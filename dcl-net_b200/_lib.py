@@ -68,7 +68,7 @@ class PmGemmProblem(ctypes.Structure):
 
 class SpLevel(ctypes.Structure):
     """Mirror of dcl_sp_level (include/dcl_b200.h)."""
-    _fields_ = [("m", _I), ("c", _I), ("out_col0", _I), ("vox_indices", _P), ("voxel_extent", ctypes.c_float * 3),
+    _fields_ = [("m", _I), ("c", _I), ("out_col0", _I), ("grid_x", _I), ("vox_indices", _P), ("voxel_extent", ctypes.c_float * 3),
                 ("offset", ctypes.c_float * 3), ("feats", _P)]
 
 

@@ -134,6 +134,8 @@ struct KnownRows {
     const float* rows;
     const int* vox;
     float ext[3], off[3], half[3];
+    // first voxel index of row k (voxel form only): rows that share it share their first centre coordinate
+    __device__ __forceinline__ int slab(int k) const { return __ldg(vox + 4 * (size_t)k + 1); }
     __device__ __forceinline__ float4 get(int k) const {
         if (rows != nullptr) return __ldg(reinterpret_cast<const float4*>(rows) + k);
         const int4 v = __ldg(reinterpret_cast<const int4*>(vox) + k);
@@ -241,10 +243,19 @@ __global__ void __launch_bounds__(256) sp_bucket_scatter_kernel(int m, KnownRows
 // All 32 lanes of the warp must call this (full-mask shuffles); afterwards every lane of a group holds the result.
 constexpr int LPQ = 8;
 constexpr int SP_SEG_TILE_FLOATS = 512 * 4;  // 512 bucket entries (8 KB) per stage
+// Slab mode (voxel levels, gx > 0): the buckets are keyed by (batch id, first voxel index), i.e. an instance's
+// entries are grouped into gx slabs that share one centre coordinate.  A query walks the slabs outwards from its
+// own and stops as soon as the squared distance to the next slab's plane exceeds what it already holds — every
+// candidate of such a slab is at least that far away — which cuts the candidates per query from the whole instance
+// (~1100 at the finest level) to a few slabs.  The instance's entries (<= SP_SLAB_CAP) sit in shared memory.
+constexpr int SP_SLAB_CAP = 2048;
+constexpr int SP_SLAB_MAX_GX = 128;
+constexpr int SP_STILE_FLOATS = SP_SLAB_CAP * 4 > 2 * SP_SEG_TILE_FLOATS ? SP_SLAB_CAP * 4 : 2 * SP_SEG_TILE_FLOATS;
 
 __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
                                                 const KnownRows& kr, int m, bool valid, float4 u,
-                                                int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+                                                int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3,
+                                                int gx = 0) {
     b1 = b2 = b3 = CUDART_INF_F;
     i1 = i2 = i3 = 0x7fffffff;  // sentinels lose every tie; mapped back to the reference's 0 at the end
     if (ws[WS_FLAG] != 0) {
@@ -265,15 +276,70 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         // Then the bucket is streamed ONCE per CTA through shared memory by TMA bulk copies (2-stage ring) and
         // all 16 query groups scan it there; ncu showed the per-group global loads stalled on the long
         // scoreboard two thirds of the time.  Mixed CTAs take the per-group global path below.
-        __shared__ __align__(16) float s_tile[2 * SP_SEG_TILE_FLOATS];
+        __shared__ __align__(16) float s_tile[SP_STILE_FLOATS];
         __shared__ uint64_t s_bar[2];
         __shared__ int s_b0;
+        __shared__ int s_slab[SP_SLAB_MAX_GX + 1];
+        const int gxe = gx > 0 ? gx : 1;  // buckets per batch id
         if (threadIdx.x == 0) s_b0 = has_bucket ? my_b : -1;
         __syncthreads();
         const int b0 = s_b0;
         const bool uniform = __syncthreads_and((!valid || (has_bucket && my_b == b0)) ? 1 : 0) && b0 >= 0;
-        if (uniform) {
-            const int beg = ws[WS_OFF + b0], end = ws[WS_OFF + b0 + 1];
+        const int ubeg = uniform ? ws[WS_OFF + b0 * gxe] : 0, uend = uniform ? ws[WS_OFF + (b0 + 1) * gxe] : 0;
+        if (uniform && gx > 0 && gx <= SP_SLAB_MAX_GX && uend - ubeg <= SP_SLAB_CAP) {
+            // ---- slab walk over the instance staged in shared memory
+            const uint32_t bytes = (uint32_t)(uend - ubeg) * 16u;
+            if (threadIdx.x == 0) {
+                dcl_mbar_init(&s_bar[0], 1);
+                dcl_fence_barrier_init();
+                if (bytes != 0) {
+                    dcl_mbar_arrive_expect_tx(&s_bar[0], bytes);
+                    dcl_bulk_g2s(s_tile, sorted + ubeg, bytes, &s_bar[0]);
+                }
+            }
+            for (int i = threadIdx.x; i <= gx; i += blockDim.x) s_slab[i] = ws[WS_OFF + b0 * gx + i] - ubeg;
+            __syncthreads();
+            if (bytes != 0) dcl_mbar_wait(&s_bar[0], 0);
+            if (valid && bytes != 0) {
+                const float4* inst = reinterpret_cast<const float4*>(s_tile);
+                const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(LPQ - 1));
+                // squared distance to the plane of slab s; its centre coordinate is formed exactly as KnownRows::get does
+                auto slab_d2 = [&](int sidx) {
+                    const float cx = __fadd_rn(__fadd_rn(__fmul_rn((float)sidx, kr.ext[0]), kr.off[0]), kr.half[0]);
+                    const float dx = __fsub_rn(u.y, cx);
+                    return __fmul_rn(dx, dx);
+                };
+                int lo = (int)floorf(__fdiv_rn(__fsub_rn(u.y, kr.off[0]), kr.ext[0]));
+                lo = max(0, min(gx - 1, lo));
+                int hi = lo + 1;
+                float bound = CUDART_INF_F;
+                while (lo >= 0 || hi < gx) {
+                    const float dl = lo >= 0 ? slab_d2(lo) : CUDART_INF_F;
+                    const float dh = hi < gx ? slab_d2(hi) : CUDART_INF_F;
+                    const bool take_lo = hi >= gx || (lo >= 0 && dl <= dh);
+                    const float dmin = take_lo ? dl : dh;
+                    // every unvisited candidate is at least dmin (1 - 3 ulp) away: nothing closer than `bound` is left
+                    if (!(dmin <= __fmul_rn(bound, 1.000001f))) break;
+                    const int sidx = take_lo ? lo-- : hi++;
+                    const int sb = s_slab[sidx], se = s_slab[sidx + 1];
+                    for (int j = sb + sub; j < se; j += LPQ) {
+                        const float4 c = inst[j];
+                        const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
+                        if (!(d > b3) && d < CUDART_INF_F)
+                            nn3_insert_lex(d, __float_as_int(c.w), b1, b2, b3, i1, i2, i3);
+                    }
+                    if (se > sb) {
+                        // the group's third-best distance is at most any of its lanes' third-best
+                        float t = b3;
+#pragma unroll
+                        for (int o = LPQ / 2; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(gmask, t, o));
+                        bound = t;
+                    }
+                }
+            }
+            __syncthreads();  // s_tile / s_bar are reused by the next level
+        } else if (uniform) {
+            const int beg = ubeg, end = uend;
             DclTilePipe<SP_SEG_TILE_FLOATS> pipe;
             pipe.init(s_tile, s_bar, reinterpret_cast<const float*>(sorted + beg), (end - beg) * 4);
             for (int t = 0; t < pipe.ntiles; ++t) {
@@ -291,7 +357,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
                 pipe.release(t);
             }
         } else if (has_bucket) {
-            const int beg = ws[WS_OFF + my_b], end = ws[WS_OFF + my_b + 1];
+            const int beg = ws[WS_OFF + my_b * gxe], end = ws[WS_OFF + (my_b + 1) * gxe];
 #pragma unroll 8
             for (int j = beg + sub; j < end; j += LPQ) {
                 const float4 c = __ldg(sorted + j);
@@ -533,10 +599,12 @@ int build_buckets(int m, const KnownRows& kr, int* ws, float4* sorted, cudaStrea
 // launch runs search + interpolation for every level (a CTA keeps its 16 queries and walks the levels).
 constexpr int SPL_MAX_LEVELS = 8;
 constexpr int SPB_THREADS = 512, SPB_CLUSTER = 8, SPB_ITEMS = 10;
-constexpr int SPL_HDR_INTS = WS_OFF + SP_SBINS + 4;  // flag, nb, offsets[SP_SBINS + 1]; multiple of 4
+constexpr int SPL_SBINS = 2048;                        // buckets per level: batch ids x slabs
+constexpr int SPL_HDR_INTS = WS_OFF + SPL_SBINS + 4;  // flag, nb, offsets[SPL_SBINS + 1]; multiple of 4
 
 struct SpLevelDev {
     int m, c, out_col0;
+    int gx;  // > 0: buckets keyed by (batch id, first voxel index in [0, gx)); 0: by batch id only
     KnownRows kr;
     int* ws;
     float4* sorted;
@@ -549,88 +617,101 @@ struct SpLevelBatch {
 
 __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREADS)
     sp_bucket_build_cluster_kernel(const __grid_constant__ SpLevelBatch batch) {
-    __shared__ int s_cnt[SP_SBINS];   // this CTA's histogram; the other CTAs of the cluster read it through DSMEM
-    __shared__ int s_base[SP_SBINS];  // where this CTA's entries of bucket b start in sorted[]
-    __shared__ int s_cur[SP_SBINS];   // bucket totals, then scatter cursors
-    __shared__ int s_meta[2];         // [0] a batch id that is no integer in [0, SP_SBINS), [1] max id + 1
+    __shared__ int s_cnt[SPL_SBINS];   // this CTA's histogram; the other CTAs of the cluster read it through DSMEM
+    __shared__ int s_base[SPL_SBINS];  // where this CTA's entries of bucket b start in sorted[]
+    __shared__ int s_cur[SPL_SBINS];   // bucket totals, then scatter cursors
+    __shared__ int s_meta[2];          // [0] an id outside the bucket range, [1] max batch id + 1
     __shared__ int s_warp[SPB_THREADS / 32];
     const SpLevelDev& lv = batch.lv[blockIdx.y];
     const uint32_t rank = dcl_cluster_ctarank();
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < SP_SBINS; i += SPB_THREADS) s_cnt[i] = 0;
+    for (int i = tid; i < SPL_SBINS; i += SPB_THREADS) s_cnt[i] = 0;
     if (tid < 2) s_meta[tid] = 0;
     __syncthreads();
     const int m = lv.m;
+    const int gxe = lv.gx > 0 ? lv.gx : 1;
     const int slice = DCL_DIVUP(m, SPB_CLUSTER);
     const int k0 = (int)rank * slice, k1 = min(m, k0 + slice);
     // Slices of up to SPB_ITEMS points per thread (m <= 40960 per level) stay in registers between the two passes
     // and all their loads are in flight at once; longer slices are re-read in pass 2.
     const bool in_regs = (k1 - k0) <= SPB_THREADS * SPB_ITEMS;
     float4 held[SPB_ITEMS];
-    int held_b[SPB_ITEMS];
+    int held_b[SPB_ITEMS], held_s[SPB_ITEMS];
     if (in_regs) {
 #pragma unroll
         for (int t = 0; t < SPB_ITEMS; ++t) {
             const int k = k0 + t * SPB_THREADS + tid;
             held[t] = (k < k1) ? lv.kr.get(k) : make_float4(-1.f, 0.f, 0.f, 0.f);
+            held_s[t] = (k < k1 && lv.gx > 0) ? lv.kr.slab(k) : 0;
         }
     }
     // pass 1: histogram of this CTA's slice; lanes with the same bucket (the usual case: clouds are stored
     // batch-major) elect one lane to add their count
-    auto classify = [&](float bf, bool live) {
+    // bucket of a point: batch id * slabs + slab; -1 (and the level's flag) when either is out of range
+    auto classify = [&](float bf, int slab, bool live) {
         int ib = -1;
-        if (live && (!batch_id_ok(bf, ib) || ib >= SP_SBINS)) {
-            ib = -1;
+        if (!live) return -1;
+        if (!batch_id_ok(bf, ib) || slab < 0 || slab >= gxe || ib >= SPL_SBINS / gxe) {
             s_meta[0] = 1;
+            return -1;
         }
-        return ib;
+        return ib * gxe + slab;
     };
-    auto count_one = [&](int ib) {
-        const unsigned peers = __match_any_sync(0xffffffffu, ib);
-        if (ib >= 0 && lane == __ffs(peers) - 1) {
-            atomicAdd(s_cnt + ib, __popc(peers));
-            atomicMax(&s_meta[1], ib + 1);
+    auto count_one = [&](int key) {
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(peers) - 1) {
+            atomicAdd(s_cnt + key, __popc(peers));
+            atomicMax(&s_meta[1], key / gxe + 1);
         }
     };
     if (in_regs) {
 #pragma unroll
         for (int t = 0; t < SPB_ITEMS; ++t) {
-            held_b[t] = classify(held[t].x, k0 + t * SPB_THREADS + tid < k1);
+            held_b[t] = classify(held[t].x, held_s[t], k0 + t * SPB_THREADS + tid < k1);
             count_one(held_b[t]);
         }
     } else {
         for (int kb = k0; kb < k1; kb += SPB_THREADS) {
             const int k = kb + tid;
-            count_one(classify(k < k1 ? lv.kr.get(k).x : 0.f, k < k1));
+            const bool live = k < k1;
+            count_one(classify(live ? lv.kr.get(k).x : 0.f, (live && lv.gx > 0) ? lv.kr.slab(k) : 0, live));
         }
     }
     __syncthreads();
     dcl_cluster_sync();
-    // combine: bucket totals and the number of entries the lower-ranked CTAs put into each bucket
-    for (int b = tid; b < SP_SBINS; b += SPB_THREADS) {
-        int total = 0, before = 0;
+    // combine: bucket totals and the number of entries the lower-ranked CTAs put into each bucket (only the
+    // buckets in use: every CTA first learns the largest batch id any of them saw)
+    int flag = 0, nb = 0;
 #pragma unroll
-        for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
-            const int cnt = dcl_ld_dsmem_s32(s_cnt + b, r);
-            total += cnt;
-            before += (r < rank) ? cnt : 0;
+    for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
+        flag |= dcl_ld_dsmem_s32(&s_meta[0], r);
+        nb = max(nb, dcl_ld_dsmem_s32(&s_meta[1], r));
+    }
+    for (int b = tid; b < SPL_SBINS; b += SPB_THREADS) {
+        int total = 0, before = 0;
+        if (b < nb * gxe) {
+#pragma unroll
+            for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
+                const int cnt = dcl_ld_dsmem_s32(s_cnt + b, r);
+                total += cnt;
+                before += (r < rank) ? cnt : 0;
+            }
         }
         s_cur[b] = total;
         s_base[b] = before;
     }
-    int flag = 0, nb = 0;
-    if (tid == 0) {
-        for (uint32_t r = 0; r < SPB_CLUSTER; ++r) {
-            flag |= dcl_ld_dsmem_s32(&s_meta[0], r);
-            nb = max(nb, dcl_ld_dsmem_s32(&s_meta[1], r));
-        }
-    }
     __syncthreads();
     dcl_cluster_sync();  // nobody reads a peer's shared memory after this point
-    // exclusive scan of the totals (two buckets per thread)
+    // exclusive scan of the totals (SPL_SBINS / SPB_THREADS consecutive buckets per thread)
     {
-        const int a = s_cur[2 * tid], bsum = s_cur[2 * tid + 1];
-        int x = a + bsum;
+        constexpr int PER = SPL_SBINS / SPB_THREADS;
+        int v[PER], x = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            v[i] = s_cur[PER * tid + i];
+            x += v[i];
+        }
+        const int mine = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -648,21 +729,23 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
             if (tid < SPB_THREADS / 32) s_warp[tid] = w;
         }
         __syncthreads();
-        const int excl = x - (a + bsum) + ((tid >= 32) ? s_warp[(tid >> 5) - 1] : 0);
-        s_base[2 * tid] += excl;
-        s_base[2 * tid + 1] += excl + a;
+        int run = x - mine + ((tid >= 32) ? s_warp[(tid >> 5) - 1] : 0);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            s_base[PER * tid + i] += run;
+            if (rank == 0) lv.ws[WS_OFF + PER * tid + i] = run;
+            run += v[i];
+        }
         if (rank == 0) {
-            lv.ws[WS_OFF + 2 * tid] = excl;
-            lv.ws[WS_OFF + 2 * tid + 1] = excl + a;
-            if (tid == SPB_THREADS - 1) lv.ws[WS_OFF + SP_SBINS] = excl + a + bsum;
+            if (tid == SPB_THREADS - 1) lv.ws[WS_OFF + SPL_SBINS] = run;
             if (tid == 0) {
                 lv.ws[WS_FLAG] = flag;
                 lv.ws[WS_NB] = nb;
             }
         }
         __syncthreads();
-        s_cur[2 * tid] = 0;
-        s_cur[2 * tid + 1] = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s_cur[PER * tid + i] = 0;
         __syncthreads();
     }
     // pass 2: scatter this CTA's slice
@@ -683,8 +766,9 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
     } else {
         for (int kb = k0; kb < k1; kb += SPB_THREADS) {
             const int k = kb + tid;
-            const float4 r = (k < k1) ? lv.kr.get(k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            place_one(r, classify(r.x, k < k1), k);
+            const bool live = k < k1;
+            const float4 r = live ? lv.kr.get(k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            place_one(r, classify(r.x, (live && lv.gx > 0) ? lv.kr.slab(k) : 0, live), k);
         }
     }
 }
@@ -704,7 +788,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int 
         if (lv.m == 0) continue;  // nothing to interpolate from (the reference would gather row 0 of an empty tensor)
         float b1, b2, b3;
         int j0, j1, j2;
-        sp_group_search(lv.ws, lv.sorted, lv.kr, lv.m, valid, u, sub, b1, b2, b3, j0, j1, j2);
+        sp_group_search(lv.ws, lv.sorted, lv.kr, lv.m, valid, u, sub, b1, b2, b3, j0, j1, j2, lv.gx);
         if (valid) {
             const int c = lv.c;
             const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
@@ -903,6 +987,7 @@ DCL_API int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nle
         lv.m = in.m;
         lv.c = in.c;
         lv.out_col0 = in.out_col0;
+        lv.gx = (in.grid_x > 0 && in.grid_x <= SP_SLAB_MAX_GX) ? in.grid_x : 0;
         lv.kr = rows_from_voxels(in.vox_indices, in.voxel_extent, in.offset);
         lv.ws = reinterpret_cast<int*>(w);
         lv.sorted = reinterpret_cast<float4*>(w + (size_t)SPL_HDR_INTS * sizeof(int));

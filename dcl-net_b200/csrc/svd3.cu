@@ -63,14 +63,16 @@ __device__ void project_so3(const double Min[3][3], float* __restrict__ R) {
         jacobi_rotate(A, V, 0, 1);
         jacobi_rotate(A, V, 0, 2);
         jacobi_rotate(A, V, 1, 2);
-        double off = 0, diag = 0;
+        // |a_p . a_q| summed over the three column pairs against the total squared norm
+        double g01 = 0, g02 = 0, g12 = 0, diag = 0;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            off += fabs(A[r][0] * A[r][1]) + fabs(A[r][0] * A[r][2]) + fabs(A[r][1] * A[r][2]);
+            g01 += A[r][0] * A[r][1];
+            g02 += A[r][0] * A[r][2];
+            g12 += A[r][1] * A[r][2];
             diag += A[r][0] * A[r][0] + A[r][1] * A[r][1] + A[r][2] * A[r][2];
         }
-        // columns orthogonal to fp64 round-off: further sweeps only churn the last bit (convergence is quadratic,
-        // 4-6 sweeps in practice; the old 1e-30 test never fired and every matrix paid all 12)
+        const double off = fabs(g01) + fabs(g02) + fabs(g12);
         if (off <= 1e-15 * diag) break;
     }
     double nrm[3];

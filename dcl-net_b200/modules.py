@@ -231,7 +231,8 @@ class Ops_GetPointFeat_spconv(nn.Module):
         specs, col = [], 0
         for scale, feats in zip(self.scale_lists, levels):
             ext = torch.as_tensor(np.asarray(self.unit_voxel_extent * scale), dtype=torch.float32).tolist()
-            specs.append((feats.indices.contiguous(), ext, off, feats.features.contiguous(), col))
+            grid_x = int(np.ceil(self.voxel_num_limit[0] / scale))   # voxel indices of this level lie in [0, grid_x)
+            specs.append((feats.indices.contiguous(), ext, off, feats.features.contiguous(), col, grid_x))
             col += feats.features.shape[1]
         pointnet2_utils_sp.nn_interpolate_vox_levels_pm(points, specs, out, width)
         return out

@@ -148,13 +148,16 @@ def nn_interpolate_vox_pm(target_points, vox_indices, voxel_extent, offset, quer
 def nn_interpolate_vox_levels_pm(target_points, levels, out_pm, c_total):
     """All pyramid levels of one tower in two launches (one bucket build, one search + interpolation), bit-identical
     to calling nn_interpolate_vox_pm per level.  `levels`: list of (vox_indices (m,4) int32, voxel_extent[3],
-    offset[3], feats (m,c) fp32, out_col0)."""
+    offset[3], feats (m,c) fp32, out_col0[, grid_x]); grid_x = size of the level's voxel grid along the first
+    axis (enables the slab walk of the search; 0 / omitted = plain per-instance scan)."""
     import ctypes
     assert target_points.is_contiguous()
     n = target_points.size(0)
     arr = (L.SpLevel * len(levels))()
     keep = []
-    for slot, (vox, ext, off, feats, col0) in zip(arr, levels):
+    for slot, spec in zip(arr, levels):
+        vox, ext, off, feats, col0 = spec[:5]
+        slot.grid_x = int(spec[5]) if len(spec) > 5 else 0
         assert vox.is_contiguous() and feats.is_contiguous()
         L.require(vox, torch.int32, "vox_indices")
         L.require(feats, torch.float32, "feats")

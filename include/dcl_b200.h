@@ -297,10 +297,14 @@ int dcl_conf_weights(int b, int n, const float* logit_1, const float* logit_2,
  * and interpolates every level into its column range of the same point-major image.
  * Same results, bit for bit, as nlevels calls of dcl_sp_nn_interpolate_vox_pm.
  * voxel_extent / offset are host values; vox_indices (m,4) int32 and feats (m,c) fp32 are
- * device pointers.  nlevels <= 8.  Batch ids >= 1024 take the full-scan fallback; a level
+ * device pointers.  nlevels <= 8.  More than 2048 (batch id, slab) buckets take the full-scan
+ * fallback; a level
  * with m == 0 leaves its columns untouched. */
 typedef struct dcl_sp_level {
     int m, c, out_col0;
+    int grid_x;   /* first voxel indices lie in [0, grid_x) (the level's grid size; <= 128): lets the
+                   * search walk slabs of equal first coordinate outwards from the query and stop early.
+                   * 0 disables it; an index outside the range only costs the full-scan fallback. */
     const int* vox_indices;
     float voxel_extent[3];
     float offset[3];

@@ -164,14 +164,22 @@ def test_nn_interpolate_vox_pm_equals_tensor2points_path(cuda_dev):
     assert torch.equal(pm_a, pm_b)
 
 
+@pytest.mark.parametrize("slabs", [False, True])
 @pytest.mark.parametrize("b,n_per,sizes", [(3, 128, (500, 200, 60, 9)), (32, 256, (30000, 9000, 2500, 700)),
-                                          (2, 128, (300, 0, 5, 1)), (1, 128, (4000,))])
-def test_nn_interpolate_levels_equals_per_level_calls(cuda_dev, b, n_per, sizes):
+                                          (2, 128, (300, 0, 5, 1)), (1, 128, (4000,)), (40, 128, (60000,))])
+def test_nn_interpolate_levels_equals_per_level_calls(cuda_dev, b, n_per, sizes, slabs):
     """The two-launch multi-level path (cluster bucket build + one search/interpolation launch) writes the same
     point-major image, bit for bit, as one nn_interpolate_vox_pm call per level — including an empty level, levels
-    with fewer than three voxels per instance and shuffled voxel order."""
+    with fewer than three voxels per instance and shuffled voxel order; with `slabs` the search walks slabs of equal
+    first voxel index instead of scanning the whole instance (40 instances x 64 slabs overflow the bucket table and
+    take the full-scan fallback; 4000 voxels in one instance overflow the shared-memory staging)."""
     g = torch.Generator().manual_seed(sum(sizes) + b)
-    unknown = flat_bxyz(23, b, n_per, shuffle=False, scale=0.3).to(cuda_dev)
+    unknown = flat_bxyz(23, b, n_per, shuffle=False, scale=0.3)
+    # every fourth query sits exactly on a corner of the finest voxel grid: equidistant (up to rounding) from the
+    # eight surrounding centres, i.e. distance ties across slabs
+    corner = torch.randint(0, 65, (unknown.shape[0], 3), generator=g).float() * (0.6 / 64) - 0.3
+    unknown[::4, 1:] = corner[::4]
+    unknown = unknown.contiguous().to(cuda_dev)
     widths = (32, 64, 128, 256)[:len(sizes)]
     total = sum(widths)
     specs, col = [], 0
@@ -187,7 +195,7 @@ def test_nn_interpolate_levels_equals_per_level_calls(cuda_dev, b, n_per, sizes)
         feats = torch.randn(ind.shape[0], c, generator=g).to(cuda_dev)
         ext = [0.6 / side] * 3
         off = [-0.3] * 3
-        specs.append((ind, ext, off, feats, col))
+        specs.append((ind, ext, off, feats, col, side if slabs else 0))
         if ind.shape[0]:
             pu_sp.nn_interpolate_vox_pm(unknown, ind, ext, off, feats, pm_a, total, col)
         col += c
@@ -196,7 +204,8 @@ def test_nn_interpolate_levels_equals_per_level_calls(cuda_dev, b, n_per, sizes)
         # an empty level: every query gets (inf, 0) neighbours -> weights NaN -> skip that column range
         rows_a, rows_b = FT.pm_unpack(pm_a, b * n_per, total), FT.pm_unpack(pm_b, b * n_per, total)
         c0 = 0
-        for (ind, _, _, _, col0), c in zip(specs, widths):
+        for spec, c in zip(specs, widths):
+            ind, col0 = spec[0], spec[4]
             if ind.shape[0]:
                 # bitwise: instances with no voxel in a level produce NaN weights in both paths
                 assert torch.equal(rows_a[:, col0:col0 + c].contiguous().view(torch.int32),
