@@ -252,7 +252,8 @@ constexpr int SP_SLAB_CAP = 2048;
 constexpr int SP_SLAB_MAX_GX = 128;
 constexpr int SP_STILE_FLOATS = SP_SLAB_CAP * 4 > 2 * SP_SEG_TILE_FLOATS ? SP_SLAB_CAP * 4 : 2 * SP_SEG_TILE_FLOATS;
 
-__device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
+template <int LPQ_>
+__device__ __forceinline__ void sp_group_search_t(const int* __restrict__ ws, const float4* __restrict__ sorted,
                                                 const KnownRows& kr, int m, bool valid, float4 u,
                                                 int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3,
                                                 int gx = 0) {
@@ -262,7 +263,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         // Some batch id is not a small non-negative integer: buckets are unusable, scan everything
         // (float equality on the id, as the reference does).
         if (valid) {
-            for (int k = sub; k < m; k += LPQ) {
+            for (int k = sub; k < m; k += LPQ_) {
                 const float4 c = kr.get(k);
                 if (c.x != u.x) continue;
                 const float d = dcl_dist2(u.y, u.z, u.w, c.y, c.z, c.w);
@@ -302,7 +303,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
             if (bytes != 0) dcl_mbar_wait(&s_bar[0], 0);
             if (valid && bytes != 0) {
                 const float4* inst = reinterpret_cast<const float4*>(s_tile);
-                const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(LPQ - 1));
+                const unsigned gmask = ((1u << LPQ_) - 1u) << ((threadIdx.x & 31) & ~(LPQ_ - 1));
                 // squared distance to the plane of slab s; its centre coordinate is formed exactly as KnownRows::get does
                 auto slab_d2 = [&](int sidx) {
                     const float cx = __fadd_rn(__fadd_rn(__fmul_rn((float)sidx, kr.ext[0]), kr.off[0]), kr.half[0]);
@@ -322,7 +323,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
                     if (!(dmin <= __fmul_rn(bound, 1.000001f))) break;
                     const int sidx = take_lo ? lo-- : hi++;
                     const int sb = s_slab[sidx], se = s_slab[sidx + 1];
-                    for (int j = sb + sub; j < se; j += LPQ) {
+                    for (int j = sb + sub; j < se; j += LPQ_) {
                         const float4 c = inst[j];
                         const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
                         if (!(d > b3) && d < CUDART_INF_F)
@@ -332,7 +333,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
                         // the group's third-best distance is at most any of its lanes' third-best
                         float t = b3;
 #pragma unroll
-                        for (int o = LPQ / 2; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(gmask, t, o));
+                        for (int o = LPQ_ / 2; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(gmask, t, o));
                         bound = t;
                     }
                 }
@@ -347,7 +348,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
                 const float4* tile = reinterpret_cast<const float4*>(pipe.tile(t));
                 if (valid) {
 #pragma unroll 4
-                    for (int j = sub; j < cnt; j += LPQ) {
+                    for (int j = sub; j < cnt; j += LPQ_) {
                         const float4 c = tile[j];
                         const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
                         if (!(d > b3) && d < CUDART_INF_F)
@@ -359,7 +360,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         } else if (has_bucket) {
             const int beg = ws[WS_OFF + my_b * gxe], end = ws[WS_OFF + (my_b + 1) * gxe];
 #pragma unroll 8
-            for (int j = beg + sub; j < end; j += LPQ) {
+            for (int j = beg + sub; j < end; j += LPQ_) {
                 const float4 c = __ldg(sorted + j);
                 const float d = dcl_dist2(u.y, u.z, u.w, c.x, c.y, c.z);
                 // one compare rejects almost every candidate; ties (d == b3) and the first three go the slow way
@@ -368,7 +369,7 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
         }
     }
 #pragma unroll
-    for (int o = LPQ / 2; o > 0; o >>= 1) {
+    for (int o = LPQ_ / 2; o > 0; o >>= 1) {
         const float ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o),
                     ob3 = __shfl_xor_sync(0xffffffffu, b3, o);
         const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o),
@@ -381,6 +382,12 @@ __device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, cons
     if (i2 == 0x7fffffff) i2 = 0;
     if (i3 == 0x7fffffff) i3 = 0;
 }
+__device__ __forceinline__ void sp_group_search(const int* __restrict__ ws, const float4* __restrict__ sorted,
+                                                const KnownRows& kr, int m, bool valid, float4 u,
+                                                int sub, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+    sp_group_search_t<LPQ>(ws, sorted, kr, m, valid, u, sub, b1, b2, b3, i1, i2, i3, 0);
+}
+
 
 __global__ void __launch_bounds__(SP_THREADS) sp_three_nn_seg_kernel(int n, int m, const float* __restrict__ unknown,
                                                                      KnownRows kr,
@@ -773,12 +780,16 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
     }
 }
 
+// Lanes per query in the multi-level kernel: the slab walk leaves few candidates per query, so the per-query work
+// every lane of a group repeats (merge butterfly, interpolation weights) weighs more than the scan; four lanes
+// halve it against the eight of the whole-instance kernels.
+constexpr int SPL_LPQ = 4;
 __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int n, const float* __restrict__ unknown,
                                                                             const __grid_constant__ SpLevelBatch batch,
                                                                             unsigned char* __restrict__ out_pm,
                                                                             int c_total) {
-    const int qi = blockIdx.x * (SP_THREADS / LPQ) + threadIdx.x / LPQ;
-    const int sub = threadIdx.x % LPQ;
+    const int qi = blockIdx.x * (SP_THREADS / SPL_LPQ) + threadIdx.x / SPL_LPQ;
+    const int sub = threadIdx.x % SPL_LPQ;
     const bool valid = qi < n;
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     unsigned char* row_base =
@@ -788,7 +799,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int 
         if (lv.m == 0) continue;  // nothing to interpolate from (the reference would gather row 0 of an empty tensor)
         float b1, b2, b3;
         int j0, j1, j2;
-        sp_group_search(lv.ws, lv.sorted, lv.kr, lv.m, valid, u, sub, b1, b2, b3, j0, j1, j2, lv.gx);
+        sp_group_search_t<SPL_LPQ>(lv.ws, lv.sorted, lv.kr, lv.m, valid, u, sub, b1, b2, b3, j0, j1, j2, lv.gx);
         if (valid) {
             const int c = lv.c;
             const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
@@ -799,7 +810,7 @@ __global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int 
             const float4* f0 = reinterpret_cast<const float4*>(lv.feats + (size_t)j0 * c);
             const float4* f1 = reinterpret_cast<const float4*>(lv.feats + (size_t)j1 * c);
             const float4* f2 = reinterpret_cast<const float4*>(lv.feats + (size_t)j2 * c);
-            for (int c8 = sub; c8 < (c >> 3); c8 += LPQ) {
+            for (int c8 = sub; c8 < (c >> 3); c8 += SPL_LPQ) {
                 float o[8];
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -996,7 +1007,7 @@ DCL_API int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nle
     }
     cudaStream_t st = (cudaStream_t)stream;
     sp_bucket_build_cluster_kernel<<<dim3(SPB_CLUSTER, nlevels), SPB_THREADS, 0, st>>>(batch);
-    sp_nn_interp_levels_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / LPQ), SP_THREADS, 0, st>>>(
+    sp_nn_interp_levels_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / SPL_LPQ), SP_THREADS, 0, st>>>(
         n, unknown, batch, reinterpret_cast<unsigned char*>(out_pm), c_total);
     return dcl_launch_status(2);
 }
