@@ -35,6 +35,7 @@ SIGNATURES = {
     "dcl_fda_align_fwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_pack": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_fwd_packed": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_workspace_layout": (_I, [_I, _I, _I, _I, _I, _P]),
     "dcl_fda_fwd_packed_pm": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_attention_map": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
@@ -63,7 +64,8 @@ class PmGemmProblem(ctypes.Structure):
     """Mirror of dcl_pm_gemm_problem (include/dcl_b200.h)."""
     _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
-                ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P)]
+                ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P),
+                ("out_qk", _P), ("qk_tile_rows", _I), ("out_v", _P), ("v_row0", _I), ("v_rows", _I)]
 
 
 class SpLevel(ctypes.Structure):

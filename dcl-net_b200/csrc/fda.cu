@@ -80,7 +80,9 @@ struct FdaCfg {
 // Element (row, k) of an operand tile with `kchunks` 8-element chunks along K lives at
 //   (row/8)*kchunks*64 + (k/8)*64 + (row%8)*8 + (k%8)      [bf16 elements]
 // Q tile: rows = queries (128), K = channels.  K tile: rows = keys (64), K = channels.
-// V chunk: rows = value channels (VROWS), K = 16 keys.
+// V chunk (16 keys): MN-major for the P V product — 16-byte units of 8 value rows of one key at
+//   (vrow/8)*128 + ((key%16)/8)*64 + (key%8)*8 + (vrow%8)   [bf16 elements]
+// which is also what a point-major producer (one thread per key) writes with 16-byte stores (dcl_pm_gemm out_v).
 template <int C>
 __global__ void __launch_bounds__(256) fda_pack_kernel(int n, int m, const float* __restrict__ RI_1,
                                                        const float* __restrict__ RI_2,
@@ -111,23 +113,22 @@ __global__ void __launch_bounds__(256) fda_pack_kernel(int n, int m, const float
         *reinterpret_cast<uint4*>(dst + half) =
             make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
     } else {
-        // thread = (value row, key chunk of 8); row fastest so each group of 8 lanes writes 128 B
-        const int vrow = tid % Cfg::VROWS, kchunk = tid / Cfg::VROWS;
-        if (kchunk >= m / 8) return;
-        const float* src = (vrow < FDA_P) ? RE_2 + ((size_t)bs * FDA_P + vrow) * m
-                                          : RI_2 + ((size_t)bs * C + (vrow - FDA_P)) * m;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + kchunk * 8));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(src + kchunk * 8 + 4));
-        const float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        // thread = (key, chunk of 8 value rows); key fastest so the global reads (fixed value row) coalesce and each
+        // group of 8 lanes writes 128 contiguous bytes.  The value image is MN-major for the P V product: a 16-byte
+        // unit holds 8 value rows of ONE key.
+        const int key = tid % m, nchunk = tid / m;
+        if (nchunk >= Cfg::VROWS / 8) return;
         __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split_bf16(v[i], hi[i], lo[i]);
-        const int key0 = kchunk * 8;
-        const int chunk = key0 / KS;          // global V chunk index within the instance
-        const int kk8 = (key0 % KS) / 8;      // which of the two 8-key halves of the chunk
-        const size_t half = (size_t)Cfg::VROWS * KS;
-        __nv_bfloat16* dst = Vp + ((size_t)bs * (m / KS) + chunk) * 2 * half + (size_t)(vrow / 8) * 128 + kk8 * 64 +
-                             (vrow % 8) * 8;
+        for (int i = 0; i < 8; ++i) {
+            const int vrow = nchunk * 8 + i;
+            const float* src = (vrow < FDA_P) ? RE_2 + ((size_t)bs * FDA_P + vrow) * m
+                                              : RI_2 + ((size_t)bs * C + (vrow - FDA_P)) * m;
+            split_bf16(__ldg(src + key), hi[i], lo[i]);
+        }
+        const size_t half = (size_t)Cfg::VROWS * KS;  // elements in one hi (or lo) image
+        __nv_bfloat16* dst = Vp + ((size_t)bs * (m / KS) + key / KS) * 2 * half + (size_t)nchunk * 128 +
+                             ((key % KS) / 8) * 64 + (key % 8) * 8;
         *reinterpret_cast<uint4*>(dst) =
             make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
         *reinterpret_cast<uint4*>(dst + half) =
@@ -431,8 +432,8 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
         if (dcl_elect_one()) {
             long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KB);
-            constexpr uint32_t idesc_o1 = umma_idesc_bf16(QT, 256);
-            constexpr uint32_t idesc_o2 = umma_idesc_bf16(QT, C);
+            constexpr uint32_t idesc_o1 = umma_idesc_bf16(QT, 256, true);   // value image is MN-major
+            constexpr uint32_t idesc_o2 = umma_idesc_bf16(QT, C, true);
             const uint32_t tO = tmem_base;
             // Descriptors differ only in their 14-bit start-address field: build one per operand image and bump it.
             const uint64_t dQh = umma_desc(sQ, Cfg::QK_LBO, Cfg::QK_SBO);
@@ -660,8 +661,8 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m, 
             // ===================== MMA issuer (leader only) =====================
             long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(2 * QT, KB);
-            constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256);
-            constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C);
+            constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256, true);   // value image is MN-major
+            constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C, true);
             const uint32_t tO = tmem_base;
             const uint64_t dQh = umma_desc(sQ, Cfg::QK_LBO, Cfg::QK_SBO);
             const uint64_t dQl = dQh + (uint64_t)(Cfg::Q_HALF >> 4);
@@ -1007,7 +1008,7 @@ int fda_pack_launch(int b, int n, int m, const float* RI_1, const float* RI_2, c
                     cudaStream_t st) {
     using Cfg = FdaCfg<C>;
     FdaWs<C> w(workspace, b, n, m);
-    const int work_q = n * (C / 8), work_k = m * (C / 8), work_v = Cfg::VROWS * (m / 8);
+    const int work_q = n * (C / 8), work_k = m * (C / 8), work_v = m * (Cfg::VROWS / 8);
     int work = work_q > work_k ? work_q : work_k;
     if (work_v > work) work = work_v;
     dim3 grid(DCL_DIVUP(work, 256), b, 3);
@@ -1150,4 +1151,13 @@ DCL_API int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* 
 DCL_API int dcl_debug_fda_set_trace(long long* device_buffer) {
     cudaError_t e = cudaMemcpyToSymbol(g_fda_trace, &device_buffer, sizeof(device_buffer));
     return (int)e;
+}
+
+DCL_API int dcl_fda_workspace_layout(int b, int c, int p, int n, int m, size_t* offsets3) {
+    DCL_RETURN_IF_BAD(offsets3 != nullptr && fda_shape_ok(b, c, p, n, m));
+    const size_t q_bytes = (size_t)b * n * c * 4, k_bytes = (size_t)b * m * c * 4;
+    offsets3[0] = 0;
+    offsets3[1] = q_bytes;
+    offsets3[2] = q_bytes + k_bytes;
+    return 0;
 }

@@ -117,16 +117,52 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
                 dot = __fmaf_rn(y[q * 4 + 3], dw.w, dot);
             }
         }
-        if (pr.out_pm != nullptr) {
-            unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
-                                  ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
+        if (pr.out_pm != nullptr || pr.out_qk != nullptr || pr.out_v != nullptr) {
+            // bf16 hi / lo halves of the 32 values, as four 8-channel (16-byte) units each
+            uint4 hq[4], lq[4];
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t h[4], l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) split2_bf16(y[ch * 8 + 2 * e], y[ch * 8 + 2 * e + 1], h[e], l[e]);
-                *reinterpret_cast<uint4*>(blob + ch * 128) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) = make_uint4(l[0], l[1], l[2], l[3]);
+                hq[ch] = make_uint4(h[0], h[1], h[2], h[3]);
+                lq[ch] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            if (pr.out_pm != nullptr) {
+                unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
+                                      ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    *reinterpret_cast<uint4*>(blob + ch * 128) = hq[ch];
+                    *reinterpret_cast<uint4*>(blob + GM_A_BLOB / 2 + ch * 128) = lq[ch];
+                }
+            }
+            if (pr.out_qk != nullptr) {
+                // FDA query / key operand image (fda.cu): tiles of T rows x cout channels, hi image then lo image,
+                // element (r, c) at (r/8)*(cout/8)*128 + (c/8)*128 + (r%8)*16 + (c%8)*2 bytes
+                const int T = pr.qk_tile_rows;
+                const size_t half = (size_t)T * cout * 2;
+                const int rt = (int)(r_glob % T);
+                unsigned char* d = reinterpret_cast<unsigned char*>(pr.out_qk) + (r_glob / T) * 2 * half +
+                                   (size_t)(rt >> 3) * (cout / 8) * 128 + (rt & 7) * 16 + (col0 / 8) * 128;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    *reinterpret_cast<uint4*>(d + ch * 128) = hq[ch];
+                    *reinterpret_cast<uint4*>(d + half + ch * 128) = lq[ch];
+                }
+            }
+            if (pr.out_v != nullptr) {
+                // FDA value image (fda.cu): chunks of 16 keys x v_rows value channels, hi then lo; this row is a key,
+                // its columns are value channels v_row0 + col: 8 channels of one key = one 16-byte unit at
+                // (vrow/8)*256 + ((key%16)/8)*128 + (key%8)*16
+                const size_t vhalf = (size_t)pr.v_rows * 32;
+                unsigned char* d = reinterpret_cast<unsigned char*>(pr.out_v) + (r_glob >> 4) * 2 * vhalf +
+                                   (size_t)((pr.v_row0 + col0) >> 3) * 256 + ((r_glob >> 3) & 1) * 128 + (r_glob & 7) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    *reinterpret_cast<uint4*>(d + ch * 256) = hq[ch];
+                    *reinterpret_cast<uint4*>(d + vhalf + ch * 256) = lq[ch];
+                }
             }
         }
         if (pr.out_cm != nullptr) {
@@ -491,6 +527,10 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
         DCL_RETURN_IF_BAD(p.out_cm == nullptr || (p.rows_per_inst > 0 && p.rows_per_inst % 32 == 0 && rows % p.rows_per_inst == 0));
         DCL_RETURN_IF_BAD(p.pool_out == nullptr || p.pool_w != nullptr);
         DCL_RETURN_IF_BAD(p.dot_out == nullptr || (p.dot_w != nullptr && cout == nt));
+        DCL_RETURN_IF_BAD(p.out_qk == nullptr || ((p.qk_tile_rows == 64 || p.qk_tile_rows == 128) && cout % 8 == 0 &&
+                                                  ((uintptr_t)p.out_qk & 15u) == 0));
+        DCL_RETURN_IF_BAD(p.out_v == nullptr || (p.v_row0 >= 0 && p.v_row0 % 8 == 0 && p.v_rows >= p.v_row0 + cout &&
+                                                 p.v_rows % 8 == 0 && rows % 16 == 0 && ((uintptr_t)p.out_v & 15u) == 0));
         DCL_RETURN_IF_BAD(((((uintptr_t)p.a0) | ((uintptr_t)p.a1) | ((uintptr_t)p.w) | ((uintptr_t)p.out_pm)) & 15u) == 0);
         batch.p[i] = p;
     }

@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .modules import fda_align_formats
+from .modules import fda_from_workspace
 
 _EPS_NAMES = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
 
@@ -128,6 +128,11 @@ def layers_from_head(head):
     return gemm, rest
 
 
+def _addr(x):
+    """Device address of a tensor, or a raw integer address (a sub-range of a workspace), or None."""
+    return x if x is None or isinstance(x, int) else L.ptr(x)
+
+
 # bench.py sets this to a list to collect (start, end, algorithmic flops, tile width) around every dcl_pm_gemm launch.
 GEMM_EVENTS = None
 
@@ -150,6 +155,8 @@ def run_gemm(problems, rows):
         slot.rows_per_inst = p.get("rows_per_inst", 0)
         slot.pool_w, slot.pool_out = L.ptr(p.get("pool_w")), L.ptr(p.get("pool_out"))
         slot.dot_w, slot.dot_out = L.ptr(p.get("dot_w")), L.ptr(p.get("dot_out"))
+        slot.out_qk, slot.qk_tile_rows = _addr(p.get("out_qk")), p.get("qk_tile_rows", 0)
+        slot.out_v, slot.v_row0, slot.v_rows = _addr(p.get("out_v")), p.get("v_row0", 0), p.get("v_rows", 0)
         keep.append(p)
     if GEMM_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -211,22 +218,40 @@ class FusedTail:
         run_gemm([{"a0": pm_xc if name.startswith("Xc") else pm_yo, "layer": self.dis[name][0], "out_pm": h1[name]}
                   for name in _EPS_NAMES], rows)
 
-        # ---- disengage layer 2: outputs in the formats their consumers read
+        # ---- disengage layer 2: outputs in the formats their consumers read — point-major images for the MLPs, and
+        # the query / key / value operand images of the two FDA launches, written by the GEMM epilogue straight into
+        # the FDA workspaces (no channel-major fp32 round trip, no pack pass)
+        lib = L.load()
+        ws_bytes = lib.dcl_fda_workspace_bytes(b, c_m, 256, n, n)
+        offs = (ctypes.c_size_t * 3)()
+        L.check(lib.dcl_fda_workspace_layout(b, c_m, 256, n, n, ctypes.cast(offs, ctypes.c_void_p)), "fda layout")
+        ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]   # [Xc->Yo direction, Yo->Xc]
+        q = [w.data_ptr() + offs[0] for w in ws]
+        k = [w.data_ptr() + offs[1] for w in ws]
+        v = [w.data_ptr() + offs[2] for w in ws]
+        vrows = 256 + c_m
         pm_out = {name: pm_empty(rows, 256 if "_p" in name else c_m, dev) for name in ("Xc_p1", "Yo_p2", "Xc_m1", "Yo_m2")}
-        cm_out = {name: torch.empty(b, 256 if "_p" in name else c_m, n, **f32)
-                  for name in ("Xc_p2", "Yo_p1", "Xc_m1", "Xc_m2", "Yo_m1", "Yo_m2")}
+        fda_out = {
+            "Xc_p2": {"out_v": v[1], "v_row0": 0, "v_rows": vrows},
+            "Yo_p1": {"out_v": v[0], "v_row0": 0, "v_rows": vrows},
+            "Xc_m1": {"out_qk": q[0], "qk_tile_rows": 128},
+            "Yo_m2": {"out_qk": q[1], "qk_tile_rows": 128},
+            "Yo_m1": {"out_qk": k[0], "qk_tile_rows": 64, "out_v": v[0], "v_row0": 256, "v_rows": vrows},
+            "Xc_m2": {"out_qk": k[1], "qk_tile_rows": 64, "out_v": v[1], "v_row0": 256, "v_rows": vrows},
+        }
         for group in (("Xc_p1", "Xc_p2", "Yo_p1", "Yo_p2"), ("Xc_m1", "Xc_m2", "Yo_m1", "Yo_m2")):
-            run_gemm([{"a0": h1[name], "layer": self.dis[name][1], "out_pm": pm_out.get(name),
-                       "out_cm": cm_out.get(name), "rows_per_inst": n} for name in group], rows)
+            run_gemm([dict({"a0": h1[name], "layer": self.dis[name][1], "out_pm": pm_out.get(name)},
+                           **fda_out.get(name, {})) for name in group], rows)
         del h1
 
         # ---- dual FDA (both attention products of a direction in one fused kernel); the aligned features leave the
         # kernel as point-major images for the MLPs below, F_Xo_p also in the reference's layout (stage 2 reads it)
         dbg = self.keep_debug
-        F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _ = fda_align_formats(
-            cm_out["Xc_m1"], cm_out["Yo_m1"], cm_out["Yo_p1"], re_cm=True, ri_cm=dbg, re_pm=True, ri_pm=True)
-        F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _ = fda_align_formats(
-            cm_out["Yo_m2"], cm_out["Xc_m2"], cm_out["Xc_p2"], re_cm=dbg, ri_cm=dbg, re_pm=True, ri_pm=True)
+        F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _ = fda_from_workspace(
+            ws[0], b, c_m, n, n, re_cm=True, ri_cm=dbg, re_pm=True, ri_pm=True)
+        F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _ = fda_from_workspace(
+            ws[1], b, c_m, n, n, re_cm=dbg, ri_cm=dbg, re_pm=True, ri_pm=True)
+        del ws
 
         # ---- confidence heads: cat([F_Xc_m1, F_Xo_m]) / cat([F_Yc_m, F_Yo_m2]) -> 128 -> 128 -> 1
         c1 = [pm_empty(rows, 128, dev) for _ in range(2)]

@@ -96,20 +96,28 @@ def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_
         raise ValueError(f"fda_align: unsupported shape C={C} P={P} N={N} M={M} "
                          "(need C in {64,128}, P=256, N%128==0, M%64==0)")
     ws = _fda_workspace(nbytes, RI_1.device)
-    dev = RI_1.device
+    st = L.stream_ptr()
+    L.check(lib.dcl_fda_pack(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), st),
+            "fda_align (pack)")
+    return fda_from_workspace(ws, B, C, N, M, re_cm, ri_cm, re_pm, ri_pm, return_lse)
+
+
+def fda_from_workspace(ws, B, C, N, M, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False):
+    """The fused kernel on operand images that already sit in `ws` (written by dcl_fda_pack, or directly by the
+    disengage GEMMs' epilogue: fused_tail.py).  Same outputs as fda_align_formats."""
+    P = 256
+    lib = L.load()
+    dev = ws.device
     RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=dev) if re_cm else None
     RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=dev) if ri_cm else None
     RE_img = torch.empty(B * N * P * 4, dtype=torch.uint8, device=dev) if re_pm else None
     RI_img = torch.empty(B * N * C * 4, dtype=torch.uint8, device=dev) if ri_pm else None
     lse = torch.empty(B, N, dtype=torch.float32, device=dev) if return_lse else None
-    st = L.stream_ptr()
-    L.check(lib.dcl_fda_pack(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), st),
-            "fda_align (pack)")
     if FDA_KERNEL_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     L.check(lib.dcl_fda_fwd_packed_pm(B, C, P, N, M, L.ptr(RE_embed), L.ptr(RI_embed), L.ptr(RE_img), L.ptr(RI_img),
-                                      L.ptr(lse), L.ptr(ws), ws.numel(), st), "fda_align")
+                                      L.ptr(lse), L.ptr(ws), ws.numel(), L.stream_ptr()), "fda_align")
     if FDA_KERNEL_EVENTS is not None:
         ev1.record()
         FDA_KERNEL_EVENTS.append((ev0, ev1))

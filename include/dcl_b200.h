@@ -163,6 +163,13 @@ int dcl_fda_pack(int b, int c, int p, int n, int m,
 int dcl_fda_fwd_packed(int b, int c, int p, int n, int m,
     float* RE_embed, float* RI_embed, float* lse_out,
     void* workspace, size_t workspace_bytes, void* stream);
+/* Byte offsets of the query, key and value operand images inside the workspace (offsets[3]), for producers
+ * that write them directly (dcl_pm_gemm_problem.out_qk / out_v) instead of calling dcl_fda_pack:
+ *   query image: per 128 queries  [hi: 128 x c | lo], element (r,ch) at (r/8)*(c/8)*128 + (ch/8)*128 + (r%8)*16 + (ch%8)*2
+ *   key image:   per 64 keys      [hi:  64 x c | lo], same element map
+ *   value image: per 16 keys      [hi: (256+c) value rows x 16 keys | lo], element (vrow,key) at
+ *                (vrow/8)*256 + ((key%16)/8)*128 + (key%8)*16 + (vrow%8)*2      (bytes; all bf16, value = hi + lo) */
+int dcl_fda_workspace_layout(int b, int c, int p, int n, int m, size_t* offsets3);
 
 /* dcl_fda_fwd_packed with a choice of output formats: each of RE_embed / RI_embed goes out
  * as the reference's fp32 channel-major tensor (RE_embed, RI_embed), as a point-major
@@ -240,6 +247,15 @@ typedef struct dcl_pm_gemm_problem {
     float* pool_out;
     const float* dot_w;   /* [cout]; needs cout == nt */
     float* dot_out;       /* [R]: sum_o Y[r,o] * dot_w[o] — a trailing cout -> 1 layer without its bias */
+    /* Y written straight into the operand images of the fused FDA kernel (dcl_fda_workspace_layout), so the
+     * disengage layers feed the attention without the dcl_fda_pack pass: out_qk = query (qk_tile_rows 128) or
+     * key (64) image, Y being the whole RI tensor (cout == the FDA's c); out_v = value image, Y's columns
+     * becoming value rows [v_row0, v_row0 + cout) of v_rows (= 256 + c) — RE_2 at row 0, RI_2 at row 256. */
+    void* out_qk;
+    int qk_tile_rows;
+    void* out_v;
+    int v_row0;
+    int v_rows;
 } dcl_pm_gemm_problem;
 
 /* Up to 8 problems with equal (cout, nt) over the same number of rows in ONE launch (grid.z = problem). */

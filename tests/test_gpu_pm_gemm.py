@@ -78,6 +78,39 @@ def test_pm_gemm_layer(cuda_dev, rows, cin, cout, relu, post, split):
     assert rel_err(pooled, want_pool.view(rows // n_inst, n_inst // 32, cout).sum(1)) < 2e-5
 
 
+@pytest.mark.parametrize("b,n,c", [(2, 128, 64), (3, 256, 128)])
+def test_pm_gemm_writes_fda_operand_images(cuda_dev, b, n, c):
+    """The disengage GEMMs write the FDA query / key / value operand images themselves; byte for byte they must be
+    what dcl_fda_pack makes of the same layers' channel-major fp32 outputs."""
+    import ctypes
+    g = torch.Generator().manual_seed(b * n + c)
+    rows = b * n
+    x = torch.randn(rows, 256, generator=g).to(cuda_dev)
+    a0 = FT.pm_pack_rows(x)
+    lays = {name: FT.Layer((torch.randn(co, 256, generator=g) / 16).to(cuda_dev), torch.randn(co, generator=g).to(cuda_dev),
+                           True, None, None) for name, co in (("q", c), ("k", c), ("p", 256))}
+    lib = L.load()
+    nbytes = lib.dcl_fda_workspace_bytes(b, c, 256, n, n)
+    offs = (ctypes.c_size_t * 3)()
+    L.check(lib.dcl_fda_workspace_layout(b, c, 256, n, n, ctypes.cast(offs, ctypes.c_void_p)), "layout")
+    ws_direct = torch.zeros(nbytes, dtype=torch.uint8, device=cuda_dev)
+    ws_packed = torch.zeros(nbytes, dtype=torch.uint8, device=cuda_dev)
+    base = ws_direct.data_ptr()
+    cm = {name: torch.empty(b, lay.cout, n, device=cuda_dev) for name, lay in lays.items()}
+    FT.run_gemm([{"a0": a0, "layer": lays["q"], "out_cm": cm["q"], "rows_per_inst": n,
+                  "out_qk": base + offs[0], "qk_tile_rows": 128},
+                 {"a0": a0, "layer": lays["k"], "out_cm": cm["k"], "rows_per_inst": n,
+                  "out_qk": base + offs[1], "qk_tile_rows": 64, "out_v": base + offs[2], "v_row0": 256, "v_rows": 256 + c}],
+                rows)
+    FT.run_gemm([{"a0": a0, "layer": lays["p"], "out_cm": cm["p"], "rows_per_inst": n,
+                  "out_v": base + offs[2], "v_row0": 0, "v_rows": 256 + c}], rows)
+    L.check(lib.dcl_fda_pack(b, c, 256, n, n, L.ptr(cm["q"]), L.ptr(cm["k"]), L.ptr(cm["p"]), L.ptr(ws_packed),
+                             ws_packed.numel(), L.stream_ptr()), "pack")
+    torch.cuda.synchronize()
+    used = offs[2] + b * n * (256 + c) * 4
+    assert torch.equal(ws_direct[:used], ws_packed[:used])
+
+
 def test_pm_gemm_batched_problems(cuda_dev):
     """Several problems (different inputs and weights) in one launch."""
     g = torch.Generator().manual_seed(3)
