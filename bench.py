@@ -253,7 +253,8 @@ def run_b200_arm(args, rank, world, local_rank):
         ms_eager = max_over_ranks(ev0.elapsed_time(ev1))
         launches = lib.dcl_b200_launch_count() - launches0
         fda_events, modules.FDA_KERNEL_EVENTS = modules.FDA_KERNEL_EVENTS, None
-        fda_ms = [a.elapsed_time(bb) for a, bb in fda_events]
+        fda_ms = [a.elapsed_time(bb) for a, bb, _ in fda_events]
+        fda_jobs_per_launch = max([nj for _, _, nj in fda_events] or [1])
         gemm_events, fused_tail.GEMM_EVENTS = fused_tail.GEMM_EVENTS, None
         gemm = [(a.elapsed_time(bb), fl) for a, bb, fl, nt in gemm_events if nt == 256]   # the 256-wide-tile kernel
         # ---- timed region 1: device-resident, the step replayed as a CUDA graph (same kernels, one launch)
@@ -317,7 +318,7 @@ def run_b200_arm(args, rank, world, local_rank):
                 "share_of_step": gemm_ms / ms_eager if gemm else None,
                 "timed_in": "eager pass of the same K steps (the graph-replayed pass launches the identical kernels)",
                 "note": split_note}
-    flops_per_launch = b * 2.0 * N_PTS * N_PTS * (args.c_m + P_DIM + args.c_m)
+    flops_per_launch = fda_jobs_per_launch * b * 2.0 * N_PTS * N_PTS * (args.c_m + P_DIM + args.c_m)
     fda_avg_ms = statistics.mean(fda_ms) if fda_ms else float("nan")
     fda_achieved = flops_per_launch / (fda_avg_ms * 1e-3) / 1e12
     fda_kernel = ("fda_pair_kernel" if (N_PTS // 128) % 2 == 0 and not os.environ.get("DCL_FDA_SINGLE")
@@ -326,6 +327,7 @@ def run_b200_arm(args, rank, world, local_rank):
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": fda_achieved / peak_tf,
                     "executed_frac": 3 * fda_achieved / peak_tf, "avg_launch_ms": fda_avg_ms,
                     "launches_timed": len(fda_ms), "algorithmic_flops_per_launch": flops_per_launch,
+                    "directions_per_launch": fda_jobs_per_launch,
                     "share_of_step": (sum(fda_ms) / ms_eager) if fda_ms else None}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

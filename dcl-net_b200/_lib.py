@@ -35,6 +35,7 @@ SIGNATURES = {
     "dcl_fda_align_fwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_pack": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_fwd_packed": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_fda_fwd_packed_jobs": (_I, [_I, _P, _I, _I, _I, _I, _I, _SZ, _P]),
     "dcl_fda_workspace_layout": (_I, [_I, _I, _I, _I, _I, _P]),
     "dcl_fda_fwd_packed_pm": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_fda_attention_map": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "dcl_conf_weights": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcl_sp_levels_workspace_bytes": (_SZ, [_I, _P]),
+    "dcl_sp_nn_interpolate_towers_pm": (_I, [_I, _P, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_levels_pm": (_I, [_I, _P, _I, _P, _P, _I, _P, _SZ, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
@@ -68,10 +70,20 @@ class PmGemmProblem(ctypes.Structure):
                 ("out_qk", _P), ("qk_tile_rows", _I), ("out_v", _P), ("v_row0", _I), ("v_rows", _I)]
 
 
+class FdaJob(ctypes.Structure):
+    """Mirror of dcl_fda_job (include/dcl_b200.h)."""
+    _fields_ = [("workspace", _P), ("RE_embed", _P), ("RI_embed", _P), ("RE_pm", _P), ("RI_pm", _P), ("lse", _P)]
+
+
 class SpLevel(ctypes.Structure):
     """Mirror of dcl_sp_level (include/dcl_b200.h)."""
     _fields_ = [("m", _I), ("c", _I), ("out_col0", _I), ("grid_x", _I), ("vox_indices", _P), ("voxel_extent", ctypes.c_float * 3),
                 ("offset", ctypes.c_float * 3), ("feats", _P)]
+
+
+class SpTower(ctypes.Structure):
+    """Mirror of dcl_sp_tower (include/dcl_b200.h)."""
+    _fields_ = [("n", _I), ("c_total", _I), ("nlevels", _I), ("unknown", _P), ("out_pm", _P), ("levels", _P)]
 
 
 class PoseHeadMlp(ctypes.Structure):

@@ -150,8 +150,9 @@ __device__ __forceinline__ long long fda_globaltimer() {
 __device__ __forceinline__ long long* fda_life_slot() {
     long long* g = g_fda_trace;
     if (g == nullptr) return nullptr;
-    if (blockIdx.x == 0 && blockIdx.y == 0) return g + 3 * 1024;
-    if (blockIdx.x == ((gridDim.x - 1) & ~1u) && blockIdx.y == gridDim.y - 1) return g + 3 * 1024 + 8;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) return g + 3 * 1024;
+    if (blockIdx.x == ((gridDim.x - 1) & ~1u) && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1)
+        return g + 3 * 1024 + 8;
     return nullptr;
 }
 __device__ __forceinline__ void fda_life(long long* slot, int ev) {
@@ -170,6 +171,17 @@ struct FdaOut {
     unsigned char* re_pm;
     unsigned char* ri_pm;
     float* lse;
+};
+
+// One launch can serve several independent problems of equal shape (grid.z = job): the two directions of the dual
+// FDA of models/DCL_Net.py:206-215 then share their partial last waves.
+constexpr int FDA_MAX_JOBS = 2;
+struct FdaJob {
+    const __nv_bfloat16 *Qp, *Kp, *Vp;
+    FdaOut out;
+};
+struct FdaJobs {
+    FdaJob j[FDA_MAX_JOBS];
 };
 
 // ------------------------------------------------------------------ softmax / correction / epilogue warps
@@ -196,7 +208,7 @@ __device__ __forceinline__ void fda_softmax_warps(unsigned char* smem, uint32_t 
     constexpr int C = Cfg::VROWS - FDA_P;
     constexpr int HK = KB / 2;                   // keys per thread and block
     constexpr int OC = Cfg::VROWS / 32;          // 32-column chunks of O
-    long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) ? g_fda_trace : nullptr;
+    long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0) ? g_fda_trace : nullptr;
     long long* life = (warp == 2 && lane == 0) ? fda_life_slot() : nullptr;
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -337,11 +349,12 @@ __device__ __forceinline__ void fda_softmax_warps(unsigned char* smem, uint32_t 
 
 // ------------------------------------------------------------------ main kernel
 template <int C>
-__global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, const __nv_bfloat16* __restrict__ Qp,
-                                                                 const __nv_bfloat16* __restrict__ Kp,
-                                                                 const __nv_bfloat16* __restrict__ Vp,
-                                                                 const FdaOut out) {
+__global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m,
+                                                                 const __grid_constant__ FdaJobs jobs) {
     using Cfg = FdaCfg<C>;
+    const FdaJob& job = jobs.j[blockIdx.z];
+    const __nv_bfloat16 *Qp = job.Qp, *Kp = job.Kp, *Vp = job.Vp;
+    const FdaOut& out = job.out;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -398,7 +411,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
             const unsigned char* gK = reinterpret_cast<const unsigned char*>(Kp) + (size_t)bs * NB * Cfg::K_BYTES;
             const unsigned char* gV =
                 reinterpret_cast<const unsigned char*>(Vp) + (size_t)bs * (m / KS) * Cfg::V_BYTES;
-            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fda_trace : nullptr;
             dcl_mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
             dcl_bulk_g2s(smem + Cfg::OFF_Q, gQ, Cfg::Q_BYTES, q_full);
             auto load_k = [&](int j) {
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m, c
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (dcl_elect_one()) {
-            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KB);
             constexpr uint32_t idesc_o1 = umma_idesc_bf16(QT, 256, true);   // value image is MN-major
             constexpr uint32_t idesc_o2 = umma_idesc_bf16(QT, C, true);
@@ -554,11 +567,12 @@ struct FdaPairCfg {
 };
 
 template <int C>
-__global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m, const __nv_bfloat16* __restrict__ Qp,
-                                                                  const __nv_bfloat16* __restrict__ Kp,
-                                                                  const __nv_bfloat16* __restrict__ Vp,
-                                                                  const FdaOut out) {
+__global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m,
+                                                                  const __grid_constant__ FdaJobs jobs) {
     using Cfg = FdaPairCfg<C>;
+    const FdaJob& job = jobs.j[blockIdx.z];
+    const __nv_bfloat16 *Qp = job.Qp, *Kp = job.Kp, *Vp = job.Vp;
+    const FdaOut& out = job.out;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -623,7 +637,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m, 
             const unsigned char* gVa = gV + (size_t)rank * Cfg::V_PART_A;                       // rows [128r, +128)
             const unsigned char* gVb = gV + (size_t)(256 + rank * (C / 2)) * (KS * 2);           // rows [256 + rC/2, ..)
             constexpr uint32_t V_PART_B = Cfg::V_HALF - Cfg::V_PART_A;
-            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            long long* trp = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fda_trace : nullptr;
             dcl_mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
             dcl_bulk_g2s(smem + Cfg::OFF_Q, gQ, Cfg::Q_BYTES, q_full);
             auto load_k = [&](int j) {
@@ -659,7 +673,7 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m, 
     } else if (warp == 1) {
         if (leader && dcl_elect_one()) {
             // ===================== MMA issuer (leader only) =====================
-            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0) ? g_fda_trace : nullptr;
+            long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(2 * QT, KB);
             constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256, true);   // value image is MN-major
             constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C, true);
@@ -1017,27 +1031,41 @@ int fda_pack_launch(int b, int n, int m, const float* RI_1, const float* RI_2, c
 }
 
 template <int C>
-int fda_main_launch(int b, int n, int m, const FdaOut& out, void* workspace, cudaStream_t st) {
+FdaJobs fda_jobs(int njobs, const dcl_fda_job* in, int b, int n, int m) {
+    FdaJobs jobs = {};
+    for (int i = 0; i < njobs; ++i) {
+        FdaWs<C> w(in[i].workspace, b, n, m);
+        jobs.j[i].Qp = w.Qp;
+        jobs.j[i].Kp = w.Kp;
+        jobs.j[i].Vp = w.Vp;
+        jobs.j[i].out = {in[i].RE_embed, in[i].RI_embed, reinterpret_cast<unsigned char*>(in[i].RE_pm),
+                         reinterpret_cast<unsigned char*>(in[i].RI_pm), in[i].lse};
+    }
+    return jobs;
+}
+
+template <int C>
+int fda_main_launch(int njobs, const dcl_fda_job* in, int b, int n, int m, cudaStream_t st) {
     using Cfg = FdaCfg<C>;
-    FdaWs<C> w(workspace, b, n, m);
+    const FdaJobs jobs = fda_jobs<C>(njobs, in, b, n, m);
     cudaError_t e = cudaFuncSetAttribute(fda_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid(n / QT, b);
-    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, w.Qp, w.Kp, w.Vp, out);
+    dim3 grid(n / QT, b, njobs);
+    fda_fwd_kernel<C><<<grid, FDA_THREADS, Cfg::SMEM_BYTES, st>>>(n, m, jobs);
     return dcl_launch_status();
 }
 
 // CTA-pair variant: needs an even number of query tiles per instance.
 template <int C>
-int fda_pair_launch(int b, int n, int m, const FdaOut& out, void* workspace, cudaStream_t st) {
+int fda_pair_launch(int njobs, const dcl_fda_job* in, int b, int n, int m, cudaStream_t st) {
     using Cfg = FdaPairCfg<C>;
-    FdaWs<C> w(workspace, b, n, m);
+    const FdaJobs jobs = fda_jobs<C>(njobs, in, b, n, m);
     cudaError_t e = cudaFuncSetAttribute(fda_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n / QT, b);
+    cfg.gridDim = dim3(n / QT, b, njobs);
     cfg.blockDim = dim3(FDA_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
@@ -1048,8 +1076,7 @@ int fda_pair_launch(int b, int n, int m, const FdaOut& out, void* workspace, cud
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const __nv_bfloat16 *q = w.Qp, *k = w.Kp, *v = w.Vp;
-    e = cudaLaunchKernelEx(&cfg, fda_pair_kernel<C>, n, m, q, k, v, out);
+    e = cudaLaunchKernelEx(&cfg, fda_pair_kernel<C>, n, m, jobs);
     if (e != cudaSuccess) return (int)e;
     return dcl_launch_status();
 }
@@ -1083,23 +1110,29 @@ DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, c
     return fda_pack_launch<128>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
 }
 
-DCL_API int dcl_fda_fwd_packed_pm(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, void* RE_pm,
-                                  void* RI_pm, float* lse_out, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
-    DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
-    DCL_RETURN_IF_BAD((((uintptr_t)RE_pm) & 15u) == 0 && (((uintptr_t)RI_pm) & 15u) == 0);
-    const FdaOut out = {RE_embed, RI_embed, reinterpret_cast<unsigned char*>(RE_pm),
-                        reinterpret_cast<unsigned char*>(RI_pm), lse_out};
-    DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 127u) == 0);
+DCL_API int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
+                                    size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(njobs >= 1 && njobs <= FDA_MAX_JOBS && jobs != nullptr && fda_shape_ok(b, c, p, n, m));
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
+    for (int i = 0; i < njobs; ++i) {
+        DCL_RETURN_IF_BAD(jobs[i].workspace != nullptr && (((uintptr_t)jobs[i].workspace) & 127u) == 0);
+        DCL_RETURN_IF_BAD((((uintptr_t)jobs[i].RE_pm) & 15u) == 0 && (((uintptr_t)jobs[i].RI_pm) & 15u) == 0);
+    }
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (fda_use_pair(n)) {
-        if (c == 64) return fda_pair_launch<64>(b, n, m, out, workspace, st);
-        return fda_pair_launch<128>(b, n, m, out, workspace, st);
+        if (c == 64) return fda_pair_launch<64>(njobs, jobs, b, n, m, st);
+        return fda_pair_launch<128>(njobs, jobs, b, n, m, st);
     }
-    if (c == 64) return fda_main_launch<64>(b, n, m, out, workspace, st);
-    return fda_main_launch<128>(b, n, m, out, workspace, st);
+    if (c == 64) return fda_main_launch<64>(njobs, jobs, b, n, m, st);
+    return fda_main_launch<128>(njobs, jobs, b, n, m, st);
+}
+
+DCL_API int dcl_fda_fwd_packed_pm(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, void* RE_pm,
+                                  void* RI_pm, float* lse_out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    const dcl_fda_job job = {workspace, RE_embed, RI_embed, RE_pm, RI_pm, lse_out};
+    return dcl_fda_fwd_packed_jobs(1, &job, b, c, p, n, m, workspace_bytes, stream);
 }
 
 DCL_API int dcl_fda_fwd_packed(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, float* lse_out,

@@ -617,8 +617,15 @@ struct SpLevelDev {
     float4* sorted;
     const float* feats;
 };
+constexpr int SPL_MAX_TOWERS = 2;
+struct SpTowerDev {  // one set of query points and the pyramid levels [lv0, lv1) it interpolates from
+    int n, c_total, lv0, lv1;
+    const float* unknown;
+    unsigned char* out_pm;
+};
 struct SpLevelBatch {
-    int nlevels;
+    int nlevels, ntowers;
+    SpTowerDev tw[SPL_MAX_TOWERS];
     SpLevelDev lv[SPL_MAX_LEVELS];
 };
 
@@ -784,17 +791,21 @@ __global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREAD
 // every lane of a group repeats (merge butterfly, interpolation weights) weighs more than the scan; four lanes
 // halve it against the eight of the whole-instance kernels.
 constexpr int SPL_LPQ = 4;
-__global__ void __launch_bounds__(SP_THREADS) sp_nn_interp_levels_pm_kernel(int n, const float* __restrict__ unknown,
-                                                                            const __grid_constant__ SpLevelBatch batch,
-                                                                            unsigned char* __restrict__ out_pm,
-                                                                            int c_total) {
+__global__ void __launch_bounds__(SP_THREADS)
+    sp_nn_interp_levels_pm_kernel(const __grid_constant__ SpLevelBatch batch) {
+    // grid = (query groups, towers)
+    const SpTowerDev& tw = batch.tw[blockIdx.y];
+    const int n = tw.n, c_total = tw.c_total;
+    if (blockIdx.x * (SP_THREADS / SPL_LPQ) >= n) return;
+    const float* __restrict__ unknown = tw.unknown;
+    unsigned char* __restrict__ out_pm = tw.out_pm;
     const int qi = blockIdx.x * (SP_THREADS / SPL_LPQ) + threadIdx.x / SPL_LPQ;
     const int sub = threadIdx.x % SPL_LPQ;
     const bool valid = qi < n;
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
     unsigned char* row_base =
         out_pm + (size_t)(qi / 128) * (c_total / 32) * 16384 + ((qi % 128) >> 3) * 512 + (qi & 7) * 16;
-    for (int li = 0; li < batch.nlevels; ++li) {
+    for (int li = tw.lv0; li < tw.lv1; ++li) {
         const SpLevelDev& lv = batch.lv[li];
         if (lv.m == 0) continue;  // nothing to interpolate from (the reference would gather row 0 of an empty tensor)
         float b1, b2, b3;
@@ -977,37 +988,60 @@ DCL_API size_t dcl_sp_levels_workspace_bytes(int nlevels, const dcl_sp_level* le
     return total;
 }
 
+DCL_API int dcl_sp_nn_interpolate_towers_pm(int ntowers, const dcl_sp_tower* towers, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    DCL_RETURN_IF_BAD(ntowers >= 1 && ntowers <= SPL_MAX_TOWERS && towers != nullptr && workspace != nullptr);
+    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0);
+    SpLevelBatch batch = {};
+    batch.ntowers = ntowers;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    size_t need = 0;
+    int nmax = 0, li = 0;
+    for (int t = 0; t < ntowers; ++t) {
+        const dcl_sp_tower& tin = towers[t];
+        DCL_RETURN_IF_BAD(tin.n > 0 && tin.n % 128 == 0 && tin.nlevels >= 1 && tin.levels != nullptr &&
+                          li + tin.nlevels <= SPL_MAX_LEVELS);
+        DCL_RETURN_IF_BAD(tin.c_total % 32 == 0 && tin.out_pm != nullptr && tin.unknown != nullptr);
+        DCL_RETURN_IF_BAD(((uintptr_t)tin.unknown & 15u) == 0 && ((uintptr_t)tin.out_pm & 15u) == 0);
+        SpTowerDev& tw = batch.tw[t];
+        tw.n = tin.n;
+        tw.c_total = tin.c_total;
+        tw.unknown = tin.unknown;
+        tw.out_pm = reinterpret_cast<unsigned char*>(tin.out_pm);
+        tw.lv0 = li;
+        for (int i = 0; i < tin.nlevels; ++i, ++li) {
+            const dcl_sp_level& in = tin.levels[i];
+            DCL_RETURN_IF_BAD(in.m >= 0 && in.c > 0 && in.c % 8 == 0 && in.out_col0 >= 0 && in.out_col0 % 8 == 0 &&
+                              tin.c_total >= in.out_col0 + in.c);
+            DCL_RETURN_IF_BAD(in.m == 0 || (in.vox_indices != nullptr && in.feats != nullptr));
+            DCL_RETURN_IF_BAD(((uintptr_t)in.vox_indices & 15u) == 0 && ((uintptr_t)in.feats & 15u) == 0);
+            need += sp_level_ws_bytes(in.m);
+            DCL_RETURN_IF_BAD(need <= workspace_bytes);
+            SpLevelDev& lv = batch.lv[li];
+            lv.m = in.m;
+            lv.c = in.c;
+            lv.out_col0 = in.out_col0;
+            lv.gx = (in.grid_x > 0 && in.grid_x <= SP_SLAB_MAX_GX) ? in.grid_x : 0;
+            lv.kr = rows_from_voxels(in.vox_indices, in.voxel_extent, in.offset);
+            lv.ws = reinterpret_cast<int*>(w);
+            lv.sorted = reinterpret_cast<float4*>(w + (size_t)SPL_HDR_INTS * sizeof(int));
+            lv.feats = in.feats;
+            w += sp_level_ws_bytes(in.m);
+        }
+        tw.lv1 = li;
+        nmax = tin.n > nmax ? tin.n : nmax;
+    }
+    batch.nlevels = li;
+    cudaStream_t st = (cudaStream_t)stream;
+    sp_bucket_build_cluster_kernel<<<dim3(SPB_CLUSTER, batch.nlevels), SPB_THREADS, 0, st>>>(batch);
+    sp_nn_interp_levels_pm_kernel<<<dim3(DCL_DIVUP(nmax, SP_THREADS / SPL_LPQ), ntowers), SP_THREADS, 0, st>>>(batch);
+    return dcl_launch_status(2);
+}
+
 DCL_API int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nlevels, const dcl_sp_level* levels,
                                             void* out_pm, int c_total, void* workspace, size_t workspace_bytes,
                                             void* stream) {
-    DCL_RETURN_IF_BAD(n > 0 && n % 128 == 0 && nlevels >= 1 && nlevels <= SPL_MAX_LEVELS && levels != nullptr);
-    DCL_RETURN_IF_BAD(c_total % 32 == 0 && workspace != nullptr && out_pm != nullptr);
-    DCL_RETURN_IF_BAD(((uintptr_t)workspace & 15u) == 0 && ((uintptr_t)unknown & 15u) == 0 &&
-                      ((uintptr_t)out_pm & 15u) == 0);
-    DCL_RETURN_IF_BAD(workspace_bytes >= dcl_sp_levels_workspace_bytes(nlevels, levels));
-    SpLevelBatch batch = {};
-    batch.nlevels = nlevels;
-    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
-    for (int i = 0; i < nlevels; ++i) {
-        const dcl_sp_level& in = levels[i];
-        DCL_RETURN_IF_BAD(in.m >= 0 && in.c > 0 && in.c % 8 == 0 && in.out_col0 >= 0 && in.out_col0 % 8 == 0 &&
-                          c_total >= in.out_col0 + in.c);
-        DCL_RETURN_IF_BAD(in.m == 0 || (in.vox_indices != nullptr && in.feats != nullptr));
-        DCL_RETURN_IF_BAD(((uintptr_t)in.vox_indices & 15u) == 0 && ((uintptr_t)in.feats & 15u) == 0);
-        SpLevelDev& lv = batch.lv[i];
-        lv.m = in.m;
-        lv.c = in.c;
-        lv.out_col0 = in.out_col0;
-        lv.gx = (in.grid_x > 0 && in.grid_x <= SP_SLAB_MAX_GX) ? in.grid_x : 0;
-        lv.kr = rows_from_voxels(in.vox_indices, in.voxel_extent, in.offset);
-        lv.ws = reinterpret_cast<int*>(w);
-        lv.sorted = reinterpret_cast<float4*>(w + (size_t)SPL_HDR_INTS * sizeof(int));
-        lv.feats = in.feats;
-        w += sp_level_ws_bytes(in.m);
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    sp_bucket_build_cluster_kernel<<<dim3(SPB_CLUSTER, nlevels), SPB_THREADS, 0, st>>>(batch);
-    sp_nn_interp_levels_pm_kernel<<<DCL_DIVUP(n, SP_THREADS / SPL_LPQ), SP_THREADS, 0, st>>>(
-        n, unknown, batch, reinterpret_cast<unsigned char*>(out_pm), c_total);
-    return dcl_launch_status(2);
+    DCL_RETURN_IF_BAD(nlevels >= 1 && nlevels <= SPL_MAX_LEVELS && levels != nullptr);
+    const dcl_sp_tower tower = {n, c_total, nlevels, unknown, out_pm, levels};
+    return dcl_sp_nn_interpolate_towers_pm(1, &tower, workspace, workspace_bytes, stream);
 }

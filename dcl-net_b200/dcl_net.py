@@ -173,8 +173,8 @@ class Network(nn.Module):
         ids_tmp = torch.arange(b, device=dev).repeat_interleave(points_tmp.shape[0] // b)
         fused = self._fused(b)
         if fused is not None:
-            pm_xc = self.stage1_get_point_feats.forward_pm(points_inp, ids_inp, *levels_inp)
-            pm_yo = self.stage1_get_point_feats.forward_pm(points_tmp, ids_tmp, *levels_tmp)
+            pm_xc, pm_yo = self.stage1_get_point_feats.forward_pm_pair(points_inp, ids_inp, levels_inp,
+                                                                        points_tmp, ids_tmp, levels_tmp)
             return fused.forward(pm_xc, pm_yo, b)
         F_Xc = self.stage1_get_point_feats(points_inp, ids_inp, *levels_inp)
         F_Yo = self.stage1_get_point_feats(points_tmp, ids_tmp, *levels_tmp)

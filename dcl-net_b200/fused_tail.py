@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .modules import fda_from_workspace
+from .modules import fda_from_workspaces
 
 _EPS_NAMES = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
 
@@ -244,13 +244,12 @@ class FusedTail:
                            **fda_out.get(name, {})) for name in group], rows)
         del h1
 
-        # ---- dual FDA (both attention products of a direction in one fused kernel); the aligned features leave the
+        # ---- dual FDA: both directions in ONE launch (both attention products of a direction in one pass over the
+        # keys); the aligned features leave the
         # kernel as point-major images for the MLPs below, F_Xo_p also in the reference's layout (stage 2 reads it)
         dbg = self.keep_debug
-        F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _ = fda_from_workspace(
-            ws[0], b, c_m, n, n, re_cm=True, ri_cm=dbg, re_pm=True, ri_pm=True)
-        F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _ = fda_from_workspace(
-            ws[1], b, c_m, n, n, re_cm=dbg, ri_cm=dbg, re_pm=True, ri_pm=True)
+        (F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _), (F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _) = fda_from_workspaces(
+            [(ws[0], True, dbg, True, True, False), (ws[1], dbg, dbg, True, True, False)], b, c_m, n, n)
         del ws
 
         # ---- confidence heads: cat([F_Xc_m1, F_Xo_m]) / cat([F_Yc_m, F_Yo_m2]) -> 128 -> 128 -> 1

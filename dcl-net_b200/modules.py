@@ -105,23 +105,37 @@ def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_
 def fda_from_workspace(ws, B, C, N, M, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False):
     """The fused kernel on operand images that already sit in `ws` (written by dcl_fda_pack, or directly by the
     disengage GEMMs' epilogue: fused_tail.py).  Same outputs as fda_align_formats."""
+    return fda_from_workspaces([(ws, re_cm, ri_cm, re_pm, ri_pm, return_lse)], B, C, N, M)[0]
+
+
+def fda_from_workspaces(jobs, B, C, N, M):
+    """Up to two independent FDA problems of equal shape in ONE launch (the two directions of the dual FDA share
+    their partial last waves).  jobs: [(workspace, re_cm, ri_cm, re_pm, ri_pm, return_lse)]; returns one
+    (RE_cm, RI_cm, RE_pm, RI_pm, lse) tuple per job."""
+    import ctypes
     P = 256
     lib = L.load()
-    dev = ws.device
-    RE_embed = torch.empty(B, P, N, dtype=torch.float32, device=dev) if re_cm else None
-    RI_embed = torch.empty(B, C, N, dtype=torch.float32, device=dev) if ri_cm else None
-    RE_img = torch.empty(B * N * P * 4, dtype=torch.uint8, device=dev) if re_pm else None
-    RI_img = torch.empty(B * N * C * 4, dtype=torch.uint8, device=dev) if ri_pm else None
-    lse = torch.empty(B, N, dtype=torch.float32, device=dev) if return_lse else None
+    dev = jobs[0][0].device
+    f32, u8 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.uint8, device=dev)
+    arr = (L.FdaJob * len(jobs))()
+    results = []
+    for slot, (ws, re_cm, ri_cm, re_pm, ri_pm, want_lse) in zip(arr, jobs):
+        out = (torch.empty(B, P, N, **f32) if re_cm else None, torch.empty(B, C, N, **f32) if ri_cm else None,
+               torch.empty(B * N * P * 4, **u8) if re_pm else None, torch.empty(B * N * C * 4, **u8) if ri_pm else None,
+               torch.empty(B, N, **f32) if want_lse else None)
+        slot.workspace = L.ptr(ws)
+        slot.RE_embed, slot.RI_embed, slot.RE_pm, slot.RI_pm, slot.lse = (L.ptr(x) for x in out)
+        results.append(out)
+    nbytes = min(j[0].numel() for j in jobs)
     if FDA_KERNEL_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.check(lib.dcl_fda_fwd_packed_pm(B, C, P, N, M, L.ptr(RE_embed), L.ptr(RI_embed), L.ptr(RE_img), L.ptr(RI_img),
-                                      L.ptr(lse), L.ptr(ws), ws.numel(), L.stream_ptr()), "fda_align")
+    L.check(lib.dcl_fda_fwd_packed_jobs(len(jobs), ctypes.cast(arr, ctypes.c_void_p), B, C, P, N, M, nbytes,
+                                        L.stream_ptr()), "fda_align")
     if FDA_KERNEL_EVENTS is not None:
         ev1.record()
-        FDA_KERNEL_EVENTS.append((ev0, ev1))
-    return RE_embed, RI_embed, RE_img, RI_img, lse
+        FDA_KERNEL_EVENTS.append((ev0, ev1, len(jobs)))
+    return results
 
 
 def fda_attention_map(RI_1, RI_2, lse):
@@ -225,16 +239,12 @@ class Ops_GetPointFeat_spconv(nn.Module):
         self.voxel_num_limit = np.asarray(voxel_num_limit)
         self.offset = -0.5 * self.unit_voxel_extent * self.voxel_num_limit
 
-    def forward_pm(self, points, batch_ids, feats1, feats2, feats3, feats4):
-        """Inference only: the concatenated (n, 480) point features as a PM image (operand of the tensor-core
-        disengage GEMMs) instead of an fp32 matrix."""
+    def _pm_tower(self, points, batch_ids, levels):
         points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()
-        levels = [feats1, feats2, feats3, feats4]
         width = sum(f.features.shape[1] for f in levels)
         out = torch.empty(points.shape[0] * width * 4, dtype=torch.uint8, device=points.device)
         # Ops_tensor2points is fused into the kernels: they take the int voxel indices and form the centres
-        # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.  All four levels go in one call
-        # (one bucket-build launch, one search + interpolation launch).
+        # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.
         off = torch.as_tensor(np.asarray(self.offset), dtype=torch.float32).tolist()
         specs, col = [], 0
         for scale, feats in zip(self.scale_lists, levels):
@@ -242,8 +252,21 @@ class Ops_GetPointFeat_spconv(nn.Module):
             grid_x = int(np.ceil(self.voxel_num_limit[0] / scale))   # voxel indices of this level lie in [0, grid_x)
             specs.append((feats.indices.contiguous(), ext, off, feats.features.contiguous(), col, grid_x))
             col += feats.features.shape[1]
-        pointnet2_utils_sp.nn_interpolate_vox_levels_pm(points, specs, out, width)
-        return out
+        return points, specs, out, width
+
+    def forward_pm(self, points, batch_ids, feats1, feats2, feats3, feats4):
+        """Inference only: the concatenated (n, 480) point features as a PM image (operand of the tensor-core
+        disengage GEMMs) instead of an fp32 matrix.  All four levels in one call (one bucket-build launch, one
+        search + interpolation launch)."""
+        tower = self._pm_tower(points, batch_ids, [feats1, feats2, feats3, feats4])
+        pointnet2_utils_sp.nn_interpolate_vox_towers_pm([tower])
+        return tower[2]
+
+    def forward_pm_pair(self, points_a, ids_a, levels_a, points_b, ids_b, levels_b):
+        """forward_pm for the observed and the template cloud together: the two towers share both launches."""
+        ta, tb = self._pm_tower(points_a, ids_a, list(levels_a)), self._pm_tower(points_b, ids_b, list(levels_b))
+        pointnet2_utils_sp.nn_interpolate_vox_towers_pm([ta, tb])
+        return ta[2], tb[2]
 
     def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):
         points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()

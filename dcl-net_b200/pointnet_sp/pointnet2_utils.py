@@ -150,26 +150,36 @@ def nn_interpolate_vox_levels_pm(target_points, levels, out_pm, c_total):
     to calling nn_interpolate_vox_pm per level.  `levels`: list of (vox_indices (m,4) int32, voxel_extent[3],
     offset[3], feats (m,c) fp32, out_col0[, grid_x]); grid_x = size of the level's voxel grid along the first
     axis (enables the slab walk of the search; 0 / omitted = plain per-instance scan)."""
-    import ctypes
-    assert target_points.is_contiguous()
-    n = target_points.size(0)
-    arr = (L.SpLevel * len(levels))()
-    keep = []
-    for slot, spec in zip(arr, levels):
-        vox, ext, off, feats, col0 = spec[:5]
-        slot.grid_x = int(spec[5]) if len(spec) > 5 else 0
-        assert vox.is_contiguous() and feats.is_contiguous()
-        L.require(vox, torch.int32, "vox_indices")
-        L.require(feats, torch.float32, "feats")
-        slot.m, slot.c, slot.out_col0 = vox.size(0), feats.size(1), col0
-        slot.vox_indices, slot.feats = L.ptr(vox), L.ptr(feats)
-        slot.voxel_extent = (ctypes.c_float * 3)(*[float(v) for v in ext])
-        slot.offset = (ctypes.c_float * 3)(*[float(v) for v in off])
-        keep.append((vox, feats))
-    lib = L.load()
-    arr_p = ctypes.cast(arr, ctypes.c_void_p)
-    ws = _workspace(lib.dcl_sp_levels_workspace_bytes(len(levels), arr_p), target_points.device)
-    L.check(lib.dcl_sp_nn_interpolate_levels_pm(n, L.ptr(target_points), len(levels), arr_p, L.ptr(out_pm), c_total,
-                                                L.ptr(ws), ws.numel(), L.stream_ptr()),
-            "pointnet_sp.nn_interpolate_vox_levels_pm")
+    nn_interpolate_vox_towers_pm([(target_points, levels, out_pm, c_total)])
     return out_pm
+
+
+def nn_interpolate_vox_towers_pm(towers):
+    """Several towers — [(target_points, levels, out_pm, c_total)], levels as in nn_interpolate_vox_levels_pm, at most 8
+    levels in total — in ONE pair of launches: the observed and the template cloud of the network share the bucket
+    build launch and the search + interpolation launch."""
+    import ctypes
+    lib = L.load()
+    tw = (L.SpTower * len(towers))()
+    keep, nbytes = [], 0
+    for tslot, (target_points, levels, out_pm, c_total) in zip(tw, towers):
+        assert target_points.is_contiguous()
+        arr = (L.SpLevel * len(levels))()
+        for slot, spec in zip(arr, levels):
+            vox, ext, off, feats, col0 = spec[:5]
+            slot.grid_x = int(spec[5]) if len(spec) > 5 else 0
+            assert vox.is_contiguous() and feats.is_contiguous()
+            L.require(vox, torch.int32, "vox_indices")
+            L.require(feats, torch.float32, "feats")
+            slot.m, slot.c, slot.out_col0 = vox.size(0), feats.size(1), col0
+            slot.vox_indices, slot.feats = L.ptr(vox), L.ptr(feats)
+            slot.voxel_extent = (ctypes.c_float * 3)(*[float(v) for v in ext])
+            slot.offset = (ctypes.c_float * 3)(*[float(v) for v in off])
+        arr_p = ctypes.cast(arr, ctypes.c_void_p)
+        nbytes += lib.dcl_sp_levels_workspace_bytes(len(levels), arr_p)
+        tslot.n, tslot.c_total, tslot.nlevels = target_points.size(0), c_total, len(levels)
+        tslot.unknown, tslot.out_pm, tslot.levels = L.ptr(target_points), L.ptr(out_pm), arr_p
+        keep.append(arr)
+    ws = _workspace(nbytes, towers[0][0].device)
+    L.check(lib.dcl_sp_nn_interpolate_towers_pm(len(towers), ctypes.cast(tw, ctypes.c_void_p), L.ptr(ws), ws.numel(),
+                                                L.stream_ptr()), "pointnet_sp.nn_interpolate_vox_towers_pm")

@@ -163,6 +163,19 @@ int dcl_fda_pack(int b, int c, int p, int n, int m,
 int dcl_fda_fwd_packed(int b, int c, int p, int n, int m,
     float* RE_embed, float* RI_embed, float* lse_out,
     void* workspace, size_t workspace_bytes, void* stream);
+/* Up to two independent problems of equal shape in ONE launch (the two directions of the dual FDA,
+ * models/DCL_Net.py:206-215, then share their partial last waves).  Fields as in dcl_fda_fwd_packed_pm;
+ * every job has its own workspace of workspace_bytes. */
+typedef struct dcl_fda_job {
+    void* workspace;
+    float* RE_embed;
+    float* RI_embed;
+    void* RE_pm;
+    void* RI_pm;
+    float* lse;
+} dcl_fda_job;
+int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
+    size_t workspace_bytes, void* stream);
 /* Byte offsets of the query, key and value operand images inside the workspace (offsets[3]), for producers
  * that write them directly (dcl_pm_gemm_problem.out_qk / out_v) instead of calling dcl_fda_pack:
  *   query image: per 128 queries  [hi: 128 x c | lo], element (r,ch) at (r/8)*(c/8)*128 + (ch/8)*128 + (r%8)*16 + (ch%8)*2
@@ -326,6 +339,17 @@ typedef struct dcl_sp_level {
     float offset[3];
     const float* feats;
 } dcl_sp_level;
+/* One tower = one set of n query points (n,4 bxyz) and its levels; both towers of the network
+ * (observed cloud / template cloud) go in ONE pair of launches, <= 8 levels in total.  The
+ * workspace must hold the sum of dcl_sp_levels_workspace_bytes over the towers. */
+typedef struct dcl_sp_tower {
+    int n, c_total, nlevels;
+    const float* unknown;
+    void* out_pm;
+    const dcl_sp_level* levels;
+} dcl_sp_tower;
+int dcl_sp_nn_interpolate_towers_pm(int ntowers, const dcl_sp_tower* towers,
+    void* workspace, size_t workspace_bytes, void* stream);
 size_t dcl_sp_levels_workspace_bytes(int nlevels, const dcl_sp_level* levels);
 int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nlevels,
     const dcl_sp_level* levels, void* out_pm, int c_total,
