@@ -33,7 +33,9 @@ namespace {
 
 constexpr int GM_BM = 128;
 constexpr int GM_BK = 32;
-constexpr int GM_THREADS = 192;
+constexpr int GM_THREADS = 192;    // simple kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int GM_P_EPI = 256;      // persistent kernel: 8 epilogue warps (two threads per row)
+constexpr int GM_P_THREADS = 64 + GM_P_EPI;
 constexpr int GM_A_BLOB = GM_BM * GM_BK * 4;  // 16384
 constexpr int GM_MAX_PROBLEMS = 8;
 
@@ -61,27 +63,34 @@ struct GmColParams {           // per output column of the tile, in shared memor
     float bias[256], scale[256], shift[256], dotw[256];
 };
 
-__device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// EPI epilogue threads: 128 (one per row) or 256 (two per row: warps w and w+4 share a TMEM lane quadrant and split
+// the tile's columns in halves — the layers with few k-blocks are paced by their epilogue, not by their MMAs).
+template <int EPI>
+__device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory"); }
 
-template <int NT>
+template <int NT, int EPI>
 __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_in, int mt, int nti, uint32_t tmem_acc,
-                                                 int quad, int lane, GmColParams& cp) {
+                                                 int ewarp, int lane, GmColParams& cp, float* s_dot) {
     const dcl_pm_gemm_problem pr = pr_in;  // registers, not repeated constant-bank loads with a dynamic index
-    const int row = quad * 32 + lane;
-    const int tid = row;
+    const int quad = ewarp & 3;            // ewarp = warp index - 2; (ewarp + 2) % 4 is the TMEM quadrant this warp may read
+    const int half = ewarp >> 2;           // which half of the columns (always 0 with 128 epilogue threads)
+    constexpr int HALVES = EPI / 128;
+    const int row = ((ewarp + 2) & 3) * 32 + lane;
+    const int tid = ewarp * 32 + lane;
+    (void)quad;
     const size_t r_glob = (size_t)mt * GM_BM + row;
-    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t t_lane = (uint32_t)(((ewarp + 2) & 3) * 32) << 16;
     const int cout = pr.cout;
     // stage the tile's column parameters (previous tile's readers are past this point: barrier first)
-    gm_epi_barrier();
-    for (int c = tid; c < NT; c += 128) {
+    gm_epi_barrier<EPI>();
+    for (int c = tid; c < NT; c += EPI) {
         const int col = nti * NT + c;
         cp.bias[c] = pr.bias != nullptr ? __ldg(pr.bias + col) : 0.f;
         cp.scale[c] = pr.post_scale != nullptr ? __ldg(pr.post_scale + col) : 1.f;
         cp.shift[c] = pr.post_shift != nullptr ? __ldg(pr.post_shift + col) : 0.f;
         cp.dotw[c] = pr.dot_w != nullptr ? __ldg(pr.dot_w + col) : 0.f;
     }
-    gm_epi_barrier();
+    gm_epi_barrier<EPI>();
     const float relu_floor = pr.relu ? 0.f : -3.402823466e+38f;
     const float rw = pr.pool_w != nullptr ? __ldg(pr.pool_w + r_glob) : 0.f;
     size_t cm_base = 0;
@@ -90,8 +99,9 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
         cm_base = inst * (size_t)cout * pr.rows_per_inst + within;
     }
     float dot = 0.f;
+    constexpr int CH = NT / 32 / HALVES;  // 32-column chunks per thread
 #pragma unroll 1
-    for (int cc = 0; cc < NT / 32; ++cc) {
+    for (int cc = half * CH; cc < (half + 1) * CH; ++cc) {
         uint32_t v[32];
         DCL_TMEM_LD32(tmem_acc + t_lane + cc * 32, v);
         tc_wait_ld();
@@ -188,7 +198,16 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
             pr.pool_out[(r_glob >> 5) * cout + col0 + lane] = pv[0];
         }
     }
-    if (pr.dot_out != nullptr) pr.dot_out[r_glob] = dot;
+    if (pr.dot_out != nullptr) {
+        if (HALVES == 1) {
+            pr.dot_out[r_glob] = dot;
+        } else {
+            // the two threads of a row add their halves (lower columns first, as a single thread would)
+            if (half == 1) s_dot[row] = dot;
+            gm_epi_barrier<EPI>();
+            if (half == 0) pr.dot_out[r_glob] = dot + s_dot[row];
+        }
+    }
 }
 
 template <int NT, int STAGES>
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
         // ===================== epilogue =====================
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
-        gm_epilogue_tile<NT>(pr, mt, nti, tmem_base, warp & 3, lane, s_colp);
+        gm_epilogue_tile<NT, 128>(pr, mt, nti, tmem_base, warp - 2, lane, s_colp, nullptr);
         tc_fence_before();
     }
     __syncwarp();
@@ -297,11 +316,12 @@ struct GmPCfg {
 };
 
 template <int NT, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     pm_gemm_cluster_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
     using Cfg = GmPCfg<NT, STAGES>;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(16) GmColParams s_colp;
+    __shared__ float s_dot[GM_BM];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;   // [2]
@@ -320,7 +340,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             dcl_mbar_init(acc_full + i, 1);
-            dcl_mbar_init(acc_empty + i, 128);
+            dcl_mbar_init(acc_empty + i, GM_P_EPI);
         }
         dcl_fence_barrier_init();
     }
@@ -359,6 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
     } else if (warp == 1) {
         if (dcl_elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
+            const uint64_t desc0 = umma_desc(dcl_smem_u32(smem), 128, 512);
             int it = 0, tl = 0;
             for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
                 const int KB = batch.p[u % nprob].kb_total;
@@ -370,13 +391,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
                     const int s = it % STAGES;
                     dcl_mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
                     tc_fence_after();
-                    const uint32_t a = dcl_smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    const uint32_t b = a + GM_A_BLOB;
+                    // descriptors differ only in their start-address field
+                    const uint64_t dAh = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
+                    const uint64_t dAl = dAh + (uint64_t)((GM_A_BLOB / 2) >> 4);
+                    const uint64_t dBh = dAh + (uint64_t)(GM_A_BLOB >> 4);
+                    const uint64_t dBl = dBh + (uint64_t)((Cfg::B_BLOB / 2) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < GM_BK / 16; ++ks) {
-                        const uint32_t off = ks * 256;
-                        mma_split3(tacc, a + off, a + GM_A_BLOB / 2 + off, b + off, b + Cfg::B_BLOB / 2 + off, 128, 512,
-                                   128, 512, idesc, kb == 0 && ks == 0);
+                        const uint64_t off = (uint64_t)((ks * 256) >> 4);
+                        tc_mma_bf16(tacc, dAh + off, dBh + off, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                        tc_mma_bf16(tacc, dAh + off, dBl + off, idesc, 1u);
+                        tc_mma_bf16(tacc, dAl + off, dBh + off, idesc, 1u);
                     }
                     tc_commit_mcast(empty + s, (uint16_t)0x3);
                 }
@@ -390,7 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
             const int acc = tl & 1;
             dcl_mbar_wait(acc_full + acc, (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
-            gm_epilogue_tile<NT>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp & 3, lane, s_colp);
+            gm_epilogue_tile<NT, GM_P_EPI>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp - 2, lane, s_colp, s_dot);
             tc_fence_before();
             dcl_mbar_arrive(acc_empty + acc);
         }
@@ -420,7 +445,7 @@ int launch_gemm_cluster(const PmGemmBatch& batch, int nprob, int rows, int cout,
     const int units = npairs_m * ntiles_n * nprob;
     int clusters = num_sms / 2;
     if (clusters > units) clusters = units;
-    pm_gemm_cluster_kernel<NT, STAGES><<<2 * clusters, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n,
+    pm_gemm_cluster_kernel<NT, STAGES><<<2 * clusters, GM_P_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n,
                                                                                         npairs_m);
     return dcl_launch_status();
 }
