@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(SP_THREADS)
             const float4* f0 = reinterpret_cast<const float4*>(lv.feats + (size_t)j0 * c);
             const float4* f1 = reinterpret_cast<const float4*>(lv.feats + (size_t)j1 * c);
             const float4* f2 = reinterpret_cast<const float4*>(lv.feats + (size_t)j2 * c);
+#pragma unroll 2
             for (int c8 = sub; c8 < (c >> 3); c8 += SPL_LPQ) {
                 float o[8];
 #pragma unroll
