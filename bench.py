@@ -309,8 +309,13 @@ def run_b200_arm(args, rank, world, local_rank):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm else float("nan")
     split_note = ("every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful, so the algorithmic "
                   "fraction is bounded by 1/3; tensor-pipe occupancy is ~3x the algorithmic fraction")
+    # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, mean of its five launches)
+    # from the `ncu --set full` capture of the default configuration: profiles/r01_gemm_fda_ncu_full.txt
+    traffic = 2.31e8 if (b == 32 and args.c_m == 128) else None
     roofline = {"kernel": "pm_gemm_cluster_kernel<256,4>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_source": "profiles/r01_gemm_fda_ncu_full.txt (bytes per launch)" if traffic else None,
+                "peak_source": peak_src,
                 "avg_launch_ms": gemm_ms / len(gemm) if gemm else None, "launches_timed": len(gemm),
                 "algorithmic_flops_per_step": gemm_flops / args.steps,
                 "executed_mma_flops_per_step": 3 * gemm_flops / args.steps,
