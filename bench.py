@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=4, help="instances per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the host-in/host-out pipeline")
     return ap.parse_args()
 
 
@@ -280,7 +281,7 @@ def run_b200_arm(args, rank, world, local_rank):
         #      from pinned host memory and reads ITS (B,12) poses back; PipelinedPoseEngine overlaps the copy of
         #      batch i+1 with the pass over batch i (two buffer sets, a copy stream).
         del engines[1:]
-        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=2, use_graph=use_graph)
+        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=args.e2e_depth, use_graph=use_graph)
         checksum = 0.0
         for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(max(3, min(args.warmup, 5)))):
             checksum += float(trans[0, 0])

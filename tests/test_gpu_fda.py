@@ -135,6 +135,27 @@ def test_fda_point_major_outputs(cuda_dev, b, c, n, m):
         assert (rows - want).abs().max().item() <= 2.0 ** -16 * want.abs().max().item()
 
 
+def test_fda_two_jobs_in_one_launch(cuda_dev):
+    """Both directions of the dual FDA in one launch (grid.z = job) == two separate launches, bit for bit."""
+    from dcl_net_b200 import modules as M
+    b, c, n = 3, 128, 256
+    lib = L.load()
+    nbytes = lib.dcl_fda_workspace_bytes(b, c, 256, n, n)
+    wss, sep = [], []
+    for seed in (5, 6):
+        ri1, ri2, re2 = (x.to(cuda_dev) for x in _inputs(seed, b, c, n, n, "relu"))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda_dev)
+        L.check(lib.dcl_fda_pack(b, c, 256, n, n, L.ptr(ri1), L.ptr(ri2), L.ptr(re2), L.ptr(ws), ws.numel(),
+                                 L.stream_ptr()), "pack")
+        wss.append(ws)
+        sep.append(M.fda_from_workspace(ws, b, c, n, n, True, True, True, True, True))
+    both = M.fda_from_workspaces([(wss[0], True, True, True, True, True), (wss[1], True, True, True, True, True)],
+                                 b, c, n, n)
+    for one, two in zip(sep, both):
+        for x, y in zip(one, two):
+            assert torch.equal(x, y)
+
+
 def test_fda_rejects_bad_shapes(cuda_dev):
     x = torch.zeros(1, 32, 128, device=cuda_dev)
     with pytest.raises(ValueError):

@@ -10,6 +10,7 @@ from dcl_testutil import GOLDEN, levels_to, rel_err, synthetic_backbone_levels
 
 pytestmark = pytest.mark.gpu
 
+from dcl_net_b200 import _lib as L                                                      # noqa: E402
 from dcl_net_b200.dcl_net import Network, ortho9d2matrix, svd3_project, weighted_kabsch  # noqa: E402
 from dcl_net_b200.modules import Ops_GetPointFeat_spconv                                # noqa: E402
 from dcl_net_b200.refiner import Refiner, refine_poses                                  # noqa: E402
@@ -224,6 +225,22 @@ def test_pose_heads_kernel_vs_torch(cuda_dev):
             want3 = trans(x.unsqueeze(-1)).squeeze(-1)
         assert o9.shape == (B, 9) and t3.shape == (B, 3)
         assert rel_err(o9, want9) < 1e-5 and rel_err(t3, want3) < 1e-5
+
+
+@pytest.mark.parametrize("b,n", [(1, 128), (32, 1024), (5, 640)])
+def test_conf_weights_kernel_vs_torch(cuda_dev, b, n):
+    """dcl_conf_weights == sigmoid(cat) -> softmax of models/DCL_Net.py:219-220."""
+    g = torch.Generator().manual_seed(b + n)
+    l1, l2 = (4 * torch.randn(b, n, generator=g)).to(cuda_dev), (4 * torch.randn(b, n, generator=g)).to(cuda_dev)
+    b1, b2 = torch.tensor([[0.3]], device=cuda_dev), torch.tensor([[-0.2]], device=cuda_dev)
+    conf = torch.empty(b, 2 * n, device=cuda_dev)
+    w1, w2 = torch.empty(b * n, device=cuda_dev), torch.empty(b * n, device=cuda_dev)
+    L.check(L.load().dcl_conf_weights(b, n, L.ptr(l1), L.ptr(l2), L.ptr(b1), L.ptr(b2), L.ptr(conf), L.ptr(w1), L.ptr(w2),
+                                      L.stream_ptr()), "conf_weights")
+    want_conf = torch.sigmoid(torch.cat([l1 + 0.3, l2 - 0.2], dim=1).double())
+    want_sm = torch.softmax(want_conf, dim=1)
+    assert rel_err(conf, want_conf) < 1e-6
+    assert rel_err(torch.cat([w1.view(b, n), w2.view(b, n)], 1), want_sm) < 2e-6
 
 
 def test_training_step_gradients_match_oracle(cuda_dev):
