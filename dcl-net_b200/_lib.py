@@ -51,6 +51,7 @@ SIGNATURES = {
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_pose_head_workspace_bytes": (_SZ, [_I, _P, _P]),
     "dcl_pose_head": (_I, [_I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "dcl_nearest_dist": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "dcl_conf_weights": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dcl_sp_levels_workspace_bytes": (_SZ, [_I, _P]),
     "dcl_sp_nn_interpolate_towers_pm": (_I, [_I, _P, _P, _SZ, _P]),

@@ -320,6 +320,14 @@ int dcl_sp_nn_interpolate_vox_pm(int n, int m, int c,
 int dcl_conf_weights(int b, int n, const float* logit_1, const float* logit_2,
     const float* bias_1, const float* bias_2, float* conf, float* w1, float* w2, void* stream);
 
+/* Nearest-point distance from every point of cloud a (b,n,3) to cloud bpts (b,m,3):
+ * min_dist[b,i] = min_j ||a_i - bpts_j|| (Euclidean), argmin (b,n; may be NULL) = the lowest such j.
+ * Replaces the B x N x M x 3 broadcast of CD_Dis (models/DCL_Net.py:307-311, models/refiner.py:129-133:
+ * 0.5 * (min over dim 2 + min over dim 1) = two calls with the clouds swapped) and of the ADD-S metric
+ * (tools/test_YCBV_stage1.py:188: mean over n of min_dist). */
+int dcl_nearest_dist(int b, int n, int m, const float* a, const float* bpts,
+    float* min_dist, int* argmin, void* stream);
+
 /* All pyramid levels of one tower at once (Ops_GetPointFeat_spconv.forward,
  * models/Modules.py:227-251, calls Ops_nearest_neighbor_interpolate once per level with the
  * same query points): one launch builds every level's batch buckets, one launch searches

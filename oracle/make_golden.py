@@ -211,6 +211,14 @@ def main():
     err = (pf_ref - pf_mine).abs().max().item()
     assert err <= 1e-6 * pf_ref.abs().max().item(), f"get_point_feats deviates: {err}"
     np.savez_compressed(os.path.join(GOLD, "model_point_feats.npz"), seed=104, point_feats=pf_ref.numpy())
+    # ---------------- loss / metric distances: the reference's own CD_Dis and the ADD-S expression of its test driver
+    g = torch.Generator().manual_seed(105)
+    pa, pb = torch.rand(2, 96, 3, generator=g), torch.rand(2, 96, 3, generator=g)
+    pa[:, 0] = pb[:, 2]
+    cd_ref = ref_net_mod.losses.CD_Dis(None, pa, pb)
+    adds_ref = torch.mean(torch.min(torch.norm(pa.unsqueeze(2) - pb.unsqueeze(1), dim=3), 2)[0], dim=1)  # test_YCBV_stage1.py:188
+    assert torch.equal(cd_ref, T.cd_dis(pa, pb)) and torch.equal(adds_ref, T.adds(pa, pb))
+    np.savez_compressed(os.path.join(GOLD, "model_losses.npz"), seed=105, cd_dis=cd_ref.numpy(), adds=adds_ref.numpy())
     print("golden fixtures written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  ", f, os.path.getsize(os.path.join(GOLD, f)))

@@ -259,3 +259,15 @@ def get_point_feats(points, batch_ids, levels, unit_voxel_extent, scale_list=(2,
         centres = voxel_centres(indices, offset, unit * scale)
         outs.append(nearest_neighbor_interpolate(pts, centres, feats, three_nn))
     return torch.cat(outs, dim=1)
+
+
+# --------------------------------------------------------------------------- losses / metric
+def cd_dis(pred, target):
+    # models/DCL_Net.py:307-311
+    dis = torch.norm(pred.unsqueeze(2) - target.unsqueeze(1), dim=3)
+    return 0.5 * (torch.min(dis, 2)[0] + torch.min(dis, 1)[0])
+
+
+def adds(points_posed_pred, points_posed_gt):
+    # tools/test_YCBV_stage1.py:188
+    return torch.mean(torch.min(torch.norm(points_posed_pred.unsqueeze(2) - points_posed_gt.unsqueeze(1), dim=3), 2)[0], dim=1)

@@ -350,3 +350,40 @@ def test_fda_align_function_gradcheck_like(cuda_dev):
     ((e_o * ge).sum() + (m_o * gi).sum()).backward()
     for gg, t in zip(got, (ri1, ri2, re2)):
         assert rel_err(gg, t.grad) < 5e-5
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 128, 128), (3, 1000, 777), (32, 2620, 2620), (1, 5, 3000)])
+def test_nearest_dist_and_adds_vs_reference_broadcast(cuda_dev, b, n, m):
+    """dcl_nearest_dist == the reference's B x N x M x 3 broadcast (ADD-S of test_YCBV_stage1.py:188, CD_Dis)."""
+    from dcl_net_b200 import losses
+    g = torch.Generator().manual_seed(b * n + m)
+    a, c = torch.rand(b, n, 3, generator=g).to(cuda_dev), torch.rand(b, m, 3, generator=g).to(cuda_dev)
+    a[:, 0] = c[:, min(2, m - 1)]                     # an exact coincidence: distance 0
+    got = losses.adds_metric(a, c)
+    want = T.adds(a.double(), c.double())
+    assert rel_err(got, want) < 1e-6
+    if n == m:
+        assert rel_err(losses.CD_Dis(a, c), T.cd_dis(a.double(), c.double())) < 1e-6
+
+
+def test_losses_golden_gpu(cuda_dev):
+    """The kernel against the fixture written by the reference's own CD_Dis / ADD-S code."""
+    from dcl_net_b200 import losses
+    gold = np.load(f"{GOLDEN}/model_losses.npz")
+    g = torch.Generator().manual_seed(int(gold["seed"]))
+    pa, pb = torch.rand(2, 96, 3, generator=g), torch.rand(2, 96, 3, generator=g)
+    pa[:, 0] = pb[:, 2]
+    pa, pb = pa.to(cuda_dev), pb.to(cuda_dev)
+    assert np.allclose(losses.CD_Dis(pa, pb).cpu().numpy(), gold["cd_dis"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(losses.adds_metric(pa, pb).cpu().numpy(), gold["adds"], rtol=1e-6, atol=1e-7)
+
+
+def test_cd_dis_gradient_vs_reference_graph(cuda_dev):
+    from dcl_net_b200 import losses
+    g = torch.Generator().manual_seed(3)
+    a0, c0 = torch.rand(2, 300, 3, generator=g).to(cuda_dev), torch.rand(2, 300, 3, generator=g).to(cuda_dev)
+    a, c = a0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    losses.CD_Dis(a, c).mean().backward()
+    ar, cr = a0.double().requires_grad_(True), c0.double().requires_grad_(True)
+    T.cd_dis(ar, cr).mean().backward()
+    assert rel_err(a.grad, ar.grad) < 1e-5 and rel_err(c.grad, cr.grad) < 1e-5

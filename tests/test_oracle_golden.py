@@ -68,6 +68,16 @@ def test_refiner_golden():
     assert np.allclose(out["trans_pred"].numpy(), gold["trans_pred"], atol=1e-6)
 
 
+def test_losses_golden():
+    """CD_Dis / ADD-S restatements against values produced by the reference's own code (oracle/make_golden.py)."""
+    gold = np.load(f"{GOLDEN}/model_losses.npz")
+    g = torch.Generator().manual_seed(int(gold["seed"]))
+    pa, pb = torch.rand(2, 96, 3, generator=g), torch.rand(2, 96, 3, generator=g)
+    pa[:, 0] = pb[:, 2]
+    assert np.array_equal(T.cd_dis(pa, pb).numpy(), gold["cd_dis"])
+    assert np.array_equal(T.adds(pa, pb).numpy(), gold["adds"])
+
+
 def test_point_feats_golden():
     gold = np.load(f"{GOLDEN}/model_point_feats.npz")
     g = torch.Generator().manual_seed(int(gold["seed"]))
