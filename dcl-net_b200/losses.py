@@ -1,5 +1,7 @@
-"""Point-set distances of the reference's loss / metric code without the B x N x M x 3 broadcast.
+"""The reference's loss modules and metric without the B x N x M x 3 broadcast.
 
+    losses             models/DCL_Net.py:261-311      (same class name, forward signature and returned keys)
+    losses_refiner     models/refiner.py:97-133
     L2_Dis, CD_Dis     models/DCL_Net.py:304-311, models/refiner.py:126-133
     ADD-S metric       tools/test_YCBV_stage1.py:186-188   (`cd_dis` there)
 
@@ -8,6 +10,7 @@ point), the backward is the gradient of ||p_i - q_j*|| at the recorded nearest n
 reference through `torch.min(...)[0]` of the broadcast norm.
 """
 import torch
+import torch.nn as nn
 
 from . import _lib as L
 
@@ -65,3 +68,62 @@ def CD_Dis(pred, target):
 def adds_metric(points_posed_pred, points_posed_gt):
     """ADD-S of tools/test_YCBV_stage1.py:188: mean over the model points of the distance to the closest GT-posed point."""
     return nearest_dist(points_posed_pred, points_posed_gt).mean(dim=1)
+
+
+class losses(nn.Module):
+    """Stage-1 training loss, models/DCL_Net.py:261-303 line by line; only CD_Dis runs on the kernel."""
+
+    def __init__(self, cfg=None) -> None:
+        super().__init__()
+
+    L2_Dis = staticmethod(L2_Dis)
+    CD_Dis = staticmethod(CD_Dis)
+
+    def forward(self, loss_inp_pred, loss_inp_gt):
+        rot_pred, trans_pred = loss_inp_pred["rot_pred"], loss_inp_pred["trans_pred"]
+        sym_flag = loss_inp_pred["sym_flag"]
+        dev = rot_pred.device
+        rot_gt, trans_gt = loss_inp_gt["rot_gt"].to(dev), loss_inp_gt["trans_gt"].to(dev)
+        points_tmp, points_inp = loss_inp_gt["points_tmp"], loss_inp_gt["points_inp"]
+        conf = loss_inp_pred["conf"]
+
+        points_tmp_posed_pred = torch.bmm(points_tmp, rot_pred.transpose(1, 2)) + trans_pred.unsqueeze(1)
+        points_tmp_posed_gt = torch.bmm(points_tmp, rot_gt.transpose(1, 2)) + trans_gt.unsqueeze(1)
+        asym, sym = (1 - sym_flag).unsqueeze(1), sym_flag.unsqueeze(1)
+        loss_pose = (asym * self.L2_Dis(points_tmp_posed_pred, points_tmp_posed_gt)
+                     + sym * self.CD_Dis(points_tmp_posed_pred, points_tmp_posed_gt)).mean(dim=1).mean()
+
+        Xo_pred, Yc_pred = loss_inp_pred["Xo_pred"], loss_inp_pred["Yc_pred"]
+        points_inp_posed_pred = torch.bmm(points_inp - trans_pred.unsqueeze(1), rot_pred).detach()
+        points_inp_posed_gt = torch.bmm(points_inp - trans_gt.unsqueeze(1), rot_gt).detach()
+        loss_Xo = asym * self.L2_Dis(Xo_pred, points_inp_posed_gt) + 0.5 * sym * (
+            self.CD_Dis(Xo_pred, points_tmp) + self.L2_Dis(Xo_pred, points_inp_posed_pred))
+        loss_Xo_ = loss_Xo.mean()
+        loss_Yc = asym * self.L2_Dis(Yc_pred, points_tmp_posed_gt) + 0.5 * sym * (
+            self.CD_Dis(Yc_pred, points_tmp_posed_gt) + self.L2_Dis(Yc_pred, points_tmp_posed_pred.detach()))
+        loss_Yc_ = loss_Yc.mean()
+        loss_conf = torch.mean(torch.cat([loss_Xo, loss_Yc], dim=1).detach() * conf - 0.01 * torch.log(conf))
+        loss_all = loss_pose + 5 * loss_Xo_ + 1 * loss_Yc_ + 1 * loss_conf
+        return {"loss_pose": loss_pose, "loss_Xo": loss_Xo_, "loss_Yc": loss_Yc_, "loss_conf": loss_conf,
+                "loss_all": loss_all}
+
+
+class losses_refiner(nn.Module):
+    """Stage-2 training loss, models/refiner.py:97-125."""
+
+    def __init__(self, cfg=None) -> None:
+        super().__init__()
+
+    L2_Dis = staticmethod(L2_Dis)
+    CD_Dis = staticmethod(CD_Dis)
+
+    def forward(self, loss_inp_pred_refiner, trans_cur, rot_cur, points_tmp, sym_flag, loss_inp_gt):
+        delta_rot_pred, delta_trans_pred = loss_inp_pred_refiner["rot_pred"], loss_inp_pred_refiner["trans_pred"]
+        dev = delta_rot_pred.device
+        rot_gt, trans_gt = loss_inp_gt["rot_gt"].to(dev), loss_inp_gt["trans_gt"].to(dev)
+        points_tmp_posed_pred = torch.bmm(points_tmp, delta_rot_pred.transpose(1, 2)) + delta_trans_pred.unsqueeze(1)
+        points_tmp_posed_gt = torch.bmm(points_tmp, rot_gt.transpose(1, 2)) + trans_gt.unsqueeze(1)
+        points_tmp_posed_refined = torch.bmm(points_tmp_posed_pred, rot_cur.transpose(1, 2)) + trans_cur.unsqueeze(1)
+        loss_pose = ((1 - sym_flag).unsqueeze(1) * self.L2_Dis(points_tmp_posed_refined, points_tmp_posed_gt)
+                     + sym_flag.unsqueeze(1) * self.CD_Dis(points_tmp_posed_refined, points_tmp_posed_gt)).mean(dim=1).mean()
+        return {"loss_pose": loss_pose, "loss_all": loss_pose}

@@ -97,6 +97,22 @@ def reference_fda_section(ref_net_mod, net, f_xc_flat, f_yo_flat, b, n_inp, n_tm
     return env
 
 
+def loss_inputs(seed, b, n):
+    """Deterministic inputs of the loss modules (shared by make_golden and the tests)."""
+    g = torch.Generator().manual_seed(seed + 1)
+    def rot(k):
+        q, _ = torch.linalg.qr(torch.randn(k, 3, 3, generator=g))
+        return q * torch.det(q).sign().view(k, 1, 1)
+    pred = {"rot_pred": rot(b), "trans_pred": 0.1 * torch.randn(b, 3, generator=g),
+            "sym_flag": torch.tensor([0.0, 1.0, 1.0][:b] + [0.0] * max(0, b - 3)),
+            "conf": torch.rand(b, 2 * n, generator=g) * 0.9 + 0.05,
+            "Xo_pred": 0.2 * torch.randn(b, n, 3, generator=g), "Yc_pred": 0.2 * torch.randn(b, n, 3, generator=g)}
+    gt = {"rot_gt": rot(b), "trans_gt": 0.1 * torch.randn(b, 3, generator=g),
+          "points_tmp": 0.2 * torch.randn(b, n, 3, generator=g), "points_inp": 0.2 * torch.randn(b, n, 3, generator=g)}
+    return {"pred": pred, "gt": gt, "refiner_pred": {"rot_pred": rot(b), "trans_pred": 0.01 * torch.randn(b, 3, generator=g)},
+            "rot_cur": rot(b), "trans_cur": 0.1 * torch.randn(b, 3, generator=g)}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     sys.path.insert(0, ROOT)
@@ -218,7 +234,15 @@ def main():
     cd_ref = ref_net_mod.losses.CD_Dis(None, pa, pb)
     adds_ref = torch.mean(torch.min(torch.norm(pa.unsqueeze(2) - pb.unsqueeze(1), dim=3), 2)[0], dim=1)  # test_YCBV_stage1.py:188
     assert torch.equal(cd_ref, T.cd_dis(pa, pb)) and torch.equal(adds_ref, T.adds(pa, pb))
-    np.savez_compressed(os.path.join(GOLD, "model_losses.npz"), seed=105, cd_dis=cd_ref.numpy(), adds=adds_ref.numpy())
+    # the reference's loss modules themselves (.cuda() is an identity here), on a mixed symmetric / asymmetric batch
+    lb, ln = 3, 64
+    li = loss_inputs(105, lb, ln)
+    ref_losses = ref_net_mod.losses(None)(li["pred"], li["gt"])
+    ref_losses_ref = ref_refiner.losses_refiner(None)(li["refiner_pred"], li["trans_cur"], li["rot_cur"],
+                                                      li["gt"]["points_tmp"], li["pred"]["sym_flag"], li["gt"])
+    np.savez_compressed(os.path.join(GOLD, "model_losses.npz"), seed=105, cd_dis=cd_ref.numpy(), adds=adds_ref.numpy(),
+                        b=lb, n=ln, **{"s1_" + k: v.numpy() for k, v in ref_losses.items()},
+                        **{"s2_" + k: v.numpy() for k, v in ref_losses_ref.items()})
     print("golden fixtures written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  ", f, os.path.getsize(os.path.join(GOLD, f)))

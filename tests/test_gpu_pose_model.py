@@ -378,6 +378,24 @@ def test_losses_golden_gpu(cuda_dev):
     assert np.allclose(losses.adds_metric(pa, pb).cpu().numpy(), gold["adds"], rtol=1e-6, atol=1e-7)
 
 
+def test_loss_modules_golden_gpu(cuda_dev):
+    """The drop-in `losses` / `losses_refiner` modules against the values the reference's own modules produced on
+    the same inputs (oracle/make_golden.py runs models/DCL_Net.py:261-303 and models/refiner.py:97-125)."""
+    from dcl_net_b200 import losses as LS
+    from oracle.make_golden import loss_inputs
+    gold = np.load(f"{GOLDEN}/model_losses.npz")
+    li = loss_inputs(int(gold["seed"]), int(gold["b"]), int(gold["n"]))
+    dev = lambda d: {k: v.to(cuda_dev) for k, v in d.items()}
+    pred, gt = dev(li["pred"]), dev(li["gt"])
+    out = LS.losses()(pred, gt)
+    for k, v in out.items():
+        assert abs(v.item() - float(gold["s1_" + k])) <= 2e-6 * max(1.0, abs(float(gold["s1_" + k]))), k
+    out2 = LS.losses_refiner()(dev(li["refiner_pred"]), li["trans_cur"].to(cuda_dev), li["rot_cur"].to(cuda_dev),
+                               gt["points_tmp"], pred["sym_flag"], gt)
+    for k, v in out2.items():
+        assert abs(v.item() - float(gold["s2_" + k])) <= 2e-6 * max(1.0, abs(float(gold["s2_" + k]))), k
+
+
 def test_cd_dis_gradient_vs_reference_graph(cuda_dev):
     from dcl_net_b200 import losses
     g = torch.Generator().manual_seed(3)
