@@ -274,6 +274,91 @@ __global__ void __launch_bounds__(IP_THREADS) three_interpolate_kernel(int c, in
     }
 }
 
+// ---- lane-per-channel backward (used when 32 transposed rows fit in shared memory) ----
+// The CG-row backward above scatters into row[j] with 32 random j per warp instruction: ~3.5-way conflicting
+// shared-memory atomics, three per element.  Here a CTA accumulates into acc_t[point][channel] (stride 33) and a
+// warp works on blocks of 32 queries x 32 channels with lane = channel: the three scatter-adds of a query are
+// conflict-free, the block's idx / weight rows are staged once and read back as broadcasts, and the gradient block
+// is read as 128-byte rows of consecutive queries and transposed through a per-warp tile.  (The same layout was
+// tried for the forward gather and lost to the CG-row kernel, 162 vs 121 us: one CTA of 16 warps per SM cannot hide
+// the dependent shared-memory chain, while the conflicting gathers above run with several CTAs per SM.)
+constexpr int IPL_THREADS = 512;
+constexpr int IPL_STRIDE = 33;
+constexpr int IPL_MAX_SMEM = 224 * 1024;
+constexpr int IPL_WARP_FLOATS = 32 * IPL_STRIDE + 32 * 8;  // per warp: transpose tile + the block's (idx, weight) rows
+
+__global__ void __launch_bounds__(IPL_THREADS) three_interpolate_grad_lane_kernel(int c, int n, int m, int n_per_cta,
+                                                                                  const float* __restrict__ grad_out,
+                                                                                  const int* __restrict__ idx,
+                                                                                  const float* __restrict__ weight,
+                                                                                  float* __restrict__ grad_points) {
+    extern __shared__ __align__(16) float s_mem[];
+    float* acc_t = s_mem;                                    // [m][33]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = s_mem + (size_t)m * IPL_STRIDE + warp * IPL_WARP_FLOATS;
+    float4* qrow = reinterpret_cast<float4*>(tile + 32 * IPL_STRIDE);
+    const int bs = blockIdx.z, c0 = blockIdx.y * 32;
+    const int ncg = min(32, c - c0);
+    for (int i = threadIdx.x; i < m * IPL_STRIDE; i += IPL_THREADS) acc_t[i] = 0.f;
+    __syncthreads();
+    idx += (size_t)bs * n * 3;
+    weight += (size_t)bs * n * 3;
+    grad_out += ((size_t)bs * c + c0) * n;
+    const int i_begin = blockIdx.x * n_per_cta;
+    const int i_end = min(n, i_begin + n_per_cta);
+    for (int i0 = i_begin + warp * 32; i0 < i_end; i0 += IPL_THREADS) {
+        const bool live = i0 + lane < i_end;
+        const int iq = min(i0 + lane, i_end - 1);
+        const int mj0 = __ldg(idx + iq * 3 + 0), mj1 = __ldg(idx + iq * 3 + 1), mj2 = __ldg(idx + iq * 3 + 2);
+        const float mw0 = __ldg(weight + iq * 3 + 0), mw1 = __ldg(weight + iq * 3 + 1), mw2 = __ldg(weight + iq * 3 + 2);
+#pragma unroll 8
+        for (int cc = 0; cc < 32; ++cc)
+            tile[cc * IPL_STRIDE + lane] = (live && cc < ncg) ? __ldg(grad_out + (size_t)cc * n + i0 + lane) : 0.f;
+        qrow[lane * 2 + 0] = make_float4(__int_as_float(mj0 * IPL_STRIDE), __int_as_float(mj1 * IPL_STRIDE),
+                                         __int_as_float(mj2 * IPL_STRIDE), 0.f);
+        qrow[lane * 2 + 1] = make_float4(mw0, mw1, mw2, 0.f);
+        __syncwarp();
+        const int nq = min(32, i_end - i0);
+#pragma unroll 4
+        for (int q = 0; q < nq; ++q) {
+            const float4 jj = qrow[q * 2 + 0], ww = qrow[q * 2 + 1];
+            const float g = tile[lane * IPL_STRIDE + q];
+            atomicAdd(acc_t + __float_as_int(jj.x) + lane, __fmul_rn(g, ww.x));
+            atomicAdd(acc_t + __float_as_int(jj.y) + lane, __fmul_rn(g, ww.y));
+            atomicAdd(acc_t + __float_as_int(jj.z) + lane, __fmul_rn(g, ww.z));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float* dst = grad_points + ((size_t)bs * c + c0) * m;
+    for (int cc = warp; cc < ncg; cc += IPL_THREADS / 32) {
+        for (int pt = lane; pt < m; pt += 32) {
+            const float v = acc_t[pt * IPL_STRIDE + cc];
+            if (gridDim.x == 1) dst[(size_t)cc * m + pt] += v;
+            else if (v != 0.f) atomicAdd(dst + (size_t)cc * m + pt, v);
+        }
+    }
+}
+
+// query chunks per (batch, channel group) so that the grid is a whole number of waves of one CTA per SM
+int ipl_chunks(int n, int groups_times_b) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ch = 1; ch <= 16; ++ch) {
+        if ((long)ch * 256 > n && ch > 1) break;
+        const long ctas = (long)ch * groups_times_b;
+        const long waves = (ctas + 147) / 148;
+        const double eff = (double)ctas / (double)(waves * 148);
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = ch;
+        }
+    }
+    return best;
+}
+
+size_t ipl_smem(int m) { return ((size_t)m * IPL_STRIDE + (size_t)(IPL_THREADS / 32) * IPL_WARP_FLOATS) * sizeof(float); }
+
 // Rows too long for shared memory: gather straight from global / L2.
 __global__ void __launch_bounds__(IP_THREADS) three_interpolate_gmem_kernel(int c, int m, int n,
                                                                             const float* __restrict__ points,
@@ -454,6 +539,15 @@ DCL_API int dcl_lib_three_interpolate_grad_kernel_launcher_fast(int b, int c, in
     DCL_RETURN_IF_BAD(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (c >= 16 && m >= 4 && m % 4 == 0 && n >= 64 && ipl_smem(m) <= IPL_MAX_SMEM) {
+        const int groups = DCL_DIVUP(c, 32);
+        const int chunks = ipl_chunks(n, groups * b);
+        const int per = DCL_DIVUP(DCL_DIVUP(n, chunks), 32) * 32;
+        allow_smem(three_interpolate_grad_lane_kernel, ipl_smem(m));
+        three_interpolate_grad_lane_kernel<<<dim3(DCL_DIVUP(n, per), groups, b), IPL_THREADS, ipl_smem(m), st>>>(
+            c, n, m, per, grad_out, idx, weight, grad_points);
+        return dcl_launch_status();
+    }
     const int cg = pick_cg(c, m);
     if (cg == 0) {
         dim3 grid(DCL_DIVUP(n, IP_THREADS), c, b);
