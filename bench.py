@@ -54,13 +54,17 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the host-in/host-out pipeline")
+    ap.add_argument("--refine-iterations", type=int, default=0,
+                    help="append the stage-2 refinement loop (tools/test_YCBV_stage2.py) with this many iterations; "
+                         "0 = stage 1 only, the configuration BASELINE.json's metric is quoted on")
     return ap.parse_args()
 
 
 def workload_config(args, n_gpus):
+    stage2 = (f" -> stage-2 refiner x{args.refine_iterations}" if getattr(args, "refine_iterations", 0) else "")
     return {
         "workload": "DCL-Net stage-1 inference (config_YCBV_bs32 shape) from synthetic backbone pyramids: "
-                    "pointnet_sp 3-NN interpolation -> disengage -> dual FDA -> heads -> SVD pose",
+                    "pointnet_sp 3-NN interpolation -> disengage -> dual FDA -> heads -> SVD pose" + stage2,
         "B_per_gpu": args.batch, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
         "weights": "random init, eval mode", "sharding": f"instances x{n_gpus}, weak scaling",
         "l2": f"{ROTATE} rotating input sets; per-step activations (> 1 GB at B=32) exceed the 126 MB L2",
@@ -213,7 +217,11 @@ def run_b200_arm(args, rank, world, local_rank):
     net = Network(Cfg, mode="test", c_m=args.c_m).eval().to(dev)
     batches = [make_host_batch(1000 * (rank + 1) + 17 * i, b, pin=True) for i in range(ROTATE)]
     caps = [max(max(bt[s][lv][0].shape[0] for bt in batches for s in ("inp", "tmp")), 1) for lv in range(4)]
-    engines = [PoseEngine(net, dev, b, caps) for _ in range(ROTATE)]
+    refiner = None
+    if args.refine_iterations > 0:
+        from dcl_net_b200.refiner import Refiner
+        refiner = Refiner().eval().to(dev)
+    engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations) for _ in range(ROTATE)]
     for eng, bt in zip(engines, batches):
         eng.load(bt)
     torch.cuda.synchronize()
@@ -281,7 +289,8 @@ def run_b200_arm(args, rank, world, local_rank):
         #      from pinned host memory and reads ITS (B,12) poses back; PipelinedPoseEngine overlaps the copy of
         #      batch i+1 with the pass over batch i (two buffer sets, a copy stream).
         del engines[1:]
-        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=args.e2e_depth, use_graph=use_graph)
+        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=args.e2e_depth, refiner=refiner,
+                                   iterations=args.refine_iterations, use_graph=use_graph)
         checksum = 0.0
         for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(max(3, min(args.warmup, 5)))):
             checksum += float(trans[0, 0])

@@ -42,6 +42,7 @@ SIGNATURES = {
     "dcl_svd3_project": (_I, [_I, _P, _I, _P, _P]),
     "dcl_weighted_kabsch": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "dcl_pose_compose": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "dcl_pose_compose_pm": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "dcl_pm_gemm": (_I, [_I, _P, _I, _P]),
     "dcl_pm_pack_rows": (_I, [_I, _I, _I, _P, _P, _P]),
     "dcl_pm_pack_cm": (_I, [_I, _I, _I, _P, _P, _P]),

@@ -16,6 +16,7 @@
 // ill-conditioned one) is never normalised.  The iteration runs in fp64 so that the
 // result is the exact projection to well below the reference's own fp32 LAPACK error.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "../../include/dcl_b200.h"
 
 namespace {
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(256) pose_compose_kernel(int n, float* __restr
                                                            const float* __restrict__ dt,
                                                            const float* __restrict__ points_in,
                                                            float* __restrict__ points_out_cm,
-                                                           int64_t out_batch_stride, int update) {
+                                                           int64_t out_batch_stride,
+                                                           unsigned char* __restrict__ points_out_pm, int update) {
     __shared__ float sR[9], sT[3];
     const int bs = blockIdx.y;
     if (threadIdx.x < 12) {
@@ -224,10 +226,34 @@ __global__ void __launch_bounds__(256) pose_compose_kernel(int n, float* __restr
     if (i < n) {
         const float* p = points_in + ((size_t)bs * n + i) * 3;
         const float x = __fsub_rn(p[0], sT[0]), y = __fsub_rn(p[1], sT[1]), z = __fsub_rn(p[2], sT[2]);
-        float* o = points_out_cm + (size_t)bs * out_batch_stride + i;
+        float v[3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-            o[(size_t)ch * n] = __fmaf_rn(z, sR[6 + ch], __fmaf_rn(y, sR[3 + ch], __fmul_rn(x, sR[ch])));
+        for (int ch = 0; ch < 3; ++ch) v[ch] = __fmaf_rn(z, sR[6 + ch], __fmaf_rn(y, sR[3 + ch], __fmul_rn(x, sR[ch])));
+        if (points_out_cm != nullptr) {
+            float* o = points_out_cm + (size_t)bs * out_batch_stride + i;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) o[(size_t)ch * n] = v[ch];
+        }
+        if (points_out_pm != nullptr) {
+            // point-major bf16 hi / lo image with 32 channels per row (pm_gemm.cu), channels 0-2 = xyz; the caller
+            // zeroed the image once, only the first 8-channel unit of the row is rewritten
+            const size_t r = (size_t)bs * n + i;
+            unsigned char* d = points_out_pm + (r >> 7) * 16384 + ((r & 127) >> 3) * 512 + (r & 7) * 16;
+            uint32_t h[2], l[2];
+            {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+                h[0] = *reinterpret_cast<const uint32_t*>(&hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[0] - __uint_as_float(h[0] << 16),
+                                                                v[1] - __uint_as_float(h[0] & 0xffff0000u));
+                l[0] = *reinterpret_cast<const uint32_t*>(&ll);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2], 0.f);
+                h[1] = *reinterpret_cast<const uint32_t*>(&h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2] - __uint_as_float(h[1] << 16), 0.f);
+                l[1] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], 0u, 0u);
+            *reinterpret_cast<uint4*>(d + 8192) = make_uint4(l[0], l[1], 0u, 0u);
+        }
     }
     // every CTA of this batch item has read R,t above; only CTA 0 commits the update, after the
     // grid-wide read is guaranteed by doing it in a second launch (see host code).
@@ -279,16 +305,23 @@ DCL_API int dcl_weighted_kabsch(int b, int n, const float* src, const float* dst
 
 DCL_API int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, const float* dt,
                              const float* points_in, float* points_out_cm, int64_t out_batch_stride, void* stream) {
+    return dcl_pose_compose_pm(b, n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride, nullptr, stream);
+}
+
+DCL_API int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* dR, const float* dt,
+                                const float* points_in, float* points_out_cm, int64_t out_batch_stride,
+                                void* points_out_pm, void* stream) {
     DCL_RETURN_IF_BAD(b >= 0 && n >= 0);
+    DCL_RETURN_IF_BAD(points_out_pm == nullptr || (((long)b * n) % 128 == 0 && ((uintptr_t)points_out_pm & 15u) == 0));
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int update = (dR != nullptr && dt != nullptr) ? 1 : 0;
     int launched = 0;
-    if (n > 0 && points_in != nullptr && points_out_cm != nullptr) {
+    if (n > 0 && points_in != nullptr && (points_out_cm != nullptr || points_out_pm != nullptr)) {
         ++launched;
         dim3 grid(DCL_DIVUP(n, 256), b);
         pose_compose_kernel<<<grid, 256, 0, st>>>(n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride,
-                                                  update);
+                                                  reinterpret_cast<unsigned char*>(points_out_pm), update);
     }
     if (update) {
         ++launched;

@@ -84,7 +84,7 @@ class PoseEngine:
         rot, trans = pred["rot_pred"], pred["trans_pred"]
         if self.refiner is not None and self.iterations > 0:
             rot, trans = refine_poses(self.refiner, self.points["inp"].view(self.b, self.n_inp, 3), rot, trans,
-                                      pred["F_Xo_p"], pred["conf"], self.iterations)
+                                      pred["F_Xo_p"], pred["conf"], self.iterations, pred.get("F_Xo_p_pm"))
         return rot, trans
 
     def infer(self, host_batch):

@@ -287,5 +287,64 @@ class FusedTail:
         from .dcl_net import pose_heads, svd3_project
         ortho9d, trans = pose_heads(pooled, net.regressor_rot, net.regressor_trans)
         rot = svd3_project(ortho9d, True)
-        return {"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p,
+        return {"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p, "F_Xo_p_pm": pm_Xo_p,
                 "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}
+
+
+class FusedRefiner:
+    """Tensor-core inference path of refiner.Refiner (models/refiner.py:57-95) inside the stage-2 loop of
+    tools/test_YCBV_stage2.py:204-225.  The refiner input cat([points_cano (3), F_Xo_p (256)]) is never built: the
+    first layer reads X = [F_Xo_p image | 32-channel image of the canonicalised points] (its weight columns are
+    permuted and zero-padded to match), the points image being rewritten by dcl_pose_compose_pm every iteration;
+    the last layer's epilogue does the confidence-weighted pooling."""
+
+    def __init__(self, refiner):
+        self.refiner = refiner
+        convs = [m for m in refiner.MLP_share.layers if isinstance(m, torch.nn.Conv1d)]
+        others = [m for m in refiner.MLP_share.layers if not isinstance(m, (torch.nn.Conv1d, torch.nn.ReLU))]
+        assert len(convs) == 3 and not others and convs[0].in_channels == 259
+        with torch.no_grad():
+            w1 = convs[0].weight.reshape(convs[0].out_channels, 259)
+            w1p = w1.new_zeros(w1.shape[0], 288)
+            w1p[:, :256] = w1[:, 3:]          # F_Xo_p channels first (8 k-blocks of the first image)
+            w1p[:, 256:259] = w1[:, :3]       # then x, y, z (k-block 9, channels 3..31 are zero)
+            self.layers = [Layer(w1p, convs[0].bias, True),
+                           Layer(convs[1].weight.reshape(convs[1].out_channels, -1), convs[1].bias, True),
+                           Layer(convs[2].weight.reshape(convs[2].out_channels, -1), convs[2].bias, True)]
+
+    @staticmethod
+    def supported(refiner, b, n):
+        return (b * n) % 256 == 0 and not refiner.training and not torch.is_grad_enabled()
+
+    @torch.no_grad()
+    def refine(self, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration, pm_feat=None):
+        from .dcl_net import pose_heads, svd3_project
+        lib = L.load()
+        b, n, _ = points_inp.shape
+        rows, dev = b * n, points_inp.device
+        points_inp = points_inp.contiguous()
+        rot, trans = rot_pred.clone().contiguous(), trans_pred.clone().contiguous()
+        if pm_feat is None:
+            pm_feat = pm_pack_cm(F_Xo_p)
+        pm_pts = torch.zeros(pm_bytes(rows, 32), dtype=torch.uint8, device=dev)
+        pool_w = torch.softmax(conf, dim=1)[:, :n].reshape(-1).contiguous()     # refiner.py:60
+        st = L.stream_ptr
+
+        def compose(dR, dt):
+            L.check(lib.dcl_pose_compose_pm(b, n, L.ptr(rot), L.ptr(trans), L.ptr(dR), L.ptr(dt), L.ptr(points_inp), None, 0,
+                                            L.ptr(pm_pts), st()), "pose_compose")
+
+        compose(None, None)
+        l1, l2, l3 = self.layers
+        for _ in range(iteration):
+            h1, h2 = pm_empty(rows, l1.cout, dev), pm_empty(rows, l2.cout, dev)
+            run_gemm([{"a0": pm_feat, "a1": pm_pts, "c0": 256, "layer": l1, "out_pm": h1}], rows)
+            run_gemm([{"a0": h1, "layer": l2, "out_pm": h2}], rows)
+            parts = torch.empty(rows // 32, l3.cout, dtype=torch.float32, device=dev)
+            run_gemm([{"a0": h2, "layer": l3, "pool_w": pool_w, "pool_out": parts}], rows)
+            pooled = torch.empty(b, l3.cout, dtype=torch.float32, device=dev)
+            L.check(lib.dcl_pm_pool_reduce(b, l3.cout, n // 32, L.ptr(parts), None, L.ptr(pooled), 0, st()), "pool")
+            ortho9d, dt = pose_heads(pooled, self.refiner.regressor_rot2, self.refiner.regressor_trans2)
+            dR = svd3_project(ortho9d, True)
+            compose(dR.contiguous(), dt.contiguous())
+        return rot, trans

@@ -23,6 +23,20 @@ class Refiner(nn.Module):
         self.MLP_share = Head_MultiLayerPerceptron([256 + 3, 512, 512, 1024], ["relu"] * 3, *plain)
         self.regressor_rot2 = Head_MultiLayerPerceptron([1024, 512, 128, 9], ["relu", "relu", "none"], *plain)
         self.regressor_trans2 = Head_MultiLayerPerceptron([1024, 512, 128, 3], ["relu", "relu", "none"], *plain)
+        self.use_fused = True          # inference: shared MLP on tensor cores inside refine_poses (fused_tail.FusedRefiner)
+        self._fused_refiner = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fused_refiner = None     # parameters moved / cast: packed copies are stale
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._fused_refiner = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        self._fused_refiner = None
+        return super().train(mode)
 
     def forward(self, input_dict):
         input_features = input_dict["input_features"]
@@ -49,11 +63,19 @@ def pose_compose_(R, t, dR, dt, points_in, out_cm):
                                       L.ptr(out_cm), out_cm.shape[1] * N, L.stream_ptr()), "pose_compose")
 
 
-def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration=2):
+def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration=2, F_Xo_p_pm=None):
     """Stage-2 iterative refinement.  points_inp (B,N,3), rot_pred (B,3,3), trans_pred (B,3),
-    F_Xo_p (B,256,N), conf (B,2N) -> refined (rot, trans).  The refiner input buffer (B,259,N) is built
-    once; each iteration only rewrites its first three channels."""
+    F_Xo_p (B,256,N), conf (B,2N) -> refined (rot, trans).  Inference runs the refiner's shared MLP on tensor
+    cores (fused_tail.FusedRefiner; F_Xo_p_pm = the point-major image of F_Xo_p if the caller already has it);
+    otherwise the refiner input buffer (B,259,N) is built once and each iteration only rewrites its first three
+    channels."""
     B, N, _ = points_inp.shape
+    from .fused_tail import FusedRefiner
+    if getattr(refiner, "use_fused", True) and FusedRefiner.supported(refiner, B, N):
+        fused = getattr(refiner, "_fused_refiner", None)
+        if fused is None:
+            fused = refiner._fused_refiner = FusedRefiner(refiner)
+        return fused.refine(points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration, F_Xo_p_pm)
     points_inp = points_inp.contiguous()
     rot_cur, trans_cur = rot_pred.clone().contiguous(), trans_pred.clone().contiguous()
     inp_refiner = torch.empty(B, 3 + F_Xo_p.shape[1], N, dtype=torch.float32, device=points_inp.device)

@@ -223,6 +223,13 @@ int dcl_weighted_kabsch(int b, int n, const float* src, const float* dst, const 
  * the (b, 3+256, n) refiner input.  points_in/points_out_cm may be NULL (pose update only). */
 int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, const float* dt,
     const float* points_in, float* points_out_cm, int64_t out_batch_stride, void* stream);
+/* Same, additionally (or instead: points_out_cm may be NULL) writing the canonicalised cloud as a
+ * point-major bf16 hi/lo image with 32 channels per row (channels 0-2 = xyz, the rest must have been
+ * zeroed once by the caller; (b*n) % 128 == 0): the second operand block of the refiner's first layer
+ * on tensor cores (models/refiner.py:61-63 via dcl_pm_gemm, X = [F_Xo_p image | this image]). */
+int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* dR, const float* dt,
+    const float* points_in, float* points_out_cm, int64_t out_batch_stride,
+    void* points_out_pm, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Group 3: pointwise MLP stacks on tensor cores (replace cuDNN/cuBLAS calls)     */

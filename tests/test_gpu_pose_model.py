@@ -205,8 +205,21 @@ def test_refiner_golden_and_loop(cuda_dev):
         r_o, t_o = T.stage2_refine(oracle_ref, pts, rot, trans, f, conf, 2)
         r_g, t_g = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), f.to(cuda_dev),
                                 conf.to(cuda_dev), 2)
+    assert ref._fused_refiner is not None, "the tensor-core refiner path did not run"
     assert T.rotation_angle_deg(r_g.cpu(), r_o).max().item() < 0.01
     assert (t_g.cpu() - t_o).abs().max().item() < 1e-5
+    # the layer-module path (what training uses) agrees as well, and the pre-packed feature image is equivalent
+    ref.use_fused = False
+    with torch.no_grad():
+        r_u, t_u = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), f.to(cuda_dev),
+                                conf.to(cuda_dev), 2)
+    assert T.rotation_angle_deg(r_u.cpu(), r_o).max().item() < 0.01 and (t_u.cpu() - t_o).abs().max().item() < 1e-5
+    ref.use_fused = True
+    from dcl_net_b200.fused_tail import pm_pack_cm
+    with torch.no_grad():
+        r_p, t_p = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), None, conf.to(cuda_dev), 2,
+                                pm_pack_cm(f.to(cuda_dev)))
+    assert torch.equal(r_p, r_g) and torch.equal(t_p, t_g)
 
 
 def test_pose_heads_kernel_vs_torch(cuda_dev):
