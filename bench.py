@@ -94,14 +94,28 @@ class Cfg:
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING a timed region.  NVML (pynvml) at ~1 kHz when it is
+    importable — a 20-step region lasts ~20 ms, too short for nvidia-smi's 100 ms polling — else `nvidia-smi -lms`."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self._stop, self._thread = None, None, threading.Event(), None
+        self.sm, self.reason_bits, self.sm_max = [], 0, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -110,11 +124,33 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            nv, bits = self.nvml, self.reason_bits
+            flags = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(self.sm), "reasons": sorted(k for k, v in flags.items() if bits & v),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -131,7 +167,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
