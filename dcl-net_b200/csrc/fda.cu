@@ -20,14 +20,17 @@
 // x = hi + lo (both bf16) and every product is evaluated as hi*hi + hi*lo + lo*hi
 // (3 MMAs, error ~2^-17): fp32-faithful results from the bf16 tensor pipe.
 //
-// Operand staging.  A pre-pass ("pack") converts the fp32 channel-major inputs into bf16
-// hi/lo tiles laid out in HBM exactly as the UMMA K-major no-swizzle ("interleave")
-// shared-memory image, so the main kernel moves every tile with ONE 1-D TMA bulk copy
-// (cp.async.bulk / UBLKCP) completing on an mbarrier.  In that layout an operand tile of
-// R rows x K elements is a grid of 8x8-element "core matrices" (8 rows x 16 B, 128 B
-// contiguous);  LBO = byte distance between core matrices adjacent in K,
+// Operand staging.  The operands reach the kernel as bf16 hi/lo tile images laid out in HBM exactly as the UMMA
+// no-swizzle ("interleave") shared-memory image, so every tile moves with 1-D TMA bulk copies (cp.async.bulk /
+// UBLKCP) completing on an mbarrier.  In the inference path the disengage GEMMs write these images in their
+// epilogue (pm_gemm.cu: out_qk / out_v); for the reference's fp32 channel-major interface a pre-pass
+// (fda_pack_kernel) makes them.  Query / key tiles are K-major: a tile of R rows x K elements is a grid of
+// 8x8-element "core matrices" (8 rows x 16 B, 128 B contiguous);
+//               LBO = byte distance between core matrices adjacent in K,
 //               SBO = byte distance between core matrices adjacent in the row direction
-// (cute::UMMA::make_umma_desc<Major::K>, INTERLEAVE: ((8,n),2):((1,SBO),LBO) in uint128).
+// (cute::UMMA::make_umma_desc<Major::K>, INTERLEAVE: ((8,n),2):((1,SBO),LBO) in uint128).  The value chunks are
+// MN-major (a 16-byte unit = 8 value rows of one key; LBO = distance between 8-key groups, SBO = between 8-row
+// chunks), which a point-major producer writes with 16-byte stores.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (in the CTA-pair kernel the
 // peer's warp 1 relays its load completions to the leader), warps 2-9 = softmax / correction / epilogue, two
