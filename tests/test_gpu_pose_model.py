@@ -158,9 +158,10 @@ def test_tail_vs_oracle(cuda_dev, b, n, c_m):
     assert ang < 0.01 and dt < 1e-5, (ang, dt)
 
 
-def test_stage1_from_backbone_vs_oracle(cuda_dev):
-    """Point-feature interpolation -> FDA -> pose on a synthetic voxel pyramid (SURVEY.md §8d config 3, B=4)."""
-    b, n = 4, 1024
+@pytest.mark.parametrize("b,n", [(4, 1024), (3, 384)])
+def test_stage1_from_backbone_vs_oracle(cuda_dev, b, n):
+    """Point-feature interpolation -> FDA -> pose on a synthetic voxel pyramid (SURVEY.md §8d config 3, B=4).
+    (3, 384): odd tile counts everywhere — the non-persistent GEMM kernel and the single-CTA FDA kernel."""
     g = torch.Generator().manual_seed(12)
     pts_inp = (torch.rand(b * n, 3, generator=g) - 0.5) * 0.16
     pts_tmp = (torch.rand(b * n, 3, generator=g) - 0.5) * 0.16
