@@ -65,6 +65,14 @@ def CD_Dis(pred, target):
     return 0.5 * (nearest_dist(pred, target) + nearest_dist(target, pred))
 
 
+def get_cano_label(points_tmp, points_inp, rot_pred, trans_gt):
+    """models/DCL_Net.py:312-317: for every canonicalised input point its nearest template point (the reference
+    runs knn(1, ...) and a gather; nearest_dist's argmin is the same lowest-index nearest neighbour)."""
+    points_inp_cano = torch.bmm((points_inp - trans_gt), rot_pred)
+    _, idx = _nearest(points_inp_cano, points_tmp, True)
+    return torch.gather(points_tmp, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+
+
 def adds_metric(points_posed_pred, points_posed_gt):
     """ADD-S of tools/test_YCBV_stage1.py:188: mean over the model points of the distance to the closest GT-posed point."""
     return nearest_dist(points_posed_pred, points_posed_gt).mean(dim=1)
@@ -78,6 +86,7 @@ class losses(nn.Module):
 
     L2_Dis = staticmethod(L2_Dis)
     CD_Dis = staticmethod(CD_Dis)
+    get_cano_label = staticmethod(get_cano_label)
 
     def forward(self, loss_inp_pred, loss_inp_gt):
         rot_pred, trans_pred = loss_inp_pred["rot_pred"], loss_inp_pred["trans_pred"]

@@ -410,6 +410,23 @@ def test_loss_modules_golden_gpu(cuda_dev):
         assert abs(v.item() - float(gold["s2_" + k])) <= 2e-6 * max(1.0, abs(float(gold["s2_" + k]))), k
 
 
+def test_get_cano_label_vs_knn_path(cuda_dev):
+    """losses.get_cano_label (argmin of the nearest-distance kernel) == the reference's knn(1) + gather."""
+    from dcl_net_b200 import losses as LS
+    from dcl_net_b200.pointnet_lib.pointnet2_utils import knn
+    g = torch.Generator().manual_seed(9)
+    b, n, m = 3, 500, 700
+    tmp, inp = torch.rand(b, m, 3, generator=g).to(cuda_dev), torch.rand(b, n, 3, generator=g).to(cuda_dev)
+    q, _ = torch.linalg.qr(torch.randn(b, 3, 3, generator=g))
+    rot = q.to(cuda_dev)
+    tr = (0.1 * torch.randn(b, 1, 3, generator=g)).to(cuda_dev)
+    got = LS.get_cano_label(tmp, inp, rot, tr)
+    cano = torch.bmm(inp - tr, rot)
+    _, idx = knn(1, cano.contiguous(), tmp.contiguous())
+    want = torch.gather(tmp, 1, idx.long().repeat(1, 1, 3))
+    assert torch.equal(got, want)
+
+
 def test_cd_dis_gradient_vs_reference_graph(cuda_dev):
     from dcl_net_b200 import losses
     g = torch.Generator().manual_seed(3)
