@@ -429,6 +429,175 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     }
 }
 
+// ------------------------------------------------------------------ persistent CTA-pair variant (cta_group::2)
+// The pair runs every k-step as ONE M = 256 tcgen05.mma issued by the leader: each CTA stages its own A blob and only
+// HALF of the W blob (output rows [r NT/2, (r+1) NT/2), hi and lo), the tensor cores of both SMs read both halves.
+// Against the multicast kernel above this takes the ingest per SM and k-block from 48 KB to 32 KB, the operand
+// reads from shared memory with it, and lets the ring hold STAGES2 = 6/9/12 stages.  Hand-offs as in fda.cu's pair
+// kernel (conventions pinned by dcl_debug_umma_pair_gemm): the peer's MMA warp relays "my stage landed" to the
+// leader's full barriers, every tcgen05.commit is multicast to both CTAs, epilogue warps of both CTAs release the
+// accumulator with one CTA-scope arrive per warp on the leader's barrier.
+template <int NT, int STAGES>
+struct GmP2Cfg {
+    static constexpr int B_BLOB = NT * GM_BK * 4;          // whole W blob in global memory: [hi | lo]
+    static constexpr int B_HALF_ROWS = B_BLOB / 4;         // this CTA's rows of the hi (or lo) image
+    static constexpr int STAGE_BYTES = GM_A_BLOB + B_BLOB / 2;
+    static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(2 * NT <= 512, "TMEM budget");
+    static_assert(2 * STAGES + 4 <= 60, "barrier area");
+};
+
+template <int NT, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
+    pm_gemm_pair_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
+    using Cfg = GmP2Cfg<NT, STAGES>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(16) GmColParams s_colp;
+    __shared__ float s_dot[GM_BM];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2] (the leader's are the ones waited on)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = dcl_cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int total_units = npairs_m * ntiles_n * nprob;   // unit = (m-tile pair, n-tile, problem); problem fastest
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            dcl_mbar_init(full + i, leader ? 2 : 1);       // leader: own producer + the peer's relay
+            dcl_mbar_init(empty + i, 1);                   // one multicast commit per phase
+        }
+        for (int i = 0; i < 2; ++i) {
+            dcl_mbar_init(acc_full + i, 1);
+            dcl_mbar_init(acc_empty + i, 2 * (GM_P_EPI / 32));  // one arrive per epilogue warp of both CTAs
+        }
+        dcl_fence_barrier_init();
+    }
+    __syncthreads();
+    dcl_cluster_sync();  // both CTAs' barriers exist before anything is signalled at them
+    if (warp == 1) tc2_alloc(tmem_slot, 2 * NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (dcl_elect_one()) {
+            int it = 0;
+            for (int u = cluster_id; u < total_units; u += nclusters) {
+                const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+                const dcl_pm_gemm_problem& pr = batch.p[prob];
+                const int KB = pr.kb_total;
+                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
+                const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
+                                          (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
+                const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB +
+                                         rank * Cfg::B_HALF_ROWS;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    if (it >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((it / STAGES) - 1) & 1));
+                    unsigned char* dst = smem + s * Cfg::STAGE_BYTES;
+                    dcl_mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                    const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * GM_A_BLOB
+                                                              : a1 + (size_t)(kb - pr.kb0) * GM_A_BLOB;
+                    const unsigned char* wsrc = w + (size_t)kb * Cfg::B_BLOB;
+                    dcl_bulk_g2s(dst, asrc, GM_A_BLOB, full + s);
+                    dcl_bulk_g2s(dst + GM_A_BLOB, wsrc, Cfg::B_HALF_ROWS, full + s);                          // hi rows
+                    dcl_bulk_g2s(dst + GM_A_BLOB + Cfg::B_HALF_ROWS, wsrc + Cfg::B_BLOB / 2, Cfg::B_HALF_ROWS,
+                                 full + s);                                                                   // lo rows
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && dcl_elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * GM_BM, NT);
+            const uint64_t desc0 = umma_desc(dcl_smem_u32(smem), 128, 512);
+            int it = 0, tl = 0;
+            for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
+                const int KB = batch.p[u % nprob].kb_total;
+                const int acc = tl & 1;
+                if (tl >= 2) dcl_mbar_wait(acc_empty + acc, (uint32_t)(((tl >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * NT;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    dcl_mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
+                    tc_fence_after();
+                    const uint64_t dAh = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
+                    const uint64_t dAl = dAh + (uint64_t)((GM_A_BLOB / 2) >> 4);
+                    const uint64_t dBh = dAh + (uint64_t)(GM_A_BLOB >> 4);
+                    const uint64_t dBl = dBh + (uint64_t)(Cfg::B_HALF_ROWS >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < GM_BK / 16; ++ks) {
+                        const uint64_t off = (uint64_t)((ks * 256) >> 4);
+                        tc2_mma_bf16(tacc, dAh + off, dBh + off, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                        tc2_mma_bf16(tacc, dAh + off, dBl + off, idesc, 1u);
+                        tc2_mma_bf16(tacc, dAl + off, dBh + off, idesc, 1u);
+                    }
+                    tc2_commit_mcast(empty + s, (uint16_t)0x3);
+                }
+                tc2_commit_mcast(acc_full + acc, (uint16_t)0x3);
+            }
+        } else if (!leader && dcl_elect_one()) {
+            // relay: "my operands of this stage have landed", in ring order (= the leader's consumption order)
+            int it = 0;
+            for (int u = cluster_id; u < total_units; u += nclusters) {
+                const int KB = batch.p[u % nprob].kb_total;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    dcl_mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
+                    dcl_mbar_arrive_remote(full + s, 0);
+                }
+            }
+        }
+    } else {
+        int tl = 0;
+        for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
+            const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+            const int acc = tl & 1;
+            dcl_mbar_wait(acc_full + acc, (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            gm_epilogue_tile<NT, GM_P_EPI>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp - 2, lane, s_colp, s_dot);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) dcl_mbar_arrive_remote(acc_empty + acc, 0);
+        }
+    }
+    __syncwarp();
+    __syncthreads();
+    dcl_cluster_sync();  // the leader's MMAs read the peer's shared memory until the last commit
+    if (warp == 1) {
+        tc_fence_after();
+        tc2_dealloc(tmem_base, 2 * NT);
+    }
+}
+
+template <int NT, int STAGES>
+int launch_gemm_pair(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
+    using Cfg = GmP2Cfg<NT, STAGES>;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_pair_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const int ntiles_n = cout / NT, npairs_m = rows / (2 * GM_BM);
+    const int units = npairs_m * ntiles_n * nprob;
+    int clusters = num_sms / 2;
+    if (clusters > units) clusters = units;
+    pm_gemm_pair_kernel<NT, STAGES><<<2 * clusters, GM_P_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n, npairs_m);
+    return dcl_launch_status();
+}
+
 template <int NT, int STAGES>
 int launch_gemm_cluster(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
     using Cfg = GmPCfg<NT, STAGES>;
@@ -560,8 +729,15 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
         batch.p[i] = p;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // Persistent cluster-of-2 kernel when the m-tiles pair up; DCL_PM_GEMM_SIMPLE=1 forces the simple kernel (A/B).
+    // Persistent kernels when the m-tiles pair up: the CTA-pair (cta_group::2) kernel by default,
+    // DCL_PM_GEMM_MCAST=1 selects the multicast one, DCL_PM_GEMM_SIMPLE=1 the simple kernel (A/B runs).
     static const bool force_simple = getenv("DCL_PM_GEMM_SIMPLE") != nullptr;
+    static const bool force_mcast = getenv("DCL_PM_GEMM_MCAST") != nullptr;
+    if (!force_simple && !force_mcast && (rows / GM_BM) % 2 == 0) {
+        if (nt == 256) return launch_gemm_pair<256, 6>(batch, nproblems, rows, cout, st);
+        if (nt == 128) return launch_gemm_pair<128, 8>(batch, nproblems, rows, cout, st);
+        return launch_gemm_pair<64, 9>(batch, nproblems, rows, cout, st);
+    }
     if (!force_simple && (rows / GM_BM) % 2 == 0) {
         if (nt == 256) return launch_gemm_cluster<256, 4>(batch, nproblems, rows, cout, st);
         if (nt == 128) return launch_gemm_cluster<128, 6>(batch, nproblems, rows, cout, st);
