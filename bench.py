@@ -363,15 +363,18 @@ def run_b200_arm(args, rank, world, local_rank):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_burst = peaks.get("bf16_tflops_burst") or peaks.get("bf16_tflops")
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"
-    # Dominant kernel: the persistent cluster GEMM with 256-wide tiles (disengage and fuser layers; 5 launches/step).
+    # Dominant kernel: the persistent CTA-pair GEMM with 256-wide tiles (disengage and fuser layers; 5 launches/step).
     gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(fl for _, fl in gemm)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm else float("nan")
     split_note = ("every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful, so the algorithmic "
                   "fraction is bounded by 1/3; tensor-pipe occupancy is ~3x the algorithmic fraction")
     # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, mean of its five launches)
-    # from the `ncu --set full` capture of the default configuration: profiles/r01_gemm_fda_ncu_full.txt
+    # from the `ncu --set full` capture of the default configuration: profiles/r01_gemm_fda_ncu_full.txt (taken on
+    # the multicast variant of the kernel; operands and outputs, hence the DRAM bytes, are the same)
     traffic = 2.31e8 if (b == 32 and args.c_m == 128) else None
-    roofline = {"kernel": "pm_gemm_cluster_kernel<256,4>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+    gemm_kernel = ("pm_gemm_cluster_kernel<256,4>" if os.environ.get("DCL_PM_GEMM_MCAST")
+                   else "pm_gemm_kernel<256,2>" if os.environ.get("DCL_PM_GEMM_SIMPLE") else "pm_gemm_pair_kernel<256,6>")
+    roofline = {"kernel": gemm_kernel, "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "traffic_source": "profiles/r01_gemm_fda_ncu_full.txt (bytes per launch)" if traffic else None,
                 "peak_source": peak_src,
