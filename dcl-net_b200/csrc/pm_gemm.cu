@@ -686,10 +686,13 @@ __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout
     const int inst = g / cout, col = g % cout;
     float acc = accumulate ? out[g] : 0.f;
     const float* p = partials + (size_t)inst * parts * cout + col;
-    for (int i = 0; i < parts; ++i) acc += p[(size_t)i * cout];
+    // the additions stay in index order; unrolling only puts 16 independent loads in flight per thread
+#pragma unroll 16
+    for (int i = 0; i < parts; ++i) acc += __ldg(p + (size_t)i * cout);
     if (partials2 != nullptr) {
         const float* q = partials2 + (size_t)inst * parts * cout + col;
-        for (int i = 0; i < parts; ++i) acc += q[(size_t)i * cout];
+#pragma unroll 16
+        for (int i = 0; i < parts; ++i) acc += __ldg(q + (size_t)i * cout);
     }
     out[g] = acc;
 }

@@ -125,13 +125,34 @@ __global__ void __launch_bounds__(CW_THREADS) conf_weights_kernel(int n, const f
     const float* l1 = logit_1 + (size_t)bi * n;
     const float* l2 = logit_2 + (size_t)bi * n;
     float* crow = conf + (size_t)bi * 2 * n;
+    // Up to CW_PER values per thread stay in registers between the three phases (2n <= CW_THREADS * CW_PER covers
+    // n <= 2048); longer rows re-read what pass 1 wrote.
+    constexpr int CW_PER = 16;
+    const int total_n = 2 * n;
+    const bool in_regs = total_n <= CW_THREADS * CW_PER;
+    float cv[CW_PER];
     // pass 1: sigmoid, row maximum
     float mx = -CUDART_INF_F;
-    for (int i = tid; i < 2 * n; i += CW_THREADS) {
-        const float x = (i < n) ? __fadd_rn(l1[i], b1) : __fadd_rn(l2[i - n], b2);
-        const float c = 1.0f / (1.0f + expf(-x));
-        crow[i] = c;
-        mx = fmaxf(mx, c);
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < CW_PER; ++k) {
+            const int i = tid + k * CW_THREADS;
+            float c = -CUDART_INF_F;
+            if (i < total_n) {
+                const float x = (i < n) ? __fadd_rn(__ldg(l1 + i), b1) : __fadd_rn(__ldg(l2 + i - n), b2);
+                c = 1.0f / (1.0f + expf(-x));
+                crow[i] = c;
+            }
+            cv[k] = c;
+            mx = fmaxf(mx, c);
+        }
+    } else {
+        for (int i = tid; i < total_n; i += CW_THREADS) {
+            const float x = (i < n) ? __fadd_rn(l1[i], b1) : __fadd_rn(l2[i - n], b2);
+            const float c = 1.0f / (1.0f + expf(-x));
+            crow[i] = c;
+            mx = fmaxf(mx, c);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -144,9 +165,17 @@ __global__ void __launch_bounds__(CW_THREADS) conf_weights_kernel(int n, const f
     }
     __syncthreads();
     mx = s_bcast;
-    // pass 2: sum of exp(c - max) (each thread re-reads what it wrote)
+    // pass 2: sum of exp(c - max)
     float sum = 0.f;
-    for (int i = tid; i < 2 * n; i += CW_THREADS) sum += expf(crow[i] - mx);
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < CW_PER; ++k) {
+            cv[k] = expf(cv[k] - mx);          // exp(-inf) = 0 for the padding slots
+            sum += cv[k];
+        }
+    } else {
+        for (int i = tid; i < total_n; i += CW_THREADS) sum += expf(crow[i] - mx);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncthreads();
@@ -159,10 +188,22 @@ __global__ void __launch_bounds__(CW_THREADS) conf_weights_kernel(int n, const f
     }
     __syncthreads();
     const float total = s_bcast;
-    for (int i = tid; i < 2 * n; i += CW_THREADS) {
-        const float w = expf(crow[i] - mx) / total;
-        if (i < n) w1[(size_t)bi * n + i] = w;
-        else w2[(size_t)bi * n + i - n] = w;
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < CW_PER; ++k) {
+            const int i = tid + k * CW_THREADS;
+            if (i < total_n) {
+                const float w = cv[k] / total;
+                if (i < n) w1[(size_t)bi * n + i] = w;
+                else w2[(size_t)bi * n + i - n] = w;
+            }
+        }
+    } else {
+        for (int i = tid; i < total_n; i += CW_THREADS) {
+            const float w = expf(crow[i] - mx) / total;
+            if (i < n) w1[(size_t)bi * n + i] = w;
+            else w2[(size_t)bi * n + i - n] = w;
+        }
     }
 }
 

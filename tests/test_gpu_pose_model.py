@@ -241,7 +241,7 @@ def test_pose_heads_kernel_vs_torch(cuda_dev):
         assert rel_err(o9, want9) < 1e-5 and rel_err(t3, want3) < 1e-5
 
 
-@pytest.mark.parametrize("b,n", [(1, 128), (32, 1024), (5, 640)])
+@pytest.mark.parametrize("b,n", [(1, 128), (32, 1024), (5, 640), (2, 4096)])
 def test_conf_weights_kernel_vs_torch(cuda_dev, b, n):
     """dcl_conf_weights == sigmoid(cat) -> softmax of models/DCL_Net.py:219-220."""
     g = torch.Generator().manual_seed(b + n)
