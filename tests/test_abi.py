@@ -24,6 +24,28 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libdcl_b200.so lacks {name}"
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in _lib.py have the size and field offsets a C compiler gives the structs of the header."""
+    import subprocess
+    structs = {"dcl_pm_gemm_problem": _lib.PmGemmProblem, "dcl_pose_head_mlp": _lib.PoseHeadMlp,
+               "dcl_sp_level": _lib.SpLevel, "dcl_sp_tower": _lib.SpTower, "dcl_fda_job": _lib.FdaJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER_PATH}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 def test_version_and_arch():
     lib = _lib.load()
     assert lib.dcl_b200_abi_version() == 3
