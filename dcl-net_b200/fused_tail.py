@@ -18,7 +18,6 @@ Dataflow (test mode), b instances of n points per side, R = b*n rows:
 import ctypes
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib as L
 from .modules import fda_from_workspaces
@@ -195,15 +194,6 @@ class FusedTail:
         c_m = net.disengage_Xc_m1[1].layers[0].out_channels
         return (net.n_inp == net.n_tmp and net.n_inp % 128 == 0 and c_m in (64, 128) and not net.training
                 and net.mode == "test")
-
-    def _tail_convs(self, rest, x):
-        for conv, relu, bn in rest:
-            x = conv(x)
-            if relu:
-                x = F.relu(x)
-            if bn is not None:
-                x = bn(x)
-        return x
 
     @torch.no_grad()
     def forward(self, pm_xc, pm_yo, b):
