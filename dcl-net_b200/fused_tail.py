@@ -1,19 +1,20 @@
-"""Inference engine for everything of Network.forward after the backbone (models/DCL_Net.py:182-244), with the
-pointwise MLP stacks on tensor cores (csrc/pm_gemm.cu) instead of fp32 cuDNN/cuBLAS calls.
+"""Inference engine for everything of Network.forward after the backbone (models/DCL_Net.py:182-244) and of the
+stage-2 refiner loop (models/refiner.py:57-95), with the pointwise MLP stacks on tensor cores (csrc/pm_gemm.cu)
+instead of fp32 cuDNN/cuBLAS calls.
 
 Activations travel between layers as "PM images" (bf16 hi/lo operand images, include/dcl_b200.h) written by the
-producing kernel's epilogue; fp32 channel-major tensors exist only where the reference interface or the FDA kernel
-needs them.  Weights are packed once per Network (eval-mode BatchNorm before a ReLU is folded into the convolution;
-BatchNorm after a ReLU becomes the GEMM epilogue's per-channel affine).
+producing kernel's epilogue; an fp32 channel-major tensor exists only where the reference interface needs one
+(F_Xo_p, which stage 2 reads).  Weights are packed once per Network (eval-mode BatchNorm before a ReLU is folded
+into the convolution; BatchNorm after a ReLU becomes the GEMM epilogue's per-channel affine).
 
-Dataflow (test mode), b instances of n points per side, R = b*n rows:
+Dataflow (test mode), b instances of n points per side, R = b*n rows — 17 launches:
    PM(F_Xc), PM(F_Yo)  (R x 480)      <- pointnet_sp fused 3-NN interpolation, or pack of an fp32 (R,480) matrix
    8 x [480 -> 256]  ReLU             one launch, 8 problems
-   4 x [256 -> 256], 4 x [256 -> c_m] two launches; outputs PM and/or fp32 (b,C,n) as their consumers need
-   dual fused FDA (csrc/fda.cu)       F_Xo_p, F_Xo_m, F_Yc_p, F_Yc_m
-   confidence heads [2c_m -> 128 -> 128] on tensor cores, [128 -> 1] + sigmoid + softmax over 2n in torch
+   4 x [256 -> 256], 4 x [256 -> c_m] two launches; epilogues write PM images and the FDA query / key / value images
+   dual fused FDA (csrc/fda.cu)       one launch, both directions: F_Xo_p (+ fp32), F_Xo_m, F_Yc_p, F_Yc_m as PM images
+   confidence heads [2c_m -> 128 -> 128 (-> 1 as a dot in the epilogue)], then dcl_conf_weights (sigmoid + softmax)
    fusers [512 -> 512 -> 512 -> 1024] ReLU+BN, the last layer pooling rows with the confidence weights
-   regressors on the pooled (b,1024) feature (tiny, torch) -> 9-D -> svd3_project, 3-D translation
+   pose heads on the pooled (b,1024) feature (dcl_pose_head) -> 9-D -> svd3_project, 3-D translation
 """
 import ctypes
 
