@@ -53,7 +53,10 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=4, help="instances per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the host-in/host-out pipeline")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the host-in/host-out pipeline")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams the timed steps alternate over (each step is still one whole pass over its own "
+                         "batch; with 2 the tail of one step's kernels overlaps the head of the next step's)")
     ap.add_argument("--refine-iterations", type=int, default=0,
                     help="append the stage-2 refinement loop (tools/test_YCBV_stage2.py) with this many iterations; "
                          "0 = stage 1 only, the configuration BASELINE.json's metric is quoted on")
@@ -68,6 +71,7 @@ def workload_config(args, n_gpus):
         "B_per_gpu": args.batch, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
         "weights": "random init, eval mode", "sharding": f"instances x{n_gpus}, weak scaling",
         "l2": f"{ROTATE} rotating input sets; per-step activations (> 1 GB at B=32) exceed the 126 MB L2",
+        "streams": f"{max(1, getattr(args, 'streams', 1))} CUDA stream(s): consecutive steps alternate over them, each step one whole pass",
     }
 
 
@@ -269,16 +273,36 @@ def run_b200_arm(args, rank, world, local_rank):
     if args.refine_iterations > 0:
         from dcl_net_b200.refiner import Refiner
         refiner = Refiner().eval().to(dev)
-    engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations) for _ in range(ROTATE)]
-    for eng, bt in zip(engines, batches):
-        eng.load(bt)
+    nstreams = max(1, args.streams)
+    n_eng = ROTATE if nstreams == 1 else nstreams * ((ROTATE + nstreams - 1) // nstreams)   # an engine stays on one stream
+    engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations) for _ in range(n_eng)]
+    for k, eng in enumerate(engines):
+        eng.load(batches[k % ROTATE])
     torch.cuda.synchronize()
+    side_streams = [torch.cuda.Stream(dev) for _ in range(nstreams)] if nstreams > 1 else []
 
-    def step_resident(i):
-        rot, trans = engines[i % ROTATE].run()
+    def step_resident(i, multi=False):
+        eng = engines[i % n_eng]
+        if side_streams and multi:
+            with torch.cuda.stream(side_streams[i % nstreams]):
+                rot, trans = eng.run()
+                if world > 1:
+                    rot, trans = sharding.gather_poses(rot, trans, equal_shards=True)
+            return rot, trans
+        rot, trans = eng.run()
         if world > 1:
             rot, trans = sharding.gather_poses(rot, trans, equal_shards=True)
         return rot, trans
+
+    def fork():
+        main = torch.cuda.current_stream(dev)
+        for st in side_streams:
+            st.wait_stream(main)
+
+    def join():
+        main = torch.cuda.current_stream(dev)
+        for st in side_streams:
+            main.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -304,7 +328,7 @@ def run_b200_arm(args, rank, world, local_rank):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(args.steps):
-            step_resident(i)
+            step_resident(i)          # one stream: the per-kernel events below must not see another step's kernels
         ev1.record()
         barrier()
         ms_eager = max_over_ranks(ev0.elapsed_time(ev1))
@@ -319,15 +343,18 @@ def run_b200_arm(args, rank, world, local_rank):
         if use_graph:
             for eng in engines:
                 eng.capture()
-            for i in range(3):
-                step_resident(i)
+            for i in range(2 * n_eng):
+                step_resident(i, multi=True)
+            barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        fork()
         for i in range(args.steps):
-            step_resident(i)
+            step_resident(i, multi=True)
+        join()
         ev1.record()
         barrier()
         ms_total = max_over_ranks(ev0.elapsed_time(ev1))
@@ -337,8 +364,9 @@ def run_b200_arm(args, rank, world, local_rank):
         #      from pinned host memory and reads ITS (B,12) poses back; PipelinedPoseEngine overlaps the copy of
         #      batch i+1 with the pass over batch i (two buffer sets, a copy stream).
         del engines[1:]
-        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=args.e2e_depth, refiner=refiner,
-                                   iterations=args.refine_iterations, use_graph=use_graph)
+        pipe = PipelinedPoseEngine(net, dev, b, caps, depth=max(args.e2e_depth, nstreams), refiner=refiner,
+                                   iterations=args.refine_iterations, use_graph=use_graph,
+                                   compute_streams=nstreams > 1)
         checksum = 0.0
         for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(max(3, min(args.warmup, 5)))):
             checksum += float(trans[0, 0])
@@ -405,6 +433,7 @@ def run_b200_arm(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": b * 12 * 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph" if use_graph else "eager",
+                "streams": nstreams,
                 "ms_per_step_eager": ms_eager / args.steps, "clocks": clocks, "roofline": roofline,
                 "roofline_fda": roofline_fda}
         if world == 1 and not args.no_cpu_baseline:

@@ -102,10 +102,14 @@ class PipelinedPoseEngine:
     copied to the device on a copy stream while batch i computes, and each batch's (B,12) poses are read back
     to pinned host memory right after its pass.  Every batch still pays its own H2D and D2H."""
 
-    def __init__(self, net, device, batch, capacities, depth=2, refiner=None, iterations=0, use_graph=True):
+    def __init__(self, net, device, batch, capacities, depth=2, refiner=None, iterations=0, use_graph=True,
+                 compute_streams=False):
         self.engines = [PoseEngine(net, device, batch, capacities, refiner, iterations) for _ in range(depth)]
         self.device, self.use_graph = device, use_graph
         self.copy_stream = torch.cuda.Stream(device)
+        # compute_streams: every engine slot runs on a stream of its own, so the tail of one pass's kernels
+        # overlaps the head of the next pass (each pass still owns its buffers and its graph)
+        self.compute_streams = [torch.cuda.Stream(device) for _ in range(depth)] if compute_streams else None
         self._captured = False
         self.h2d_bytes = 0
 
@@ -142,6 +146,8 @@ class PipelinedPoseEngine:
 
         for ev in done:
             ev.record(main)
+        for cs in self.compute_streams or []:
+            cs.wait_stream(main)
         stage(0, first)
         i = 0
         nxt = next(host_batches, None)
@@ -150,10 +156,12 @@ class PipelinedPoseEngine:
             eng = self.engines[slot]
             if nxt is not None:
                 stage((i + 1) % depth, nxt)                   # overlaps with the pass launched below
-            main.wait_event(loaded[slot])
-            rot, trans = eng.run()
-            eng.out_host.copy_(torch.cat([rot.reshape(eng.b, 9), trans], dim=1), non_blocking=True)
-            done[slot].record(main)
+            cs = self.compute_streams[slot] if self.compute_streams else main
+            cs.wait_event(loaded[slot])
+            with torch.cuda.stream(cs):
+                rot, trans = eng.run()
+                eng.out_host.copy_(torch.cat([rot.reshape(eng.b, 9), trans], dim=1), non_blocking=True)
+                done[slot].record(cs)
             pending.append(slot)
             if len(pending) == depth or nxt is None:
                 while pending and (len(pending) == depth or nxt is None):

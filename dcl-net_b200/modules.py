@@ -20,6 +20,8 @@ FDA_KERNEL_EVENTS = None
 
 
 def _fda_workspace(nbytes, device):
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)   # private to the graph being captured
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _fda_ws.get(key)
     if ws is None or ws.numel() < nbytes:

@@ -19,6 +19,10 @@ _ws_cache = {}
 def _workspace(nbytes, device):
     """Per-(device, stream) scratch for the bucket build; grown on demand, never shared across
     streams (the kernels of one call are ordered on their stream, so reuse on it is safe)."""
+    if torch.cuda.is_current_stream_capturing():
+        # a captured graph gets scratch of its own (from its private pool): graphs captured on the same capture
+        # stream would otherwise share one buffer and race when they are replayed on different streams
+        return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
