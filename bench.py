@@ -175,11 +175,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
+def host_cores():
+    """CPUs this process may run on (the GPU arm binds itself to its GPU's NUMA node before it gets here)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_pass_builder(args):
     """The oracle port of one step on the host: torch 3-NN interpolation + TailNetwork, all host threads."""
     import torch
     from oracle import torch_oracle as T
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     b = args.cpu_batch
     torch.manual_seed(0)
     net = T.TailNetwork(mode="test", c_m=args.c_m).eval()
@@ -213,7 +221,7 @@ def run_reference_arm(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -229,9 +237,9 @@ def cpu_baseline(args):
         dt = time.perf_counter() - t0
         if (dt >= 10.0 and n >= 3) or dt >= 30.0:
             break
-    return {"value": b * n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": b * n / dt, "unit": UNIT, "cores": host_cores(), "kind": "port",
             "sample": f"{n} passes x {b} instances (B={b} slice of the same workload), {dt:.1f} s, "
-                      f"torch {os.cpu_count()} threads, oracle/torch_oracle.py"}
+                      f"torch {host_cores()} threads, oracle/torch_oracle.py"}
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
