@@ -266,7 +266,8 @@ def run_b200_arm(args, rank, world, local_rank):
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    pin_to_gpu_numa_node(local_rank)
+    if world > 1:
+        pin_to_gpu_numa_node(local_rank)   # eight ranks sharing the host: keep each one's pinned buffers local
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     if world > 1:
