@@ -629,7 +629,7 @@ struct SpLevelBatch {
     SpLevelDev lv[SPL_MAX_LEVELS];
 };
 
-__global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREADS)
+__global__ void __cluster_dims__(SPB_CLUSTER, 1, 1) __launch_bounds__(SPB_THREADS, 1)
     sp_bucket_build_cluster_kernel(const __grid_constant__ SpLevelBatch batch) {
     __shared__ int s_cnt[SPL_SBINS];   // this CTA's histogram; the other CTAs of the cluster read it through DSMEM
     __shared__ int s_base[SPL_SBINS];  // where this CTA's entries of bucket b start in sorted[]
