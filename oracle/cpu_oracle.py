@@ -157,6 +157,21 @@ def sp_three_nn(unknown, known):
     return d2, idx
 
 
+def sp_three_nn_slab_model(unknown, vox, ext, off, gx):
+    """Model of the product's slab-walk search (see neighbour_oracle.c); returns (dist2, idx, candidates visited)."""
+    import ctypes
+    unknown, pu = _f(unknown)
+    vox, pv = _i(vox)
+    ext, pe = _f(np.asarray(ext, np.float32))
+    off, po = _f(np.asarray(off, np.float32))
+    n, m = unknown.shape[0], vox.shape[0]
+    d2, pd = _f(np.empty((n, 3), np.float32))
+    idx, pi = _i(np.empty((n, 3), np.int32))
+    visited = ctypes.c_long(0)
+    lib().oracle_sp_three_nn_slab_model(n, m, int(gx), pu, pv, pe, po, pd, pi, ctypes.byref(visited))
+    return d2, idx, visited.value
+
+
 def sp_three_interpolate(features, idx, weight):
     features, pf = _f(features)
     idx, pi = _i(idx)

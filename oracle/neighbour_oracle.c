@@ -270,6 +270,62 @@ ORACLE_API void oracle_sp_three_nn(int n, int m, const float* unknown, const flo
     }
 }
 
+/* Model (not a restatement of the reference) of the product's slab-walk search (csrc/sp_interpolate.cu,
+ * sp_group_search_t, slab mode): the known points are voxel centres ((i * ext) + off) + 0.5 * ext formed in fp32; an
+ * instance's voxels are grouped into slabs of equal first index; a query visits slabs outwards from its own and stops
+ * when the squared distance to the nearest unvisited slab plane exceeds 1.000001 x its current third-best; candidates
+ * are ranked by the key (d, original index).  tests/test_cpu_oracle.py checks on the CPU that this returns exactly what
+ * the reference-order scan oracle_sp_three_nn returns, i.e. that the pruning rule and the key are sound, ties included.
+ * vox: (m,4) int32 (b, ix, iy, iz); unknown: (n,4) float bxyz. */
+static int lex_lt(float d, int k, float bd, int bk) { return d < bd || (d == bd && k < bk); }
+static void insert_lex(float d, int k, float* bd, int* bk) {
+    if (!lex_lt(d, k, bd[2], bk[2])) return;
+    if (lex_lt(d, k, bd[1], bk[1])) {
+        bd[2] = bd[1]; bk[2] = bk[1];
+        if (lex_lt(d, k, bd[0], bk[0])) { bd[1] = bd[0]; bk[1] = bk[0]; bd[0] = d; bk[0] = k; }
+        else { bd[1] = d; bk[1] = k; }
+    } else { bd[2] = d; bk[2] = k; }
+}
+ORACLE_API void oracle_sp_three_nn_slab_model(int n, int m, int gx, const float* unknown, const int* vox,
+                                              const float* ext, const float* off, float* dist2, int* idx,
+                                              long* visited_out) {
+    long visited = 0;
+    const float half0 = 0.5f * ext[0], half1 = 0.5f * ext[1], half2 = 0.5f * ext[2];
+    for (int pt = 0; pt < n; ++pt) {
+        const float* u = unknown + (size_t)pt * 4;
+        float bd[3] = {INFINITY, INFINITY, INFINITY};
+        int bk[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        int lo = (int)floorf((u[1] - off[0]) / ext[0]);
+        if (lo < 0) lo = 0;
+        if (lo > gx - 1) lo = gx - 1;
+        int hi = lo + 1;
+        while (lo >= 0 || hi < gx) {
+            float dl = INFINITY, dh = INFINITY;
+            if (lo >= 0) { const float cx = (((float)lo * ext[0]) + off[0]) + half0; const float dx = u[1] - cx; dl = dx * dx; }
+            if (hi < gx) { const float cx = (((float)hi * ext[0]) + off[0]) + half0; const float dx = u[1] - cx; dh = dx * dx; }
+            const int take_lo = hi >= gx || (lo >= 0 && dl <= dh);
+            const float dmin = take_lo ? dl : dh;
+            if (!(dmin <= bd[2] * 1.000001f)) break;
+            const int s = take_lo ? lo-- : hi++;
+            for (int k = 0; k < m; ++k) {   /* the slab's members, in any order */
+                const int* v = vox + (size_t)k * 4;
+                if ((float)v[0] != u[0] || v[1] != s) continue;
+                const float cx = (((float)v[1] * ext[0]) + off[0]) + half0;
+                const float cy = (((float)v[2] * ext[1]) + off[1]) + half1;
+                const float cz = (((float)v[3] * ext[2]) + off[2]) + half2;
+                const float d = dist2f(u[1], u[2], u[3], cx, cy, cz);
+                ++visited;
+                if (d < INFINITY) insert_lex(d, k, bd, bk);
+            }
+        }
+        for (int j = 0; j < 3; ++j) {
+            dist2[pt * 3 + j] = bd[j];
+            idx[pt * 3 + j] = bk[j] == 0x7fffffff ? 0 : bk[j];
+        }
+    }
+    if (visited_out) *visited_out = visited;
+}
+
 /* libs/pointnet_sp/src/interpolate_gpu.cu:80-102 */
 ORACLE_API void oracle_sp_three_interpolate(int c, int m, int n, const float* points, const int* idx,
                                             const float* weight, float* out) {

@@ -187,3 +187,32 @@ def test_c_oracle_equals_reference_kernels_fixture():
     feats = torch.randn(k.shape[0], 8, generator=g(13)).numpy()
     w = torch.rand(300, 3, generator=g(14)).numpy()
     assert np.array_equal(O.sp_three_interpolate(feats, i, w), gold["sp_interp"])
+
+
+@pytest.mark.parametrize("seed,b,side,m,n_per", [(1, 3, 32, 1500, 200), (2, 2, 16, 300, 150), (3, 4, 8, 60, 100),
+                                                  (4, 1, 64, 40, 64), (5, 8, 64, 12, 32)])
+def test_slab_walk_pruning_rule_is_exact(seed, b, side, m, n_per):
+    """The search the product runs on the pyramid levels (slabs of equal first voxel index, walked outwards, pruned by
+    the plane distance with a 1e-6 margin, candidates ranked by (d, index)) returns exactly what the reference-order
+    scan returns — including queries on voxel corners, where up to eight centres tie, instances with fewer than three
+    voxels, and voxels given in shuffled order — while visiting a fraction of the candidates."""
+    rng = np.random.default_rng(seed)
+    vox = np.concatenate([rng.integers(0, b, (m, 1)), rng.integers(0, side, (m, 3))], 1).astype(np.int32)
+    vox = np.unique(vox, axis=0)
+    vox = vox[rng.permutation(len(vox))]
+    ext = np.full(3, 0.6 / side, np.float32)
+    off = np.full(3, -0.3, np.float32)
+    centres = ((vox[:, 1:].astype(np.float32) * ext) + off) + np.float32(0.5) * ext      # torch's evaluation order
+    known = np.concatenate([vox[:, :1].astype(np.float32), centres.astype(np.float32)], 1)
+    ids = np.repeat(np.arange(b), n_per).astype(np.float32)[:, None]
+    pts = ((rng.random((b * n_per, 3)) - 0.5) * 0.7).astype(np.float32)
+    corner = (rng.integers(0, side + 1, (b * n_per, 3)).astype(np.float32) * ext + off).astype(np.float32)
+    pts[::3] = corner[::3]                                                                # distance ties
+    unknown = np.concatenate([ids, pts], 1).astype(np.float32)
+    d_ref, i_ref = O.sp_three_nn(unknown, known)
+    d_got, i_got, visited = O.sp_three_nn_slab_model(unknown, vox, ext, off, side)
+    assert np.array_equal(i_got, i_ref)
+    assert np.array_equal(d_got, d_ref.astype(np.float32))
+    full = sum(int((vox[:, 0] == k).sum()) for k in range(b)) * n_per
+    if len(vox) > 200:
+        assert visited < 0.6 * full, (visited, full)
