@@ -1,0 +1,98 @@
+"""Host-side packing of the tensor-core path, checked on the CPU: the packed weight image follows the byte formula
+of include/dcl_b200.h, eval-mode BatchNorm folding reproduces the layer modules, and the refiner's first layer is
+permuted / padded the way FusedRefiner feeds it."""
+import torch
+
+from dcl_net_b200 import fused_tail as FT
+from dcl_net_b200.modules import BasicBlock_3DCONV, Head_MultiLayerPerceptron
+from dcl_net_b200.refiner import Refiner
+
+
+def unpack_weight(packed, cout, cin, nt):
+    """Inverse of pack_weight through the documented map:
+    byte(o,i,half) = ((o/nt)(cin/32) + i/32)(nt*128) + half*(nt*64) + ((o%nt)/8)*512 + ((i%32)/8)*128 + (o%8)*16 + (i%8)*2"""
+    raw = packed.view(torch.int16)          # bf16 bit patterns, 2 bytes each
+    o = torch.arange(cout).view(-1, 1).expand(cout, cin)
+    i = torch.arange(cin).view(1, -1).expand(cout, cin)
+    base = ((o // nt) * (cin // 32) + i // 32) * (nt * 128) + ((o % nt) // 8) * 512 + ((i % 32) // 8) * 128 + (o % 8) * 16 + (i % 8) * 2
+    out = torch.zeros(cout, cin, dtype=torch.float64)
+    for half in (0, 1):
+        bits = raw[((base + half * nt * 64) // 2).reshape(-1)].reshape(cout, cin)
+        out += bits.view(torch.bfloat16).double()
+    return out
+
+
+def test_pack_weight_follows_the_header_formula():
+    g = torch.Generator().manual_seed(0)
+    for cout, cin in ((256, 480), (128, 256), (64, 32), (1024, 512)):
+        w = torch.randn(cout, cin, generator=g)
+        nt = FT.pick_nt(cout)
+        packed = FT.pack_weight(w, nt)
+        assert packed.numel() == cout * cin * 4
+        back = unpack_weight(packed, cout, cin, nt)
+        assert (back - w.double()).abs().max().item() <= 2.0 ** -16 * w.abs().max().item()   # hi + lo carries 16 bits
+
+
+def _randomise_bn(mod, g):
+    for m in mod.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm3d)):
+            m.running_mean.copy_(0.2 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.bias.data.copy_(0.2 * torch.randn(m.num_features, generator=g))
+
+
+def _apply(layer, x):
+    w = unpack_weight(layer.w, layer.cout, layer.cin, layer.nt)
+    y = x.double() @ w.T + (layer.bias.double() if layer.bias is not None else 0.0)
+    if layer.relu:
+        y = y.clamp_min(0)
+    if layer.post_scale is not None:
+        y = y * layer.post_scale.double() + layer.post_shift.double()
+    return y
+
+
+def test_disengage_stack_folding_matches_the_modules():
+    g = torch.Generator().manual_seed(1)
+    torch.manual_seed(1)
+    stack = torch.nn.Sequential(BasicBlock_3DCONV(480, 256, False, 1, 1, 0, True, "relu", 0.0),
+                                BasicBlock_3DCONV(256, 128, False, 1, 1, 0, True, "relu", 0.0)).eval()
+    _randomise_bn(stack, g)
+    x = torch.randn(40, 480, generator=g)
+    with torch.no_grad():
+        want = stack(x.T.reshape(1, 480, 40, 1, 1)).reshape(128, 40).T.double()
+        y = x
+        for layer in FT.layers_from_disengage(stack):
+            y = _apply(layer, y).float()
+    assert (y.double() - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
+def test_head_folding_relu_then_batchnorm():
+    g = torch.Generator().manual_seed(2)
+    torch.manual_seed(2)
+    head = Head_MultiLayerPerceptron([512, 512, 512, 1024], ["relu"] * 3, [True] * 3, [0.0] * 3).eval()
+    _randomise_bn(head, g)
+    x = torch.randn(24, 512, generator=g)
+    with torch.no_grad():
+        want = head(x.T.unsqueeze(0)).squeeze(0).T.double()
+        gemm, rest = FT.layers_from_head(head)
+        assert len(gemm) == 3 and not rest
+        y = x
+        for layer in gemm:
+            y = _apply(layer, y).float()
+    assert (y.double() - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
+def test_refiner_first_layer_permutation():
+    torch.manual_seed(3)
+    ref = Refiner().eval()
+    fused = FT.FusedRefiner(ref)
+    l1 = fused.layers[0]
+    assert (l1.cin, l1.cout) == (288, 512)
+    w = unpack_weight(l1.w, 512, 288, l1.nt)
+    conv = [m for m in ref.MLP_share.layers if isinstance(m, torch.nn.Conv1d)][0]
+    w_ref = conv.weight.detach().reshape(512, 259).double()
+    tol = 2.0 ** -16 * w_ref.abs().max().item()
+    assert (w[:, :256] - w_ref[:, 3:]).abs().max().item() <= tol       # F_Xo_p channels first
+    assert (w[:, 256:259] - w_ref[:, :3]).abs().max().item() <= tol    # then x, y, z
+    assert w[:, 259:].abs().max().item() == 0.0                        # zero padding to a whole k-block
