@@ -96,3 +96,34 @@ def test_refiner_first_layer_permutation():
     assert (w[:, :256] - w_ref[:, 3:]).abs().max().item() <= tol       # F_Xo_p channels first
     assert (w[:, 256:259] - w_ref[:, :3]).abs().max().item() <= tol    # then x, y, z
     assert w[:, 259:].abs().max().item() == 0.0                        # zero padding to a whole k-block
+
+
+def test_split_product_precision_rule():
+    """The precision rule of every tensor-core contraction here: x = hi + lo in bf16, products
+    hi*hi + hi*lo + lo*hi accumulated in fp32.  Emulated on the CPU: the result is fp32-faithful (normwise error
+    ~1e-5 or better) where plain bf16 operands miss the 1e-3 bar by an order of magnitude on unscaled post-ReLU dot
+    products."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(256, 480, generator=g).relu()
+    w = torch.randn(256, 480, generator=g) / 480 ** 0.5
+
+    def split(t):
+        hi = t.to(torch.bfloat16).float()
+        return hi, (t - hi).to(torch.bfloat16).float()
+    xh, xl = split(x)
+    wh, wl = split(w)
+    exact = x.double() @ w.double().T
+    three = (xh @ wh.T + xh @ wl.T + xl @ wh.T).double()          # fp32 accumulation, as the TMEM accumulator
+    plain = (xh @ wh.T).double()
+    scale = exact.abs().max().item()
+    assert (three - exact).abs().max().item() <= 2e-5 * scale
+    assert (plain - exact).abs().max().item() >= 1e-3 * scale     # why a single bf16 product is not enough
+    # logits of the FDA: unscaled dot products of post-ReLU features, |S| ~ 40 -> softmax weights
+    q, k = torch.randn(128, 128, generator=g).relu(), torch.randn(1024, 128, generator=g).relu()
+    qh, ql = split(q)
+    kh, kl = split(k)
+    a_exact = torch.softmax(q.double() @ k.double().T, dim=1)
+    a_three = torch.softmax((qh @ kh.T + qh @ kl.T + ql @ kh.T).double(), dim=1)
+    a_plain = torch.softmax((qh @ kh.T).double(), dim=1)
+    rel = lambda a: ((a - a_exact).abs().max() / a_exact.abs().max()).item()
+    assert rel(a_three) < 1e-3 and rel(a_plain) > 1e-2
