@@ -60,6 +60,7 @@ SIGNATURES = {
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_fda_set_trace": (_I, [_P]),
+    "dcl_debug_umma_ts_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
 }
 
 

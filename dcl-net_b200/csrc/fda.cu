@@ -1006,6 +1006,92 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     }
 }
 
+// ------------------------------------------------------------------ A-from-TMEM UMMA probe (bring-up)
+// D (128 x N) = bf16(A) (128 x K) * bf16(B)^T with the A operand read from tensor memory (the "TS" form of
+// tcgen05.mma) — the building block for keeping a hidden activation tile on chip between two GEMM layers.
+// variant 0: A stored two bf16 per 32-bit TMEM column (K = 16 -> 8 columns per MMA); variant 1: one bf16 per column.
+// Not used by the product yet; tools/probe_umma_ts.py reports which convention the hardware follows.
+__global__ void __launch_bounds__(128, 1) umma_ts_probe_kernel(int N, int K, const float* __restrict__ A,
+                                                               const float* __restrict__ B, float* __restrict__ D,
+                                                               int variant) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    unsigned char* sB = smem;
+    const int kch = K / 8;
+    for (int i = threadIdx.x; i < N * kch; i += 128) {
+        const int r = i % N, kc = i / N;
+        uint32_t h[4], l[4];
+        for (int e = 0; e < 4; ++e)
+            split2_bf16(B[(size_t)r * K + kc * 8 + 2 * e], B[(size_t)r * K + kc * 8 + 2 * e + 1], h[e], l[e]);
+        *reinterpret_cast<uint4*>(sB + ((r >> 3) * kch + kc) * 128 + (r & 7) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
+    if (threadIdx.x == 0) {
+        dcl_mbar_init(&bar, 1);
+        dcl_fence_barrier_init();
+    }
+    if ((threadIdx.x >> 5) == 0) tc_alloc(&tmem_slot, 512);
+    dcl_fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int quad = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t a_col = 256;
+    // this thread's row of A into its TMEM lane
+    const int words = variant == 0 ? K / 2 : K;
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) {
+            const int wj = w0 + j;
+            uint32_t h = 0, l = 0;
+            if (wj < words) {
+                if (variant == 0) split2_bf16(A[(size_t)row * K + 2 * wj], A[(size_t)row * K + 2 * wj + 1], h, l);
+                else { split2_bf16(A[(size_t)row * K + wj], 0.f, h, l); h &= 0xffffu; }
+            }
+            v[j] = h;
+        }
+        DCL_TMEM_ST32(tmem_base + t_lane + a_col + w0, v);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, N);
+        const uint64_t dB = umma_desc(dcl_smem_u32(sB), 128, (uint32_t)kch * 128);
+        const uint32_t cols_per_step = variant == 0 ? 8u : 16u;
+        for (int kk = 0; kk < K / 16; ++kk) {
+            const uint32_t ta = tmem_base + a_col + kk * cols_per_step;
+            const uint64_t db = dB + (uint64_t)((kk * 256) >> 4);
+            const uint32_t acc = kk == 0 ? 0u : 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                ::"r"(tmem_base), "r"(ta), "l"(db), "r"(idesc), "r"(acc)
+                : "memory");
+        }
+        tc_commit(&bar);
+    }
+    dcl_mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int cc = 0; cc < N / 32; ++cc) {
+        uint32_t ov[32];
+        DCL_TMEM_LD32(tmem_base + t_lane + cc * 32, ov);
+        tc_wait_ld();
+        for (int i = 0; i < 32; ++i) D[(size_t)row * N + cc * 32 + i] = __uint_as_float(ov[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, 512);
+    }
+}
+
 template <int C>
 struct FdaWs {
     __nv_bfloat16 *Qp, *Kp, *Vp;
@@ -1196,4 +1282,15 @@ DCL_API int dcl_fda_workspace_layout(int b, int c, int p, int n, int m, size_t* 
     offsets3[1] = q_bytes;
     offsets3[2] = q_bytes + k_bytes;
     return 0;
+}
+
+DCL_API int dcl_debug_umma_ts_gemm(int N, int K, const float* A, const float* B, float* D, int variant, void* stream) {
+    DCL_RETURN_IF_BAD(N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0 && K <= 256 && variant >= 0 &&
+                      variant < 2);
+    const size_t smem = (size_t)N * K * 2;
+    DCL_RETURN_IF_BAD(smem <= 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    umma_ts_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D, variant);
+    return dcl_launch_status();
 }

@@ -388,6 +388,13 @@ int dcl_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D,
 int dcl_debug_umma_pair_gemm(int N, int K, const float* A, const float* B, float* D,
     int mode, void* stream);
 
+/* D (128 x N) = bf16(A) bf16(B)^T with the A operand read from TENSOR memory (the "TS" form of
+ * tcgen05.mma), single bf16 product.  variant 0: two bf16 per 32-bit TMEM column; 1: one per column.
+ * Bring-up probe for keeping a hidden activation tile on chip between two layers; not used by the
+ * product (tools/probe_umma_ts.py). */
+int dcl_debug_umma_ts_gemm(int N, int K, const float* A, const float* B, float* D,
+    int variant, void* stream);
+
 /* Installs (or, with NULL, removes) a device buffer of 4*1024 int64 into which CTA (0,0) of
  * the FDA kernels stamps clock64() at its role hand-offs: [role*1024 + key_block*8 + event],
  * roles 0 = MMA issuer, 1 = softmax warp 2, 2 = TMA producer; [3*1024 + slot*8 + event] holds
