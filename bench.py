@@ -17,8 +17,11 @@ all_gather of the (B,12) poses, which is inside the timed region.
 `value`  : device-resident throughput — inputs already in HBM, CUDA events, max over ranks.
 `e2e`    : the same pass through PoseEngine.infer() from pinned HOST buffers: H2D copies of that step's batch and
            the D2H read of the poses are inside the timed region.
-`roofline`: the fused FDA kernel (dominant kernel written here), timed live with CUDA events around each of its
-           launches inside the timed region; algorithmic FLOPs = 2*N*M*(C + P + C) per instance and direction.
+`roofline`: the dominant kernel — the persistent CTA-pair tensor-core GEMM of the pointwise MLP stacks
+           (pm_gemm_pair_kernel<256,6>, 5 launches per step) — timed live with CUDA events around each of its launches
+           in an eager pass of the same K steps; algorithmic FLOPs = sum of 2*rows*cin*cout over the layers in those
+           launches; peak = the measured cuBLAS bf16 BURST figure (the timed region is tens of milliseconds).
+           `roofline_fda`: the same for the fused FDA kernel, 2*N*M*(C + P + C) FLOPs per instance and direction.
 `cpu_baseline`: the oracle port (pure PyTorch restatement of the same pass, oracle/torch_oracle.py) timed on this
            box's host cores on a bounded sample.  `--impl reference` prints that arm as its own line.
 """
@@ -57,22 +60,61 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps alternate over (each step is still one whole pass over its own "
                          "batch; with 2 the tail of one step's kernels overlaps the head of the next step's)")
+    ap.add_argument("--config", default="stage1", choices=["stage1", "stage2", "train"],
+                    help="stage1 = BASELINE.json configs[2] (the headline); stage2 = configs[3]: stage 1 + 2 refiner "
+                         "iterations over --batch-total instances sharded across the GPUs (strong scaling); "
+                         "train = configs[4]: one DDP training step (fwd + bwd + Adam) at --batch instances per GPU")
+    ap.add_argument("--batch-total", type=int, default=0,
+                    help="stage2: instances per step over ALL GPUs (32..4096); each GPU runs its shard in passes of "
+                         "--batch instances")
+    ap.add_argument("--gather", default="end", choices=["end", "step"],
+                    help="multi-GPU: all_gather of the poses once at the end of the timed region (every step's poses, "
+                         "one collective) or after every step")
     ap.add_argument("--refine-iterations", type=int, default=0,
                     help="append the stage-2 refinement loop (tools/test_YCBV_stage2.py) with this many iterations; "
                          "0 = stage 1 only, the configuration BASELINE.json's metric is quoted on")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config == "stage2" and args.refine_iterations == 0:
+        args.refine_iterations = 2          # scripts/script_eval_YCBV_stage2.sh:11
+    if args.config == "train" and args.batch == 32:
+        args.batch = 40                      # config_LM: bs40
+    return args
 
 
-def workload_config(args, n_gpus):
+def shard_plan(args, n_gpus):
+    """(instances per GPU and step, instances per pass, passes per step).  stage1: one pass of --batch instances per
+    GPU (weak scaling).  stage2 with --batch-total: the total is split evenly over the GPUs (strong scaling) and
+    every GPU walks its shard in passes of at most --batch instances."""
+    if args.config == "stage2" and args.batch_total > 0:
+        if args.batch_total % n_gpus:
+            raise SystemExit("--batch-total must be a multiple of the number of GPUs")
+        per_gpu = args.batch_total // n_gpus
+        chunk = min(args.batch, per_gpu)
+        if per_gpu % chunk:
+            raise SystemExit("--batch-total / gpus must be a multiple of --batch (or smaller than it)")
+        return per_gpu, chunk, per_gpu // chunk
+    return args.batch, args.batch, 1
+
+
+def workload_config(args, n_gpus, cpu_arm=False):
     stage2 = (f" -> stage-2 refiner x{args.refine_iterations}" if getattr(args, "refine_iterations", 0) else "")
-    return {
+    per_gpu, chunk, passes = shard_plan(args, n_gpus)
+    strong = args.config == "stage2" and args.batch_total > 0
+    extra = {}
+    if cpu_arm:
+        # the CPU arm times a bounded sample: --cpu-batch instances per step, not the GPU arm's batch
+        extra = {"B_per_step_cpu_arm": args.cpu_batch}
+    if strong:
+        extra.update({"B_total": args.batch_total, "passes_per_step": passes, "B_per_pass": chunk})
+    return dict({
         "workload": "DCL-Net stage-1 inference (config_YCBV_bs32 shape) from synthetic backbone pyramids: "
                     "pointnet_sp 3-NN interpolation -> disengage -> dual FDA -> heads -> SVD pose" + stage2,
-        "B_per_gpu": args.batch, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
-        "weights": "random init, eval mode", "sharding": f"instances x{n_gpus}, weak scaling",
+        "B_per_gpu": per_gpu, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
+        "weights": "random init, eval mode",
+        "sharding": f"instances x{n_gpus}, " + ("strong scaling (B_total fixed)" if strong else "weak scaling"),
         "l2": f"{ROTATE} rotating input sets; per-step activations (> 1 GB at B=32) exceed the 126 MB L2",
-        "streams": f"{max(1, getattr(args, 'streams', 1))} CUDA stream(s): consecutive steps alternate over them, each step one whole pass",
-    }
+        "streams": f"{max(1, getattr(args, 'streams', 1))} CUDA stream(s): consecutive passes alternate over them, each pass one whole batch",
+    }, **extra)
 
 
 # ----------------------------------------------------------------------------------------------- inputs
@@ -191,6 +233,7 @@ def cpu_pass_builder(args):
     b = args.cpu_batch
     torch.manual_seed(0)
     net = T.TailNetwork(mode="test", c_m=args.c_m).eval()
+    refiner = T.RefinerNet().eval() if args.refine_iterations > 0 else None
     batch = make_host_batch(1234, b, pin=False)
     ids = torch.arange(b).repeat_interleave(N_PTS)
 
@@ -199,6 +242,9 @@ def cpu_pass_builder(args):
             f_xc = T.get_point_feats(batch["points_inp"], ids, batch["inp"], Cfg.unit_voxel_extent)
             f_yo = T.get_point_feats(batch["points_tmp"], ids, batch["tmp"], Cfg.unit_voxel_extent)
             out = net(f_xc, f_yo, b, N_PTS, N_PTS)
+            if refiner is not None:
+                return T.stage2_refine(refiner, batch["points_inp"].view(b, N_PTS, 3), out["rot_pred"],
+                                       out["trans_pred"], out["F_Xo_p"], out["conf"], args.refine_iterations)
         return out["rot_pred"], out["trans_pred"]
     return one_pass, b
 
@@ -219,8 +265,9 @@ def run_reference_arm(args, rank):
     sample = f"{args.steps} steps x {b} instances of the same workload on the host (oracle/torch_oracle.py)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "higher_is_better": True, "scaling": "strong" if (args.config == "stage2" and args.batch_total) else "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args, args.gpus, cpu_arm=True),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -273,7 +320,7 @@ def run_b200_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    b = args.batch
+    per_gpu, b, passes = shard_plan(args, world)      # b = instances per pass
     torch.manual_seed(0)
     net = Network(Cfg, mode="test", c_m=args.c_m).eval().to(dev)
     batches = [make_host_batch(1000 * (rank + 1) + 17 * i, b, pin=True) for i in range(ROTATE)]
@@ -290,18 +337,33 @@ def run_b200_arm(args, rank, world, local_rank):
     torch.cuda.synchronize()
     side_streams = [torch.cuda.Stream(dev) for _ in range(nstreams)] if nstreams > 1 else []
 
-    def step_resident(i, multi=False):
+    # Poses of every pass of the timed region, rank-local: (steps * passes, b, 12).  --gather end (default): ONE
+    # all_gather of this buffer closes the timed region (each rank needs only its own slice until then);
+    # --gather step: an all_gather after every pass, as in round 1.
+    n_pass_total = args.steps * passes
+    poses_local = torch.zeros(n_pass_total, b, 12, dtype=torch.float32, device=dev)
+    poses_all = torch.empty(world * n_pass_total, b, 12, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def one_pass(i):
         eng = engines[i % n_eng]
-        if side_streams and multi:
-            with torch.cuda.stream(side_streams[i % nstreams]):
-                rot, trans = eng.run()
-                if world > 1:
-                    rot, trans = sharding.gather_poses(rot, trans, equal_shards=True)
-            return rot, trans
         rot, trans = eng.run()
-        if world > 1:
-            rot, trans = sharding.gather_poses(rot, trans, equal_shards=True)
-        return rot, trans
+        torch.cat([rot.reshape(b, 9), trans], dim=1, out=poses_local[i % n_pass_total])
+        if world > 1 and args.gather == "step":
+            sharding.gather_poses(rot, trans, equal_shards=True)
+
+    def step_resident(i, multi=False):
+        """One step = `passes` passes of b instances (1 unless --batch-total shards a larger batch)."""
+        for k in range(passes):
+            j = i * passes + k
+            if side_streams and multi:
+                with torch.cuda.stream(side_streams[j % nstreams]):
+                    one_pass(j)
+            else:
+                one_pass(j)
+
+    def gather_end():
+        if world > 1 and args.gather == "end":
+            dist.all_gather_into_tensor(poses_all.view(-1), poses_local.view(-1))
 
     def fork():
         main = torch.cuda.current_stream(dev)
@@ -338,6 +400,7 @@ def run_b200_arm(args, rank, world, local_rank):
         ev0.record()
         for i in range(args.steps):
             step_resident(i)          # one stream: the per-kernel events below must not see another step's kernels
+        gather_end()
         ev1.record()
         barrier()
         ms_eager = max_over_ranks(ev0.elapsed_time(ev1))
@@ -364,6 +427,7 @@ def run_b200_arm(args, rank, world, local_rank):
         for i in range(args.steps):
             step_resident(i, multi=True)
         join()
+        gather_end()
         ev1.record()
         barrier()
         ms_total = max_over_ranks(ev0.elapsed_time(ev1))
@@ -383,23 +447,27 @@ def run_b200_arm(args, rank, world, local_rank):
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(args.steps)):
-            checksum += float(trans[0, 0]) + float(rot[-1, 2, 2])    # the host consumes every step's result
+        for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(args.steps * passes)):
+            checksum += float(trans[0, 0]) + float(rot[-1, 2, 2])    # the host consumes every pass's result
         e1.record()
         barrier()
         h2d = pipe.h2d_bytes
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
 
-    value = world * b * args.steps / (ms_total / 1e3)
-    e2e_value = world * b * args.steps / (e2e_ms / 1e3)
+    value = world * per_gpu * args.steps / (ms_total / 1e3)
+    e2e_value = world * per_gpu * args.steps / (e2e_ms / 1e3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_burst = peaks.get("bf16_tflops_burst") or peaks.get("bf16_tflops")
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"
+    # The kernels are timed alone (CUDA events around single launches in a region of tens of milliseconds, GPU far
+    # from its power limit): the applicable peak is the measured BURST cuBLAS figure, not the sustained one.
+    peak_sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_burst = peaks.get("bf16_tflops_burst") or peaks.get("bf16_tflops") or 1600.0
+    peak_tf = peak_burst
+    peak_src = ("MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks
+                else "B200_PROFILING.md fallback (of fallback)")
     # Dominant kernel: the persistent CTA-pair GEMM with 256-wide tiles (disengage and fuser layers; 5 launches/step).
     gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(fl for _, fl in gemm)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm else float("nan")
@@ -419,7 +487,7 @@ def run_b200_arm(args, rank, world, local_rank):
                 "algorithmic_flops_per_step": gemm_flops / args.steps,
                 "executed_mma_flops_per_step": 3 * gemm_flops / args.steps,
                 "executed_frac": 3 * achieved / peak_tf,
-                "executed_frac_of_burst_peak": 3 * achieved / peak_burst if peak_burst else None,
+                "frac_of_sustained_peak": achieved / peak_sustained,
                 "share_of_step": gemm_ms / ms_eager if gemm else None,
                 "timed_in": "eager pass of the same K steps (the graph-replayed pass launches the identical kernels)",
                 "note": split_note}
@@ -437,12 +505,14 @@ def run_b200_arm(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (FDA contraction: bf16 hi/lo split, fp32 accumulate)",
+                "scaling": "strong" if (args.config == "stage2" and args.batch_total) else "weak", "vs_baseline": None,
+                "dtype": "fp32 (tensor-core contractions: bf16 hi/lo split operands, fp32 accumulate)",
                 "data": "synthetic", "config": workload_config(args, world), "impl": "b200",
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": b * 12 * 4,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * passes,
+                        "d2h_bytes_per_step": per_gpu * 12 * 4,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph" if use_graph else "eager",
-                "streams": nstreams,
+                "streams": nstreams, "pose_gather": args.gather if world > 1 else None,
                 "ms_per_step_eager": ms_eager / args.steps, "clocks": clocks, "roofline": roofline,
                 "roofline_fda": roofline_fda}
         if world == 1 and not args.no_cpu_baseline:
@@ -459,6 +529,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.config == "train":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_step_ddp
+        train_step_ddp.run(args.batch, args.steps, max(args.warmup, 3), rank, world, local_rank, contract=True)
         return
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

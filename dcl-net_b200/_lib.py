@@ -131,6 +131,18 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_warned = set()
+
+
+def warn_once(key, message):
+    """One RuntimeWarning per process and key: used where an inference call leaves the tensor-core path for the
+    PyTorch layer modules (still CUDA, never CPU) so that the switch is never silent."""
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+        warnings.warn(message, RuntimeWarning, stacklevel=3)
+
+
 def check(err, what):
     if err != 0:
         raise RuntimeError(f"{what} failed: cudaError {err}")

@@ -5,7 +5,9 @@
 // The reference materialises B x N x M x 3 floats (82 MB per instance at 2 620 points).  Here one thread keeps QPT
 // query points in registers and scans the other cloud from a shared-memory ring fed by TMA bulk copies (the
 // three_nn pattern with a single slot); sqrt is taken once per query (sqrt is monotone: min of norms == norm at the
-// min squared distance).  Ties keep the lowest index.
+// min squared distance).  Ties keep the lowest index.  A NaN distance (NaN coordinates on either side) makes the
+// query's result NaN, as torch.min over the reference's norm tensor does; it is latched separately because no
+// ordered comparison ever selects a NaN.
 #include "common.cuh"
 #include "tile_pipe.cuh"
 #include "../../include/dcl_b200.h"
@@ -30,8 +32,10 @@ __global__ void __launch_bounds__(CH_THREADS) nearest_dist_kernel(int n, int m, 
     const int q0 = (blockIdx.x * CH_THREADS + threadIdx.x) * QPT;
     float ux[QPT], uy[QPT], uz[QPT], best[QPT];
     int besti[QPT];
+    bool bad[QPT];
 #pragma unroll
     for (int q = 0; q < QPT; ++q) {
+        bad[q] = false;
         const int qi = min(q0 + q, n - 1);
         ux[q] = a[qi * 3 + 0];
         uy[q] = a[qi * 3 + 1];
@@ -51,6 +55,7 @@ __global__ void __launch_bounds__(CH_THREADS) nearest_dist_kernel(int n, int m, 
 #pragma unroll
             for (int q = 0; q < QPT; ++q) {
                 const float d = dcl_dist2(ux[q], uy[q], uz[q], x, y, z);
+                bad[q] |= d != d;
                 if (d < best[q]) {
                     best[q] = d;
                     besti[q] = kbase + j;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(CH_THREADS) nearest_dist_kernel(int n, int m, 
     for (int q = 0; q < QPT; ++q) {
         const int qi = q0 + q;
         if (qi < n) {
-            min_dist[(size_t)bs * n + qi] = __fsqrt_rn(best[q]);
+            min_dist[(size_t)bs * n + qi] = bad[q] ? CUDART_NAN_F : __fsqrt_rn(best[q]);
             if (argmin != nullptr) argmin[(size_t)bs * n + qi] = besti[q];
         }
     }

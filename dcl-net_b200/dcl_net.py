@@ -55,6 +55,8 @@ def pose_heads(pooled, rot_head, trans_head):
     hs, ht = _head_struct(rot_head, keep), _head_struct(trans_head, keep)
     pooled = pooled.contiguous()
     if hs is None or ht is None or pooled.dtype != torch.float32:
+        L.warn_once("pose_heads", "dcl_net_b200.pose_heads: head is not a fp32 [d_in -> h1 -> h2 -> out] Conv1d/ReLU "
+                                  "stack of width <= 1024; running it as PyTorch layers instead of csrc/pose_head.cu")
         x = pooled.unsqueeze(-1)
         return rot_head(x).squeeze(-1), trans_head(x).squeeze(-1)
     B = pooled.shape[0]
@@ -135,7 +137,8 @@ class Network(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode=True):
-        self._fused_tail = None
+        if mode != self.training:    # BatchNorm folding depends on the mode; an unchanged mode keeps the packed weights
+            self._fused_tail = None
         return super().train(mode)
 
     # ---- entry points -----------------------------------------------------------------
@@ -153,10 +156,16 @@ class Network(nn.Module):
         return pred
 
     def _fused(self, b):
-        """The tensor-core inference path (fused_tail.FusedTail), or None when it does not apply (training,
-        autograd, train-mode outputs, unsupported widths)."""
+        """The tensor-core inference path (fused_tail.FusedTail).  None — i.e. the PyTorch layer modules, whose GEMMs
+        are library calls — only (i) while autograd is recording or the module is in training mode (BatchNorm
+        batch statistics; the training path), (ii) when the caller switched it off, or (iii) for shapes the packed
+        kernels do not take, and then with a warning: inference never leaves the tensor-core path silently."""
         from .fused_tail import FusedTail
-        if torch.is_grad_enabled() or not self.use_fused_tail or not FusedTail.supported(self, b):
+        if torch.is_grad_enabled() or self.training or not self.use_fused_tail:
+            return None
+        why = FusedTail.unsupported_reason(self, b)
+        if why is not None:
+            L.warn_once(("fused_tail", why), f"dcl_net_b200.Network: inference falls back to PyTorch layer modules ({why})")
             return None
         if self._fused_tail is None:
             self._fused_tail = FusedTail(self)

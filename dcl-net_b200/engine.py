@@ -21,7 +21,9 @@ from .refiner import refine_poses
 class PoseEngine:
     def __init__(self, net, device, batch, capacities, refiner=None, iterations=0):
         """capacities: per level, the maximum number of voxel rows of a batch (both towers use the same)."""
-        self.net, self.refiner, self.iterations = net.eval(), refiner, iterations
+        if net.training or (refiner is not None and refiner.training):
+            raise ValueError("PoseEngine is an inference engine: put the network (and the refiner) in eval() mode first")
+        self.net, self.refiner, self.iterations = net, refiner, iterations
         self.device, self.b = device, batch
         self.n_inp, self.n_tmp = net.n_inp, net.n_tmp
         L.load()
@@ -36,6 +38,10 @@ class PoseEngine:
         self.h2d_bytes = 0
         self._graph = None
         self._static = None
+        self._packed = (None, None)   # the packed-weight objects the captured graph holds raw pointers into
+
+    def _current_packed(self):
+        return (getattr(self.net, "_fused_tail", None), getattr(self.refiner, "_fused_refiner", None))
 
     def load(self, host_batch):
         """Asynchronous host->device copy of one batch into the static buffers."""
@@ -68,11 +74,18 @@ class PoseEngine:
         with torch.cuda.graph(graph):
             self._static = self._run_eager()
         self._graph = graph
+        # The graph replays raw pointers into the packed weights of net._fused_tail / refiner._fused_refiner, which
+        # live outside the graph's private pool: keep them alive here, and re-capture (run()) if the modules
+        # rebuilt them since (load_state_dict, .to(), a train()/eval() round trip).
+        self._packed = self._current_packed()
         return self
 
     def run(self):
         """Device-resident pass over the loaded batch -> (rot (B,3,3), trans (B,3)) on the device."""
         if self._graph is not None:
+            if any(cur is not old for cur, old in zip(self._current_packed(), self._packed)):
+                self._graph = None
+                self.capture()             # weights were re-packed: the old graph points at the previous copies
             self._graph.replay()
             return self._static
         return self._run_eager()

@@ -183,6 +183,20 @@ class FusedTail:
             self.fuser, rest_a = layers_from_head(net.neck_fuser)
             self.fuser_bi, rest_b = layers_from_head(net.neck_fuser_bi)
         assert not rest_a and not rest_b and len(self.fuser) == 3 and len(self.conf) == 2
+        # train-mode outputs evaluated without autograd (Xo_pred / Yc_pred, models/DCL_Net.py:207-210): the
+        # 256 -> 256 -> 128 layers as they are, the trailing 128 -> 3 layer zero-padded to one 64-wide n-tile
+        self.coord = {}
+        if net.mode != "test":
+            with torch.no_grad():
+                for key, head in (("Xo", net.regressor_Xo), ("Yc", net.regressor_Yc)):
+                    gemm, rest = layers_from_head(head)
+                    (conv, relu, bn), = rest
+                    assert len(gemm) == 2 and conv.out_channels <= 64 and not relu and bn is None
+                    w = conv.weight.new_zeros(64, conv.in_channels)
+                    w[:conv.out_channels] = conv.weight.reshape(conv.out_channels, conv.in_channels)
+                    bias = conv.bias.new_zeros(64)
+                    bias[:conv.out_channels] = conv.bias
+                    self.coord[key] = (gemm + [Layer(w, bias, relu=False)], conv.out_channels)
         self.conf_dot, self.conf_dot_bias = [], []
         for rest in (self.conf_rest, self.conf_bi_rest):
             (conv, relu, bn), = rest
@@ -191,10 +205,20 @@ class FusedTail:
             self.conf_dot_bias.append(conv.bias.detach().float().reshape(1, 1).clone())
 
     @staticmethod
-    def supported(net, b):
+    def unsupported_reason(net, b):
+        """None when the packed path takes this network / batch, else a short reason."""
         c_m = net.disengage_Xc_m1[1].layers[0].out_channels
-        return (net.n_inp == net.n_tmp and net.n_inp % 128 == 0 and c_m in (64, 128) and not net.training
-                and net.mode == "test")
+        if net.training:
+            return "module is in training mode (BatchNorm uses batch statistics)"
+        if net.n_inp != net.n_tmp or net.n_inp % 128 != 0:
+            return f"n_inp={net.n_inp}, n_tmp={net.n_tmp}: need equal sizes that are multiples of 128"
+        if c_m not in (64, 128):
+            return f"c_m={c_m}: the fused FDA kernel takes 64 or 128"
+        return None
+
+    @staticmethod
+    def supported(net, b):
+        return FusedTail.unsupported_reason(net, b) is None
 
     @torch.no_grad()
     def forward(self, pm_xc, pm_yo, b):
@@ -243,6 +267,19 @@ class FusedTail:
             [(ws[0], True, dbg, True, True, False), (ws[1], dbg, dbg, True, True, False)], b, c_m, n, n)
         del ws
 
+        # ---- coordinate regressors of the train-mode interface (regressor_Xo on F_Xo_p, regressor_Yc on F_Yc_p)
+        coords = {}
+        if self.coord:
+            (lx, dx), (ly, dy) = self.coord["Xo"], self.coord["Yc"]
+            t1 = [pm_empty(rows, lx[0].cout, dev) for _ in range(2)]
+            run_gemm([{"a0": pm_Xo_p, "layer": lx[0], "out_pm": t1[0]}, {"a0": pm_Yc_p, "layer": ly[0], "out_pm": t1[1]}], rows)
+            t2 = [pm_empty(rows, lx[1].cout, dev) for _ in range(2)]
+            run_gemm([{"a0": t1[0], "layer": lx[1], "out_pm": t2[0]}, {"a0": t1[1], "layer": ly[1], "out_pm": t2[1]}], rows)
+            xyz = [torch.empty(b, 64, n, **f32) for _ in range(2)]
+            run_gemm([{"a0": t2[0], "layer": lx[2], "out_cm": xyz[0], "rows_per_inst": n},
+                      {"a0": t2[1], "layer": ly[2], "out_cm": xyz[1], "rows_per_inst": n}], rows)
+            coords = {"Xo_pred": xyz[0][:, :dx].transpose(1, 2), "Yc_pred": xyz[1][:, :dy].transpose(1, 2)}
+
         # ---- confidence heads: cat([F_Xc_m1, F_Xo_m]) / cat([F_Yc_m, F_Yo_m2]) -> 128 -> 128 -> 1
         c1 = [pm_empty(rows, 128, dev) for _ in range(2)]
         run_gemm([{"a0": pm_out["Xc_m1"], "a1": pm_Xo_m, "c0": c_m, "layer": self.conf[0], "out_pm": c1[0]},
@@ -278,8 +315,8 @@ class FusedTail:
         from .dcl_net import pose_heads, svd3_project
         ortho9d, trans = pose_heads(pooled, net.regressor_rot, net.regressor_trans)
         rot = svd3_project(ortho9d, True)
-        return {"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p, "F_Xo_p_pm": pm_Xo_p,
-                "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}
+        return dict({"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p, "F_Xo_p_pm": pm_Xo_p,
+                     "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}, **coords)
 
 
 class FusedRefiner:
@@ -304,8 +341,17 @@ class FusedRefiner:
                            Layer(convs[2].weight.reshape(convs[2].out_channels, -1), convs[2].bias, True)]
 
     @staticmethod
-    def supported(refiner, b, n):
-        return (b * n) % 256 == 0 and not refiner.training and not torch.is_grad_enabled()
+    def supported(refiner, b, n, F_Xo_p=None, conf=None, pm_feat=None):
+        """The pooling epilogue writes one partial per 32 global rows and dcl_pm_pool_reduce folds n/32 of them per
+        instance, so an instance must be a whole number of 128-row tiles; the feature must be 256 wide and the
+        confidence row must cover the n observed points."""
+        if refiner.training or torch.is_grad_enabled() or n % 128 != 0 or (b * n) % 256 != 0:
+            return False
+        if F_Xo_p is None and pm_feat is None:
+            return False
+        if F_Xo_p is not None and (F_Xo_p.shape[1] != 256 or F_Xo_p.shape[2] != n):
+            return False
+        return conf is not None and conf.shape[1] >= n
 
     @torch.no_grad()
     def refine(self, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration, pm_feat=None):

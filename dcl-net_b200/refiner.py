@@ -8,12 +8,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .dcl_net import svd3_project
+from .dcl_net import ortho9d2matrix  # noqa: F401  (models/refiner.py:35-56 duplicates models/DCL_Net.py:15-36)
 from .modules import Head_MultiLayerPerceptron
-
-
-def ortho9d2matrix(x_raw, y_raw, z_raw):
-    return svd3_project(torch.cat((x_raw, y_raw, z_raw), dim=1), True)
 
 
 class Refiner(nn.Module):
@@ -35,7 +31,8 @@ class Refiner(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode=True):
-        self._fused_refiner = None
+        if mode != self.training:
+            self._fused_refiner = None
         return super().train(mode)
 
     def forward(self, input_dict):
@@ -50,7 +47,9 @@ class Refiner(nn.Module):
         else:
             from .dcl_net import pose_heads
             ortho9d_pred2, delta_t = pose_heads(shared_feature.squeeze(-1), self.regressor_rot2, self.regressor_trans2)
-        delta_R = svd3_project(ortho9d_pred2, True)
+        # differentiable (torch.svd formula) when autograd records a gradient through it, as the reference's
+        # losses_refiner needs (models/refiner.py:35-56,97-125); the dcl_svd3_project kernel otherwise
+        delta_R = ortho9d2matrix(ortho9d_pred2[:, :3], ortho9d_pred2[:, 3:6], ortho9d_pred2[:, 6:])
         return {"trans_pred": delta_t, "rot_pred": delta_R}
 
 
@@ -71,7 +70,7 @@ def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iterat
     channels."""
     B, N, _ = points_inp.shape
     from .fused_tail import FusedRefiner
-    if getattr(refiner, "use_fused", True) and FusedRefiner.supported(refiner, B, N):
+    if getattr(refiner, "use_fused", True) and FusedRefiner.supported(refiner, B, N, F_Xo_p, conf, F_Xo_p_pm):
         fused = getattr(refiner, "_fused_refiner", None)
         if fused is None:
             fused = refiner._fused_refiner = FusedRefiner(refiner)

@@ -124,16 +124,20 @@ def _tail_pair(seed, n, mode, dev, c_m=64):
     return oracle_net, net.to(dev)
 
 
-def test_tail_golden(cuda_dev):
+def test_tail_golden(cuda_dev, monkeypatch):
     """Fixture produced by exec'ing the reference's own Network.forward FDA section (DCL_Net.py:187-235)."""
     gold = np.load(f"{GOLDEN}/model_tail_b2_n128.npz")
     oracle_net, net = _tail_pair(int(gold["seed_weights"]), 128, "train", cuda_dev)
+    from dcl_net_b200.fused_tail import FusedTail
+    monkeypatch.setattr(FusedTail, "keep_debug", True)   # also return F_Yc_p / F_Xo_m / F_Yc_m in the reference layout
     from oracle.make_golden import param_checksum
     assert abs(param_checksum(oracle_net) - float(gold["param_checksum"])) < 1e-6 * abs(float(gold["param_checksum"]))
     g = torch.Generator().manual_seed(int(gold["seed_inputs"]))
     f_xc, f_yo = torch.randn(256, 480, generator=g), torch.randn(256, 480, generator=g)
     with torch.no_grad():
         out = net.forward_from_point_feats(f_xc.to(cuda_dev), f_yo.to(cuda_dev), 2)
+    # mode="train" outputs (Xo_pred / Yc_pred) under eval() + no_grad run on the tensor-core path too
+    assert net._fused_tail is not None, "the tensor-core path did not run"
     for k in ("F_Xo_p", "Xo_pred", "Yc_pred", "conf"):
         assert rel_err(out[k], torch.from_numpy(gold[k])) < 1e-3, k
     for k in ("F_Yc_p", "F_Xo_m", "F_Yc_m"):
@@ -436,3 +440,50 @@ def test_cd_dis_gradient_vs_reference_graph(cuda_dev):
     ar, cr = a0.double().requires_grad_(True), c0.double().requires_grad_(True)
     T.cd_dis(ar, cr).mean().backward()
     assert rel_err(a.grad, ar.grad) < 1e-5 and rel_err(c.grad, cr.grad) < 1e-5
+
+
+def test_refiner_backward_reaches_rotation_head(cuda_dev):
+    """Stage-2 training: the pose loss must reach regressor_rot2 through the SO(3) projection (the reference
+    backpropagates through torch.svd, models/refiner.py:35-56); gradients match the restated graph."""
+    torch.manual_seed(41)
+    oracle_ref = T.RefinerNet().train()
+    ref = Refiner().train()
+    ref.load_state_dict(oracle_ref.state_dict())
+    oracle_ref, ref = oracle_ref.to(cuda_dev), ref.to(cuda_dev)
+    g = torch.Generator().manual_seed(42)
+    inp = {"input_features": torch.randn(3, 259, 1024, generator=g).to(cuda_dev),
+           "conf": torch.rand(3, 2048, generator=g).to(cuda_dev), "obj_idx": None}
+    target = torch.randn(3, 3, 3, generator=g).to(cuda_dev)
+
+    def loss(out):
+        return ((out["rot_pred"] - target) ** 2).sum() + out["trans_pred"].pow(2).sum()
+    loss(ref(inp)).backward()
+    loss(oracle_ref(inp)).backward()
+    want = dict(oracle_ref.named_parameters())
+    seen = 0
+    for name, p in ref.named_parameters():
+        assert p.grad is not None, f"{name} received no gradient"
+        if name.startswith("regressor_rot2"):
+            assert float(p.grad.abs().max()) > 0, name
+            seen += 1
+        assert rel_err(p.grad, want[name].grad) < 1e-3, name
+    assert seen >= 6
+
+
+def test_nearest_dist_propagates_nan(cuda_dev):
+    """torch.min over the reference's norm tensor returns NaN when any distance is NaN (models/DCL_Net.py:307-311)."""
+    from dcl_net_b200 import losses
+    g = torch.Generator().manual_seed(2)
+    a, c = torch.rand(2, 70, 3, generator=g).to(cuda_dev), torch.rand(2, 90, 3, generator=g).to(cuda_dev)
+    a[0, 5, 1] = float("nan")          # a NaN query: only that query's distance is NaN
+    c[1, 80, 2] = float("nan")         # a NaN candidate: every query of that instance sees a NaN distance
+    got = losses.adds_metric(a, c)
+    want = T.adds(a, c)
+    assert torch.isnan(got).tolist() == torch.isnan(want).tolist() == [True, True]
+    d = torch.empty(2, 70, device=cuda_dev)
+    L.check(L.load().dcl_nearest_dist(2, 70, 90, L.ptr(a), L.ptr(c), L.ptr(d), None, L.stream_ptr()), "nearest_dist")
+    ref = torch.min(torch.norm(a.unsqueeze(2) - c.unsqueeze(1), dim=3), 2)[0]
+    assert torch.equal(torch.isnan(d), torch.isnan(ref))
+    assert torch.isnan(d[0]).sum().item() == 1 and torch.isnan(d[1]).all()
+    ok = ~torch.isnan(ref)
+    assert rel_err(d[ok], ref[ok]) < 1e-6

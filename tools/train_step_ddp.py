@@ -39,36 +39,34 @@ def losses(out, pts_tmp, pts_inp, rot_gt, trans_gt):
     return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=40)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    args = ap.parse_args()
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+class FromPointFeats(torch.nn.Module):
+    """DDP wraps a module whose forward takes the tensors, so that its reducer arms the gradient hooks."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, f_xc, f_yo, nb):
+        return self.inner.forward_from_point_feats(f_xc, f_yo, nb)
+
+
+def run(batch, steps, warmup, rank, world, local, contract=False):
+    """One process per GPU.  Times `steps` training steps (max over ranks), then — multi-GPU — the same steps with
+    the gradient all-reduce switched off (DDP.no_sync) and the all-reduce of a gradient-sized buffer on its own:
+    exposed all-reduce time = synced step - unsynced step; overlap = 1 - exposed / standalone."""
+    import contextlib
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     net = Network(Cfg, mode="train").to(dev).train()
-    class FromPointFeats(torch.nn.Module):
-        """DDP wraps a module whose forward takes the tensors, so that its reducer arms the gradient hooks."""
-
-        def __init__(self, inner):
-            super().__init__()
-            self.inner = inner
-
-        def forward(self, f_xc, f_yo, nb):
-            return self.inner.forward_from_point_feats(f_xc, f_yo, nb)
-
     wrapped = FromPointFeats(net)
     model = torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local]) if world > 1 else wrapped
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-    b, n = args.batch, 1024
+    b, n = batch, 1024
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     f_xc = torch.randn(b * n, 480, device=dev, generator=g)
     f_yo = torch.randn(b * n, 480, device=dev, generator=g)
@@ -77,37 +75,88 @@ def main():
     q, _ = torch.linalg.qr(torch.randn(b, 3, 3, device=dev, generator=g))
     rot_gt = q * torch.det(q).sign().view(b, 1, 1)
     trans_gt = (torch.rand(b, 3, device=dev, generator=g) - 0.5) * 0.1
-    fwd = lambda: model(f_xc, f_yo, b)
 
-    def step():
+    def step(sync=True):
         opt.zero_grad(set_to_none=True)
-        loss = losses(fwd(), pts_tmp, pts_inp, rot_gt, trans_gt)
-        loss.backward()
+        ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
+        with ctx:
+            loss = losses(model(f_xc, f_yo, b), pts_tmp, pts_inp, rot_gt, trans_gt)
+            loss.backward()
         opt.step()
         return loss
 
-    for _ in range(args.warmup):
+    def timed(k, sync=True):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            loss = step(sync)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / k], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), loss
+
+    for _ in range(warmup):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms, loss = timed(steps)
     nparam = sum(p.numel() for p in net.parameters())
+    extra = {}
+    if world > 1:
+        ms_nosync, _ = timed(steps, sync=False)
+        flat = torch.zeros(nparam, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / 10
+        exposed = max(ms - ms_nosync, 0.0)
+        extra = {"ms_per_step_without_allreduce": ms_nosync, "allreduce_ms_exposed": exposed,
+                 "allreduce_ms_standalone": ar_ms, "allreduce_bytes_per_step": 4 * nparam,
+                 "allreduce_busbw_gbs": 2 * (world - 1) / world * 4 * nparam / (ar_ms * 1e-3) / 1e9,
+                 "allreduce_overlap": 1.0 - min(1.0, exposed / ar_ms) if ar_ms > 0 else None}
     if rank == 0:
-        print(json.dumps({"what": "training step (fwd+bwd+Adam) through the FDA section, train mode",
-                          "n_gpus": world, "B_per_gpu": b, "ms_per_step": float(ms.item()),
-                          "instances_per_s": world * b / (float(ms.item()) / 1e3), "loss": float(loss.item()),
-                          "allreduce_bytes_per_step": 4 * nparam if world > 1 else 0, "params": nparam}), flush=True)
+        value = world * b / (ms / 1e3)
+        if contract:
+            line = {"metric": "training instances/s (N=M=1024)", "value": value, "unit": "instances/s", "n_gpus": world,
+                    "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "fp32 (FDA forward: bf16 hi/lo split tensor-core kernel)",
+                    "data": "synthetic",
+                    "config": {"workload": "config_LM-shaped training step through the FDA section: fwd + bwd + Adam, "
+                                           "train-mode BatchNorm, losses of models/DCL_Net.py:265-303; entry = point "
+                                           "features (b*n, 480) per tower", "B_per_gpu": b, "N": n, "M": n, "C": 64,
+                               "parallelism": f"DDP x{world} (NCCL all-reduce of {nparam} fp32 gradients, bucketed, "
+                                              "overlapped with backward)"},
+                    "impl": "b200", "loss": float(loss.item()), "params": nparam}
+            line.update(extra)
+        else:
+            line = dict({"what": "training step (fwd+bwd+Adam) through the FDA section, train mode", "n_gpus": world,
+                         "B_per_gpu": b, "ms_per_step": ms, "instances_per_s": value, "loss": float(loss.item()),
+                         "params": nparam}, **extra)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    run(args.batch, args.steps, args.warmup, int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
+        int(os.environ.get("LOCAL_RANK", 0)))
 
 
 if __name__ == "__main__":
