@@ -22,11 +22,18 @@
 // Packed weights: per (n-tile of NT output channels, k-block of 32 input channels) one blob
 //   [hi (NT x 32) | lo (NT x 32)], same layout with NT rows — one bulk copy per stage.
 //
+// Second operand format ("PM16", a_fmt / out_fmt == 1): activations stored ONCE-rounded in fp16 (2 bytes per element,
+// blobs of 128 rows x 32 channels = 8 KB, same core-matrix layout), weights split into fp16 hi + lo: every product is
+// X*Whi + X*Wlo — 2 MMAs instead of 3 and half the activation traffic.  What the rounding costs was measured against
+// the tolerances of the path (tools/emulate_precision.py -> profiles/r02_precision_emulation_*.json; GPU parity
+// tests): features ~4e-5 relative (bar 1e-3), poses ~1e-5 deg (bar 0.01 deg).  Values are clamped to the fp16 range.
+//
 // CTA = 128 rows x NT output channels; warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue.
 // Two CTAs are resident per SM (TMEM NT <= 256 columns each), so one CTA's epilogue overlaps the other's MMAs.
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/dcl_b200.h"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -36,17 +43,35 @@ constexpr int GM_BK = 32;
 constexpr int GM_THREADS = 192;    // simple kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int GM_P_EPI = 256;      // persistent kernel: 8 epilogue warps (two threads per row)
 constexpr int GM_P_THREADS = 64 + GM_P_EPI;
-constexpr int GM_A_BLOB = GM_BM * GM_BK * 4;  // 16384
+constexpr int GM_A_BLOB = GM_BM * GM_BK * 4;  // 16384: bf16 hi image + bf16 lo image
+constexpr int GM_A16_BLOB = GM_BM * GM_BK * 2;  // 8192: one fp16 image (PM16)
 constexpr int GM_MAX_PROBLEMS = 8;
+// operand formats (dcl_pm_gemm_problem.a_fmt / out_fmt)
+constexpr int FMT_BF16X2 = 0, FMT_F16 = 1;
+template <int FMT> struct GmFmt {
+    static constexpr int A_BLOB = FMT == FMT_F16 ? GM_A16_BLOB : GM_A_BLOB;
+};
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool b_mn_major = false) {
+    // kind::f16, A and B fp16 (format 0), fp32 accumulator
+    return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two fp32 -> packed fp16x2, clamped to the finite fp16 range
+__device__ __forceinline__ uint32_t pack_f16x2(float x0, float x1) {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 struct PmGemmBatch {
     dcl_pm_gemm_problem p[GM_MAX_PROBLEMS];
 };
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT = FMT_BF16X2>
 struct GmCfg {
+    static constexpr int A_BLOB = GmFmt<FMT>::A_BLOB;
     static constexpr int B_BLOB = NT * GM_BK * 4;
-    static constexpr int STAGE_BYTES = GM_A_BLOB + B_BLOB;
+    static constexpr int STAGE_BYTES = A_BLOB + B_BLOB;
     static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 128;
 };
@@ -127,7 +152,30 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
                 dot = __fmaf_rn(y[q * 4 + 3], dw.w, dot);
             }
         }
-        if (pr.out_pm != nullptr || pr.out_qk != nullptr || pr.out_v != nullptr) {
+        if (pr.out_fmt == FMT_F16 && (pr.out_pm != nullptr || pr.out_v != nullptr)) {
+            // PM16: the 32 values once-rounded to fp16, as four 8-channel (16-byte) units
+            uint4 fq[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                fq[ch] = make_uint4(pack_f16x2(y[ch * 8 + 0], y[ch * 8 + 1]), pack_f16x2(y[ch * 8 + 2], y[ch * 8 + 3]),
+                                    pack_f16x2(y[ch * 8 + 4], y[ch * 8 + 5]), pack_f16x2(y[ch * 8 + 6], y[ch * 8 + 7]));
+            if (pr.out_pm != nullptr) {
+                unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
+                                      ((size_t)mt * (cout / 32) + col0 / 32) * GM_A16_BLOB + (row >> 3) * 512 + (row & 7) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(blob + ch * 128) = fq[ch];
+            }
+            if (pr.out_v != nullptr) {
+                // fp16 value image of the fused FDA kernel: chunks of 16 keys x v_rows channels, one image per chunk
+                const size_t vchunk = (size_t)pr.v_rows * 32;
+                unsigned char* d = reinterpret_cast<unsigned char*>(pr.out_v) + (r_glob >> 4) * vchunk +
+                                   (size_t)((pr.v_row0 + col0) >> 3) * 256 + ((r_glob >> 3) & 1) * 128 + (r_glob & 7) * 16;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(d + ch * 256) = fq[ch];
+            }
+        }
+        const bool pm_v_bf16 = pr.out_fmt == FMT_BF16X2;
+        if ((pm_v_bf16 && (pr.out_pm != nullptr || pr.out_v != nullptr)) || pr.out_qk != nullptr) {
             // bf16 hi / lo halves of the 32 values, as four 8-channel (16-byte) units each
             uint4 hq[4], lq[4];
 #pragma unroll
@@ -138,7 +186,7 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
                 hq[ch] = make_uint4(h[0], h[1], h[2], h[3]);
                 lq[ch] = make_uint4(l[0], l[1], l[2], l[3]);
             }
-            if (pr.out_pm != nullptr) {
+            if (pm_v_bf16 && pr.out_pm != nullptr) {
                 unsigned char* blob = reinterpret_cast<unsigned char*>(pr.out_pm) +
                                       ((size_t)mt * (cout / 32) + col0 / 32) * GM_A_BLOB + (row >> 3) * 512 + (row & 7) * 16;
 #pragma unroll
@@ -161,7 +209,7 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
                     *reinterpret_cast<uint4*>(d + half + ch * 128) = lq[ch];
                 }
             }
-            if (pr.out_v != nullptr) {
+            if (pm_v_bf16 && pr.out_v != nullptr) {
                 // FDA value image (fda.cu): chunks of 16 keys x v_rows value channels, hi then lo; this row is a key,
                 // its columns are value channels v_row0 + col: 8 channels of one key = one 16-byte unit at
                 // (vrow/8)*256 + ((key%16)/8)*128 + (key%8)*16
@@ -210,9 +258,10 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
     }
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT>
 __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch) {
-    using Cfg = GmCfg<NT, STAGES>;
+    using Cfg = GmCfg<NT, STAGES, FMT>;
+    constexpr int A_BLOB = Cfg::A_BLOB;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(16) GmColParams s_colp;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -244,35 +293,42 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
 
     if (warp == 0) {
         if (dcl_elect_one()) {
-            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB;
             const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
-                                      (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
+                                      (size_t)mt * (KB - pr.kb0) * A_BLOB;
             const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB;
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((kb / STAGES) - 1) & 1));
                 unsigned char* dst = smem + s * Cfg::STAGE_BYTES;
                 dcl_mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
-                const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * GM_A_BLOB
-                                                          : a1 + (size_t)(kb - pr.kb0) * GM_A_BLOB;
-                dcl_bulk_g2s(dst, asrc, GM_A_BLOB, full + s);
-                dcl_bulk_g2s(dst + GM_A_BLOB, w + (size_t)kb * Cfg::B_BLOB, Cfg::B_BLOB, full + s);
+                const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * A_BLOB
+                                                          : a1 + (size_t)(kb - pr.kb0) * A_BLOB;
+                dcl_bulk_g2s(dst, asrc, A_BLOB, full + s);
+                dcl_bulk_g2s(dst + A_BLOB, w + (size_t)kb * Cfg::B_BLOB, Cfg::B_BLOB, full + s);
             }
         }
     } else if (warp == 1) {
         if (dcl_elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, NT);
+            constexpr uint32_t idesc = FMT == FMT_F16 ? umma_idesc_f16(GM_BM, NT) : umma_idesc_bf16(GM_BM, NT);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % STAGES;
                 dcl_mbar_wait(full + s, (uint32_t)((kb / STAGES) & 1));
                 tc_fence_after();
                 const uint32_t a = dcl_smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t b = a + GM_A_BLOB;
+                const uint32_t b = a + A_BLOB;
 #pragma unroll
                 for (int ks = 0; ks < GM_BK / 16; ++ks) {
                     const uint32_t off = ks * 256;
-                    mma_split3(tmem_base, a + off, a + GM_A_BLOB / 2 + off, b + off, b + Cfg::B_BLOB / 2 + off, 128, 512,
-                               128, 512, idesc, kb == 0 && ks == 0);
+                    if constexpr (FMT == FMT_F16) {
+                        // X (fp16, once-rounded) * (W_hi + W_lo): two MMAs
+                        const uint64_t dA = umma_desc(a + off, 128, 512);
+                        tc_mma_bf16(tmem_base, dA, umma_desc(b + off, 128, 512), idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                        tc_mma_bf16(tmem_base, dA, umma_desc(b + Cfg::B_BLOB / 2 + off, 128, 512), idesc, 1u);
+                    } else {
+                        mma_split3(tmem_base, a + off, a + A_BLOB / 2 + off, b + off, b + Cfg::B_BLOB / 2 + off, 128, 512,
+                                   128, 512, idesc, kb == 0 && ks == 0);
+                    }
                 }
                 tc_commit(empty + s);
             }
@@ -437,11 +493,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
 // kernel (conventions pinned by dcl_debug_umma_pair_gemm): the peer's MMA warp relays "my stage landed" to the
 // leader's full barriers, every tcgen05.commit is multicast to both CTAs, epilogue warps of both CTAs release the
 // accumulator with one CTA-scope arrive per warp on the leader's barrier.
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT = FMT_BF16X2>
 struct GmP2Cfg {
+    static constexpr int A_BLOB = GmFmt<FMT>::A_BLOB;
     static constexpr int B_BLOB = NT * GM_BK * 4;          // whole W blob in global memory: [hi | lo]
     static constexpr int B_HALF_ROWS = B_BLOB / 4;         // this CTA's rows of the hi (or lo) image
-    static constexpr int STAGE_BYTES = GM_A_BLOB + B_BLOB / 2;
+    static constexpr int STAGE_BYTES = A_BLOB + B_BLOB / 2;
     static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -449,10 +506,11 @@ struct GmP2Cfg {
     static_assert(2 * STAGES + 4 <= 60, "barrier area");
 };
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     pm_gemm_pair_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
-    using Cfg = GmP2Cfg<NT, STAGES>;
+    using Cfg = GmP2Cfg<NT, STAGES, FMT>;
+    constexpr int A_BLOB = Cfg::A_BLOB;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(16) GmColParams s_colp;
     __shared__ float s_dot[GM_BM];
@@ -494,9 +552,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
                 const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
                 const dcl_pm_gemm_problem& pr = batch.p[prob];
                 const int KB = pr.kb_total;
-                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * GM_A_BLOB;
+                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB;
                 const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
-                                          (size_t)mt * (KB - pr.kb0) * GM_A_BLOB;
+                                          (size_t)mt * (KB - pr.kb0) * A_BLOB;
                 const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB +
                                          rank * Cfg::B_HALF_ROWS;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -504,19 +562,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
                     if (it >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((it / STAGES) - 1) & 1));
                     unsigned char* dst = smem + s * Cfg::STAGE_BYTES;
                     dcl_mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
-                    const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * GM_A_BLOB
-                                                              : a1 + (size_t)(kb - pr.kb0) * GM_A_BLOB;
+                    const unsigned char* asrc = (kb < pr.kb0) ? a0 + (size_t)kb * A_BLOB
+                                                              : a1 + (size_t)(kb - pr.kb0) * A_BLOB;
                     const unsigned char* wsrc = w + (size_t)kb * Cfg::B_BLOB;
-                    dcl_bulk_g2s(dst, asrc, GM_A_BLOB, full + s);
-                    dcl_bulk_g2s(dst + GM_A_BLOB, wsrc, Cfg::B_HALF_ROWS, full + s);                          // hi rows
-                    dcl_bulk_g2s(dst + GM_A_BLOB + Cfg::B_HALF_ROWS, wsrc + Cfg::B_BLOB / 2, Cfg::B_HALF_ROWS,
+                    dcl_bulk_g2s(dst, asrc, A_BLOB, full + s);
+                    dcl_bulk_g2s(dst + A_BLOB, wsrc, Cfg::B_HALF_ROWS, full + s);                          // hi rows
+                    dcl_bulk_g2s(dst + A_BLOB + Cfg::B_HALF_ROWS, wsrc + Cfg::B_BLOB / 2, Cfg::B_HALF_ROWS,
                                  full + s);                                                                   // lo rows
                 }
             }
         }
     } else if (warp == 1) {
         if (leader && dcl_elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * GM_BM, NT);
+            constexpr uint32_t idesc = FMT == FMT_F16 ? umma_idesc_f16(2 * GM_BM, NT) : umma_idesc_bf16(2 * GM_BM, NT);
             const uint64_t desc0 = umma_desc(dcl_smem_u32(smem), 128, 512);
             int it = 0, tl = 0;
             for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
@@ -530,15 +588,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
                     dcl_mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
                     tc_fence_after();
                     const uint64_t dAh = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
-                    const uint64_t dAl = dAh + (uint64_t)((GM_A_BLOB / 2) >> 4);
-                    const uint64_t dBh = dAh + (uint64_t)(GM_A_BLOB >> 4);
+                    const uint64_t dAl = dAh + (uint64_t)((A_BLOB / 2) >> 4);   // bf16 hi/lo format only
+                    const uint64_t dBh = dAh + (uint64_t)(A_BLOB >> 4);
                     const uint64_t dBl = dBh + (uint64_t)(Cfg::B_HALF_ROWS >> 4);
 #pragma unroll
                     for (int ks = 0; ks < GM_BK / 16; ++ks) {
                         const uint64_t off = (uint64_t)((ks * 256) >> 4);
                         tc2_mma_bf16(tacc, dAh + off, dBh + off, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
                         tc2_mma_bf16(tacc, dAh + off, dBl + off, idesc, 1u);
-                        tc2_mma_bf16(tacc, dAl + off, dBh + off, idesc, 1u);
+                        if constexpr (FMT == FMT_BF16X2) tc2_mma_bf16(tacc, dAl + off, dBh + off, idesc, 1u);
                     }
                     tc2_commit_mcast(empty + s, (uint16_t)0x3);
                 }
@@ -578,23 +636,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     }
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT>
 int launch_gemm_pair(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
-    using Cfg = GmP2Cfg<NT, STAGES>;
+    using Cfg = GmP2Cfg<NT, STAGES, FMT>;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaError_t e = cudaFuncSetAttribute(pm_gemm_pair_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_pair_kernel<NT, STAGES, FMT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int ntiles_n = cout / NT, npairs_m = rows / (2 * GM_BM);
     const int units = npairs_m * ntiles_n * nprob;
     int clusters = num_sms / 2;
     if (clusters > units) clusters = units;
-    pm_gemm_pair_kernel<NT, STAGES><<<2 * clusters, GM_P_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n, npairs_m);
+    pm_gemm_pair_kernel<NT, STAGES, FMT><<<2 * clusters, GM_P_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n,
+                                                                                             npairs_m);
     return dcl_launch_status();
 }
 
@@ -622,13 +681,23 @@ int launch_gemm_cluster(const PmGemmBatch& batch, int nprob, int rows, int cout,
 // ------------------------------------------------------------------ packing helpers
 // fp32 row-major (rows x c, row stride `ld`) -> PM image.  Thread = (row, chunk of 8 channels).
 __global__ void __launch_bounds__(256) pm_pack_rows_kernel(int rows, int c, int ld, const float* __restrict__ src,
-                                                           unsigned char* __restrict__ dst) {
+                                                           unsigned char* __restrict__ dst, int fmt) {
     const long g = (long)blockIdx.x * 256 + threadIdx.x;
     const int nchunk = c / 8;
     if (g >= (long)rows * nchunk) return;
     // consecutive threads -> consecutive rows of the same chunk: 8 lanes write one 128-B run
     const int r = (int)(g % rows), ch = (int)(g / rows);
     const float* s = src + (size_t)r * ld + ch * 8;
+    if (fmt == FMT_F16) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(s + e);
+        unsigned char* d = dst + ((size_t)(r / 128) * (c / 32) + ch / 4) * GM_A16_BLOB + ((r % 128) >> 3) * 512 +
+                           (ch & 3) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                                  pack_f16x2(v[6], v[7]));
+        return;
+    }
     __nv_bfloat16 h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) split_bf16(__ldg(s + e), h[e], l[e]);
@@ -642,7 +711,7 @@ __global__ void __launch_bounds__(256) pm_pack_rows_kernel(int rows, int c, int 
 // fp32 channel-major (b, c, n) -> PM image of the (b*n x c) activation.  Thread = (row, chunk); reads coalesce
 // along n for a fixed channel.
 __global__ void __launch_bounds__(256) pm_pack_cm_kernel(int b, int c, int n, const float* __restrict__ src,
-                                                         unsigned char* __restrict__ dst) {
+                                                         unsigned char* __restrict__ dst, int fmt) {
     const long g = (long)blockIdx.x * 256 + threadIdx.x;
     const long rows = (long)b * n;
     const int nchunk = c / 8;
@@ -651,6 +720,16 @@ __global__ void __launch_bounds__(256) pm_pack_cm_kernel(int b, int c, int n, co
     const int ch = (int)(g / rows);
     const int inst = (int)(r / n), within = (int)(r % n);
     const float* s = src + ((size_t)inst * c + ch * 8) * n + within;
+    if (fmt == FMT_F16) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(s + (size_t)e * n);
+        unsigned char* d = dst + ((size_t)(r / 128) * (c / 32) + ch / 4) * GM_A16_BLOB + ((r % 128) >> 3) * 512 +
+                           (ch & 3) * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                                  pack_f16x2(v[6], v[7]));
+        return;
+    }
     __nv_bfloat16 h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) split_bf16(__ldg(s + (size_t)e * n), h[e], l[e]);
@@ -663,10 +742,16 @@ __global__ void __launch_bounds__(256) pm_pack_cm_kernel(int b, int c, int n, co
 
 // PM image -> fp32 row-major (hi + lo); tests / inspection.
 __global__ void __launch_bounds__(256) pm_unpack_kernel(int rows, int c, const unsigned char* __restrict__ src,
-                                                        float* __restrict__ dst) {
+                                                        float* __restrict__ dst, int fmt) {
     const long g = (long)blockIdx.x * 256 + threadIdx.x;
     if (g >= (long)rows * c) return;
     const int r = (int)(g / c), ch = (int)(g % c);
+    if (fmt == FMT_F16) {
+        const unsigned char* s16 = src + ((size_t)(r / 128) * (c / 32) + ch / 32) * GM_A16_BLOB + ((r % 128) >> 3) * 512 +
+                                   ((ch % 32) >> 3) * 128 + (r & 7) * 16 + (ch & 7) * 2;
+        dst[g] = __half2float(*reinterpret_cast<const __half*>(s16));
+        return;
+    }
     const unsigned char* s = src + ((size_t)(r / 128) * (c / 32) + ch / 32) * GM_A_BLOB + ((r % 128) >> 3) * 512 +
                              ((ch % 32) >> 3) * 128 + (r & 7) * 16 + (ch & 7) * 2;
     const float hi = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(s));
@@ -697,14 +782,14 @@ __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout
     out[g] = acc;
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int FMT>
 int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
-    using Cfg = GmCfg<NT, STAGES>;
-    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    using Cfg = GmCfg<NT, STAGES, FMT>;
+    cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<NT, STAGES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(nprob, cout / NT, rows / GM_BM);
-    pm_gemm_kernel<NT, STAGES><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch);
+    pm_gemm_kernel<NT, STAGES, FMT><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch);
     return dcl_launch_status();
 }
 
@@ -714,11 +799,13 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
     DCL_RETURN_IF_BAD(nproblems >= 1 && nproblems <= GM_MAX_PROBLEMS && problems != nullptr);
     DCL_RETURN_IF_BAD(rows > 0 && rows % GM_BM == 0 && rows / GM_BM <= 65535);
     PmGemmBatch batch;
-    const int cout = problems[0].cout, nt = problems[0].nt;
+    const int cout = problems[0].cout, nt = problems[0].nt, a_fmt = problems[0].a_fmt;
     DCL_RETURN_IF_BAD((nt == 64 || nt == 128 || nt == 256) && cout % nt == 0);
+    DCL_RETURN_IF_BAD(a_fmt == FMT_BF16X2 || a_fmt == FMT_F16);
     for (int i = 0; i < nproblems; ++i) {
         const dcl_pm_gemm_problem& p = problems[i];
         DCL_RETURN_IF_BAD(p.cout == cout && p.nt == nt && p.kb_total >= 1 && p.kb0 >= 0 && p.kb0 <= p.kb_total);
+        DCL_RETURN_IF_BAD(p.a_fmt == a_fmt && (p.out_fmt == FMT_BF16X2 || p.out_fmt == FMT_F16));
         DCL_RETURN_IF_BAD(p.a0 != nullptr && p.w != nullptr && (p.kb0 == p.kb_total || p.a1 != nullptr));
         DCL_RETURN_IF_BAD((p.post_scale == nullptr) == (p.post_shift == nullptr));
         DCL_RETURN_IF_BAD(p.out_cm == nullptr || (p.rows_per_inst > 0 && p.rows_per_inst % 32 == 0 && rows % p.rows_per_inst == 0));
@@ -733,47 +820,59 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
     }
     cudaStream_t st = (cudaStream_t)stream;
     // Persistent kernels when the m-tiles pair up: the CTA-pair (cta_group::2) kernel by default,
-    // DCL_PM_GEMM_MCAST=1 selects the multicast one, DCL_PM_GEMM_SIMPLE=1 the simple kernel (A/B runs).
+    // DCL_PM_GEMM_MCAST=1 selects the multicast one (bf16 hi/lo operands only), DCL_PM_GEMM_SIMPLE=1 the simple
+    // kernel (A/B runs).
     static const bool force_simple = getenv("DCL_PM_GEMM_SIMPLE") != nullptr;
     static const bool force_mcast = getenv("DCL_PM_GEMM_MCAST") != nullptr;
-    if (!force_simple && !force_mcast && (rows / GM_BM) % 2 == 0) {
-        if (nt == 256) return launch_gemm_pair<256, 6>(batch, nproblems, rows, cout, st);
-        if (nt == 128) return launch_gemm_pair<128, 8>(batch, nproblems, rows, cout, st);
-        return launch_gemm_pair<64, 9>(batch, nproblems, rows, cout, st);
+    const bool paired = (rows / GM_BM) % 2 == 0;
+    if (a_fmt == FMT_F16) {
+        if (!force_simple && paired) {
+            if (nt == 256) return launch_gemm_pair<256, 8, FMT_F16>(batch, nproblems, rows, cout, st);
+            if (nt == 128) return launch_gemm_pair<128, 12, FMT_F16>(batch, nproblems, rows, cout, st);
+            return launch_gemm_pair<64, 12, FMT_F16>(batch, nproblems, rows, cout, st);
+        }
+        if (nt == 256) return launch_gemm<256, 2, FMT_F16>(batch, nproblems, rows, cout, st);
+        if (nt == 128) return launch_gemm<128, 4, FMT_F16>(batch, nproblems, rows, cout, st);
+        return launch_gemm<64, 6, FMT_F16>(batch, nproblems, rows, cout, st);
     }
-    if (!force_simple && (rows / GM_BM) % 2 == 0) {
+    if (!force_simple && !force_mcast && paired) {
+        if (nt == 256) return launch_gemm_pair<256, 6, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+        if (nt == 128) return launch_gemm_pair<128, 8, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+        return launch_gemm_pair<64, 9, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+    }
+    if (!force_simple && paired) {
         if (nt == 256) return launch_gemm_cluster<256, 4>(batch, nproblems, rows, cout, st);
         if (nt == 128) return launch_gemm_cluster<128, 6>(batch, nproblems, rows, cout, st);
         return launch_gemm_cluster<64, 8>(batch, nproblems, rows, cout, st);
     }
-    if (nt == 256) return launch_gemm<256, 2>(batch, nproblems, rows, cout, st);
-    if (nt == 128) return launch_gemm<128, 3>(batch, nproblems, rows, cout, st);
-    return launch_gemm<64, 4>(batch, nproblems, rows, cout, st);
+    if (nt == 256) return launch_gemm<256, 2, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+    if (nt == 128) return launch_gemm<128, 3, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+    return launch_gemm<64, 4, FMT_BF16X2>(batch, nproblems, rows, cout, st);
 }
 
-DCL_API int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, void* stream) {
-    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0 && ld >= c);
+DCL_API int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, int fmt, void* stream) {
+    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0 && ld >= c && (fmt == 0 || fmt == 1));
     DCL_RETURN_IF_BAD((((uintptr_t)dst_pm) & 15u) == 0);
     const long total = (long)rows * (c / 8);
     pm_pack_rows_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
-        rows, c, ld, src, reinterpret_cast<unsigned char*>(dst_pm));
+        rows, c, ld, src, reinterpret_cast<unsigned char*>(dst_pm), fmt);
     return dcl_launch_status();
 }
 
-DCL_API int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, void* stream) {
-    DCL_RETURN_IF_BAD(b > 0 && n > 0 && ((long)b * n) % 128 == 0 && c > 0 && c % 32 == 0);
+DCL_API int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, int fmt, void* stream) {
+    DCL_RETURN_IF_BAD(b > 0 && n > 0 && ((long)b * n) % 128 == 0 && c > 0 && c % 32 == 0 && (fmt == 0 || fmt == 1));
     DCL_RETURN_IF_BAD((((uintptr_t)dst_pm) & 15u) == 0);
     const long total = (long)b * n * (c / 8);
     pm_pack_cm_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
-        b, c, n, src, reinterpret_cast<unsigned char*>(dst_pm));
+        b, c, n, src, reinterpret_cast<unsigned char*>(dst_pm), fmt);
     return dcl_launch_status();
 }
 
-DCL_API int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void* stream) {
-    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0);
+DCL_API int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, int fmt, void* stream) {
+    DCL_RETURN_IF_BAD(rows > 0 && rows % 128 == 0 && c > 0 && c % 32 == 0 && (fmt == 0 || fmt == 1));
     const long total = (long)rows * c;
     pm_unpack_kernel<<<(unsigned)DCL_DIVUP(total, 256L), 256, 0, (cudaStream_t)stream>>>(
-        rows, c, reinterpret_cast<const unsigned char*>(src_pm), dst);
+        rows, c, reinterpret_cast<const unsigned char*>(src_pm), dst, fmt);
     return dcl_launch_status();
 }
 

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header; bumped on any signature change. */
-#define DCL_B200_ABI_VERSION 3
+#define DCL_B200_ABI_VERSION 4
 int dcl_b200_abi_version(void);
 /* Compiled-for architecture as an integer (100 for sm_100a). */
 int dcl_b200_arch(void);
@@ -238,6 +238,12 @@ int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* dR, const
 /* "PM image" of an (R x C) activation (R % 128 == 0, C % 32 == 0; 4*R*C bytes): blobs of 128 rows x 32
  * channels, each blob = bf16 hi image (8 KB) then bf16 lo image (8 KB), value = hi + lo:
  *   byte(r,c,half) = ((r/128)*(C/32) + c/32)*16384 + half*8192 + ((r%128)/8)*512 + ((c%32)/8)*128 + (r%8)*16 + (c%8)*2
+ * "PM16 image" (format DCL_PM_FMT_F16; 2*R*C bytes): the same blobs holding ONE fp16 image (8 KB) of the value
+ * rounded once to fp16 (clamped to +-65504):
+ *   byte(r,c) = ((r/128)*(C/32) + c/32)*8192 + ((r%128)/8)*512 + ((c%32)/8)*128 + (r%8)*16 + (c%8)*2
+ * Its packed weights have the layout below with fp16 hi / lo halves instead of bf16 ones.  The inference path uses
+ * PM16 for every activation (2 MMAs per product instead of 3, half the bytes); what the single rounding costs
+ * against the path's tolerances is measured in profiles/r02_precision_emulation_*.json and by the parity tests.
  * Packed weights of a (cout x cin) layer, n-tile width nt in {64,128,256} (cout % nt == 0, cin % 32 == 0):
  *   byte(o,i,half) = ((o/nt)*(cin/32) + i/32)*(nt*128) + half*(nt*64) + ((o%nt)/8)*512 + ((i%32)/8)*128 + (o%8)*16 + (i%8)*2
  *
@@ -276,16 +282,24 @@ typedef struct dcl_pm_gemm_problem {
     void* out_v;
     int v_row0;
     int v_rows;
+    /* Operand formats (DCL_PM_FMT_*), see "PM16 image" above.  a_fmt: format of a0 / a1 AND of the packed weights
+     * (0: bf16 hi/lo images, 3 MMAs per product; 1: fp16 activations rounded once + fp16 hi/lo weights, 2 MMAs);
+     * equal for all problems of a launch.  out_fmt: format of out_pm and out_v (out_qk is always bf16 hi/lo: the
+     * logits of the FDA softmax keep split operands). */
+    int a_fmt;
+    int out_fmt;
 } dcl_pm_gemm_problem;
+#define DCL_PM_FMT_BF16X2 0
+#define DCL_PM_FMT_F16 1
 
 /* Up to 8 problems with equal (cout, nt) over the same number of rows in ONE launch (grid.z = problem). */
 int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int rows, void* stream);
-/* fp32 row-major (rows x c, leading dimension ld) -> PM image. */
-int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, void* stream);
-/* fp32 channel-major (b, c, n) -> PM image of the (b*n x c) activation. */
-int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, void* stream);
-/* PM image -> fp32 row-major (rows x c). */
-int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, void* stream);
+/* fp32 row-major (rows x c, leading dimension ld) -> PM image (fmt 0) or PM16 image (fmt 1). */
+int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, int fmt, void* stream);
+/* fp32 channel-major (b, c, n) -> PM / PM16 image of the (b*n x c) activation. */
+int dcl_pm_pack_cm(int b, int c, int n, const float* src, void* dst_pm, int fmt, void* stream);
+/* PM / PM16 image -> fp32 row-major (rows x c). */
+int dcl_pm_unpack(int rows, int c, const void* src_pm, float* dst, int fmt, void* stream);
 /* out[inst, :] (+)= sum of `parts` consecutive partial rows per instance, in index order, then
  * (partials2 != NULL) of the second set's, continuing the same running sum. */
 int dcl_pm_pool_reduce(int insts, int cout, int parts, const float* partials, const float* partials2,
