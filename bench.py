@@ -43,6 +43,8 @@ UNIT = "instances/s"
 N_PTS = 1024
 P_DIM = 256
 ROTATE = 3  # distinct input sets cycled through the timed steps
+# DRAM bytes per launch of the dominant kernel in the fp16 configuration (ncu --set full, mean of its launches)
+TRAFFIC_FP16, TRAFFIC_FP16_SRC = None, None
 
 
 def parse_args():
@@ -53,6 +55,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU per step")
     ap.add_argument("--c_m", type=int, default=128, help="FDA similarity width: 128 = BASELINE.json, 64 = reference")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32-faithful"],
+                    help="operand format of the tensor-core path: fp16 = activations rounded once to fp16, fp16 hi/lo "
+                         "weights (2 MMAs per product), split-operand FDA logits, fp16 P V (the product's default); "
+                         "fp32-faithful = every operand a bf16 hi/lo pair (3 MMAs per product)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="instances per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -110,7 +116,7 @@ def workload_config(args, n_gpus, cpu_arm=False):
         "workload": "DCL-Net stage-1 inference (config_YCBV_bs32 shape) from synthetic backbone pyramids: "
                     "pointnet_sp 3-NN interpolation -> disengage -> dual FDA -> heads -> SVD pose" + stage2,
         "B_per_gpu": per_gpu, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
-        "weights": "random init, eval mode",
+        "weights": "random init, eval mode", "precision": getattr(args, "precision", "fp16"),
         "sharding": f"instances x{n_gpus}, " + ("strong scaling (B_total fixed)" if strong else "weak scaling"),
         "l2": f"{ROTATE} rotating input sets; per-step activations (> 1 GB at B=32) exceed the 126 MB L2",
         "streams": f"{max(1, getattr(args, 'streams', 1))} CUDA stream(s): consecutive passes alternate over them, each pass one whole batch",
@@ -323,12 +329,15 @@ def run_b200_arm(args, rank, world, local_rank):
     per_gpu, b, passes = shard_plan(args, world)      # b = instances per pass
     torch.manual_seed(0)
     net = Network(Cfg, mode="test", c_m=args.c_m).eval().to(dev)
+    net.precision = args.precision
+    fp16 = args.precision == "fp16"
     batches = [make_host_batch(1000 * (rank + 1) + 17 * i, b, pin=True) for i in range(ROTATE)]
     caps = [max(max(bt[s][lv][0].shape[0] for bt in batches for s in ("inp", "tmp")), 1) for lv in range(4)]
     refiner = None
     if args.refine_iterations > 0:
         from dcl_net_b200.refiner import Refiner
         refiner = Refiner().eval().to(dev)
+        refiner.precision = args.precision
     nstreams = max(1, args.streams)
     n_eng = ROTATE if nstreams == 1 else nstreams * ((ROTATE + nstreams - 1) // nstreams)   # an engine stays on one stream
     engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations) for _ in range(n_eng)]
@@ -347,9 +356,10 @@ def run_b200_arm(args, rank, world, local_rank):
     def one_pass(i):
         eng = engines[i % n_eng]
         rot, trans = eng.run()
-        torch.cat([rot.reshape(b, 9), trans], dim=1, out=poses_local[i % n_pass_total])
         if world > 1 and args.gather == "step":
             sharding.gather_poses(rot, trans, equal_shards=True)
+        elif world > 1:
+            poses_local[i % n_pass_total].copy_(eng.poses12)   # kept for the one all_gather that ends the region
 
     def step_resident(i, multi=False):
         """One step = `passes` passes of b instances (1 unless --batch-total shards a larger batch)."""
@@ -471,22 +481,30 @@ def run_b200_arm(args, rank, world, local_rank):
     # Dominant kernel: the persistent CTA-pair GEMM with 256-wide tiles (disengage and fuser layers; 5 launches/step).
     gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(fl for _, fl in gemm)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm else float("nan")
-    split_note = ("every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful, so the algorithmic "
+    mmas = 2 if fp16 else 3
+    split_note = ("fp16 activations rounded once x fp16 hi/lo weights: 2 MMAs per product, so the algorithmic fraction is "
+                  "bounded by 1/2; tensor-pipe occupancy is ~2x the algorithmic fraction" if fp16 else
+                  "every product runs as 3 bf16 MMAs (hi/lo operand split) to stay fp32-faithful, so the algorithmic "
                   "fraction is bounded by 1/3; tensor-pipe occupancy is ~3x the algorithmic fraction")
     # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, mean of its five launches)
     # from the `ncu --set full` capture of the default configuration: profiles/r01_gemm_fda_ncu_full.txt (taken on
     # the multicast variant of the kernel; operands and outputs, hence the DRAM bytes, are the same)
-    traffic = 2.31e8 if (b == 32 and args.c_m == 128) else None
-    gemm_kernel = ("pm_gemm_cluster_kernel<256,4>" if os.environ.get("DCL_PM_GEMM_MCAST")
+    traffic, traffic_src = None, None
+    if b == 32 and args.c_m == 128:
+        traffic, traffic_src = ((TRAFFIC_FP16, TRAFFIC_FP16_SRC) if fp16 else
+                                (2.31e8, "profiles/r01_gemm_fda_ncu_full.txt (bytes per launch)"))
+    gemm_kernel = ("pm_gemm_pair_kernel<256,8,fp16>" if fp16 else
+                   "pm_gemm_cluster_kernel<256,4>" if os.environ.get("DCL_PM_GEMM_MCAST")
                    else "pm_gemm_kernel<256,2>" if os.environ.get("DCL_PM_GEMM_SIMPLE") else "pm_gemm_pair_kernel<256,6>")
     roofline = {"kernel": gemm_kernel, "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "traffic_source": "profiles/r01_gemm_fda_ncu_full.txt (bytes per launch)" if traffic else None,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "avg_launch_ms": gemm_ms / len(gemm) if gemm else None, "launches_timed": len(gemm),
                 "algorithmic_flops_per_step": gemm_flops / args.steps,
-                "executed_mma_flops_per_step": 3 * gemm_flops / args.steps,
-                "executed_frac": 3 * achieved / peak_tf,
+                "mmas_per_product": mmas,
+                "executed_mma_flops_per_step": mmas * gemm_flops / args.steps,
+                "executed_frac": mmas * achieved / peak_tf,
                 "frac_of_sustained_peak": achieved / peak_sustained,
                 "share_of_step": gemm_ms / ms_eager if gemm else None,
                 "timed_in": "eager pass of the same K steps (the graph-replayed pass launches the identical kernels)",
@@ -494,11 +512,15 @@ def run_b200_arm(args, rank, world, local_rank):
     flops_per_launch = fda_jobs_per_launch * b * 2.0 * N_PTS * N_PTS * (args.c_m + P_DIM + args.c_m)
     fda_avg_ms = statistics.mean(fda_ms) if fda_ms else float("nan")
     fda_achieved = flops_per_launch / (fda_avg_ms * 1e-3) / 1e12
+    # executed MMA work per algorithmic FLOP: logits (share C / (2C + P)) on split operands, P V on fp16 or split ones
+    qk_share = args.c_m / (2.0 * args.c_m + P_DIM)
+    fda_exec = (3 * qk_share + 1 * (1 - qk_share)) if fp16 else 3.0
     fda_kernel = ("fda_pair_kernel" if (N_PTS // 128) % 2 == 0 and not os.environ.get("DCL_FDA_SINGLE")
                   else "fda_fwd_kernel")
     roofline_fda = {"kernel": f"{fda_kernel}<{args.c_m}>", "bound": "tensor", "achieved": fda_achieved,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": fda_achieved / peak_tf,
-                    "executed_frac": 3 * fda_achieved / peak_tf, "avg_launch_ms": fda_avg_ms,
+                    "executed_frac": fda_exec * fda_achieved / peak_tf, "avg_launch_ms": fda_avg_ms,
+                    "mmas_per_product": "logits 3, P V 1" if fp16 else "3",
                     "launches_timed": len(fda_ms), "algorithmic_flops_per_launch": flops_per_launch,
                     "directions_per_launch": fda_jobs_per_launch,
                     "share_of_step": (sum(fda_ms) / ms_eager) if fda_ms else None}
@@ -506,7 +528,8 @@ def run_b200_arm(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (args.config == "stage2" and args.batch_total) else "weak", "vs_baseline": None,
-                "dtype": "fp32 (tensor-core contractions: bf16 hi/lo split operands, fp32 accumulate)",
+                "dtype": ("fp16 activations x fp16 hi/lo weights, fp32 accumulate (FDA logits: bf16 hi/lo split operands)"
+                          if fp16 else "fp32 (tensor-core contractions: bf16 hi/lo split operands, fp32 accumulate)"),
                 "data": "synthetic", "config": workload_config(args, world), "impl": "b200",
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * passes,
                         "d2h_bytes_per_step": per_gpu * 12 * 4,

@@ -10,6 +10,9 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dcl_b200.h")
 
 _I, _F, _P, _SZ, _I64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
 
+# activation / operand formats of the tensor-core kernels (include/dcl_b200.h: DCL_PM_FMT_*)
+FMT_BF16X2, FMT_F16 = 0, 1
+
 # name -> (restype, argtypes); must list every function include/dcl_b200.h declares
 SIGNATURES = {
     "dcl_b200_abi_version": (_I, []),
@@ -44,9 +47,12 @@ SIGNATURES = {
     "dcl_pose_compose": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "dcl_pose_compose_pm": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "dcl_pm_gemm": (_I, [_I, _P, _I, _P]),
-    "dcl_pm_pack_rows": (_I, [_I, _I, _I, _P, _P, _P]),
-    "dcl_pm_pack_cm": (_I, [_I, _I, _I, _P, _P, _P]),
-    "dcl_pm_unpack": (_I, [_I, _I, _P, _P, _P]),
+    "dcl_pm_pack_rows": (_I, [_I, _I, _I, _P, _P, _I, _P]),
+    "dcl_pm_pack_cm": (_I, [_I, _I, _I, _P, _P, _I, _P]),
+    "dcl_pm_unpack": (_I, [_I, _I, _P, _P, _I, _P]),
+    "dcl_fda_fwd_packed_jobs_fmt": (_I, [_I, _P, _I, _I, _I, _I, _I, _SZ, _I, _P]),
+    "dcl_fda_pack_fmt": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _SZ, _I, _P]),
+    "dcl_pose_compose_pm16": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "dcl_pm_pool_reduce": (_I, [_I, _I, _I, _P, _P, _P, _I, _P]),
     "dcl_sp_nn_interpolate_fused_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_vox_pm": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
@@ -70,7 +76,8 @@ class PmGemmProblem(ctypes.Structure):
     _fields_ = [("a0", _P), ("a1", _P), ("kb0", _I), ("kb_total", _I), ("w", _P), ("bias", _P), ("post_scale", _P),
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
                 ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P),
-                ("out_qk", _P), ("qk_tile_rows", _I), ("out_v", _P), ("v_row0", _I), ("v_rows", _I)]
+                ("out_qk", _P), ("qk_tile_rows", _I), ("out_v", _P), ("v_row0", _I), ("v_rows", _I),
+                ("a_fmt", _I), ("out_fmt", _I)]
 
 
 class FdaJob(ctypes.Structure):
@@ -86,7 +93,8 @@ class SpLevel(ctypes.Structure):
 
 class SpTower(ctypes.Structure):
     """Mirror of dcl_sp_tower (include/dcl_b200.h)."""
-    _fields_ = [("n", _I), ("c_total", _I), ("nlevels", _I), ("unknown", _P), ("out_pm", _P), ("levels", _P)]
+    _fields_ = [("n", _I), ("c_total", _I), ("nlevels", _I), ("unknown", _P), ("out_pm", _P), ("levels", _P),
+                ("out_fmt", _I)]
 
 
 class PoseHeadMlp(ctypes.Structure):
@@ -110,7 +118,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if lib.dcl_b200_abi_version() != 3:
+        if lib.dcl_b200_abi_version() != 4:
             raise RuntimeError("libdcl_b200.so ABI version mismatch with dcl_net_b200/_lib.py")
         _lib = lib
     return _lib

@@ -38,6 +38,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/dcl_b200.h"
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -53,6 +54,7 @@ constexpr float RESCALE_TH = 8.0f;  // lazy rescale threshold (log2 units)
 
 template <int C>
 struct FdaCfg {
+    static constexpr bool PV16 = false;               // P and V as bf16 hi/lo pairs (3 MMAs per P V product)
     static constexpr int VROWS = FDA_P + C;           // value rows: RE_2 then RI_2
     static constexpr int NK = (C == 64) ? 2 : 1;      // K block ring depth
     static constexpr int NV = (C == 64) ? 4 : 2;      // V chunk ring depth
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256) fda_pack_kernel(int n, int m, const float
                                                        const float* __restrict__ RE_2,
                                                        __nv_bfloat16* __restrict__ Qp,
                                                        __nv_bfloat16* __restrict__ Kp,
-                                                       __nv_bfloat16* __restrict__ Vp) {
+                                                       __nv_bfloat16* __restrict__ Vp, int pv_fmt) {
     using Cfg = FdaCfg<C>;
     const int bs = blockIdx.y;
     const int section = blockIdx.z;  // 0: Q, 1: K, 2: V
@@ -122,14 +124,30 @@ __global__ void __launch_bounds__(256) fda_pack_kernel(int n, int m, const float
         const int key = tid % m, nchunk = tid / m;
         if (nchunk >= Cfg::VROWS / 8) return;
         __nv_bfloat16 hi[8], lo[8];
+        float val[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int vrow = nchunk * 8 + i;
             const float* src = (vrow < FDA_P) ? RE_2 + ((size_t)bs * FDA_P + vrow) * m
                                               : RI_2 + ((size_t)bs * C + (vrow - FDA_P)) * m;
-            split_bf16(__ldg(src + key), hi[i], lo[i]);
+            val[i] = __ldg(src + key);
+            split_bf16(val[i], hi[i], lo[i]);
         }
         const size_t half = (size_t)Cfg::VROWS * KS;  // elements in one hi (or lo) image
+        if (pv_fmt == 1) {
+            // one fp16 image per chunk (values rounded once, clamped to the fp16 range)
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half2 hh = __floats2half2_rn(fminf(fmaxf(val[2 * e], -65504.f), 65504.f),
+                                                     fminf(fmaxf(val[2 * e + 1], -65504.f), 65504.f));
+                w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            __nv_bfloat16* d16 = Vp + ((size_t)bs * (m / KS) + key / KS) * half + (size_t)nchunk * 128 +
+                                 ((key % KS) / 8) * 64 + (key % 8) * 8;
+            *reinterpret_cast<uint4*>(d16) = make_uint4(w[0], w[1], w[2], w[3]);
+            return;
+        }
         __nv_bfloat16* dst = Vp + ((size_t)bs * (m / KS) + key / KS) * 2 * half + (size_t)nchunk * 128 +
                              ((key % KS) / 8) * 64 + (key % 8) * 8;
         *reinterpret_cast<uint4*>(dst) =
@@ -270,12 +288,22 @@ __device__ __forceinline__ void fda_softmax_warps(unsigned char* smem, uint32_t 
                 for (int e = 0; e < 4; ++e) {
                     const float p0 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e]), LOG2E, neg_m));
                     const float p1 = ex2_approx(__fmaf_rn(__uint_as_float(sv[kc * 8 + 2 * e + 1]), LOG2E, neg_m));
-                    split2_bf16(p0, p1, h[e], lw[e]);
-                    sum0 += __uint_as_float(h[e] << 16) + __uint_as_float(lw[e] << 16);
-                    sum1 += __uint_as_float(h[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                    if constexpr (Cfg::PV16) {
+                        // p <= 2^RESCALE_TH = 256 between rescales: inside the fp16 range
+                        const __half2 hp = __floats2half2_rn(p0, p1);
+                        h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+                        const float2 back = __half22float2(hp);
+                        sum0 += back.x;
+                        sum1 += back.y;
+                    } else {
+                        split2_bf16(p0, p1, h[e], lw[e]);
+                        sum0 += __uint_as_float(h[e] << 16) + __uint_as_float(lw[e] << 16);
+                        sum1 += __uint_as_float(h[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                    }
                 }
                 *reinterpret_cast<uint4*>(pd + kc * Cfg::P_LBO) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                if constexpr (!Cfg::PV16)
+                    *reinterpret_cast<uint4*>(pd + Cfg::P_HALF + kc * Cfg::P_LBO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
             l = __fmaf_rn(l, alpha, sum0 + sum1);
         }
@@ -332,7 +360,24 @@ __device__ __forceinline__ void fda_softmax_warps(unsigned char* smem, uint32_t 
             for (int i = 0; i < 32; ++i) o[(size_t)i * n] = y[i];
         }
         unsigned char* pm = is_re ? out.re_pm : out.ri_pm;
-        if (pm != nullptr) {
+        if constexpr (Cfg::PV16) {
+            if (pm != nullptr) {
+                // PM16: one whole 8 KB blob (128 rows x 32 channels, fp16) per CTA and iteration
+                unsigned char* blob = pm + (tile * ((is_re ? FDA_P : C) / 32) + kb) * 8192 + pm_row;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t h[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a0 = fminf(fmaxf(y[ch * 8 + 2 * e], -65504.f), 65504.f);
+                        const float a1 = fminf(fmaxf(y[ch * 8 + 2 * e + 1], -65504.f), 65504.f);
+                        const __half2 hh = __floats2half2_rn(a0, a1);
+                        h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(blob + ch * 128) = make_uint4(h[0], h[1], h[2], h[3]);
+                }
+            }
+        } else if (pm != nullptr) {
             // one whole 16 KB blob (128 rows x 32 channels, hi | lo) per CTA and iteration
             unsigned char* blob = pm + (tile * ((is_re ? FDA_P : C) / 32) + kb) * 16384 + pm_row;
 #pragma unroll
@@ -539,21 +584,28 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_fwd_kernel(int n, int m,
 //   * tcgen05.commit multicasts every completion (S ready, K/V slot free, PV done) to both CTAs.
 //   * Softmax warps of both CTAs announce "S read" / "P written" with one cluster-scope arrive per warp on the
 //     leader's barriers (count 8).
-template <int C>
+// PV16_: the P V products run on once-rounded fp16 operands — P = exp2(..) in (0,1] and the values (activations that
+// are held in fp16 everywhere on the inference path) — as ONE MMA each instead of three; the value image then holds
+// one fp16 image per 16-key chunk and the point-major outputs are PM16 images.  The logits (Q K^T) keep split
+// operands.  Measured cost: profiles/r02_precision_emulation_*.json ("P single fp16": 3e-5 relative on the features).
+template <int C, bool PV16_ = false>
 struct FdaPairCfg {
+    static constexpr bool PV16 = PV16_;
     static constexpr int VROWS = FDA_P + C;
     static constexpr int VH = VROWS / 2;               // value rows staged per CTA
     static constexpr int NK = 2;
-    static constexpr int NV = (C == 64) ? 8 : 5;
+    static constexpr int NV = PV16_ ? 8 : ((C == 64) ? 8 : 5);
     static constexpr int NP = 2;
     static constexpr int Q_HALF = QT * C * 2;
     static constexpr int K_HALF = (KB / 2) * C * 2;    // hi (or lo) image of this CTA's 32 keys
     static constexpr int V_HALF = VH * KS * 2;         // hi (or lo) image of this CTA's value rows, one chunk
     static constexpr int V_PART_A = 128 * KS * 2;      // rows of the N=256 product come first, then the N=C product's
     static constexpr int P_HALF = QT * KB * 2;
-    static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = 2 * V_HALF, P_BYTES = 2 * P_HALF;
+    static constexpr int PV_IMAGES = PV16_ ? 1 : 2;    // images per P buffer / V chunk
+    static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = PV_IMAGES * V_HALF,
+                         P_BYTES = PV_IMAGES * P_HALF;
     static constexpr int G_K_HALF = KB * C * 2, G_K_BYTES = 2 * G_K_HALF;         // images written by fda_pack_kernel
-    static constexpr int G_V_HALF = VROWS * KS * 2, G_V_BYTES = 2 * G_V_HALF;
+    static constexpr int G_V_HALF = VROWS * KS * 2, G_V_BYTES = PV_IMAGES * G_V_HALF;
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = OFF_Q + Q_BYTES;
     static constexpr int OFF_V = OFF_K + NK * K_BYTES;
@@ -569,10 +621,10 @@ struct FdaPairCfg {
     static constexpr int P_LBO = 128, P_SBO = (KB / 8) * 128;
 };
 
-template <int C>
+template <int C, bool PV16>
 __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m,
                                                                   const __grid_constant__ FdaJobs jobs) {
-    using Cfg = FdaPairCfg<C>;
+    using Cfg = FdaPairCfg<C, PV16>;
     const FdaJob& job = jobs.j[blockIdx.z];
     const __nv_bfloat16 *Qp = job.Qp, *Kp = job.Kp, *Vp = job.Vp;
     const FdaOut& out = job.out;
@@ -668,8 +720,10 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m,
                     const size_t g = (size_t)vi * Cfg::G_V_BYTES;
                     dcl_bulk_g2s(dst, gVa + g, Cfg::V_PART_A, v_full + s);
                     dcl_bulk_g2s(dst + Cfg::V_PART_A, gVb + g, V_PART_B, v_full + s);
-                    dcl_bulk_g2s(dst + Cfg::V_HALF, gVa + g + Cfg::G_V_HALF, Cfg::V_PART_A, v_full + s);
-                    dcl_bulk_g2s(dst + Cfg::V_HALF + Cfg::V_PART_A, gVb + g + Cfg::G_V_HALF, V_PART_B, v_full + s);
+                    if constexpr (!PV16) {
+                        dcl_bulk_g2s(dst + Cfg::V_HALF, gVa + g + Cfg::G_V_HALF, Cfg::V_PART_A, v_full + s);
+                        dcl_bulk_g2s(dst + Cfg::V_HALF + Cfg::V_PART_A, gVb + g + Cfg::G_V_HALF, V_PART_B, v_full + s);
+                    }
                 }
             }
         }
@@ -678,8 +732,10 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m,
             // ===================== MMA issuer (leader only) =====================
             long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_fda_trace : nullptr;
             constexpr uint32_t idesc_s = umma_idesc_bf16(2 * QT, KB);
-            constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256, true);   // value image is MN-major
-            constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C, true);
+            // value image is MN-major; PV16: fp16 x fp16 (a_format = b_format = 0)
+            constexpr uint32_t f16_mask = PV16 ? ~((1u << 7) | (1u << 10)) : ~0u;
+            constexpr uint32_t idesc_o1 = umma_idesc_bf16(2 * QT, 256, true) & f16_mask;
+            constexpr uint32_t idesc_o2 = umma_idesc_bf16(2 * QT, C, true) & f16_mask;
             const uint32_t tO = tmem_base;
             const uint64_t dQh = umma_desc(sQ, Cfg::QK_LBO, Cfg::QK_SBO);
             const uint64_t dQl = dQh + (uint64_t)(Cfg::Q_HALF >> 4);
@@ -730,13 +786,17 @@ __global__ void __launch_bounds__(FDA_THREADS, 1) fda_pair_kernel(int n, int m,
                     const uint64_t dAh = dPh + (uint64_t)((ks * 2 * Cfg::P_LBO) >> 4);
                     const uint64_t dAl = dAh + (uint64_t)(Cfg::P_HALF >> 4);
                     const uint32_t acc = (j == 0 && ks == 0) ? 0u : 1u;
-                    tc2_mma_bf16(tO, dAh, dVh, idesc_o1, acc);
-                    tc2_mma_bf16(tO, dAh, dVl, idesc_o1, 1u);
-                    tc2_mma_bf16(tO, dAl, dVh, idesc_o1, 1u);
                     constexpr uint64_t v2 = (uint64_t)(Cfg::V_PART_A >> 4);
+                    tc2_mma_bf16(tO, dAh, dVh, idesc_o1, acc);
+                    if constexpr (!PV16) {
+                        tc2_mma_bf16(tO, dAh, dVl, idesc_o1, 1u);
+                        tc2_mma_bf16(tO, dAl, dVh, idesc_o1, 1u);
+                    }
                     tc2_mma_bf16(tO + 256, dAh, dVh + v2, idesc_o2, acc);
-                    tc2_mma_bf16(tO + 256, dAh, dVl + v2, idesc_o2, 1u);
-                    tc2_mma_bf16(tO + 256, dAl, dVh + v2, idesc_o2, 1u);
+                    if constexpr (!PV16) {
+                        tc2_mma_bf16(tO + 256, dAh, dVl + v2, idesc_o2, 1u);
+                        tc2_mma_bf16(tO + 256, dAl, dVh + v2, idesc_o2, 1u);
+                    }
                     tc2_commit_mcast(v_empty + s, (uint16_t)0x3);
                 }
                 tc2_commit_mcast(o_done + (j & 1), (uint16_t)0x3);
@@ -1108,14 +1168,14 @@ struct FdaWs {
 
 template <int C>
 int fda_pack_launch(int b, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2, void* workspace,
-                    cudaStream_t st) {
+                    int pv_fmt, cudaStream_t st) {
     using Cfg = FdaCfg<C>;
     FdaWs<C> w(workspace, b, n, m);
     const int work_q = n * (C / 8), work_k = m * (C / 8), work_v = m * (Cfg::VROWS / 8);
     int work = work_q > work_k ? work_q : work_k;
     if (work_v > work) work = work_v;
     dim3 grid(DCL_DIVUP(work, 256), b, 3);
-    fda_pack_kernel<C><<<grid, 256, 0, st>>>(n, m, RI_1, RI_2, RE_2, w.Qp, w.Kp, w.Vp);
+    fda_pack_kernel<C><<<grid, 256, 0, st>>>(n, m, RI_1, RI_2, RE_2, w.Qp, w.Kp, w.Vp, pv_fmt);
     return dcl_launch_status();
 }
 
@@ -1146,11 +1206,11 @@ int fda_main_launch(int njobs, const dcl_fda_job* in, int b, int n, int m, cudaS
 }
 
 // CTA-pair variant: needs an even number of query tiles per instance.
-template <int C>
+template <int C, bool PV16>
 int fda_pair_launch(int njobs, const dcl_fda_job* in, int b, int n, int m, cudaStream_t st) {
-    using Cfg = FdaPairCfg<C>;
+    using Cfg = FdaPairCfg<C, PV16>;
     const FdaJobs jobs = fda_jobs<C>(njobs, in, b, n, m);
-    cudaError_t e = cudaFuncSetAttribute(fda_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fda_pair_kernel<C, PV16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
@@ -1165,7 +1225,7 @@ int fda_pair_launch(int njobs, const dcl_fda_job* in, int b, int n, int m, cudaS
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, fda_pair_kernel<C>, n, m, jobs);
+    e = cudaLaunchKernelEx(&cfg, fda_pair_kernel<C, PV16>, n, m, jobs);
     if (e != cudaSuccess) return (int)e;
     return dcl_launch_status();
 }
@@ -1187,21 +1247,28 @@ DCL_API size_t dcl_fda_workspace_bytes(int b, int c, int p, int n, int m) {
     return (size_t)b * ((size_t)n * c + (size_t)m * c + (size_t)m * (p + c)) * 4 + 1024;
 }
 
-DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2,
-                         void* workspace, size_t workspace_bytes, void* stream) {
-    DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m));
+DCL_API int dcl_fda_pack_fmt(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2,
+                             const float* RE_2, void* workspace, size_t workspace_bytes, int pv_fmt, void* stream) {
+    DCL_RETURN_IF_BAD(fda_shape_ok(b, c, p, n, m) && (pv_fmt == 0 || pv_fmt == 1));
     DCL_RETURN_IF_BAD(workspace != nullptr && (((uintptr_t)workspace) & 127u) == 0);
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     DCL_RETURN_IF_BAD(((((uintptr_t)RE_2) | ((uintptr_t)RI_2)) & 15u) == 0);
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c == 64) return fda_pack_launch<64>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
-    return fda_pack_launch<128>(b, n, m, RI_1, RI_2, RE_2, workspace, st);
+    if (c == 64) return fda_pack_launch<64>(b, n, m, RI_1, RI_2, RE_2, workspace, pv_fmt, st);
+    return fda_pack_launch<128>(b, n, m, RI_1, RI_2, RE_2, workspace, pv_fmt, st);
 }
 
-DCL_API int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
-                                    size_t workspace_bytes, void* stream) {
+DCL_API int dcl_fda_pack(int b, int c, int p, int n, int m, const float* RI_1, const float* RI_2, const float* RE_2,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    return dcl_fda_pack_fmt(b, c, p, n, m, RI_1, RI_2, RE_2, workspace, workspace_bytes, 0, stream);
+}
+
+DCL_API int dcl_fda_fwd_packed_jobs_fmt(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
+                                        size_t workspace_bytes, int pv_fmt, void* stream) {
     DCL_RETURN_IF_BAD(njobs >= 1 && njobs <= FDA_MAX_JOBS && jobs != nullptr && fda_shape_ok(b, c, p, n, m));
+    // the fp16 P V form exists in the CTA-pair kernel only: an even number of 128-query tiles per instance
+    DCL_RETURN_IF_BAD(pv_fmt == 0 || (pv_fmt == 1 && (n / QT) % 2 == 0));
     DCL_RETURN_IF_BAD(workspace_bytes >= dcl_fda_workspace_bytes(b, c, p, n, m));
     for (int i = 0; i < njobs; ++i) {
         DCL_RETURN_IF_BAD(jobs[i].workspace != nullptr && (((uintptr_t)jobs[i].workspace) & 127u) == 0);
@@ -1209,12 +1276,21 @@ DCL_API int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, i
     }
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pv_fmt == 1) {
+        if (c == 64) return fda_pair_launch<64, true>(njobs, jobs, b, n, m, st);
+        return fda_pair_launch<128, true>(njobs, jobs, b, n, m, st);
+    }
     if (fda_use_pair(n)) {
-        if (c == 64) return fda_pair_launch<64>(njobs, jobs, b, n, m, st);
-        return fda_pair_launch<128>(njobs, jobs, b, n, m, st);
+        if (c == 64) return fda_pair_launch<64, false>(njobs, jobs, b, n, m, st);
+        return fda_pair_launch<128, false>(njobs, jobs, b, n, m, st);
     }
     if (c == 64) return fda_main_launch<64>(njobs, jobs, b, n, m, st);
     return fda_main_launch<128>(njobs, jobs, b, n, m, st);
+}
+
+DCL_API int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
+                                    size_t workspace_bytes, void* stream) {
+    return dcl_fda_fwd_packed_jobs_fmt(njobs, jobs, b, c, p, n, m, workspace_bytes, 0, stream);
 }
 
 DCL_API int dcl_fda_fwd_packed_pm(int b, int c, int p, int n, int m, float* RE_embed, float* RI_embed, void* RE_pm,

@@ -16,6 +16,7 @@
 // feature-row reads and the output write are coalesced 128-bit accesses (the
 // reference strides by C between lanes).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "tile_pipe.cuh"
 #include "umma.cuh"
 #include "../../include/dcl_b200.h"
@@ -622,6 +623,7 @@ struct SpTowerDev {  // one set of query points and the pyramid levels [lv0, lv1
     int n, c_total, lv0, lv1;
     const float* unknown;
     unsigned char* out_pm;
+    int out_fmt;  // 0: PM image (bf16 hi/lo, 16 KB blobs); 1: PM16 image (fp16, 8 KB blobs)
 };
 struct SpLevelBatch {
     int nlevels, ntowers;
@@ -803,8 +805,9 @@ __global__ void __launch_bounds__(SP_THREADS)
     const int sub = threadIdx.x % SPL_LPQ;
     const bool valid = qi < n;
     const float4 u = reinterpret_cast<const float4*>(unknown)[valid ? qi : (n - 1)];
-    unsigned char* row_base =
-        out_pm + (size_t)(qi / 128) * (c_total / 32) * 16384 + ((qi % 128) >> 3) * 512 + (qi & 7) * 16;
+    const bool f16 = tw.out_fmt == 1;
+    const size_t blob = f16 ? 8192 : 16384;
+    unsigned char* row_base = out_pm + (size_t)(qi / 128) * (c_total / 32) * blob + ((qi % 128) >> 3) * 512 + (qi & 7) * 16;
     for (int li = tw.lv0; li < tw.lv1; ++li) {
         const SpLevelDev& lv = batch.lv[li];
         if (lv.m == 0) continue;  // nothing to interpolate from (the reference would gather row 0 of an empty tensor)
@@ -833,12 +836,22 @@ __global__ void __launch_bounds__(SP_THREADS)
                     o[hh * 4 + 3] = dcl_interp3(a0, x0.w, a1, x1.w, a2, x2.w);
                 }
                 uint32_t h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split2_bf16(o[2 * e], o[2 * e + 1], h[e], l[e]);
                 const int chunk = (lv.out_col0 >> 3) + c8;
-                unsigned char* d = row_base + (size_t)(chunk >> 2) * 16384 + (chunk & 3) * 128;
-                *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(d + 8192) = make_uint4(l[0], l[1], l[2], l[3]);
+                unsigned char* d = row_base + (size_t)(chunk >> 2) * blob + (chunk & 3) * 128;
+                if (f16) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 hh = __floats2half2_rn(fminf(fmaxf(o[2 * e], -65504.f), 65504.f),
+                                                             fminf(fmaxf(o[2 * e + 1], -65504.f), 65504.f));
+                        h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split2_bf16(o[2 * e], o[2 * e + 1], h[e], l[e]);
+                    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(d + 8192) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
             }
         }
     }
@@ -1009,6 +1022,8 @@ DCL_API int dcl_sp_nn_interpolate_towers_pm(int ntowers, const dcl_sp_tower* tow
         tw.c_total = tin.c_total;
         tw.unknown = tin.unknown;
         tw.out_pm = reinterpret_cast<unsigned char*>(tin.out_pm);
+        DCL_RETURN_IF_BAD(tin.out_fmt == 0 || tin.out_fmt == 1);
+        tw.out_fmt = tin.out_fmt;
         tw.lv0 = li;
         for (int i = 0; i < tin.nlevels; ++i, ++li) {
             const dcl_sp_level& in = tin.levels[i];
@@ -1043,6 +1058,6 @@ DCL_API int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nle
                                             void* out_pm, int c_total, void* workspace, size_t workspace_bytes,
                                             void* stream) {
     DCL_RETURN_IF_BAD(nlevels >= 1 && nlevels <= SPL_MAX_LEVELS && levels != nullptr);
-    const dcl_sp_tower tower = {n, c_total, nlevels, unknown, out_pm, levels};
+    const dcl_sp_tower tower = {n, c_total, nlevels, unknown, out_pm, levels, 0};
     return dcl_sp_nn_interpolate_towers_pm(1, &tower, workspace, workspace_bytes, stream);
 }

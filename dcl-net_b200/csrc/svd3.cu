@@ -16,6 +16,7 @@
 // ill-conditioned one) is never normalised.  The iteration runs in fp64 so that the
 // result is the exact projection to well below the reference's own fp32 LAPACK error.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "../../include/dcl_b200.h"
 
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(256) pose_compose_kernel(int n, float* __restr
                                                            const float* __restrict__ points_in,
                                                            float* __restrict__ points_out_cm,
                                                            int64_t out_batch_stride,
-                                                           unsigned char* __restrict__ points_out_pm, int update) {
+                                                           unsigned char* __restrict__ points_out_pm, int update,
+                                                           int pm_fmt) {
     __shared__ float sR[9], sT[3];
     const int bs = blockIdx.y;
     if (threadIdx.x < 12) {
@@ -234,7 +236,23 @@ __global__ void __launch_bounds__(256) pose_compose_kernel(int n, float* __restr
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) o[(size_t)ch * n] = v[ch];
         }
-        if (points_out_pm != nullptr) {
+        if (points_out_pm != nullptr && pm_fmt == 1) {
+            // PM16 image with 32 channels per row: channels 0-2 = fp16(xyz), 3-5 = fp16(xyz - fp16(xyz)); the caller
+            // zeroed the image once, only the first 8-channel unit of the row is rewritten
+            const size_t r = (size_t)bs * n + i;
+            unsigned char* d = points_out_pm + (r >> 7) * 8192 + ((r & 127) >> 3) * 512 + (r & 7) * 16;
+            __half hi[3], lo[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                hi[ch] = __float2half_rn(fminf(fmaxf(v[ch], -65504.f), 65504.f));
+                lo[ch] = __float2half_rn(v[ch] - __half2float(hi[ch]));
+            }
+            const __half2 w0 = __halves2half2(hi[0], hi[1]), w1 = __halves2half2(hi[2], lo[0]),
+                          w2 = __halves2half2(lo[1], lo[2]);
+            *reinterpret_cast<uint4*>(d) = make_uint4(*reinterpret_cast<const uint32_t*>(&w0),
+                                                      *reinterpret_cast<const uint32_t*>(&w1),
+                                                      *reinterpret_cast<const uint32_t*>(&w2), 0u);
+        } else if (points_out_pm != nullptr) {
             // point-major bf16 hi / lo image with 32 channels per row (pm_gemm.cu), channels 0-2 = xyz; the caller
             // zeroed the image once, only the first 8-channel unit of the row is rewritten
             const size_t r = (size_t)bs * n + i;
@@ -308,9 +326,25 @@ DCL_API int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, 
     return dcl_pose_compose_pm(b, n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride, nullptr, stream);
 }
 
+static int pose_compose_any(int b, int n, float* R, float* t, const float* dR, const float* dt, const float* points_in,
+                            float* points_out_cm, int64_t out_batch_stride, void* points_out_pm, int pm_fmt,
+                            void* stream);
+
 DCL_API int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* dR, const float* dt,
                                 const float* points_in, float* points_out_cm, int64_t out_batch_stride,
                                 void* points_out_pm, void* stream) {
+    return pose_compose_any(b, n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride, points_out_pm, 0, stream);
+}
+
+DCL_API int dcl_pose_compose_pm16(int b, int n, float* R, float* t, const float* dR, const float* dt,
+                                  const float* points_in, float* points_out_cm, int64_t out_batch_stride,
+                                  void* points_out_pm16, void* stream) {
+    return pose_compose_any(b, n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride, points_out_pm16, 1, stream);
+}
+
+static int pose_compose_any(int b, int n, float* R, float* t, const float* dR, const float* dt, const float* points_in,
+                            float* points_out_cm, int64_t out_batch_stride, void* points_out_pm, int pm_fmt,
+                            void* stream) {
     DCL_RETURN_IF_BAD(b >= 0 && n >= 0);
     DCL_RETURN_IF_BAD(points_out_pm == nullptr || (((long)b * n) % 128 == 0 && ((uintptr_t)points_out_pm & 15u) == 0));
     if (b == 0) return 0;
@@ -321,7 +355,7 @@ DCL_API int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* d
         ++launched;
         dim3 grid(DCL_DIVUP(n, 256), b);
         pose_compose_kernel<<<grid, 256, 0, st>>>(n, R, t, dR, dt, points_in, points_out_cm, out_batch_stride,
-                                                  reinterpret_cast<unsigned char*>(points_out_pm), update);
+                                                  reinterpret_cast<unsigned char*>(points_out_pm), update, pm_fmt);
     }
     if (update) {
         ++launched;

@@ -126,6 +126,10 @@ class Network(nn.Module):
         self.regressor_rot = Head_MultiLayerPerceptron([1024, 512, 128, 9], *plain)
         self.regressor_trans = Head_MultiLayerPerceptron([1024, 512, 128, 3], *plain)
         self.use_fused_tail = True   # inference: pointwise MLPs on tensor cores (fused_tail.py)
+        # operand precision of the tensor-core inference path (fused_tail.py): "fp16" = activations rounded once to
+        # fp16, fp16 hi/lo weights, split-operand FDA logits (default; ~4e-5 on features, ~1e-5 deg on poses against
+        # the fp32 graph); "fp32-faithful" = every operand a bf16 hi/lo pair (3 MMAs per product, ~1e-6)
+        self.precision = "fp16"
         self._fused_tail = None
 
     def _apply(self, fn, *args, **kwargs):
@@ -167,8 +171,9 @@ class Network(nn.Module):
         if why is not None:
             L.warn_once(("fused_tail", why), f"dcl_net_b200.Network: inference falls back to PyTorch layer modules ({why})")
             return None
-        if self._fused_tail is None:
-            self._fused_tail = FusedTail(self)
+        fmt = FusedTail.pick_fmt(self)
+        if self._fused_tail is None or self._fused_tail.fmt != fmt:
+            self._fused_tail = FusedTail(self, fmt)
         return self._fused_tail
 
     def invalidate_packed_weights(self):
@@ -183,7 +188,7 @@ class Network(nn.Module):
         fused = self._fused(b)
         if fused is not None:
             pm_xc, pm_yo = self.stage1_get_point_feats.forward_pm_pair(points_inp, ids_inp, levels_inp,
-                                                                        points_tmp, ids_tmp, levels_tmp)
+                                                                        points_tmp, ids_tmp, levels_tmp, fused.fmt)
             return fused.forward(pm_xc, pm_yo, b)
         F_Xc = self.stage1_get_point_feats(points_inp, ids_inp, *levels_inp)
         F_Yo = self.stage1_get_point_feats(points_tmp, ids_tmp, *levels_tmp)
@@ -194,7 +199,7 @@ class Network(nn.Module):
         fused = self._fused(b)
         if fused is not None:
             from .fused_tail import pm_pack_rows
-            return fused.forward(pm_pack_rows(F_Xc), pm_pack_rows(F_Yo), b)
+            return fused.forward(pm_pack_rows(F_Xc, fused.fmt), pm_pack_rows(F_Yo, fused.fmt), b)
         F_Xc = F_Xc.view(b, self.n_inp, -1).transpose(1, 2)[:, :, :, None, None]
         F_Yo = F_Yo.view(b, self.n_tmp, -1).transpose(1, 2)[:, :, :, None, None]
         sq = lambda t: t.squeeze(-1).squeeze(-1)

@@ -38,6 +38,7 @@ class PoseEngine:
         self.h2d_bytes = 0
         self._graph = None
         self._static = None
+        self.poses12 = None
         self._packed = (None, None)   # the packed-weight objects the captured graph holds raw pointers into
 
     def _current_packed(self):
@@ -81,14 +82,17 @@ class PoseEngine:
         return self
 
     def run(self):
-        """Device-resident pass over the loaded batch -> (rot (B,3,3), trans (B,3)) on the device."""
+        """Device-resident pass over the loaded batch -> (rot (B,3,3), trans (B,3)) on the device; the same poses
+        packed as (B,12) rows [R row-major | t] are left in self.poses12 (what goes back to the host)."""
         if self._graph is not None:
             if any(cur is not old for cur, old in zip(self._current_packed(), self._packed)):
                 self._graph = None
                 self.capture()             # weights were re-packed: the old graph points at the previous copies
             self._graph.replay()
-            return self._static
-        return self._run_eager()
+            rot, trans, self.poses12 = self._static
+            return rot, trans
+        rot, trans, self.poses12 = self._run_eager()
+        return rot, trans
 
     @torch.no_grad()
     def _run_eager(self):
@@ -97,14 +101,15 @@ class PoseEngine:
         rot, trans = pred["rot_pred"], pred["trans_pred"]
         if self.refiner is not None and self.iterations > 0:
             rot, trans = refine_poses(self.refiner, self.points["inp"].view(self.b, self.n_inp, 3), rot, trans,
-                                      pred["F_Xo_p"], pred["conf"], self.iterations, pred.get("F_Xo_p_pm"))
-        return rot, trans
+                                      pred["F_Xo_p"], pred["conf"], self.iterations, pred.get("F_Xo_p_pm"),
+                                      pred.get("F_Xo_p_pm_fmt", 0))
+        return rot, trans, torch.cat([rot.reshape(self.b, 9), trans], dim=1)
 
     def infer(self, host_batch):
         """Host in, host out: H2D copies + pass + D2H of the (B,12) poses; returns after the poses have landed."""
         self.load(host_batch)
-        rot, trans = self.run()
-        self.out_host.copy_(torch.cat([rot.reshape(self.b, 9), trans], dim=1), non_blocking=True)
+        self.run()
+        self.out_host.copy_(self.poses12, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self.out_host[:, :9].view(self.b, 3, 3), self.out_host[:, 9:]
 
@@ -172,8 +177,8 @@ class PipelinedPoseEngine:
             cs = self.compute_streams[slot] if self.compute_streams else main
             cs.wait_event(loaded[slot])
             with torch.cuda.stream(cs):
-                rot, trans = eng.run()
-                eng.out_host.copy_(torch.cat([rot.reshape(eng.b, 9), trans], dim=1), non_blocking=True)
+                eng.run()
+                eng.out_host.copy_(eng.poses12, non_blocking=True)
                 done[slot].record(cs)
             pending.append(slot)
             if len(pending) == depth or nxt is None:

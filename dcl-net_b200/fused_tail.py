@@ -2,9 +2,14 @@
 stage-2 refiner loop (models/refiner.py:57-95), with the pointwise MLP stacks on tensor cores (csrc/pm_gemm.cu)
 instead of fp32 cuDNN/cuBLAS calls.
 
-Activations travel between layers as "PM images" (bf16 hi/lo operand images, include/dcl_b200.h) written by the
-producing kernel's epilogue; an fp32 channel-major tensor exists only where the reference interface needs one
-(F_Xo_p, which stage 2 reads).  Weights are packed once per Network (eval-mode BatchNorm before a ReLU is folded
+Activations travel between layers as operand images (include/dcl_b200.h) written by the producing kernel's epilogue;
+an fp32 channel-major tensor exists only where the reference interface needs one (F_Xo_p, which stage 2 reads).
+Two formats (`fmt`):
+   1  "PM16": activations rounded once to fp16, weights split into fp16 hi + lo — 2 MMAs per product, 2 bytes per
+      activation element; the FDA logits keep bf16 hi/lo operands (3 MMAs), its P V products run on fp16 P and V
+      (1 MMA).  The default of the inference path (Network.precision = "fp16"): measured 4e-5 relative on the
+      features and ~1e-5 deg on the poses against the fp32 graph (bars 1e-3 / 0.01 deg).
+   0  "PM": every operand as a bf16 hi/lo pair, 3 MMAs per product (~2^-17; Network.precision = "fp32-faithful").  Weights are packed once per Network (eval-mode BatchNorm before a ReLU is folded
 into the convolution; BatchNorm after a ReLU becomes the GEMM epilogue's per-channel affine).
 
 Dataflow (test mode), b instances of n points per side, R = b*n rows — 17 launches:
@@ -26,35 +31,38 @@ from .modules import fda_from_workspaces
 _EPS_NAMES = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
 
 
-def pm_bytes(rows, c):
-    return rows * c * 4
+def pm_bytes(rows, c, fmt=0):
+    return rows * c * (2 if fmt == L.FMT_F16 else 4)
 
 
-def pm_empty(rows, c, device):
-    return torch.empty(pm_bytes(rows, c), dtype=torch.uint8, device=device)
+def pm_empty(rows, c, device, fmt=0):
+    return torch.empty(pm_bytes(rows, c, fmt), dtype=torch.uint8, device=device)
 
 
-def pm_pack_rows(x):
-    """fp32 (R, C) row-major -> PM image (R % 128 == 0, C % 32 == 0)."""
+_pm_empty = pm_empty
+
+
+def pm_pack_rows(x, fmt=0):
+    """fp32 (R, C) row-major -> PM image (fmt 0) / PM16 image (fmt 1); R % 128 == 0, C % 32 == 0."""
     x = x.contiguous()
     rows, c = x.shape
-    out = pm_empty(rows, c, x.device)
-    L.check(L.load().dcl_pm_pack_rows(rows, c, c, L.ptr(x), L.ptr(out), L.stream_ptr()), "pm_pack_rows")
+    out = pm_empty(rows, c, x.device, fmt)
+    L.check(L.load().dcl_pm_pack_rows(rows, c, c, L.ptr(x), L.ptr(out), fmt, L.stream_ptr()), "pm_pack_rows")
     return out
 
 
-def pm_pack_cm(x):
-    """fp32 (B, C, N) channel-major -> PM image of the (B*N, C) activation."""
+def pm_pack_cm(x, fmt=0):
+    """fp32 (B, C, N) channel-major -> PM / PM16 image of the (B*N, C) activation."""
     x = x.contiguous()
     b, c, n = x.shape
-    out = pm_empty(b * n, c, x.device)
-    L.check(L.load().dcl_pm_pack_cm(b, c, n, L.ptr(x), L.ptr(out), L.stream_ptr()), "pm_pack_cm")
+    out = pm_empty(b * n, c, x.device, fmt)
+    L.check(L.load().dcl_pm_pack_cm(b, c, n, L.ptr(x), L.ptr(out), fmt, L.stream_ptr()), "pm_pack_cm")
     return out
 
 
-def pm_unpack(pm, rows, c):
+def pm_unpack(pm, rows, c, fmt=0):
     out = torch.empty(rows, c, dtype=torch.float32, device=pm.device)
-    L.check(L.load().dcl_pm_unpack(rows, c, L.ptr(pm), L.ptr(out), L.stream_ptr()), "pm_unpack")
+    L.check(L.load().dcl_pm_unpack(rows, c, L.ptr(pm), L.ptr(out), fmt, L.stream_ptr()), "pm_unpack")
     return out
 
 
@@ -65,12 +73,13 @@ def pick_nt(cout):
     raise ValueError(f"pm_gemm: cout={cout} is not a multiple of 64")
 
 
-def pack_weight(w, nt):
-    """(cout, cin) fp32 -> packed bf16 hi/lo blobs, one per (n-tile, k-block of 32)."""
+def pack_weight(w, nt, fmt=0):
+    """(cout, cin) fp32 -> packed hi/lo blobs, one per (n-tile, k-block of 32): bf16 halves (fmt 0) or fp16 (fmt 1)."""
     cout, cin = w.shape
     assert cout % nt == 0 and cin % 32 == 0
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
+    dt = torch.float16 if fmt == L.FMT_F16 else torch.bfloat16
+    hi = w.to(dt)
+    lo = (w - hi.float()).to(dt)
 
     def img(x):  # (tile, rg, r, kb, ch, e) -> (tile, kb, rg, ch, r, e)
         return x.view(cout // nt, nt // 8, 8, cin // 32, 4, 8).permute(0, 3, 1, 4, 2, 5)
@@ -81,10 +90,11 @@ def pack_weight(w, nt):
 class Layer:
     """One packed GEMM layer: y = post(relu(x W^T + bias))."""
 
-    def __init__(self, w, bias, relu, post_scale=None, post_shift=None):
+    def __init__(self, w, bias, relu, post_scale=None, post_shift=None, fmt=0):
         self.cout, self.cin = w.shape
         self.nt = pick_nt(self.cout)
-        self.w = pack_weight(w.float().contiguous(), self.nt)
+        self.fmt = fmt                 # format of the A operand this layer reads (and of its packed weights)
+        self.w = pack_weight(w.float().contiguous(), self.nt, fmt)
         self.bias = None if bias is None else bias.float().contiguous()
         self.relu = int(relu)
         self.post_scale = None if post_scale is None else post_scale.float().contiguous()
@@ -96,18 +106,18 @@ def _bn_affine(bn):
     return s, bn.bias - bn.running_mean * s
 
 
-def layers_from_disengage(stack):
+def layers_from_disengage(stack, fmt=0):
     """nn.Sequential of two BasicBlock_3DCONV (Conv3d 1x1x1 no bias -> BN3d -> ReLU): BN folded into the conv."""
     out = []
     for block in stack:
         conv, bn = block.layers[0], block.layers[1]
         s, t = _bn_affine(bn)
         w = conv.weight.reshape(conv.out_channels, conv.in_channels) * s[:, None]
-        out.append(Layer(w, t, relu=True))
+        out.append(Layer(w, t, relu=True, fmt=fmt))
     return out
 
 
-def layers_from_head(head):
+def layers_from_head(head, fmt=0):
     """Head_MultiLayerPerceptron: Conv1d(k=1) -> [ReLU] -> [BN]; returns (gemm layers, trailing torch convs).
     Layers whose width is not a multiple of 64 (the final 1/3/9-wide ones) stay in torch."""
     mods = list(head.layers)
@@ -121,7 +131,7 @@ def layers_from_head(head):
         j += int(bn is not None)
         if conv.out_channels % 64 == 0 and conv.in_channels % 32 == 0 and not rest:
             ps, pt = _bn_affine(bn) if bn is not None else (None, None)
-            gemm.append(Layer(conv.weight.reshape(conv.out_channels, conv.in_channels), conv.bias, relu, ps, pt))
+            gemm.append(Layer(conv.weight.reshape(conv.out_channels, conv.in_channels), conv.bias, relu, ps, pt, fmt))
         else:
             rest.append((conv, relu, bn))
         i = j
@@ -157,6 +167,7 @@ def run_gemm(problems, rows):
         slot.dot_w, slot.dot_out = L.ptr(p.get("dot_w")), L.ptr(p.get("dot_out"))
         slot.out_qk, slot.qk_tile_rows = _addr(p.get("out_qk")), p.get("qk_tile_rows", 0)
         slot.out_v, slot.v_row0, slot.v_rows = _addr(p.get("out_v")), p.get("v_row0", 0), p.get("v_rows", 0)
+        slot.a_fmt, slot.out_fmt = lay.fmt, p.get("out_fmt", lay.fmt)
         keep.append(p)
     if GEMM_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -173,15 +184,16 @@ class FusedTail:
 
     keep_debug = False  # True: also materialise F_Xo_m / F_Yc_p / F_Yc_m in the reference layout (tests)
 
-    def __init__(self, net):
+    def __init__(self, net, fmt=0):
         self.net = net
+        self.fmt = fmt
         self.c_m = net.disengage_Xc_m1[1].layers[0].out_channels
         with torch.no_grad():
-            self.dis = {name: layers_from_disengage(getattr(net, "disengage_" + name)) for name in _EPS_NAMES}
-            self.conf, self.conf_rest = layers_from_head(net.regressor_conf)
-            self.conf_bi, self.conf_bi_rest = layers_from_head(net.regressor_conf_bi)
-            self.fuser, rest_a = layers_from_head(net.neck_fuser)
-            self.fuser_bi, rest_b = layers_from_head(net.neck_fuser_bi)
+            self.dis = {name: layers_from_disengage(getattr(net, "disengage_" + name), fmt) for name in _EPS_NAMES}
+            self.conf, self.conf_rest = layers_from_head(net.regressor_conf, fmt)
+            self.conf_bi, self.conf_bi_rest = layers_from_head(net.regressor_conf_bi, fmt)
+            self.fuser, rest_a = layers_from_head(net.neck_fuser, fmt)
+            self.fuser_bi, rest_b = layers_from_head(net.neck_fuser_bi, fmt)
         assert not rest_a and not rest_b and len(self.fuser) == 3 and len(self.conf) == 2
         # train-mode outputs evaluated without autograd (Xo_pred / Yc_pred, models/DCL_Net.py:207-210): the
         # 256 -> 256 -> 128 layers as they are, the trailing 128 -> 3 layer zero-padded to one 64-wide n-tile
@@ -189,14 +201,14 @@ class FusedTail:
         if net.mode != "test":
             with torch.no_grad():
                 for key, head in (("Xo", net.regressor_Xo), ("Yc", net.regressor_Yc)):
-                    gemm, rest = layers_from_head(head)
+                    gemm, rest = layers_from_head(head, fmt)
                     (conv, relu, bn), = rest
                     assert len(gemm) == 2 and conv.out_channels <= 64 and not relu and bn is None
                     w = conv.weight.new_zeros(64, conv.in_channels)
                     w[:conv.out_channels] = conv.weight.reshape(conv.out_channels, conv.in_channels)
                     bias = conv.bias.new_zeros(64)
                     bias[:conv.out_channels] = conv.bias
-                    self.coord[key] = (gemm + [Layer(w, bias, relu=False)], conv.out_channels)
+                    self.coord[key] = (gemm + [Layer(w, bias, relu=False, fmt=fmt)], conv.out_channels)
         self.conf_dot, self.conf_dot_bias = [], []
         for rest in (self.conf_rest, self.conf_bi_rest):
             (conv, relu, bn), = rest
@@ -220,6 +232,13 @@ class FusedTail:
     def supported(net, b):
         return FusedTail.unsupported_reason(net, b) is None
 
+    @staticmethod
+    def pick_fmt(net):
+        """PM16 when the network asks for it and the fp16 form of the fused FDA kernel applies (CTA pairs: an even
+        number of 128-query tiles per instance); the bf16 hi/lo format otherwise."""
+        want16 = getattr(net, "precision", "fp16") == "fp16"
+        return L.FMT_F16 if want16 and (net.n_inp // 128) % 2 == 0 else L.FMT_BF16X2
+
     @torch.no_grad()
     def forward(self, pm_xc, pm_yo, b):
         net, c_m = self.net, self.c_m
@@ -227,6 +246,8 @@ class FusedTail:
         rows = b * n
         dev = pm_xc.device
         f32 = dict(dtype=torch.float32, device=dev)
+        fmt = self.fmt
+        pm_empty = lambda r, c, d: _pm_empty(r, c, d, fmt)      # every activation image of this pass has format `fmt`
 
         # ---- disengage layer 1: eight 480 -> 256 problems in one launch
         h1 = {name: pm_empty(rows, 256, dev) for name in _EPS_NAMES}
@@ -264,7 +285,7 @@ class FusedTail:
         # kernel as point-major images for the MLPs below, F_Xo_p also in the reference's layout (stage 2 reads it)
         dbg = self.keep_debug
         (F_Xo_p, F_Xo_m, pm_Xo_p, pm_Xo_m, _), (F_Yc_p, F_Yc_m, pm_Yc_p, pm_Yc_m, _) = fda_from_workspaces(
-            [(ws[0], True, dbg, True, True, False), (ws[1], dbg, dbg, True, True, False)], b, c_m, n, n)
+            [(ws[0], True, dbg, True, True, False), (ws[1], dbg, dbg, True, True, False)], b, c_m, n, n, pv_fmt=fmt)
         del ws
 
         # ---- coordinate regressors of the train-mode interface (regressor_Xo on F_Xo_p, regressor_Yc on F_Yc_p)
@@ -316,6 +337,7 @@ class FusedTail:
         ortho9d, trans = pose_heads(pooled, net.regressor_rot, net.regressor_trans)
         rot = svd3_project(ortho9d, True)
         return dict({"trans_pred": trans, "rot_pred": rot, "conf": conf, "F_Xo_p": F_Xo_p, "F_Xo_p_pm": pm_Xo_p,
+                     "F_Xo_p_pm_fmt": fmt,
                      "_debug": {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d}}, **coords)
 
 
@@ -326,8 +348,9 @@ class FusedRefiner:
     permuted and zero-padded to match), the points image being rewritten by dcl_pose_compose_pm every iteration;
     the last layer's epilogue does the confidence-weighted pooling."""
 
-    def __init__(self, refiner):
+    def __init__(self, refiner, fmt=0):
         self.refiner = refiner
+        self.fmt = fmt
         convs = [m for m in refiner.MLP_share.layers if isinstance(m, torch.nn.Conv1d)]
         others = [m for m in refiner.MLP_share.layers if not isinstance(m, (torch.nn.Conv1d, torch.nn.ReLU))]
         assert len(convs) == 3 and not others and convs[0].in_channels == 259
@@ -336,9 +359,13 @@ class FusedRefiner:
             w1p = w1.new_zeros(w1.shape[0], 288)
             w1p[:, :256] = w1[:, 3:]          # F_Xo_p channels first (8 k-blocks of the first image)
             w1p[:, 256:259] = w1[:, :3]       # then x, y, z (k-block 9, channels 3..31 are zero)
-            self.layers = [Layer(w1p, convs[0].bias, True),
-                           Layer(convs[1].weight.reshape(convs[1].out_channels, -1), convs[1].bias, True),
-                           Layer(convs[2].weight.reshape(convs[2].out_channels, -1), convs[2].bias, True)]
+            if fmt == L.FMT_F16:
+                # PM16 points image: channels 3-5 hold the fp16 remainder of the coordinates (dcl_pose_compose_pm16),
+                # so the coordinates enter the product with ~22 bits: the same weight columns once more
+                w1p[:, 259:262] = w1[:, :3]
+            self.layers = [Layer(w1p, convs[0].bias, True, fmt=fmt),
+                           Layer(convs[1].weight.reshape(convs[1].out_channels, -1), convs[1].bias, True, fmt=fmt),
+                           Layer(convs[2].weight.reshape(convs[2].out_channels, -1), convs[2].bias, True, fmt=fmt)]
 
     @staticmethod
     def supported(refiner, b, n, F_Xo_p=None, conf=None, pm_feat=None):
@@ -355,21 +382,26 @@ class FusedRefiner:
 
     @torch.no_grad()
     def refine(self, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration, pm_feat=None):
+        """pm_feat: the point-major image of F_Xo_p in THIS object's format (stage 1 returns it with its format in
+        prediction["F_Xo_p_pm_fmt"]); packed here from F_Xo_p when absent."""
         from .dcl_net import pose_heads, svd3_project
         lib = L.load()
+        fmt = self.fmt
+        pm_empty = lambda r, c, d: _pm_empty(r, c, d, fmt)
         b, n, _ = points_inp.shape
         rows, dev = b * n, points_inp.device
         points_inp = points_inp.contiguous()
         rot, trans = rot_pred.clone().contiguous(), trans_pred.clone().contiguous()
         if pm_feat is None:
-            pm_feat = pm_pack_cm(F_Xo_p)
-        pm_pts = torch.zeros(pm_bytes(rows, 32), dtype=torch.uint8, device=dev)
+            pm_feat = pm_pack_cm(F_Xo_p, fmt)
+        pm_pts = torch.zeros(pm_bytes(rows, 32, fmt), dtype=torch.uint8, device=dev)
         pool_w = torch.softmax(conf, dim=1)[:, :n].reshape(-1).contiguous()     # refiner.py:60
         st = L.stream_ptr
+        compose_fn = lib.dcl_pose_compose_pm16 if fmt == L.FMT_F16 else lib.dcl_pose_compose_pm
 
         def compose(dR, dt):
-            L.check(lib.dcl_pose_compose_pm(b, n, L.ptr(rot), L.ptr(trans), L.ptr(dR), L.ptr(dt), L.ptr(points_inp), None, 0,
-                                            L.ptr(pm_pts), st()), "pose_compose")
+            L.check(compose_fn(b, n, L.ptr(rot), L.ptr(trans), L.ptr(dR), L.ptr(dt), L.ptr(points_inp), None, 0,
+                               L.ptr(pm_pts), st()), "pose_compose")
 
         compose(None, None)
         l1, l2, l3 = self.layers

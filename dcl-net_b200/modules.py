@@ -80,11 +80,12 @@ def _fda_align_kernel(RI_1, RI_2, RE_2, return_lse=False):
     return (RE_embed, RI_embed, lse) if return_lse else (RE_embed, RI_embed)
 
 
-def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False):
+def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False, pv_fmt=0):
     """fda_align (inference only) with a choice of output formats: `*_cm` = the reference's fp32 (B,ch,N) tensors,
     `*_pm` = point-major bf16 hi/lo images over the B*N query rows (fused_tail.pm_unpack restores (B*N, ch)), which
     the tensor-core MLPs that consume the aligned features (models/DCL_Net.py:216-228) read without a repack.
-    Returns (RE_cm, RI_cm, RE_pm, RI_pm, lse) with None for the formats not requested."""
+    pv_fmt 1: the P V products on once-rounded fp16 operands (1 MMA instead of 3; needs (N/128) even), `*_pm` outputs
+    as PM16 images.  Returns (RE_cm, RI_cm, RE_pm, RI_pm, lse) with None for the formats not requested."""
     RI_1 = L.require(RI_1.contiguous(), torch.float32, "RI_1")
     RI_2 = L.require(RI_2.contiguous(), torch.float32, "RI_2")
     RE_2 = L.require(RE_2.contiguous(), torch.float32, "RE_2")
@@ -99,18 +100,18 @@ def fda_align_formats(RI_1, RI_2, RE_2, re_cm=True, ri_cm=True, re_pm=False, ri_
                          "(need C in {64,128}, P=256, N%128==0, M%64==0)")
     ws = _fda_workspace(nbytes, RI_1.device)
     st = L.stream_ptr()
-    L.check(lib.dcl_fda_pack(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), st),
+    L.check(lib.dcl_fda_pack_fmt(B, C, P, N, M, L.ptr(RI_1), L.ptr(RI_2), L.ptr(RE_2), L.ptr(ws), ws.numel(), pv_fmt, st),
             "fda_align (pack)")
-    return fda_from_workspace(ws, B, C, N, M, re_cm, ri_cm, re_pm, ri_pm, return_lse)
+    return fda_from_workspace(ws, B, C, N, M, re_cm, ri_cm, re_pm, ri_pm, return_lse, pv_fmt)
 
 
-def fda_from_workspace(ws, B, C, N, M, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False):
+def fda_from_workspace(ws, B, C, N, M, re_cm=True, ri_cm=True, re_pm=False, ri_pm=False, return_lse=False, pv_fmt=0):
     """The fused kernel on operand images that already sit in `ws` (written by dcl_fda_pack, or directly by the
     disengage GEMMs' epilogue: fused_tail.py).  Same outputs as fda_align_formats."""
-    return fda_from_workspaces([(ws, re_cm, ri_cm, re_pm, ri_pm, return_lse)], B, C, N, M)[0]
+    return fda_from_workspaces([(ws, re_cm, ri_cm, re_pm, ri_pm, return_lse)], B, C, N, M, pv_fmt)[0]
 
 
-def fda_from_workspaces(jobs, B, C, N, M):
+def fda_from_workspaces(jobs, B, C, N, M, pv_fmt=0):
     """Up to two independent FDA problems of equal shape in ONE launch (the two directions of the dual FDA share
     their partial last waves).  jobs: [(workspace, re_cm, ri_cm, re_pm, ri_pm, return_lse)]; returns one
     (RE_cm, RI_cm, RE_pm, RI_pm, lse) tuple per job."""
@@ -121,9 +122,10 @@ def fda_from_workspaces(jobs, B, C, N, M):
     f32, u8 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.uint8, device=dev)
     arr = (L.FdaJob * len(jobs))()
     results = []
+    esz = 2 if pv_fmt == 1 else 4     # bytes per element of a point-major output image
     for slot, (ws, re_cm, ri_cm, re_pm, ri_pm, want_lse) in zip(arr, jobs):
         out = (torch.empty(B, P, N, **f32) if re_cm else None, torch.empty(B, C, N, **f32) if ri_cm else None,
-               torch.empty(B * N * P * 4, **u8) if re_pm else None, torch.empty(B * N * C * 4, **u8) if ri_pm else None,
+               torch.empty(B * N * P * esz, **u8) if re_pm else None, torch.empty(B * N * C * esz, **u8) if ri_pm else None,
                torch.empty(B, N, **f32) if want_lse else None)
         slot.workspace = L.ptr(ws)
         slot.RE_embed, slot.RI_embed, slot.RE_pm, slot.RI_pm, slot.lse = (L.ptr(x) for x in out)
@@ -132,8 +134,8 @@ def fda_from_workspaces(jobs, B, C, N, M):
     if FDA_KERNEL_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.check(lib.dcl_fda_fwd_packed_jobs(len(jobs), ctypes.cast(arr, ctypes.c_void_p), B, C, P, N, M, nbytes,
-                                        L.stream_ptr()), "fda_align")
+    L.check(lib.dcl_fda_fwd_packed_jobs_fmt(len(jobs), ctypes.cast(arr, ctypes.c_void_p), B, C, P, N, M, nbytes, pv_fmt,
+                                            L.stream_ptr()), "fda_align")
     if FDA_KERNEL_EVENTS is not None:
         ev1.record()
         FDA_KERNEL_EVENTS.append((ev0, ev1, len(jobs)))
@@ -241,10 +243,10 @@ class Ops_GetPointFeat_spconv(nn.Module):
         self.voxel_num_limit = np.asarray(voxel_num_limit)
         self.offset = -0.5 * self.unit_voxel_extent * self.voxel_num_limit
 
-    def _pm_tower(self, points, batch_ids, levels):
+    def _pm_tower(self, points, batch_ids, levels, fmt=0):
         points = torch.cat([batch_ids.view(-1, 1).float(), points], 1).contiguous()
         width = sum(f.features.shape[1] for f in levels)
-        out = torch.empty(points.shape[0] * width * 4, dtype=torch.uint8, device=points.device)
+        out = torch.empty(points.shape[0] * width * (2 if fmt == 1 else 4), dtype=torch.uint8, device=points.device)
         # Ops_tensor2points is fused into the kernels: they take the int voxel indices and form the centres
         # ((i * ext) + offset) + 0.5 * ext in fp32, in torch's evaluation order.
         off = torch.as_tensor(np.asarray(self.offset), dtype=torch.float32).tolist()
@@ -264,10 +266,12 @@ class Ops_GetPointFeat_spconv(nn.Module):
         pointnet2_utils_sp.nn_interpolate_vox_towers_pm([tower])
         return tower[2]
 
-    def forward_pm_pair(self, points_a, ids_a, levels_a, points_b, ids_b, levels_b):
-        """forward_pm for the observed and the template cloud together: the two towers share both launches."""
-        ta, tb = self._pm_tower(points_a, ids_a, list(levels_a)), self._pm_tower(points_b, ids_b, list(levels_b))
-        pointnet2_utils_sp.nn_interpolate_vox_towers_pm([ta, tb])
+    def forward_pm_pair(self, points_a, ids_a, levels_a, points_b, ids_b, levels_b, fmt=0):
+        """forward_pm for the observed and the template cloud together: the two towers share both launches.
+        fmt 1 writes PM16 images (fp16), the activation format of the fp16 inference path."""
+        ta = self._pm_tower(points_a, ids_a, list(levels_a), fmt)
+        tb = self._pm_tower(points_b, ids_b, list(levels_b), fmt)
+        pointnet2_utils_sp.nn_interpolate_vox_towers_pm([ta, tb], fmt)
         return ta[2], tb[2]
 
     def forward(self, points, batch_ids, feats1, feats2, feats3, feats4):

@@ -158,10 +158,10 @@ def nn_interpolate_vox_levels_pm(target_points, levels, out_pm, c_total):
     return out_pm
 
 
-def nn_interpolate_vox_towers_pm(towers):
+def nn_interpolate_vox_towers_pm(towers, fmt=0):
     """Several towers — [(target_points, levels, out_pm, c_total)], levels as in nn_interpolate_vox_levels_pm, at most 8
     levels in total — in ONE pair of launches: the observed and the template cloud of the network share the bucket
-    build launch and the search + interpolation launch."""
+    build launch and the search + interpolation launch.  fmt: 0 = PM image (bf16 hi/lo), 1 = PM16 image (fp16)."""
     import ctypes
     lib = L.load()
     tw = (L.SpTower * len(towers))()
@@ -183,6 +183,7 @@ def nn_interpolate_vox_towers_pm(towers):
         nbytes += lib.dcl_sp_levels_workspace_bytes(len(levels), arr_p)
         tslot.n, tslot.c_total, tslot.nlevels = target_points.size(0), c_total, len(levels)
         tslot.unknown, tslot.out_pm, tslot.levels = L.ptr(target_points), L.ptr(out_pm), arr_p
+        tslot.out_fmt = fmt
         keep.append(arr)
     ws = _workspace(nbytes, towers[0][0].device)
     L.check(lib.dcl_sp_nn_interpolate_towers_pm(len(towers), ctypes.cast(tw, ctypes.c_void_p), L.ptr(ws), ws.numel(),

@@ -20,6 +20,7 @@ class Refiner(nn.Module):
         self.regressor_rot2 = Head_MultiLayerPerceptron([1024, 512, 128, 9], ["relu", "relu", "none"], *plain)
         self.regressor_trans2 = Head_MultiLayerPerceptron([1024, 512, 128, 3], ["relu", "relu", "none"], *plain)
         self.use_fused = True          # inference: shared MLP on tensor cores inside refine_poses (fused_tail.FusedRefiner)
+        self.precision = "fp16"        # operand format when the caller brings no packed feature image (see dcl_net.Network)
         self._fused_refiner = None
 
     def _apply(self, fn, *args, **kwargs):
@@ -62,18 +63,21 @@ def pose_compose_(R, t, dR, dt, points_in, out_cm):
                                       L.ptr(out_cm), out_cm.shape[1] * N, L.stream_ptr()), "pose_compose")
 
 
-def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration=2, F_Xo_p_pm=None):
+def refine_poses(refiner, points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration=2, F_Xo_p_pm=None, pm_fmt=0):
     """Stage-2 iterative refinement.  points_inp (B,N,3), rot_pred (B,3,3), trans_pred (B,3),
     F_Xo_p (B,256,N), conf (B,2N) -> refined (rot, trans).  Inference runs the refiner's shared MLP on tensor
-    cores (fused_tail.FusedRefiner; F_Xo_p_pm = the point-major image of F_Xo_p if the caller already has it);
+    cores (fused_tail.FusedRefiner; F_Xo_p_pm = the point-major image of F_Xo_p if the caller already has it, in
+    format pm_fmt — stage 1 returns both; without an image the refiner's own `precision` picks the format);
     otherwise the refiner input buffer (B,259,N) is built once and each iteration only rewrites its first three
     channels."""
     B, N, _ = points_inp.shape
     from .fused_tail import FusedRefiner
     if getattr(refiner, "use_fused", True) and FusedRefiner.supported(refiner, B, N, F_Xo_p, conf, F_Xo_p_pm):
+        if F_Xo_p_pm is None:
+            pm_fmt = L.FMT_F16 if getattr(refiner, "precision", "fp16") == "fp16" else L.FMT_BF16X2
         fused = getattr(refiner, "_fused_refiner", None)
-        if fused is None:
-            fused = refiner._fused_refiner = FusedRefiner(refiner)
+        if fused is None or fused.fmt != pm_fmt:
+            fused = refiner._fused_refiner = FusedRefiner(refiner, pm_fmt)
         return fused.refine(points_inp, rot_pred, trans_pred, F_Xo_p, conf, iteration, F_Xo_p_pm)
     points_inp = points_inp.contiguous()
     rot_cur, trans_cur = rot_pred.clone().contiguous(), trans_pred.clone().contiguous()

@@ -176,6 +176,17 @@ typedef struct dcl_fda_job {
 } dcl_fda_job;
 int dcl_fda_fwd_packed_jobs(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
     size_t workspace_bytes, void* stream);
+/* The same with a choice of format for the P V products (pv_fmt):
+ *   0  P and the values as bf16 hi/lo pairs, 3 MMAs per product (what every entry point above runs);
+ *   1  P = exp2(..) and the values rounded once to fp16, ONE MMA per product; needs (n/128) even.  The value image
+ *      then holds one fp16 image per 16-key chunk (chunk stride (256+c)*32 bytes instead of twice that; same
+ *      element map), and RE_pm / RI_pm are written as PM16 images.  The logits keep split operands either way.
+ * dcl_fda_pack_fmt is dcl_fda_pack writing the value image in that format. */
+int dcl_fda_fwd_packed_jobs_fmt(int njobs, const dcl_fda_job* jobs, int b, int c, int p, int n, int m,
+    size_t workspace_bytes, int pv_fmt, void* stream);
+int dcl_fda_pack_fmt(int b, int c, int p, int n, int m,
+    const float* RI_1, const float* RI_2, const float* RE_2,
+    void* workspace, size_t workspace_bytes, int pv_fmt, void* stream);
 /* Byte offsets of the query, key and value operand images inside the workspace (offsets[3]), for producers
  * that write them directly (dcl_pm_gemm_problem.out_qk / out_v) instead of calling dcl_fda_pack:
  *   query image: per 128 queries  [hi: 128 x c | lo], element (r,ch) at (r/8)*(c/8)*128 + (ch/8)*128 + (r%8)*16 + (ch%8)*2
@@ -230,6 +241,12 @@ int dcl_pose_compose(int b, int n, float* R, float* t, const float* dR, const fl
 int dcl_pose_compose_pm(int b, int n, float* R, float* t, const float* dR, const float* dt,
     const float* points_in, float* points_out_cm, int64_t out_batch_stride,
     void* points_out_pm, void* stream);
+/* The same writing a PM16 image (fp16, 32 channels per row): channels 0-2 = fp16(xyz), channels 3-5 = fp16 of the
+ * remainder xyz - fp16(xyz) — coordinates keep ~22 bits; the consumer's weight columns for channels 3-5 repeat those
+ * of channels 0-2 (X W^T = hi W^T + lo W^T). */
+int dcl_pose_compose_pm16(int b, int n, float* R, float* t, const float* dR, const float* dt,
+    const float* points_in, float* points_out_cm, int64_t out_batch_stride,
+    void* points_out_pm16, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Group 3: pointwise MLP stacks on tensor cores (replace cuDNN/cuBLAS calls)     */
@@ -376,6 +393,7 @@ typedef struct dcl_sp_tower {
     const float* unknown;
     void* out_pm;
     const dcl_sp_level* levels;
+    int out_fmt;   /* DCL_PM_FMT_BF16X2 (PM image) or DCL_PM_FMT_F16 (PM16 image) */
 } dcl_sp_tower;
 int dcl_sp_nn_interpolate_towers_pm(int ntowers, const dcl_sp_tower* towers,
     void* workspace, size_t workspace_bytes, void* stream);

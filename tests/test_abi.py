@@ -48,7 +48,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 def test_version_and_arch():
     lib = _lib.load()
-    assert lib.dcl_b200_abi_version() == 3
+    assert lib.dcl_b200_abi_version() == 4
     assert lib.dcl_b200_arch() == 100
 
 

@@ -63,8 +63,9 @@ def _oracle_poses(net_state, c_m, batch, b, dev, refiner_state=None, iterations=
     return rot.cpu(), trans.cpu()
 
 
+@pytest.mark.parametrize("precision", ["fp16", "fp32-faithful"])
 @pytest.mark.parametrize("iterations", [0, 2])
-def test_headline_config_engine_vs_oracle(cuda_dev, iterations):
+def test_headline_config_engine_vs_oracle(cuda_dev, iterations, precision):
     """The exact configuration bench.py times — B=32, N=M=1024, C=128, entered at the backbone pyramids, through
     PoseEngine.infer (static buffers, CUDA graph) — against the oracle: 0.01 deg / 1e-5 m (north_star).
     iterations=2: the same with the stage-2 refinement loop appended (BASELINE.json configs[3])."""
@@ -72,6 +73,7 @@ def test_headline_config_engine_vs_oracle(cuda_dev, iterations):
     b = 32
     torch.manual_seed(0)
     net = Network(bench.Cfg, mode="test", c_m=128).eval().to(cuda_dev)
+    net.precision = precision
     refiner = Refiner().eval().to(cuda_dev) if iterations else None
     batch = bench.make_host_batch(1017, b, pin=True)
     caps = [max(batch[s][lv][0].shape[0] for s in ("inp", "tmp")) for lv in range(4)]
@@ -81,6 +83,7 @@ def test_headline_config_engine_vs_oracle(cuda_dev, iterations):
     eng.capture()
     rot, trans = eng.infer(batch)
     assert eng._graph is not None
+    assert net._fused_tail.fmt == (1 if precision == "fp16" else 0)
     state = {k: v.cpu() for k, v in net.state_dict().items()}
     rstate = {k: v.cpu() for k, v in refiner.state_dict().items()} if iterations else None
     want_rot, want_trans = _oracle_poses(state, 128, batch, b, cuda_dev, rstate, iterations)

@@ -178,3 +178,58 @@ def test_fda_linearity_in_values_full_size(cuda_dev):
     assert rel_err(o12, 2.0 * o1 - 3.0 * o2) < 1e-4
     ones, _ = fda_align(ri1, ri2, torch.full((b, 256, m), 0.75, device=cuda_dev))
     assert (ones - 0.75).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ fp16 P V form
+@pytest.mark.parametrize("kind", ["relu", "peaked", "growing"])
+@pytest.mark.parametrize("b,c,n,m", [(2, 64, 256, 192), (3, 64, 1024, 1024), (2, 128, 256, 64), (2, 128, 1024, 1024),
+                                     (1, 64, 256, 2048)])
+def test_fda_pv16_within_tolerance(cuda_dev, kind, b, c, n, m):
+    """pv_fmt = 1 (the inference path's form): logits on split operands, P and the values rounded once to fp16, one
+    MMA per P V product.  Bar (north_star): soft correspondences within 1e-3; measured ~1e-4 normwise."""
+    from dcl_net_b200.modules import fda_align_formats
+    ri1, ri2, re2 = _inputs(7 + n + m, b, c, n, m, kind)
+    re_e, ri_e, _, _, lse = fda_align_formats(ri1.to(cuda_dev), ri2.to(cuda_dev), re2.to(cuda_dev), return_lse=True,
+                                              pv_fmt=1)
+    torch.cuda.synchronize()
+    want_re, want_ri, _ = T.fda_direction(ri1.double(), ri2.double(), re2.double())
+    _check(re_e, want_re, f"RE_embed {kind} pv16", tol_norm=1e-3, atol_rel=1e-3)
+    _check(ri_e, want_ri, f"RI_embed {kind} pv16", tol_norm=1e-3, atol_rel=1e-3)
+    # ... and it is much tighter than the bar
+    scale = want_re.abs().max().item()
+    assert (re_e.double().cpu() - want_re).abs().max().item() < 4e-4 * scale
+    want_lse = torch.logsumexp(torch.bmm(ri2.double().transpose(1, 2), ri1.double()), dim=1)
+    assert (lse.double().cpu() - want_lse).abs().max().item() < 1e-3 * max(1.0, want_lse.abs().max().item())
+
+
+def test_fda_pv16_against_exactly_rounded_operands(cuda_dev):
+    """With values that are exactly representable in fp16 and equal within every softmax row's support, the only
+    difference to the split path is the rounding of P: constant value rows come back as the constant (numerator and
+    denominator carry the same rounded weights)."""
+    from dcl_net_b200.modules import fda_align_formats
+    b, c, n, m = 2, 128, 256, 256
+    ri1, ri2, _ = (t.to(cuda_dev) for t in _inputs(11, b, c, n, m, "relu"))
+    const = torch.full((b, 256, m), 0.75, device=cuda_dev)
+    out, _, _, _, _ = fda_align_formats(ri1, ri2, const, pv_fmt=1)
+    assert (out - 0.75).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("b,c,n,m", [(2, 64, 256, 128), (3, 128, 1024, 1024)])
+def test_fda_pv16_point_major_outputs(cuda_dev, b, c, n, m):
+    """PM16 outputs == fp16 rounding of the fp32 outputs of the same launch."""
+    from dcl_net_b200.modules import fda_align_formats
+    from dcl_net_b200.fused_tail import pm_unpack
+    ri1, ri2, re2 = (x.to(cuda_dev) for x in _inputs(3 + n, b, c, n, m, "relu"))
+    re_cm, ri_cm, re_pm, ri_pm, _ = fda_align_formats(ri1, ri2, re2, re_pm=True, ri_pm=True, pv_fmt=1)
+    for cm, pm, ch in ((re_cm, re_pm, 256), (ri_cm, ri_pm, c)):
+        assert pm.numel() == b * n * ch * 2
+        rows = pm_unpack(pm, b * n, ch, L.FMT_F16)
+        want = cm.transpose(1, 2).reshape(b * n, ch)
+        assert torch.equal(rows, want.to(torch.float16).float())
+
+
+def test_fda_pv16_needs_cta_pairs(cuda_dev):
+    from dcl_net_b200.modules import fda_align_formats
+    x = torch.zeros(1, 64, 128, device=cuda_dev)
+    with pytest.raises(RuntimeError):
+        fda_align_formats(x, x, torch.zeros(1, 256, 128, device=cuda_dev), pv_fmt=1)

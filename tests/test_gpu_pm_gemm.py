@@ -266,3 +266,114 @@ def test_pm_gemm_persistent_many_tiles(cuda_dev, rows, cin, cout, nprob):
         scale = want.abs().max().item()
         assert (FT.pm_unpack(outs[i], rows, cout).double() - want).abs().max().item() <= 3e-5 * scale, i
         assert (cms[i].transpose(1, 2).reshape(rows, cout).double() - want).abs().max().item() <= 2e-5 * scale, i
+
+
+# ------------------------------------------------------------------------------------------------ PM16 (fp16) format
+def _f16(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
+@pytest.mark.parametrize("rows,c", [(128, 32), (256, 480), (1024, 64)])
+def test_pm16_pack_roundtrip(cuda_dev, rows, c):
+    x = torch.randn(rows, c, generator=torch.Generator().manual_seed(rows + c)).to(cuda_dev)
+    x[0, 0], x[1, 1] = 1e6, -1e6                                    # beyond the fp16 range: clamped, not inf
+    pm = FT.pm_pack_rows(x, L.FMT_F16)
+    assert pm.numel() == rows * c * 2
+    back = FT.pm_unpack(pm, rows, c, L.FMT_F16)
+    assert torch.equal(back, _f16(x.clamp(-65504, 65504)))
+    b = rows // 128
+    x_cm = x.view(b, 128, c).transpose(1, 2).contiguous()
+    assert torch.equal(FT.pm_pack_cm(x_cm, L.FMT_F16), pm)
+
+
+@pytest.mark.parametrize("rows,cin,cout,relu,post,split", [
+    (256, 480, 256, True, False, 0), (128, 256, 64, True, False, 0), (384, 256, 128, False, False, 0),
+    (256, 512, 512, True, True, 256), (128, 128, 1024, True, True, 0), (256, 256, 128, True, False, 128),
+    (128, 32, 64, False, False, 0), (4096, 512, 1024, True, True, 0)])
+def test_pm16_gemm_layer(cuda_dev, rows, cin, cout, relu, post, split):
+    """PM16 operands: X rounded once to fp16, W as fp16 hi + lo, 2 MMAs.  Against the fp64 product of the SAME rounded
+    X the kernel must be fp32-faithful (the weight split keeps ~2^-22): the only precision given up is the rounding
+    of the stored activation, which is asserted separately on the written PM16 image (half an fp16 ulp)."""
+    g = torch.Generator().manual_seed(rows + cin + cout)
+    x = torch.randn(rows, cin, generator=g).to(cuda_dev)
+    w = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(cuda_dev)
+    bias = torch.randn(cout, generator=g).to(cuda_dev)
+    ps = (torch.rand(cout, generator=g) + 0.5).to(cuda_dev) if post else None
+    pt = torch.randn(cout, generator=g).to(cuda_dev) if post else None
+    lay = FT.Layer(w, bias, relu, ps, pt, fmt=L.FMT_F16)
+    n_inst = 128
+    out_pm = FT.pm_empty(rows, cout, cuda_dev, L.FMT_F16)
+    out_cm = torch.full((rows // n_inst, cout, n_inst), float("nan"), device=cuda_dev)
+    pool_w = torch.rand(rows, generator=g).to(cuda_dev)
+    pool_out = torch.full((rows // 32, cout), float("nan"), device=cuda_dev)
+    prob = {"layer": lay, "out_pm": out_pm, "out_cm": out_cm, "rows_per_inst": n_inst, "pool_w": pool_w, "pool_out": pool_out}
+    if split:
+        prob.update(a0=FT.pm_pack_rows(x[:, :split], L.FMT_F16), a1=FT.pm_pack_rows(x[:, split:], L.FMT_F16), c0=split)
+    else:
+        prob.update(a0=FT.pm_pack_rows(x, L.FMT_F16))
+    FT.run_gemm([prob], rows)
+    torch.cuda.synchronize()
+    want = _ref_layer(_f16(x), w, bias, relu, ps, pt)
+    scale = want.abs().max().item()
+    got_cm = out_cm.transpose(1, 2).reshape(rows, cout)
+    assert (got_cm.double() - want).abs().max().item() <= 4e-6 * scale
+    got_pm = FT.pm_unpack(out_pm, rows, cout, L.FMT_F16)
+    assert torch.equal(got_pm, _f16(got_cm)), "the PM16 image is the fp16 rounding of the fp32 result"
+    want_pool = (want * pool_w.double()[:, None]).view(rows // 32, 32, cout).sum(1)
+    assert (pool_out.double() - want_pool).abs().max().item() <= 4e-6 * want_pool.abs().max().item()
+    # and against the unrounded input: the price of the format, well inside the 1e-3 bar of the path
+    exact = _ref_layer(x, w, bias, relu, ps, pt)
+    assert (got_cm.double() - exact).abs().max().item() <= 3e-4 * exact.abs().max().item()
+
+
+@pytest.mark.parametrize("b,n,c", [(2, 256, 64), (3, 256, 128)])
+def test_pm16_gemm_writes_fda_operand_images(cuda_dev, b, n, c):
+    """fp16 path: query / key images stay bf16 hi/lo, the value image is one fp16 image per chunk; byte for byte what
+    dcl_fda_pack_fmt(pv_fmt=1) makes of the same layers' fp32 outputs."""
+    import ctypes
+    g = torch.Generator().manual_seed(b * n + c)
+    rows = b * n
+    x = torch.randn(rows, 256, generator=g).to(cuda_dev)
+    a0 = FT.pm_pack_rows(x, L.FMT_F16)
+    lays = {name: FT.Layer((torch.randn(co, 256, generator=g) / 16).to(cuda_dev), torch.randn(co, generator=g).to(cuda_dev),
+                           True, None, None, fmt=L.FMT_F16) for name, co in (("q", c), ("k", c), ("p", 256))}
+    lib = L.load()
+    nbytes = lib.dcl_fda_workspace_bytes(b, c, 256, n, n)
+    offs = (ctypes.c_size_t * 3)()
+    L.check(lib.dcl_fda_workspace_layout(b, c, 256, n, n, ctypes.cast(offs, ctypes.c_void_p)), "layout")
+    ws_direct = torch.zeros(nbytes, dtype=torch.uint8, device=cuda_dev)
+    ws_packed = torch.zeros(nbytes, dtype=torch.uint8, device=cuda_dev)
+    base = ws_direct.data_ptr()
+    cm = {name: torch.empty(b, lay.cout, n, device=cuda_dev) for name, lay in lays.items()}
+    FT.run_gemm([{"a0": a0, "layer": lays["q"], "out_cm": cm["q"], "rows_per_inst": n,
+                  "out_qk": base + offs[0], "qk_tile_rows": 128},
+                 {"a0": a0, "layer": lays["k"], "out_cm": cm["k"], "rows_per_inst": n,
+                  "out_qk": base + offs[1], "qk_tile_rows": 64, "out_v": base + offs[2], "v_row0": 256, "v_rows": 256 + c}],
+                rows)
+    FT.run_gemm([{"a0": a0, "layer": lays["p"], "out_cm": cm["p"], "rows_per_inst": n,
+                  "out_v": base + offs[2], "v_row0": 0, "v_rows": 256 + c}], rows)
+    L.check(lib.dcl_fda_pack_fmt(b, c, 256, n, n, L.ptr(cm["q"]), L.ptr(cm["k"]), L.ptr(cm["p"]), L.ptr(ws_packed),
+                                 ws_packed.numel(), 1, L.stream_ptr()), "pack")
+    torch.cuda.synchronize()
+    used = offs[2] + b * n * (256 + c) * 2
+    assert torch.equal(ws_direct[:used], ws_packed[:used])
+
+
+def test_pm16_interpolation_image_equals_fp16_of_fp32(cuda_dev):
+    """The multi-level 3-NN interpolation writing a PM16 image == fp16 rounding of what it writes as a PM image."""
+    import types
+    from dcl_net_b200.modules import Ops_GetPointFeat_spconv
+    import bench
+    b = 2
+    batch = bench.make_host_batch(5, b, pin=False)
+    getter = Ops_GetPointFeat_spconv(scale_lists=[2, 4, 6, 8], unit_voxel_extent=np.array([0.006] * 3),
+                                     voxel_num_limit=[64, 64, 64])
+    ids = torch.arange(b, device=cuda_dev).repeat_interleave(bench.N_PTS)
+    lv = lambda side: [types.SimpleNamespace(features=f.to(cuda_dev), indices=i.to(cuda_dev)) for f, i in batch[side]]
+    args = (batch["points_inp"].to(cuda_dev), ids, lv("inp"), batch["points_tmp"].to(cuda_dev), ids, lv("tmp"))
+    pm_a, pm_b = getter.forward_pm_pair(*args)
+    h_a, h_b = getter.forward_pm_pair(*args, fmt=L.FMT_F16)
+    rows = b * bench.N_PTS
+    for full, half in ((pm_a, h_a), (pm_b, h_b)):
+        assert half.numel() * 2 == full.numel()
+        assert torch.equal(FT.pm_unpack(half, rows, 480, L.FMT_F16), _f16(FT.pm_unpack(full, rows, 480)))
