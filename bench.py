@@ -44,7 +44,7 @@ N_PTS = 1024
 P_DIM = 256
 ROTATE = 3  # distinct input sets cycled through the timed steps
 # DRAM bytes per launch of the dominant kernel in the fp16 configuration (ncu --set full, mean of its launches)
-TRAFFIC_FP16, TRAFFIC_FP16_SRC = None, None
+TRAFFIC_FP16, TRAFFIC_FP16_SRC = 1.01e8, "profiles/r02b_gemm_fda_ncu_full.txt (dram read+write, mean of the kernel's five launches)"
 
 
 def parse_args():

@@ -195,9 +195,11 @@ def test_fda_pv16_within_tolerance(cuda_dev, kind, b, c, n, m):
     want_re, want_ri, _ = T.fda_direction(ri1.double(), ri2.double(), re2.double())
     _check(re_e, want_re, f"RE_embed {kind} pv16", tol_norm=1e-3, atol_rel=1e-3)
     _check(ri_e, want_ri, f"RI_embed {kind} pv16", tol_norm=1e-3, atol_rel=1e-3)
-    # ... and it is much tighter than the bar
-    scale = want_re.abs().max().item()
-    assert (re_e.double().cpu() - want_re).abs().max().item() < 4e-4 * scale
+    # ... and for network-like inputs it is much tighter than the bar (the "peaked" family has logits ~300 and
+    # near one-hot weights: a single fp16-rounded value dominates a row, 2^-11 of the value range)
+    if kind != "peaked":
+        scale = want_re.abs().max().item()
+        assert (re_e.double().cpu() - want_re).abs().max().item() < 4e-4 * scale
     want_lse = torch.logsumexp(torch.bmm(ri2.double().transpose(1, 2), ri1.double()), dim=1)
     assert (lse.double().cpu() - want_lse).abs().max().item() < 1e-3 * max(1.0, want_lse.abs().max().item())
 
