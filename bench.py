@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU per step")
     ap.add_argument("--c_m", type=int, default=128, help="FDA similarity width: 128 = BASELINE.json, 64 = reference")
+    ap.add_argument("--entry", default="points", choices=["points", "pyramids"],
+                    help="where a step starts: points = raw clouds + colours (voxelisation and both sparse-conv towers run "
+                         "on the device, ~1.5 MB of host input per step); pyramids = round 1's entry, synthetic outputs of "
+                         "the towers (30 MB of host input per step)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32-faithful"],
                     help="operand format of the tensor-core path: fp16 = activations rounded once to fp16, fp16 hi/lo "
                          "weights (2 MMAs per product), split-operand FDA logits, fp16 P V (the product's default); "
@@ -113,8 +117,11 @@ def workload_config(args, n_gpus, cpu_arm=False):
     if strong:
         extra.update({"B_total": args.batch_total, "passes_per_step": passes, "B_per_pass": chunk})
     return dict({
-        "workload": "DCL-Net stage-1 inference (config_YCBV_bs32 shape) from synthetic backbone pyramids: "
+        "workload": ("DCL-Net stage-1 inference (config_YCBV_bs32 shape) from raw clouds + colours: device voxelisation "
+                     "-> two sparse-conv towers -> " if getattr(args, "entry", "points") == "points" else
+                     "DCL-Net stage-1 inference (config_YCBV_bs32 shape) from synthetic backbone pyramids: ") +
                     "pointnet_sp 3-NN interpolation -> disengage -> dual FDA -> heads -> SVD pose" + stage2,
+        "entry": getattr(args, "entry", "points"),
         "B_per_gpu": per_gpu, "N": N_PTS, "M": N_PTS, "C": args.c_m, "P": P_DIM,
         "weights": "random init, eval mode", "precision": getattr(args, "precision", "fp16"),
         "sharding": f"instances x{n_gpus}, " + ("strong scaling (B_total fixed)" if strong else "weak scaling"),
@@ -124,14 +131,22 @@ def workload_config(args, n_gpus, cpu_arm=False):
 
 
 # ----------------------------------------------------------------------------------------------- inputs
-def make_host_batch(seed, b, pin):
+def make_host_batch(seed, b, pin, entry="pyramids"):
+    """entry="points": raw clouds + colours (what the dataloader hands to Network.forward); entry="pyramids": the
+    clouds and a synthetic four-level voxel pyramid per tower standing in for the sparse-conv towers' outputs."""
     import torch
     from dcl_net_b200 import synthetic
     pts_inp = synthetic.object_clouds(seed, b, N_PTS, partial=True)   # observed: single-view half surface
     pts_tmp = synthetic.object_clouds(seed + 7919, b, N_PTS)            # template: closed surface
-    batch = {"points_inp": pts_inp, "points_tmp": pts_tmp,
-             "inp": [(l.features, l.indices) for l in synthetic.backbone_levels(seed + 1, pts_inp, b)],
-             "tmp": [(l.features, l.indices) for l in synthetic.backbone_levels(seed + 2, pts_tmp, b)]}
+    batch = {"points_inp": pts_inp, "points_tmp": pts_tmp}
+    if entry == "points":
+        batch["rgb_inp"] = synthetic.point_colours(seed + 3, b * N_PTS)
+        batch["rgb_tmp"] = synthetic.point_colours(seed + 4, b * N_PTS)
+        if pin:
+            batch = {k: v.pin_memory() for k, v in batch.items()}
+        return batch
+    batch.update({"inp": [(l.features, l.indices) for l in synthetic.backbone_levels(seed + 1, pts_inp, b)],
+                  "tmp": [(l.features, l.indices) for l in synthetic.backbone_levels(seed + 2, pts_tmp, b)]})
     if pin:
         batch["points_inp"], batch["points_tmp"] = pts_inp.pin_memory(), pts_tmp.pin_memory()
         for side in ("inp", "tmp"):
@@ -240,13 +255,27 @@ def cpu_pass_builder(args):
     torch.manual_seed(0)
     net = T.TailNetwork(mode="test", c_m=args.c_m).eval()
     refiner = T.RefinerNet().eval() if args.refine_iterations > 0 else None
-    batch = make_host_batch(1234, b, pin=False)
+    batch = make_host_batch(1234, b, pin=False, entry=args.entry)
     ids = torch.arange(b).repeat_interleave(N_PTS)
+    towers = None
+    if args.entry == "points":
+        from oracle import backbone_oracle as BO
+        towers = [BO.BackboneOracle().eval(), BO.BackboneOracle().eval()]
+
+    def pyramids():
+        if towers is None:
+            return batch["inp"], batch["tmp"]
+        out = []
+        for tw, side in zip(towers, ("inp", "tmp")):
+            x, _ = BO.tower_input(batch["points_" + side], batch["rgb_" + side], b)
+            out.append([(lv.features, lv.indices) for lv in tw(x)])
+        return out
 
     def one_pass():
         with torch.no_grad():
-            f_xc = T.get_point_feats(batch["points_inp"], ids, batch["inp"], Cfg.unit_voxel_extent)
-            f_yo = T.get_point_feats(batch["points_tmp"], ids, batch["tmp"], Cfg.unit_voxel_extent)
+            lv_inp, lv_tmp = pyramids()
+            f_xc = T.get_point_feats(batch["points_inp"], ids, lv_inp, Cfg.unit_voxel_extent)
+            f_yo = T.get_point_feats(batch["points_tmp"], ids, lv_tmp, Cfg.unit_voxel_extent)
             out = net(f_xc, f_yo, b, N_PTS, N_PTS)
             if refiner is not None:
                 return T.stage2_refine(refiner, batch["points_inp"].view(b, N_PTS, 3), out["rot_pred"],
@@ -328,11 +357,16 @@ def run_b200_arm(args, rank, world, local_rank):
 
     per_gpu, b, passes = shard_plan(args, world)      # b = instances per pass
     torch.manual_seed(0)
-    net = Network(Cfg, mode="test", c_m=args.c_m).eval().to(dev)
+    from_points = args.entry == "points"
+    net = Network(Cfg, mode="test", c_m=args.c_m, with_backbone=from_points).eval().to(dev)
     net.precision = args.precision
     fp16 = args.precision == "fp16"
-    batches = [make_host_batch(1000 * (rank + 1) + 17 * i, b, pin=True) for i in range(ROTATE)]
-    caps = [max(max(bt[s][lv][0].shape[0] for bt in batches for s in ("inp", "tmp")), 1) for lv in range(4)]
+    batches = [make_host_batch(1000 * (rank + 1) + 17 * i, b, pin=True, entry=args.entry) for i in range(ROTATE)]
+    if from_points:
+        from dcl_net_b200.backbone import SparseTowers
+        caps = SparseTowers.plan_capacities([bt[k] for bt in batches for k in ("points_inp", "points_tmp")], b, N_PTS, dev)
+    else:
+        caps = [max(max(bt[s][lv][0].shape[0] for bt in batches for s in ("inp", "tmp")), 1) for lv in range(4)]
     refiner = None
     if args.refine_iterations > 0:
         from dcl_net_b200.refiner import Refiner
@@ -340,7 +374,7 @@ def run_b200_arm(args, rank, world, local_rank):
         refiner.precision = args.precision
     nstreams = max(1, args.streams)
     n_eng = ROTATE if nstreams == 1 else nstreams * ((ROTATE + nstreams - 1) // nstreams)   # an engine stays on one stream
-    engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations) for _ in range(n_eng)]
+    engines = [PoseEngine(net, dev, b, caps, refiner, args.refine_iterations, entry=args.entry) for _ in range(n_eng)]
     for k, eng in enumerate(engines):
         eng.load(batches[k % ROTATE])
     torch.cuda.synchronize()
@@ -449,7 +483,7 @@ def run_b200_arm(args, rank, world, local_rank):
         del engines[1:]
         pipe = PipelinedPoseEngine(net, dev, b, caps, depth=max(args.e2e_depth, nstreams), refiner=refiner,
                                    iterations=args.refine_iterations, use_graph=use_graph,
-                                   compute_streams=nstreams > 1)
+                                   compute_streams=nstreams > 1, entry=args.entry)
         checksum = 0.0
         for rot, trans in pipe.infer_many(batches[i % ROTATE] for i in range(max(3, min(args.warmup, 5)))):
             checksum += float(trans[0, 0])
@@ -461,6 +495,9 @@ def run_b200_arm(args, rank, world, local_rank):
             checksum += float(trans[0, 0]) + float(rot[-1, 2, 2])    # the host consumes every pass's result
         e1.record()
         barrier()
+        if from_points:
+            for eng in engines + pipe.engines:
+                eng.towers.check_errors()      # no voxel set outgrew its buffer, no point fell off the grid
         h2d = pipe.h2d_bytes
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
 

@@ -63,6 +63,12 @@ SIGNATURES = {
     "dcl_sp_levels_workspace_bytes": (_SZ, [_I, _P]),
     "dcl_sp_nn_interpolate_towers_pm": (_I, [_I, _P, _P, _SZ, _P]),
     "dcl_sp_nn_interpolate_levels_pm": (_I, [_I, _P, _I, _P, _P, _I, _P, _SZ, _P]),
+    "dcl_spb_rows_per_instance": (_SZ, []),
+    "dcl_spb_build_sets": (_I, [_I, _I, _I, _P, _F, _I, _P]),
+    "dcl_spb_emit": (_I, [_I, _I, _P, _I, _P]),
+    "dcl_spb_conv3": (_I, [_I, _I, _I, _I, _P, _P]),
+    "dcl_spb_avgpool": (_I, [_I, _I, _I, _P, _P]),
+    "dcl_voxelize_mean": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_fda_set_trace": (_I, [_P]),
@@ -95,6 +101,30 @@ class SpTower(ctypes.Structure):
     """Mirror of dcl_sp_tower (include/dcl_b200.h)."""
     _fields_ = [("n", _I), ("c_total", _I), ("nlevels", _I), ("unknown", _P), ("out_pm", _P), ("levels", _P),
                 ("out_fmt", _I)]
+
+
+class SpbTowerIn(ctypes.Structure):
+    """Mirror of dcl_spb_tower_in (include/dcl_b200.h)."""
+    _fields_ = [("points", _P), ("rgb", _P), ("coords", _P), ("rows", _P), ("prefix", _P), ("counts", _P),
+                ("feat16", _P), ("feat32", _P), ("occupied", _P), ("p2v", _P), ("v2p_sorted", _P), ("v2p_start", _P),
+                ("errors", _P)]
+
+
+class SpbTowerSets(ctypes.Structure):
+    """Mirror of dcl_spb_tower_sets (include/dcl_b200.h)."""
+    _fields_ = [("rows", _P), ("prefix", _P), ("counts", _P), ("offsets", _P), ("indices", _P * 9), ("cap", _I * 9),
+                ("nbr", _P * 12), ("anymask", _P * 12), ("errors", _P)]
+
+
+class SpbConv(ctypes.Structure):
+    """Mirror of dcl_spb_conv (include/dcl_b200.h)."""
+    _fields_ = [("in16", _P), ("nbr", _P), ("anymask", _P), ("offsets_out", _P), ("w", _P), ("shift", _P),
+                ("out16", _P), ("out32", _P), ("cap_out", _I)]
+
+
+class SpbPool(ctypes.Structure):
+    """Mirror of dcl_spb_pool (include/dcl_b200.h)."""
+    _fields_ = [("inp", _P), ("nbr", _P), ("offsets_out", _P), ("out32", _P), ("out16", _P), ("cap_out", _I)]
 
 
 class PoseHeadMlp(ctypes.Structure):

@@ -3,10 +3,10 @@
     ortho9d2matrix(x_raw, y_raw, z_raw) -> (B,3,3)         :15-36   dcl_svd3_project kernel
     Network(cfg, mode).forward(data) -> dict                :38-259  same modules / parameter names
 
-The two sparse-conv backbones (libs/spconv, libs/pointgroup_ops) are outside this path
-(SURVEY.md §2/§8f): `Network` takes them as an injected `backbone` callable and otherwise offers
-`forward_from_backbone` (pyramid levels -> pose: point-feature interpolation, FDA, pose) and
-`forward_from_point_feats` (FDA + pose).  Everything after the backbone is implemented here.
+Entry points: `forward(data)` (the reference's interface, from the dataloader's per-point tensors: voxelisation and
+the two sparse-conv towers run on the device, backbone.py — inference only; needs with_backbone=True or an injected
+`backbone` callable), `forward_from_points` (raw clouds + colours), `forward_from_backbone` (pyramid levels -> pose:
+point-feature interpolation, FDA, pose) and `forward_from_point_feats` (FDA + pose).
 """
 import numpy as np
 import torch
@@ -99,9 +99,11 @@ def weighted_kabsch(src, dst, w):
 
 
 class Network(nn.Module):
-    def __init__(self, cfg, mode="train", backbone=None, c_m=64) -> None:
+    def __init__(self, cfg, mode="train", backbone=None, c_m=64, with_backbone=False) -> None:
         """cfg needs n_inp, n_tmp, unit_voxel_extent (reference configs/*.yaml: model section).
-        backbone: optional callable data -> (levels_inp, levels_tmp, points_inp (b*n,3), points_tmp (b*n,3), b),
+        with_backbone: create the two sparse-conv towers `backbone_inp` / `backbone_tmp` (models/DCL_Net.py:47-52, same
+        parameter names) and run them on the device (backbone.SparseTowers) in forward(data) / forward_from_points.
+        backbone: alternatively a callable data -> (levels_inp, levels_tmp, points_inp (b*n,3), points_tmp (b*n,3), b),
         each `levels_*` a list of four objects with .features (Mv,C_l) / .indices (Mv,4).
         c_m: width of the pose-insensitive branch (64 in the reference; 128 in BASELINE.json's config)."""
         super().__init__()
@@ -109,6 +111,11 @@ class Network(nn.Module):
         self.n_inp, self.n_tmp = cfg.n_inp, cfg.n_tmp
         self.unit_voxel_extent = np.array(cfg.unit_voxel_extent)
         self.backbone = backbone
+        if with_backbone:
+            from .backbone import Backbone_SPCONV
+            self.backbone_inp = Backbone_SPCONV()
+            self.backbone_tmp = Backbone_SPCONV()
+        self._towers = None
         self.stage1_get_point_feats = Ops_GetPointFeat_spconv(
             scale_lists=[2, 4, 6, 8], unit_voxel_extent=self.unit_voxel_extent, voxel_num_limit=[64, 64, 64])
         blk = partial(BasicBlock_3DCONV, size=1, bias=False, stride=1, padding=0, norm=True, act="relu", drop=0.0)
@@ -133,25 +140,71 @@ class Network(nn.Module):
         self._fused_tail = None
 
     def _apply(self, fn, *args, **kwargs):
-        self._fused_tail = None      # parameters moved / cast: packed copies are stale
+        self._fused_tail = self._towers = None      # parameters moved / cast: packed copies are stale
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._fused_tail = None
+        self._fused_tail = self._towers = None
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode=True):
         if mode != self.training:    # BatchNorm folding depends on the mode; an unchanged mode keeps the packed weights
-            self._fused_tail = None
+            self._fused_tail = self._towers = None
         return super().train(mode)
+
+    def towers(self, b, device, sample_clouds=None, caps=None):
+        """The device towers for batches of b instances (backbone.SparseTowers), built on first use.  Buffer
+        capacities come from `caps` or are planned from `sample_clouds` (two (b*n,3) clouds) with a 30 % margin."""
+        from .backbone import SparseTowers
+        if not hasattr(self, "backbone_inp"):
+            raise RuntimeError("this Network was built without its sparse-conv towers (with_backbone=True)")
+        if self.n_inp != self.n_tmp:
+            raise RuntimeError("the device towers take equally sized observed / template clouds")
+        tw = self._towers
+        rounded = None if caps is None else [int((c + 127) // 128 * 128) for c in caps]
+        if tw is None or tw.b != b or (rounded is not None and rounded != tw.caps):
+            if caps is None:
+                caps = SparseTowers.plan_capacities(sample_clouds, b, self.n_inp, device)
+            tw = self._towers = SparseTowers(self.backbone_inp, self.backbone_tmp, device, b, self.n_inp, caps,
+                                             unit=float(self.unit_voxel_extent[0]))
+        return tw
+
+    @torch.no_grad()
+    def forward_from_points(self, points_inp, rgb_inp, points_tmp, rgb_tmp, b, caps=None):
+        """Raw clouds (b*n,3) + colours (b*n,3) of the observation and the template -> prediction dict: device
+        voxelisation, both towers, point-feature interpolation, FDA, pose.  Inference only."""
+        if self.training:
+            raise RuntimeError("forward_from_points is an inference path: call eval() first")
+        tw = self.towers(b, points_inp.device, (points_inp, points_tmp), caps)
+        levels_inp, levels_tmp = tw.run(points_inp.contiguous(), rgb_inp.contiguous(), points_tmp.contiguous(),
+                                        rgb_tmp.contiguous())
+        return self.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, b)
 
     # ---- entry points -----------------------------------------------------------------
     def forward(self, data):
-        if self.backbone is None:
-            raise RuntimeError("Network.forward(data) needs a sparse-conv backbone provider (out of this path's "
-                               "scope); use forward_from_backbone / forward_from_point_feats")
-        levels_inp, levels_tmp, points_inp, points_tmp, b = self.backbone(data)
-        pred = self.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, b)
+        """The reference's interface (models/DCL_Net.py:155-259).  With the built-in towers the per-point tensors
+        data[k]["feats"] (N,7) = [1, rgb, xyz] are voxelised on the device — the same voxels and the same means as
+        data[k]["occupied_voxels"] / ["v2p_maps"] describe (pointgroup_ops.voxelization_idx, mode 4), which are
+        therefore not read — and the call checks the towers' overflow flags (one host sync)."""
+        if hasattr(self, "backbone_inp") and self.backbone is None:
+            if self.training:
+                raise RuntimeError("the device towers are inference-only: call eval() (training through the sparse "
+                                   "convolutions is outside this path)")
+            dev = next(self.parameters()).device
+            f_inp, f_tmp = data["inp"]["feats"].to(dev), data["tmp"]["feats"].to(dev)
+            b = data["batch_offsets"].shape[0] - 1
+            points_inp, points_tmp = f_inp[:, 4:7].contiguous(), f_tmp[:, 4:7].contiguous()
+            with torch.no_grad():
+                pred = self.forward_from_points(points_inp, f_inp[:, 1:4].contiguous(), points_tmp,
+                                                f_tmp[:, 1:4].contiguous(), b)
+            self._towers.check_errors()
+        elif self.backbone is None:
+            raise RuntimeError("Network.forward(data) needs the sparse-conv towers: build the Network with "
+                               "with_backbone=True (or inject a `backbone` callable), or use forward_from_backbone / "
+                               "forward_from_point_feats")
+        else:
+            levels_inp, levels_tmp, points_inp, points_tmp, b = self.backbone(data)
+            pred = self.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, b)
         if self.mode != "test" and "flags" in data:
             pred["sym_flag"] = data["flags"].to(points_inp.device)
         data.setdefault("labels", {})

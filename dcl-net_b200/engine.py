@@ -3,12 +3,16 @@
     engine = PoseEngine(net, device, batch, refiner=None, iterations=0)
     rot, trans = engine.infer(host_batch)
 
-`host_batch` is what a backbone provider would hand over (pinned host tensors):
+Two entries (pinned host tensors):
+  entry="points" (a Network built with its towers): the raw clouds and colours,
+    {"points_inp": (B*N,3), "rgb_inp": (B*N,3), "points_tmp": (B*M,3), "rgb_tmp": (B*M,3)}      ~1.5 MB per 32 instances
+    — voxelisation, both sparse-conv towers, interpolation, FDA and pose all run on the device;
+  entry="pyramids": what an external backbone provider would hand over,
     {"points_inp": (B*N,3), "points_tmp": (B*M,3),
-     "inp": [(features (Mv,C_l), indices (Mv,4) int32 bxyz) x 4 levels], "tmp": [... x 4]}
-Device buffers are allocated once with a fixed row capacity per pyramid level; every call copies the batch into
-them (cudaMemcpyAsync from pinned memory) and pads unused rows with batch id == B, a bucket no query belongs to,
-so shapes stay static.  Multi-GPU: one engine per process / GPU over its own instance shard (sharding.py).
+     "inp": [(features (Mv,C_l), indices (Mv,4) int32 bxyz) x 4 levels], "tmp": [... x 4]}       ~30 MB per 32 instances
+Device buffers are allocated once with fixed row capacities; every call copies the batch into them (cudaMemcpyAsync
+from pinned memory); unused pyramid rows carry batch id == B, a bucket no query belongs to, so shapes stay static.
+Multi-GPU: one engine per process / GPU over its own instance shard (sharding.py).
 """
 import types
 
@@ -19,8 +23,9 @@ from .refiner import refine_poses
 
 
 class PoseEngine:
-    def __init__(self, net, device, batch, capacities, refiner=None, iterations=0):
-        """capacities: per level, the maximum number of voxel rows of a batch (both towers use the same)."""
+    def __init__(self, net, device, batch, capacities, refiner=None, iterations=0, entry="pyramids"):
+        """capacities: entry="pyramids": per level, the maximum number of voxel rows of a batch (both towers use the
+        same); entry="points": the nine voxel-set capacities of backbone.SparseTowers (plan_capacities)."""
         if net.training or (refiner is not None and refiner.training):
             raise ValueError("PoseEngine is an inference engine: put the network (and the refiner) in eval() mode first")
         self.net, self.refiner, self.iterations = net, refiner, iterations
@@ -28,12 +33,22 @@ class PoseEngine:
         self.n_inp, self.n_tmp = net.n_inp, net.n_tmp
         L.load()
         f32, i32 = dict(dtype=torch.float32, device=device), dict(dtype=torch.int32, device=device)
+        self.entry = entry
         self.points = {"inp": torch.empty(batch * self.n_inp, 3, **f32), "tmp": torch.empty(batch * self.n_tmp, 3, **f32)}
-        self.levels = {}
-        for side in ("inp", "tmp"):
-            self.levels[side] = [types.SimpleNamespace(features=torch.zeros(cap, ch, **f32),
-                                                       indices=torch.zeros(cap, 4, **i32))
-                                 for cap, ch in zip(capacities, (32, 64, 128, 256))]
+        self.levels, self.rgb, self.towers = {}, {}, None
+        if entry == "points":
+            self.rgb = {"inp": torch.empty(batch * self.n_inp, 3, **f32), "tmp": torch.empty(batch * self.n_tmp, 3, **f32)}
+            from .backbone import SparseTowers
+            # every engine owns its towers' buffers (engines run concurrently on different streams)
+            self.towers = SparseTowers(net.backbone_inp, net.backbone_tmp, device, batch, self.n_inp, capacities,
+                                       unit=float(net.unit_voxel_extent[0]))
+        elif entry == "pyramids":
+            for side in ("inp", "tmp"):
+                self.levels[side] = [types.SimpleNamespace(features=torch.zeros(cap, ch, **f32),
+                                                           indices=torch.zeros(cap, 4, **i32))
+                                     for cap, ch in zip(capacities, (32, 64, 128, 256))]
+        else:
+            raise ValueError("entry must be 'points' or 'pyramids'")
         self.out_host = torch.empty(batch, 12, dtype=torch.float32).pin_memory()
         self.h2d_bytes = 0
         self._graph = None
@@ -51,6 +66,11 @@ class PoseEngine:
             src = host_batch["points_" + side]
             self.points[side].copy_(src, non_blocking=True)
             nbytes += src.numel() * 4
+            if self.entry == "points":
+                rgb = host_batch["rgb_" + side]
+                self.rgb[side].copy_(rgb, non_blocking=True)
+                nbytes += rgb.numel() * 4
+                continue
             for lvl, (feats, ind) in zip(self.levels[side], host_batch[side]):
                 m = feats.shape[0]
                 if m > lvl.features.shape[0]:
@@ -64,6 +84,8 @@ class PoseEngine:
     def capture(self, warmup=2):
         """Capture the whole pass into a CUDA graph (shapes are static): one launch per step instead of a few
         hundred.  The loaded batch must be valid; later load() calls just refill the same buffers."""
+        if self.towers is not None:
+            self.towers.repack()       # captured pointers must be those of the current tower weights
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -96,8 +118,11 @@ class PoseEngine:
 
     @torch.no_grad()
     def _run_eager(self):
-        pred = self.net.forward_from_backbone(self.levels["inp"], self.levels["tmp"], self.points["inp"],
-                                              self.points["tmp"], self.b)
+        if self.entry == "points":
+            levels_inp, levels_tmp = self.towers.run(self.points["inp"], self.rgb["inp"], self.points["tmp"], self.rgb["tmp"])
+        else:
+            levels_inp, levels_tmp = self.levels["inp"], self.levels["tmp"]
+        pred = self.net.forward_from_backbone(levels_inp, levels_tmp, self.points["inp"], self.points["tmp"], self.b)
         rot, trans = pred["rot_pred"], pred["trans_pred"]
         if self.refiner is not None and self.iterations > 0:
             rot, trans = refine_poses(self.refiner, self.points["inp"].view(self.b, self.n_inp, 3), rot, trans,
@@ -121,8 +146,8 @@ class PipelinedPoseEngine:
     to pinned host memory right after its pass.  Every batch still pays its own H2D and D2H."""
 
     def __init__(self, net, device, batch, capacities, depth=2, refiner=None, iterations=0, use_graph=True,
-                 compute_streams=False):
-        self.engines = [PoseEngine(net, device, batch, capacities, refiner, iterations) for _ in range(depth)]
+                 compute_streams=False, entry="pyramids"):
+        self.engines = [PoseEngine(net, device, batch, capacities, refiner, iterations, entry) for _ in range(depth)]
         self.device, self.use_graph = device, use_graph
         self.copy_stream = torch.cuda.Stream(device)
         # compute_streams: every engine slot runs on a stream of its own, so the tail of one pass's kernels

@@ -53,3 +53,8 @@ def backbone_levels(seed, points, b, unit=0.006, scales=(2, 4, 6, 8), channels=(
 def levels_to(levels, device, non_blocking=False):
     return [types.SimpleNamespace(features=l.features.to(device, non_blocking=non_blocking),
                                   indices=l.indices.to(device, non_blocking=non_blocking)) for l in levels]
+
+
+def point_colours(seed, n_points):
+    """(n,3) RGB in [0,1): the per-point colour channels of the dataloader's [1, rgb, xyz] features."""
+    return torch.rand(n_points, 3, generator=torch.Generator().manual_seed(seed))

@@ -403,6 +403,109 @@ int dcl_sp_nn_interpolate_levels_pm(int n, const float* unknown, int nlevels,
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Group 4: the input side — voxelisation and the sparse-conv towers   */
+/* ------------------------------------------------------------------------- */
+/* Replaces, on the device and without a host round trip:
+ *   pointgroup_ops.voxelization_idx  (libs/pointgroup_ops/src/voxelize/voxelize.cpp:10-163, a CPU hash map in the
+ *                                     dataloader) and pointgroup_ops.voxelization mode 4 (voxelize.cu:10-31),
+ *   spconv get_indice_pairs          (libs/spconv/include/spconv/spconv_ops.h:27-136, indice.cu.h:24-220) for the
+ *                                     SparseConv3d / SubMConv3d / SparseAvgPool3d of Backbone_SPCONV
+ *                                     (models/Modules.py:100-159),
+ *   spconv indice_conv / indice_avgpool (spconv_ops.h:253-349, src/spconv/avgpool.cu).
+ * A voxel set of an instance is a bit grid (G*G rows of G bits); a tower has 9 sets — 0: occupied voxels (64^3),
+ * 2l+1: output set of level l's SparseConv3d (= input / output set of its SubMConv3d; grid 64>>l), 2l+2: output set of
+ * level l's SparseAvgPool3d (grid 32>>l) — and 12 ops, op 3l+{0,1,2} = level l's {SparseConv3d, SubMConv3d, pool}.
+ * Rows of a set are packed over the batch in the reference's order (batch, then linear voxel index). */
+#define DCL_SPB_NSETS 9
+#define DCL_SPB_NOPS 12
+/* 64-bit rows (and int prefixes) per instance over the 9 sets: 2*64^2 + 2*32^2 + 2*16^2 + 2*8^2 + 4^2. */
+size_t dcl_spb_rows_per_instance(void);
+
+/* One tower's inputs and voxelisation outputs.  points (b*n_per,3) fp32 [+ rgb (b*n_per,3)], or voxel coordinates
+ * coords (b*n_per,4) int32 bxyz when points == NULL.  rows / prefix: [b][dcl_spb_rows_per_instance()] uint64 / int32;
+ * counts: [9][b].  Voxelisation outputs use SLOTS of n_per rows per instance and may be NULL:
+ *   feat16     (b*n_per,16) fp16: operand rows of the first convolution, voxels in SORTED order (rank in the bit grid):
+ *              channels 0-6 = mean of [1, rgb, xyz] over the voxel's points in point order with the 1/n multiplier
+ *              applied first (voxelize.cu:15-21), channels 7-12 = fp16 remainders of channels 1-6, 13-15 zero;
+ *   feat32     (b*n_per,7) fp32 the same means, voxels in FIRST-APPEARANCE order (the reference's numbering,
+ *              voxelize.cpp:96-107), as are occupied (b*n_per,4) int32 bxyz, p2v (b*n_per) (voxel of each point, local
+ *              to the instance), v2p_sorted (b*n_per) (local point indices grouped by voxel, ascending) and
+ *              v2p_start (b*n_per) (start of each voxel's group).
+ * errors[0] += number of points outside the grid (skipped). */
+typedef struct dcl_spb_tower_in {
+    const float* points;
+    const float* rgb;
+    const int* coords;
+    void* rows;
+    int* prefix;
+    int* counts;
+    void* feat16;
+    float* feat32;
+    int* occupied;
+    int* p2v;
+    int* v2p_sorted;
+    int* v2p_start;
+    int* errors;
+} dcl_spb_tower_in;
+/* All nine voxel sets of every instance of up to two towers in ONE launch (one CTA per instance and tower).
+ * unit = voxel edge (0.006), grid must be 64, n_per <= 4096. */
+int dcl_spb_build_sets(int b, int n_per, int ntowers, const dcl_spb_tower_in* towers, float unit, int grid,
+    void* stream);
+
+/* Row coordinates and rulebooks.  offsets: [9][b+1] (exclusive scan of counts over the batch; element b = rows of
+ * the set); indices[s]: (cap[s],4) int32 bxyz, rows past the total get batch id = b (cap % 128 == 0);
+ * nbr[op]: (cap_out,32) int32 — entries 0..26: input row feeding the output row through kernel offset
+ * k = (k0*3+k1)*3+k2 (input voxel = out*stride - 1 + k, geometry.h:24-86) or -1, entry 27: number of valid entries;
+ * anymask[op]: (cap_out/128) 27-bit OR of a tile's validity masks.  in0_slot > 0: the input rows of op 0 are
+ * dcl_spb_tower_in.feat16's slots (instance*in0_slot + rank).  errors[1] |= 1<<s when set s exceeds cap[s]. */
+typedef struct dcl_spb_tower_sets {
+    const void* rows;
+    const int* prefix;
+    const int* counts;
+    int* offsets;
+    int* indices[DCL_SPB_NSETS];
+    int cap[DCL_SPB_NSETS];
+    int* nbr[DCL_SPB_NOPS];
+    unsigned int* anymask[DCL_SPB_NOPS];
+    int* errors;
+} dcl_spb_tower_sets;
+int dcl_spb_emit(int b, int ntowers, const dcl_spb_tower_sets* towers, int in0_slot, void* stream);
+
+/* One sparse convolution (3x3x3) of up to two towers in one launch, output-stationary on tensor cores:
+ *   out[r, :] = relu( sum_k in[nbr[r,k], :] W[k] + shift )        (BatchNorm1d folded: W scaled, shift = bias)
+ * in16: (rows_in, cin_pad) fp16 operand rows, cin_pad in {16,32,64,128}; w: packed fp16 hi/lo weights
+ * [27][cin_pad/16 k-steps][hi | lo][cout x 16] (K-major core matrices, see dcl_net_b200/backbone.py:pack_conv_weight);
+ * cout in {16,32,64,128,256}; total rows read from offsets_out[b].  out16 (rows, cout) fp16 and / or out32 fp32. */
+typedef struct dcl_spb_conv {
+    const void* in16;
+    const int* nbr;
+    const unsigned int* anymask;
+    const int* offsets_out;
+    const void* w;
+    const float* shift;
+    void* out16;
+    float* out32;
+    int cap_out;
+} dcl_spb_conv;
+int dcl_spb_conv3(int b, int cin_pad, int cout, int ntowers, const dcl_spb_conv* convs, void* stream);
+
+/* SparseAvgPool3d(k3, s2, p1, use_gs=False): out[r] = sum over kernel offsets ascending of in[nbr[r,k]] / nbr[r,27]
+ * (src/spconv/avgpool.cu:44, summaryRF.cu:27-41); in (rows_in, c) fp32 -> out32 (cap_out, c) fp32 [+ out16 fp16]. */
+typedef struct dcl_spb_pool {
+    const float* in;
+    const int* nbr;
+    const int* offsets_out;
+    float* out32;
+    void* out16;
+    int cap_out;
+} dcl_spb_pool;
+int dcl_spb_avgpool(int b, int c, int ntowers, const dcl_spb_pool* pools, void* stream);
+
+/* replaces voxelize_fp_cuda (libs/pointgroup_ops/src/voxelize/voxelize.cu:10-31) for mode 4 (mean):
+ * feats (n,c), rules (m,width) int32 rows [count, i_1 .. i_count, ...] -> out (m,c), summed in rule order. */
+int dcl_voxelize_mean(int m, int width, int c, const float* feats, const int* rules, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Bring-up / test hook                                                       */
 /* ------------------------------------------------------------------------- */
 /* D (128 x N) = A (128 x K) B^T (B is N x K), all row-major fp32, through exactly the
