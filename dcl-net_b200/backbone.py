@@ -75,8 +75,7 @@ class Backbone_SPCONV(nn.Module):
 
 def pack_conv_weight(w, scale, chan_map=None, cin_pad=None):
     """(3,3,3,Cin,Cout) fp32 weights with the BatchNorm scale folded -> the packed fp16 hi/lo image of
-    dcl_spb_conv3: reduction axis kv = k*cin_pad + c padded to a multiple of 64; per (n-tile of NT = min(Cout,128)
-    output channels, stage of 64 kv): [hi | lo] images of NT rows x 64, K-major 8x8 core matrices:
+    dcl_spb_conv3: reduction axis kv = k*cin_pad + c padded to a multiple of 64; per stage of 64 kv: [hi | lo] images of Cout rows x 64, K-major 8x8 core matrices:
         byte(o, kk) = (o/8)*1024 + (kk/8)*128 + (o%8)*16 + (kk%8)*2.
     chan_map[c] = source input channel of operand channel c (-1: zero), for the first layer's [value | remainder] rows."""
     cin, cout = w.shape[3], w.shape[4]
@@ -84,14 +83,13 @@ def pack_conv_weight(w, scale, chan_map=None, cin_pad=None):
     wf = (w.reshape(27, cin, cout) * scale.view(1, 1, cout)).float()
     if chan_map is None:
         chan_map = list(range(cin)) + [-1] * (cin_pad - cin)
-    wv = wf.new_zeros(27, cin_pad, cout)
-    for c, src in enumerate(chan_map):
-        if src >= 0:
-            wv[:, c] = wf[:, src]
+    src = torch.as_tensor([max(c, 0) for c in chan_map], dtype=torch.long, device=wf.device)
+    live = torch.as_tensor([float(c >= 0) for c in chan_map], dtype=wf.dtype, device=wf.device)
+    wv = wf.index_select(1, src) * live.view(1, -1, 1)
     kp = (27 * cin_pad + 63) // 64 * 64
     flat = wf.new_zeros(kp, cout)
     flat[:27 * cin_pad] = wv.reshape(27 * cin_pad, cout)
-    nt = min(cout, 128)
+    nt = cout                                                    # one n-tile (NT = Cout <= 256)
     wt = flat.t().contiguous()                                   # (cout, kp)
     hi = wt.to(torch.float16)
     lo = (wt - hi.float()).to(torch.float16)

@@ -28,21 +28,22 @@ namespace {
 
 constexpr int SC_BM = 128;
 constexpr int SC_KC = 64;            // virtual channels per stage
-constexpr int SC_MT = 4;             // row tiles per CTA
-constexpr int SC_NA = 6;             // A-stage ring
-constexpr int SC_NW = 3;             // W-stage ring
 constexpr int SC_THREADS = 192;
 constexpr int SC_A_BYTES = SC_BM * SC_KC * 2;   // 16384
-constexpr int SC_LOOKAHEAD = 4;      // gather stages in flight per thread (< SC_NA)
 
-template <int NT>
+// MT = row tiles per CTA (they share every W stage): 4 where a layer has thousands of tiles, 1 for the deep levels,
+// whose few hundred tiles must spread over all SMs.  Ring depths: NT = 128 keeps one CTA per SM with deep rings;
+// narrower layers use shallower rings so that two CTAs share an SM (one's epilogue under the other's main loop).
+template <int NT, int MT>
 struct ScCfg {
+    static constexpr int NA = NT == 128 ? 6 : 4;          // A-stage ring
+    static constexpr int NW = NT == 128 ? 3 : 2;          // W-stage ring
     static constexpr int W_HALF = NT * SC_KC * 2;
     static constexpr int W_BYTES = 2 * W_HALF;
-    static constexpr int OFF_W = SC_NA * SC_A_BYTES;
-    static constexpr int OFF_BAR = OFF_W + SC_NW * W_BYTES;
+    static constexpr int OFF_W = NA * SC_A_BYTES;
+    static constexpr int OFF_BAR = OFF_W + NW * W_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
-    static constexpr int TMEM_COLS = (SC_MT * NT) < 32 ? 32 : (SC_MT * NT);   // 64, 128, 256, 512: powers of two
+    static constexpr int TMEM_COLS = (MT * NT) < 32 ? 32 : (MT * NT);   // powers of two: NT and MT are
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
@@ -64,11 +65,10 @@ struct ScArgs {
 };
 
 __device__ __forceinline__ void sc_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    // .ca: the 16-byte requests of the lanes that share a 32-byte sector merge in L1's tag stage (with .cg every
+    // lane pulled its own sector from L2: twice the bytes, ncu sectors/request 25 instead of 16)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void sc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void sc_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // bit mask over stages: stage s is needed when any of the kernel offsets it covers is used by a row of this CTA
 __device__ __forceinline__ unsigned long long sc_stage_mask(unsigned int kmask, int cin, int nstages) {
@@ -82,9 +82,15 @@ __device__ __forceinline__ unsigned long long sc_stage_mask(unsigned int kmask, 
     return m;
 }
 
-template <int NT>
+// CS = CTAs per cluster.  CS > 1 (the wide, deep layers, which are bound by streaming W from L2): the CTAs of a
+// cluster own consecutive tile groups and walk the same stage list; each fetches 1/CS of every W stage and
+// multicasts it into all of them, and a W buffer is refilled only after every CTA's MMAs have released it
+// (tcgen05.commit multicast, CS arrivals per phase).  A CTA of an active cluster that has no tiles of its own still
+// loads and releases its share.
+template <int NT, int MT, int CS>
 __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __grid_constant__ ScArgs args) {
-    using Cfg = ScCfg<NT>;
+    using Cfg = ScCfg<NT, MT>;
+    constexpr int SC_NA = Cfg::NA, SC_NW = Cfg::NW, SC_MT = MT;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* a_full = bars;                 // [SC_NA] 128 gather threads
@@ -99,13 +105,15 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __gri
     const int total = min(*tw.total_ptr, tw.cap_out);
     const int ntiles = (total + SC_BM - 1) / SC_BM;
     const int tile0 = blockIdx.x * SC_MT;
-    if (tile0 >= ntiles) return;                       // uniform for the CTA: nothing was allocated yet
-    const int nt_mine = min(SC_MT, ntiles - tile0);
+    const int ctile0 = (blockIdx.x / CS) * CS * SC_MT;     // first tile of the cluster
+    if (ctile0 >= ntiles) return;                      // uniform for the cluster: nothing was allocated yet
+    const int nt_mine = max(0, min(SC_MT, ntiles - tile0));
     const int nti = blockIdx.y;
     const int cin = args.cin, cout = args.cout, nstages = args.nstages;
+    const uint32_t crank = CS > 1 ? dcl_cluster_ctarank() : 0u;
 
-    unsigned int kmask = 0;
-    for (int t = 0; t < nt_mine; ++t) kmask |= tw.anymask[tile0 + t];
+    unsigned int kmask = 0;                            // kernel offsets used by any row of the cluster's tiles
+    for (int t = ctile0; t < min(ntiles, ctile0 + CS * SC_MT); ++t) kmask |= tw.anymask[t];
     const unsigned long long smask = sc_stage_mask(kmask, cin, nstages);
 
     if (threadIdx.x == 0) {
@@ -115,64 +123,85 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __gri
         }
         for (int i = 0; i < SC_NW; ++i) {
             dcl_mbar_init(w_full + i, 1);
-            dcl_mbar_init(w_empty + i, 1);
+            dcl_mbar_init(w_empty + i, CS);
         }
         dcl_mbar_init(acc_full, 1);
         dcl_fence_barrier_init();
     }
-    if (warp == 4) tc_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 4 && nt_mine > 0) tc_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CS > 1) dcl_cluster_sync();          // the peers' barriers exist before anything is multicast at them
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = nt_mine > 0 ? *tmem_slot : 0u;
 
     if (warp < 4) {
-        // ===================== gather: thread = output row of each tile =====================
-        const int row = threadIdx.x;
-        const uint32_t a_row = (uint32_t)(row >> 3) * (SC_KC / 8) * 128u + (uint32_t)(row & 7) * 16u;
+      if (nt_mine > 0) {
+        // ===================== gather =====================
+        // A warp instruction covers 8 rows x 4 chunks of 16 bytes: lane%8 = row within an 8-row group (the eight
+        // 16-byte slots of a core-matrix row block: conflict-free shared-memory writes), lane/8 = chunk, so that each
+        // input row is read 64 contiguous bytes at a time (two instructions per row) instead of 16.
+        const int rl = lane & 7, jc = lane >> 3;
         const uint32_t sA = dcl_smem_u32(smem);
-        int issued = 0, signalled = 0;
-        int pend_buf[SC_LOOKAHEAD + 1];
+        // rulebook entries of one (stage, tile): this thread's 4 rows x 2 chunks.  They are fetched ONE iteration ahead
+        // of the copies that need them, so that the gather never waits on a dependent global load.
+        auto load_rows = [&](int s, int t, int (&rows)[8]) {
 #pragma unroll
-        for (int i = 0; i <= SC_LOOKAHEAD; ++i) pend_buf[i] = 0;
-        for (int s = 0; s < nstages; ++s) {
-            if (!((smask >> s) & 1ull)) continue;
-            for (int t = 0; t < nt_mine; ++t) {
-                const int buf = issued % SC_NA;
-                if (issued >= SC_NA) dcl_mbar_wait(a_empty + buf, (uint32_t)(((issued / SC_NA) - 1) & 1));
-                const int r = (tile0 + t) * SC_BM + row;
-                const int* nb = tw.nbr + (size_t)r * 32;
-                const uint32_t dst = sA + buf * SC_A_BYTES + a_row;
+            for (int h = 0; h < 2; ++h) {
+                const int k = (s * SC_KC + (jc + 4 * h) * 8) / cin;
 #pragma unroll
-                for (int j = 0; j < SC_KC / 8; ++j) {
-                    const int kv = s * SC_KC + j * 8;
-                    const int k = kv / cin, c0 = kv - k * cin;
-                    int src_row = -1;
-                    if (k < 27 && r < total) src_row = __ldg(nb + k);
-                    const __half* src = tw.in16 + (size_t)(src_row < 0 ? 0 : src_row) * cin + c0;
-                    sc_cp_async16(dst + j * 128, src, src_row < 0 ? 0u : 16u);
-                }
-                sc_cp_commit();
-                pend_buf[issued % (SC_LOOKAHEAD + 1)] = buf;
-                ++issued;
-                if (issued - signalled > SC_LOOKAHEAD) {
-                    sc_cp_wait<SC_LOOKAHEAD>();          // the oldest outstanding stage of this thread has landed
-                    dcl_fence_proxy_async();             // generic-proxy writes -> visible to the tensor core
-                    dcl_mbar_arrive(a_full + pend_buf[signalled % (SC_LOOKAHEAD + 1)]);
-                    ++signalled;
+                for (int g = 0; g < 4; ++g) {
+                    const int rt = warp * 32 + g * 8 + rl;
+                    const int r = (tile0 + t) * SC_BM + rt;
+                    rows[g * 2 + h] = (k < 27 && r < total) ? __ldg(tw.nbr + ((size_t)(tile0 + t) * 32 + k) * 128 + rt) : -1;
                 }
             }
-        }
-        sc_cp_wait<0>();
-        dcl_fence_proxy_async();
-        while (signalled < issued) {
-            dcl_mbar_arrive(a_full + pend_buf[signalled % (SC_LOOKAHEAD + 1)]);
-            ++signalled;
+        };
+        auto next_stage = [&](int s) {
+            ++s;
+            while (s < nstages && !((smask >> s) & 1ull)) ++s;
+            return s;
+        };
+        int issued = 0;
+        int s = next_stage(-1), t = 0;
+        int cur[8], nxt[8];
+        if (s < nstages) load_rows(s, 0, cur);
+        while (s < nstages) {
+            int s2 = s, t2 = t + 1;
+            if (t2 == nt_mine) {
+                t2 = 0;
+                s2 = next_stage(s);
+            }
+            if (s2 < nstages) load_rows(s2, t2, nxt);
+            const int buf = issued % SC_NA;
+            if (issued >= SC_NA) dcl_mbar_wait(a_empty + buf, (uint32_t)(((issued / SC_NA) - 1) & 1));
+            const uint32_t dst0 = sA + buf * SC_A_BYTES + (uint32_t)rl * 16u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kv = s * SC_KC + (jc + 4 * h) * 8;
+                const int c0 = kv - (kv / cin) * cin;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int src_row = cur[g * 2 + h];
+                    const __half* src = tw.in16 + (size_t)(src_row < 0 ? 0 : src_row) * cin + c0;
+                    sc_cp_async16(dst0 + (uint32_t)(warp * 4 + g) * (SC_KC / 8) * 128u + (uint32_t)(jc + 4 * h) * 128u, src,
+                                  src_row < 0 ? 0u : 16u);
+                }
+            }
+            // the stage's barrier receives this thread's arrival when its copies have landed (no wait, no stall: the
+            // thread runs ahead until the ring is full) — the hand-off CUTLASS's sm100 cp.async mainloop uses
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(dcl_smem_u32(a_full + buf)) : "memory");
+            ++issued;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            s = s2;
+            t = t2;
         }
         // ===================== epilogue: TMEM lane = output row =====================
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+        const int row = threadIdx.x;
         for (int t = 0; t < nt_mine; ++t) {
             const int r = (tile0 + t) * SC_BM + row;
 #pragma unroll 1
@@ -212,6 +241,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __gri
             }
         }
         tc_fence_before();
+      }
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         if (dcl_elect_one()) {
@@ -242,10 +272,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __gri
                     tc_commit(a_empty + ab);
                 }
                 first = false;
-                tc_commit(w_empty + wb);
+                if constexpr (CS > 1) tc_commit_mcast(w_empty + wb, (uint16_t)((1u << CS) - 1u));
+                else tc_commit(w_empty + wb);
                 ++wi;
             }
-            tc_commit(acc_full);
+            if (nt_mine > 0) tc_commit(acc_full);
         }
     } else {
         // ===================== weight stream =====================
@@ -257,29 +288,63 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sparse_conv3_kernel(const __gri
                 const int wb = wi % SC_NW;
                 if (wi >= SC_NW) dcl_mbar_wait(w_empty + wb, (uint32_t)(((wi / SC_NW) - 1) & 1));
                 dcl_mbar_arrive_expect_tx(w_full + wb, Cfg::W_BYTES);
-                dcl_bulk_g2s(smem + Cfg::OFF_W + wb * Cfg::W_BYTES, w + (size_t)s * Cfg::W_BYTES, Cfg::W_BYTES, w_full + wb);
+                if constexpr (CS > 1) {
+                    constexpr uint32_t SLICE = Cfg::W_BYTES / CS;
+                    dcl_bulk_g2s_mcast(smem + Cfg::OFF_W + wb * Cfg::W_BYTES + crank * SLICE,
+                                       w + (size_t)s * Cfg::W_BYTES + crank * SLICE, SLICE, w_full + wb,
+                                       (uint16_t)((1u << CS) - 1u));
+                } else {
+                    dcl_bulk_g2s(smem + Cfg::OFF_W + wb * Cfg::W_BYTES, w + (size_t)s * Cfg::W_BYTES, Cfg::W_BYTES,
+                                 w_full + wb);
+                }
                 ++wi;
             }
         }
     }
     __syncwarp();
     __syncthreads();
-    if (warp == 4) {
+    if constexpr (CS > 1) dcl_cluster_sync();          // no CTA leaves while a peer may still multicast into it
+    if (warp == 4 && nt_mine > 0) {
         tc_fence_after();
         tc_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-template <int NT>
+template <int NT, int MT>
 int sc_launch(const ScArgs& args, int ntowers, int max_cap, cudaStream_t st) {
-    using Cfg = ScCfg<NT>;
-    cudaError_t e = cudaFuncSetAttribute(sparse_conv3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    using Cfg = ScCfg<NT, MT>;
+    constexpr int CS = NT >= 128 ? 4 : 1;          // W multicast where W streaming is what binds
+    cudaError_t e = cudaFuncSetAttribute(sparse_conv3_kernel<NT, MT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    const int groups = DCL_DIVUP(max_cap / SC_BM, SC_MT);
-    dim3 grid(groups, args.cout / NT, ntowers);
-    sparse_conv3_kernel<NT><<<grid, SC_THREADS, Cfg::SMEM_BYTES, st>>>(args);
+    int groups = DCL_DIVUP(max_cap / SC_BM, MT);
+    groups = DCL_DIVUP(groups, CS) * CS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups, args.cout / NT, ntowers);
+    cfg.blockDim = dim3(SC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, sparse_conv3_kernel<NT, MT, CS>, args);
+    if (e != cudaSuccess) return (int)e;
     return dcl_launch_status();
+}
+
+template <int NT>
+int sc_launch_nt(const ScArgs& args, int ntowers, int max_cap, int tiles_total, cudaStream_t st) {
+    // row tiles per CTA: every W stage is fetched once per CTA, so more tiles per CTA = less L2 traffic (the deep,
+    // wide layers are bound by exactly that), as long as there are still CTAs for every SM
+    if constexpr (NT * 4 <= 512) {
+        if (tiles_total >= 148 * 4) return sc_launch<NT, 4>(args, ntowers, max_cap, st);
+    }
+    if (tiles_total >= 148) return sc_launch<NT, 2>(args, ntowers, max_cap, st);
+    return sc_launch<NT, 1>(args, ntowers, max_cap, st);
 }
 
 }  // namespace
@@ -305,9 +370,12 @@ DCL_API int dcl_spb_conv3(int b, int cin_pad, int cout, int ntowers, const dcl_s
         if (c.cap_out > max_cap) max_cap = c.cap_out;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = cout < 128 ? cout : 128;
-    if (nt == 16) return sc_launch<16>(args, ntowers, max_cap, st);
-    if (nt == 32) return sc_launch<32>(args, ntowers, max_cap, st);
-    if (nt == 64) return sc_launch<64>(args, ntowers, max_cap, st);
-    return sc_launch<128>(args, ntowers, max_cap, st);
+    const int nt = cout;                      // one n-tile: the gathered rows are read once for all output channels
+    int tiles_total = 0;
+    for (int t = 0; t < ntowers; ++t) tiles_total += convs[t].cap_out / SC_BM;
+    if (nt == 16) return sc_launch_nt<16>(args, ntowers, max_cap, tiles_total, st);
+    if (nt == 32) return sc_launch_nt<32>(args, ntowers, max_cap, tiles_total, st);
+    if (nt == 64) return sc_launch_nt<64>(args, ntowers, max_cap, tiles_total, st);
+    if (nt == 128) return sc_launch_nt<128>(args, ntowers, max_cap, tiles_total, st);
+    return sc_launch_nt<256>(args, ntowers, max_cap, tiles_total, st);
 }

@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(256) spb_emit_indices_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------ kernel C: rulebooks
-// nbr[op][row][32]: entries 0..26 = input row feeding output row `row` through kernel offset k = (k0*3+k1)*3+k2
-// (input position = out*stride - 1 + k, geometry.h:24-86), -1 when that voxel is not in the input set; entry 27 =
-// number of valid entries (the pool's divisor, summaryRF.cu:27-41).  anymask[op][tile] = OR over the tile's 128
+// nbr[op][tile][32][128] (tile = 128 consecutive output rows): slot k in 0..26 = input row feeding the tile's row
+// through kernel offset k = (k0*3+k1)*3+k2 (input position = out*stride - 1 + k, geometry.h:24-86), -1 when that
+// voxel is not in the input set; slot 27 = number of valid entries (the pool's divisor, summaryRF.cu:27-41).  anymask[op][tile] = OR over the tile's 128
 // rows of their 27-bit validity masks, so the convolution skips kernel offsets no row of a tile uses.
 struct SpbRuleTower {
     const unsigned long long* rows;
@@ -444,6 +444,13 @@ struct SpbRuleArgs {
 };
 
 __global__ void __launch_bounds__(256) spb_rulebook_kernel(const __grid_constant__ SpbRuleArgs args) {
+    // block = one tile of 128 output rows of one op: 8 warps x 16 rows; lanes 0..8 fetch the nine (x+dx, y+dy) bit rows
+    // of the input set (each serves the three dz of its column), every lane k < 27 then ranks its neighbour.  The
+    // tile's table is assembled in shared memory and written out TRANSPOSED — nbr[tile][k][row in tile] — so that the
+    // consumers read, per kernel offset, 128 consecutive entries (sparse_conv.cu gathers by offset); the tile's
+    // validity mask is OR-ed through shared memory and stored once (no atomics, nothing to clear).
+    __shared__ int s_tab[32][128 + 1];
+    __shared__ unsigned int s_any[8];
     const SpbRuleTower& tw = args.tw[blockIdx.z];
     const int op = blockIdx.y, B = args.B;
     const int level = op / 3, kind = op - 3 * level;              // 0 conv, 1 subm, 2 pool
@@ -451,31 +458,56 @@ __global__ void __launch_bounds__(256) spb_rulebook_kernel(const __grid_constant
     const int s_in = kind == 0 ? 2 * level : 2 * level + 1;
     const int stride = kind == 2 ? 2 : 1;
     const int total = min(tw.offsets[s_out * (B + 1) + B], tw.cap[s_out]);
+    const int tile = blockIdx.x;
+    if (tile * 128 >= total) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Gin = spb_grid(s_in);
     const int in_base = spb_row_base(s_in);
-    int* nbr = tw.nbr[op];
     const int4* ind = reinterpret_cast<const int4*>(tw.indices[s_out]);
-    for (int r = blockIdx.x * 8 + warp; r < total; r += gridDim.x * 8) {
-        const int4 o = ind[r];
+    const int k0 = lane / 9, k1 = (lane / 3) % 3, k2 = lane % 3;    // lane < 27: kernel offset; lane < 9: (dx, dy) = (lane/3, lane%3)
+    unsigned int any = 0;
+    for (int i = 0; i < 16; ++i) {
+        const int rt = warp * 16 + i;
+        const int r = tile * 128 + rt;
         int val = -1;
-        if (lane < 27) {
-            const int k0 = lane / 9, k1 = (lane / 3) % 3, k2 = lane % 3;
-            const int x = o.y * stride - 1 + k0, y = o.z * stride - 1 + k1, z = o.w * stride - 1 + k2;
-            if ((unsigned)x < (unsigned)Gin && (unsigned)y < (unsigned)Gin && (unsigned)z < (unsigned)Gin) {
-                const size_t rb = (size_t)o.x * SPB_ROWS_PER_INST + in_base + x * Gin + y;
-                const unsigned long long bits = tw.rows[rb];
-                if ((bits >> z) & 1ull) {
-                    const int rank = tw.prefix[rb] + __popcll(bits & ((1ull << z) - 1ull));
+        if (r < total) {                                           // uniform per warp
+            const int4 o = ind[r];
+            unsigned long long bits = 0ull;
+            int pre = 0;
+            if (lane < 9) {
+                const int x = o.y * stride - 1 + lane / 3, y = o.z * stride - 1 + lane % 3;
+                if ((unsigned)x < (unsigned)Gin && (unsigned)y < (unsigned)Gin) {
+                    const size_t rb = (size_t)o.x * SPB_ROWS_PER_INST + in_base + x * Gin + y;
+                    bits = tw.rows[rb];
+                    pre = tw.prefix[rb];
+                }
+            }
+            const int srcl = (lane < 27) ? (k0 * 3 + k1) : 0;
+            const unsigned long long nb_bits = __shfl_sync(0xffffffffu, bits, srcl);
+            const int nb_pre = __shfl_sync(0xffffffffu, pre, srcl);
+            if (lane < 27) {
+                const int z = o.w * stride - 1 + k2;
+                if ((unsigned)z < (unsigned)Gin && ((nb_bits >> z) & 1ull)) {
+                    const int rank = nb_pre + __popcll(nb_bits & ((1ull << z) - 1ull));
                     val = (op == 0 && tw.in0_slot > 0) ? o.x * tw.in0_slot + rank
                                                        : tw.offsets[s_in * (B + 1) + o.x] + rank;
                 }
             }
+            const unsigned int valid = __ballot_sync(0xffffffffu, val >= 0);
+            if (lane == 27) val = __popc(valid);
+            any |= valid;
         }
-        const unsigned int valid = __ballot_sync(0xffffffffu, val >= 0);
-        if (lane == 27) val = __popc(valid);
-        nbr[(size_t)r * 32 + lane] = val;
-        if (lane == 0) atomicOr(tw.anymask[op] + (r >> 7), valid);
+        s_tab[lane][rt] = val;
+    }
+    if (lane == 0) s_any[warp] = any;
+    __syncthreads();
+    int* nbr = tw.nbr[op] + (size_t)tile * 32 * 128;
+    for (int e = threadIdx.x; e < 28 * 128; e += 256) nbr[e] = s_tab[e >> 7][e & 127];
+    if (threadIdx.x == 0) {
+        unsigned int m = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m |= s_any[w];
+        tw.anymask[op][tile] = m;
     }
 }
 
@@ -483,7 +515,7 @@ __global__ void __launch_bounds__(256) spb_rulebook_kernel(const __grid_constant
 // out[o] = sum over the kernel offsets, ascending, of in[i] / rf[o]   (avgpool.cu:44: out = out + in / rf)
 struct SpbPoolTower {
     const float* in;           // (rows_in, c) fp32
-    const int* nbr;            // (cap_out, 32)
+    const int* nbr;            // (cap_out / 128, 32, 128)
     const int* offsets_out;    // &offsets[s_out * (B+1)]  (element B = total)
     float* out32;              // (cap_out, c)
     __half* out16;             // (cap_out, c) the same rounded once to fp16 (operand rows of the next conv), or null
@@ -494,6 +526,15 @@ struct SpbPoolArgs {
     SpbPoolTower tw[2];
 };
 
+// x / d, correctly rounded, for a divisor that is a small positive integer and a finite x whose quotient is normal or
+// zero: q0 = RN(x * rc) with rc = RN(1/d), one exact residual, one correction (Markstein).  IEEE division
+// (__fdiv_rn) gives the same bits but takes its slow path for every zero numerator — half of all post-ReLU features.
+__device__ __forceinline__ float spb_div(float x, float d, float rc) {
+    const float q0 = __fmul_rn(x, rc);
+    const float e = __fmaf_rn(-q0, d, x);
+    return __fmaf_rn(e, rc, q0);
+}
+
 __global__ void __launch_bounds__(256) spb_avgpool_kernel(const __grid_constant__ SpbPoolArgs args) {
     const SpbPoolTower& tw = args.tw[blockIdx.y];
     const int c4 = args.c >> 2;
@@ -501,18 +542,30 @@ __global__ void __launch_bounds__(256) spb_avgpool_kernel(const __grid_constant_
     const long work = (long)total * c4;
     for (long g = (long)blockIdx.x * 256 + threadIdx.x; g < work; g += (long)gridDim.x * 256) {
         const int r = (int)(g / c4), q = (int)(g - (long)r * c4);
-        const int* nb = tw.nbr + (size_t)r * 32;
-        const float rf = (float)nb[27];
+        const int* ncol = tw.nbr + (size_t)(r >> 7) * 32 * 128 + (r & 127);    // entry k of row r at ncol[k * 128]
+        const float rf = (float)__ldg(ncol + 27 * 128);
+        const float rc = __frcp_rn(rf);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // additions in ascending kernel-offset order (avgpool.cu:44 runs one launch per offset)
 #pragma unroll 1
-        for (int k = 0; k < 27; ++k) {
-            const int i = nb[k];
-            if (i < 0) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(tw.in + (size_t)i * args.c) + q);
-            acc.x = __fadd_rn(acc.x, __fdiv_rn(v.x, rf));
-            acc.y = __fadd_rn(acc.y, __fdiv_rn(v.y, rf));
-            acc.z = __fadd_rn(acc.z, __fdiv_rn(v.z, rf));
-            acc.w = __fadd_rn(acc.w, __fdiv_rn(v.w, rf));
+        for (int i = 0; i < 7; ++i) {
+            int nb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nb[j] = 4 * i + j < 27 ? __ldg(ncol + (4 * i + j) * 128) : -1;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = (nb[j] >= 0 && 4 * i + j < 27)
+                           ? __ldg(reinterpret_cast<const float4*>(tw.in + (size_t)nb[j] * args.c) + q)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (nb[j] < 0 || 4 * i + j >= 27) continue;
+                acc.x = __fadd_rn(acc.x, spb_div(v[j].x, rf, rc));
+                acc.y = __fadd_rn(acc.y, spb_div(v[j].y, rf, rc));
+                acc.z = __fadd_rn(acc.z, spb_div(v[j].z, rf, rc));
+                acc.w = __fadd_rn(acc.w, spb_div(v[j].w, rf, rc));
+            }
         }
         reinterpret_cast<float4*>(tw.out32 + (size_t)r * args.c)[q] = acc;
         if (tw.out16 != nullptr) {
@@ -616,16 +669,11 @@ DCL_API int dcl_spb_emit(int b, int ntowers, const dcl_spb_tower_sets* towers, i
             const int level = op / 3, kind = op % 3;
             const int s_out = kind == 2 ? 2 * level + 2 : 2 * level + 1;
             DCL_RETURN_IF_BAD(in.nbr[op] != nullptr && in.anymask[op] != nullptr && in.indices[s_out] != nullptr);
-            cudaError_t ce = cudaMemsetAsync(in.anymask[op], 0, (size_t)(in.cap[s_out] / 128) * sizeof(unsigned int), st);
-            if (ce != cudaSuccess) return (int)ce;
             if (in.cap[s_out] > max_cap) max_cap = in.cap[s_out];
         }
     }
     spb_emit_indices_kernel<<<dim3(b, SPB_NSETS, ntowers), 256, 0, st>>>(ea);
-    int blocks = DCL_DIVUP(max_cap, 8 * 4);
-    if (blocks < 1) blocks = 1;
-    if (blocks > 2048) blocks = 2048;
-    spb_rulebook_kernel<<<dim3(blocks, SPB_NOPS, ntowers), 256, 0, st>>>(ra);
+    spb_rulebook_kernel<<<dim3(max_cap / 128, SPB_NOPS, ntowers), 256, 0, st>>>(ra);
     return dcl_launch_status(2);
 }
 

@@ -454,8 +454,9 @@ int dcl_spb_build_sets(int b, int n_per, int ntowers, const dcl_spb_tower_in* to
 
 /* Row coordinates and rulebooks.  offsets: [9][b+1] (exclusive scan of counts over the batch; element b = rows of
  * the set); indices[s]: (cap[s],4) int32 bxyz, rows past the total get batch id = b (cap % 128 == 0);
- * nbr[op]: (cap_out,32) int32 — entries 0..26: input row feeding the output row through kernel offset
- * k = (k0*3+k1)*3+k2 (input voxel = out*stride - 1 + k, geometry.h:24-86) or -1, entry 27: number of valid entries;
+ * nbr[op]: (cap_out/128, 32, 128) int32, tile-transposed — nbr[tile][k][row % 128], k in 0..26: input row feeding
+ * output row tile*128 + row%128 through kernel offset k = (k0*3+k1)*3+k2 (input voxel = out*stride - 1 + k,
+ * geometry.h:24-86) or -1; slot 27: number of valid entries;
  * anymask[op]: (cap_out/128) 27-bit OR of a tile's validity masks.  in0_slot > 0: the input rows of op 0 are
  * dcl_spb_tower_in.feat16's slots (instance*in0_slot + rank).  errors[1] |= 1<<s when set s exceeds cap[s]. */
 typedef struct dcl_spb_tower_sets {
@@ -474,7 +475,7 @@ int dcl_spb_emit(int b, int ntowers, const dcl_spb_tower_sets* towers, int in0_s
 /* One sparse convolution (3x3x3) of up to two towers in one launch, output-stationary on tensor cores:
  *   out[r, :] = relu( sum_k in[nbr[r,k], :] W[k] + shift )        (BatchNorm1d folded: W scaled, shift = bias)
  * in16: (rows_in, cin_pad) fp16 operand rows, cin_pad in {16,32,64,128}; w: packed fp16 hi/lo weights
- * [27][cin_pad/16 k-steps][hi | lo][cout x 16] (K-major core matrices, see dcl_net_b200/backbone.py:pack_conv_weight);
+ * [stage of 64 virtual channels kv = k*cin_pad + c][hi | lo][cout x 64] (K-major core matrices, see dcl_net_b200/backbone.py:pack_conv_weight);
  * cout in {16,32,64,128,256}; total rows read from offsets_out[b].  out16 (rows, cout) fp16 and / or out32 fp32. */
 typedef struct dcl_spb_conv {
     const void* in16;
@@ -489,7 +490,7 @@ typedef struct dcl_spb_conv {
 } dcl_spb_conv;
 int dcl_spb_conv3(int b, int cin_pad, int cout, int ntowers, const dcl_spb_conv* convs, void* stream);
 
-/* SparseAvgPool3d(k3, s2, p1, use_gs=False): out[r] = sum over kernel offsets ascending of in[nbr[r,k]] / nbr[r,27]
+/* SparseAvgPool3d(k3, s2, p1, use_gs=False): out[r] = sum over kernel offsets k ascending of in[nbr(r,k)] / nbr(r,27)
  * (src/spconv/avgpool.cu:44, summaryRF.cu:27-41); in (rows_in, c) fp32 -> out32 (cap_out, c) fp32 [+ out16 fp16]. */
 typedef struct dcl_spb_pool {
     const float* in;

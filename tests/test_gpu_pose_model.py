@@ -222,9 +222,15 @@ def test_refiner_golden_and_loop(cuda_dev):
     ref.use_fused = True
     from dcl_net_b200.fused_tail import pm_pack_cm
     with torch.no_grad():
+        # a pre-packed feature image in the default (fp16) format is equivalent to passing the fp32 tensor ...
         r_p, t_p = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), None, conf.to(cuda_dev), 2,
-                                pm_pack_cm(f.to(cuda_dev)))
-    assert torch.equal(r_p, r_g) and torch.equal(t_p, t_g)
+                                pm_pack_cm(f.to(cuda_dev), L.FMT_F16), L.FMT_F16)
+        assert torch.equal(r_p, r_g) and torch.equal(t_p, t_g)
+        # ... and the bf16 hi/lo ("fp32-faithful") format agrees with the oracle as well
+        r_b, t_b = refine_poses(ref, pts.to(cuda_dev), rot.to(cuda_dev), trans.to(cuda_dev), None, conf.to(cuda_dev), 2,
+                                pm_pack_cm(f.to(cuda_dev), L.FMT_BF16X2), L.FMT_BF16X2)
+    assert ref._fused_refiner.fmt == L.FMT_BF16X2
+    assert T.rotation_angle_deg(r_b.cpu(), r_o).max().item() < 0.01 and (t_b.cpu() - t_o).abs().max().item() < 1e-5
 
 
 def test_pose_heads_kernel_vs_torch(cuda_dev):
