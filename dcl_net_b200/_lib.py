@@ -143,7 +143,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(or `make -C dcl-net_b200/csrc`).  dcl_net_b200 has no CPU / PyTorch fallback.")
+                "(or `make -C dcl_net_b200/csrc`).  dcl_net_b200 has no CPU / PyTorch fallback.")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol

@@ -12,5 +12,5 @@ CPU / reference-side checkers for the DCL-Net hot path:
                    container only) and writes the fixtures under tests/golden/.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-may import this package; the product (dcl-net_b200/) never does.
+may import this package; the product (dcl_net_b200/) never does.
 """

@@ -3,7 +3,7 @@ memory per kernel, plus a census of the SASS mnemonics that prove the Blackwell 
 UBLKCP = cp.async.bulk, UTCBAR / SYNCS = tcgen05.commit / mbarrier, LDTM / STTM = tcgen05.ld / st)."""
 import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "dcl-net_b200", "csrc")
+CSRC = os.path.join(ROOT, "dcl_net_b200", "csrc")
 files = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 print("| file | kernel | registers | spill st/ld (B) | static smem (B) |")
 print("|---|---|---:|---:|---:|")
@@ -17,7 +17,7 @@ for f in files:
         name = re.sub(r"\(anonymous namespace\)::", "", name)
         name = re.sub(r"^void ", "", re.sub(r"\(.*", "", name))
         print(f"| {f} | `{name}` | {m.group(5)} | {m.group(3)}/{m.group(4)} | {m.group(6) or 0} |")
-lib = os.path.join(ROOT, "dcl-net_b200", "libdcl_b200.so")
+lib = os.path.join(ROOT, "dcl_net_b200", "libdcl_b200.so")
 if os.path.exists(lib):
     sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     fn, census = None, {}
