@@ -69,6 +69,7 @@ SIGNATURES = {
     "dcl_spb_conv3": (_I, [_I, _I, _I, _I, _P, _P]),
     "dcl_spb_avgpool": (_I, [_I, _I, _I, _P, _P]),
     "dcl_voxelize_mean": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "dcl_debug_spconv_set_trace": (_I, [_P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_fda_set_trace": (_I, [_P]),

@@ -440,75 +440,91 @@ struct SpbRuleTower {
 };
 struct SpbRuleArgs {
     int B, ntowers;
+    int tile_end[2 * SPB_NOPS];   // flat grid: blocks [tile_end[j-1], tile_end[j]) are the tiles of (tower, op) = (j / 12, j % 12)
     SpbRuleTower tw[2];
 };
 
 __global__ void __launch_bounds__(256) spb_rulebook_kernel(const __grid_constant__ SpbRuleArgs args) {
-    // block = one tile of 128 output rows of one op: 8 warps x 16 rows; lanes 0..8 fetch the nine (x+dx, y+dy) bit rows
-    // of the input set (each serves the three dz of its column), every lane k < 27 then ranks its neighbour.  The
-    // tile's table is assembled in shared memory and written out TRANSPOSED — nbr[tile][k][row in tile] — so that the
-    // consumers read, per kernel offset, 128 consecutive entries (sparse_conv.cu gathers by offset); the tile's
-    // validity mask is OR-ed through shared memory and stored once (no atomics, nothing to clear).
-    __shared__ int s_tab[32][128 + 1];
-    __shared__ unsigned int s_any[8];
-    const SpbRuleTower& tw = args.tw[blockIdx.z];
-    const int op = blockIdx.y, B = args.B;
+    // block = one tile of 128 output rows of one op, in three phases of INDEPENDENT accesses (the first version walked
+    // its rows one warp-iteration at a time through three dependent global loads and was latency-bound):
+    //   1. the tile's 128 row coordinates -> shared memory;
+    //   2. the 128 x 9 (row, dx, dy) bit rows of the input set and their prefixes -> shared memory (each serves
+    //      the three dz of its column);
+    //   3. the 128 x 27 rank queries from shared memory into the tile's table, which is written out TRANSPOSED —
+    //      nbr[tile][k][row in tile] — so that the consumers read, per kernel offset, 128 consecutive entries;
+    //      slot 27 = number of valid entries; the tile's validity mask is OR-ed in shared memory (no atomics).
+    __shared__ int4 s_ind[128];
+    __shared__ unsigned long long s_bits[128][9];
+    __shared__ int s_pre[128][9];
+    __shared__ int s_base[128];
+    __shared__ unsigned int s_valid[128];
+    __shared__ unsigned int s_any;
+    // flat grid over the tiles of every (tower, op): a (tiles, ops, towers) grid sized by the largest set launched
+    // four times as many blocks as there are tiles, most of which exited at once
+    int j = 0;
+    while (j < 2 * SPB_NOPS - 1 && (int)blockIdx.x >= args.tile_end[j]) ++j;
+    const SpbRuleTower& tw = args.tw[j / SPB_NOPS];
+    const int op = j % SPB_NOPS, B = args.B;
     const int level = op / 3, kind = op - 3 * level;              // 0 conv, 1 subm, 2 pool
     const int s_out = kind == 2 ? 2 * level + 2 : 2 * level + 1;
     const int s_in = kind == 0 ? 2 * level : 2 * level + 1;
     const int stride = kind == 2 ? 2 : 1;
     const int total = min(tw.offsets[s_out * (B + 1) + B], tw.cap[s_out]);
-    const int tile = blockIdx.x;
+    const int tile = (int)blockIdx.x - (j == 0 ? 0 : args.tile_end[j - 1]);
     if (tile * 128 >= total) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
     const int Gin = spb_grid(s_in);
     const int in_base = spb_row_base(s_in);
-    const int4* ind = reinterpret_cast<const int4*>(tw.indices[s_out]);
-    const int k0 = lane / 9, k1 = (lane / 3) % 3, k2 = lane % 3;    // lane < 27: kernel offset; lane < 9: (dx, dy) = (lane/3, lane%3)
-    unsigned int any = 0;
-    for (int i = 0; i < 16; ++i) {
-        const int rt = warp * 16 + i;
-        const int r = tile * 128 + rt;
-        int val = -1;
-        if (r < total) {                                           // uniform per warp
-            const int4 o = ind[r];
-            unsigned long long bits = 0ull;
-            int pre = 0;
-            if (lane < 9) {
-                const int x = o.y * stride - 1 + lane / 3, y = o.z * stride - 1 + lane % 3;
-                if ((unsigned)x < (unsigned)Gin && (unsigned)y < (unsigned)Gin) {
-                    const size_t rb = (size_t)o.x * SPB_ROWS_PER_INST + in_base + x * Gin + y;
-                    bits = tw.rows[rb];
-                    pre = tw.prefix[rb];
-                }
-            }
-            const int srcl = (lane < 27) ? (k0 * 3 + k1) : 0;
-            const unsigned long long nb_bits = __shfl_sync(0xffffffffu, bits, srcl);
-            const int nb_pre = __shfl_sync(0xffffffffu, pre, srcl);
-            if (lane < 27) {
-                const int z = o.w * stride - 1 + k2;
-                if ((unsigned)z < (unsigned)Gin && ((nb_bits >> z) & 1ull)) {
-                    const int rank = nb_pre + __popcll(nb_bits & ((1ull << z) - 1ull));
-                    val = (op == 0 && tw.in0_slot > 0) ? o.x * tw.in0_slot + rank
-                                                       : tw.offsets[s_in * (B + 1) + o.x] + rank;
-                }
-            }
-            const unsigned int valid = __ballot_sync(0xffffffffu, val >= 0);
-            if (lane == 27) val = __popc(valid);
-            any |= valid;
-        }
-        s_tab[lane][rt] = val;
+    const bool slots = op == 0 && tw.in0_slot > 0;
+    if (tid == 0) s_any = 0;
+    if (tid < 128) {
+        const int r = tile * 128 + tid;
+        int4 o = make_int4(-1, 0, 0, 0);
+        if (r < total) o = reinterpret_cast<const int4*>(tw.indices[s_out])[r];
+        s_ind[tid] = o;
+        s_valid[tid] = 0;
+        s_base[tid] = o.x < 0 ? 0 : (slots ? o.x * tw.in0_slot : tw.offsets[s_in * (B + 1) + o.x]);
     }
-    if (lane == 0) s_any[warp] = any;
+    __syncthreads();
+    for (int e = tid; e < 128 * 9; e += 256) {
+        const int rt = e / 9, d = e - rt * 9;
+        const int4 o = s_ind[rt];
+        unsigned long long bits = 0ull;
+        int pre = 0;
+        if (o.x >= 0) {
+            const int x = o.y * stride - 1 + d / 3, y = o.z * stride - 1 + d % 3;
+            if ((unsigned)x < (unsigned)Gin && (unsigned)y < (unsigned)Gin) {
+                const size_t rb = (size_t)o.x * SPB_ROWS_PER_INST + in_base + x * Gin + y;
+                bits = tw.rows[rb];
+                pre = tw.prefix[rb];
+            }
+        }
+        s_bits[rt][d] = bits;
+        s_pre[rt][d] = pre;
+    }
     __syncthreads();
     int* nbr = tw.nbr[op] + (size_t)tile * 32 * 128;
-    for (int e = threadIdx.x; e < 28 * 128; e += 256) nbr[e] = s_tab[e >> 7][e & 127];
-    if (threadIdx.x == 0) {
-        unsigned int m = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) m |= s_any[w];
-        tw.anymask[op][tile] = m;
+    for (int e = tid; e < 27 * 128; e += 256) {
+        const int k = e >> 7, rt = e & 127;                        // consecutive threads = consecutive rows: coalesced
+        const int4 o = s_ind[rt];
+        int val = -1;
+        if (o.x >= 0) {
+            const int z = o.w * stride - 1 + k % 3;
+            const unsigned long long bits = s_bits[rt][k / 3];
+            if ((unsigned)z < (unsigned)Gin && ((bits >> z) & 1ull))
+                val = s_base[rt] + s_pre[rt][k / 3] + __popcll(bits & ((1ull << z) - 1ull));
+        }
+        nbr[e] = val;
+        if (val >= 0) atomicOr(&s_valid[rt], 1u << k);
     }
+    __syncthreads();
+    if (tid < 128) {
+        const unsigned int v = s_valid[tid];
+        nbr[27 * 128 + tid] = __popc(v);
+        if (v) atomicOr(&s_any, v);
+    }
+    __syncthreads();
+    if (tid == 0) tw.anymask[op][tile] = s_any;
 }
 
 // ------------------------------------------------------------------ SparseAvgPool3d (k3, s2, p1, use_gs = False)
@@ -673,7 +689,15 @@ DCL_API int dcl_spb_emit(int b, int ntowers, const dcl_spb_tower_sets* towers, i
         }
     }
     spb_emit_indices_kernel<<<dim3(b, SPB_NSETS, ntowers), 256, 0, st>>>(ea);
-    spb_rulebook_kernel<<<dim3(max_cap / 128, SPB_NOPS, ntowers), 256, 0, st>>>(ra);
+    int blocks = 0;
+    for (int j = 0; j < 2 * SPB_NOPS; ++j) {
+        const int t = j / SPB_NOPS, op = j % SPB_NOPS;
+        const int level = op / 3, kind = op % 3;
+        if (t < ntowers) blocks += towers[t].cap[kind == 2 ? 2 * level + 2 : 2 * level + 1] / 128;
+        ra.tile_end[j] = blocks;
+    }
+    (void)max_cap;
+    if (blocks > 0) spb_rulebook_kernel<<<blocks, 256, 0, st>>>(ra);
     return dcl_launch_status(2);
 }
 

@@ -537,6 +537,10 @@ int dcl_debug_umma_ts_gemm(int N, int K, const float* A, const float* B, float* 
  * globaltimer life-cycle stamps of the first and the last CTA (tools/trace_fda.py). */
 int dcl_debug_fda_set_trace(long long* device_buffer);
 
+/* Installs (or, with NULL, removes) a device buffer of 6*512 int64 into which CTA (0,0,0) of the sparse convolution
+ * stamps clock64() per role and pipeline iteration (csrc/sparse_conv.cu; tools/trace_spconv.py). */
+int dcl_debug_spconv_set_trace(long long* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif
