@@ -69,6 +69,10 @@ SIGNATURES = {
     "dcl_spb_conv3": (_I, [_I, _I, _I, _I, _P, _P]),
     "dcl_spb_avgpool": (_I, [_I, _I, _I, _P, _P]),
     "dcl_voxelize_mean": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "dcl_tr_tile_pass": (_I, [_I, _P, _P]),
+    "dcl_tr_bn_stats": (_I, [_I, _P, _P]),
+    "dcl_tr_bn_bwd_reduce": (_I, [_I, _P, _P]),
+    "dcl_tr_pack_weights": (_I, [_I, _P, _P]),
     "dcl_debug_spconv_set_trace": (_I, [_P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
@@ -84,7 +88,36 @@ class PmGemmProblem(ctypes.Structure):
                 ("post_shift", _P), ("relu", _I), ("cout", _I), ("nt", _I), ("out_pm", _P), ("out_cm", _P),
                 ("rows_per_inst", _I), ("pool_w", _P), ("pool_out", _P), ("dot_w", _P), ("dot_out", _P),
                 ("out_qk", _P), ("qk_tile_rows", _I), ("out_v", _P), ("v_row0", _I), ("v_rows", _I),
-                ("a_fmt", _I), ("out_fmt", _I)]
+                ("a_fmt", _I), ("out_fmt", _I), ("inst_count", _I), ("a_inst_stride", ctypes.c_longlong),
+                ("w_inst_stride", ctypes.c_longlong), ("out_cm_inst_stride", ctypes.c_longlong)]
+
+
+_LL = ctypes.c_longlong
+
+
+class TrTile(ctypes.Structure):
+    """Mirror of dcl_tr_tile (include/dcl_b200.h)."""
+    _fields_ = [("x", _P), ("u", _P), ("x_sb", _LL), ("x_sc", _LL), ("x_sn", _LL), ("b", _I), ("c", _I), ("n", _I),
+                ("mode", _I), ("scale", _P), ("shift", _P), ("mean", _P), ("rstd", _P), ("s1", _P), ("s2", _P),
+                ("out_k", _P), ("out_t", _P), ("t_row0", _I), ("t_rows", _I), ("out_cm", _P), ("col_partial", _P)]
+
+
+class TrBn(ctypes.Structure):
+    """Mirror of dcl_tr_bn (include/dcl_b200.h)."""
+    _fields_ = [("u", _P), ("b", _I), ("c", _I), ("n", _I), ("gamma", _P), ("beta", _P), ("eps", _F), ("momentum", _F),
+                ("running_mean", _P), ("running_var", _P), ("mean", _P), ("rstd", _P), ("scale", _P), ("shift", _P)]
+
+
+class TrBnBwd(ctypes.Structure):
+    """Mirror of dcl_tr_bn_bwd (include/dcl_b200.h)."""
+    _fields_ = [("dy", _P), ("u", _P), ("dy_sb", _LL), ("dy_sc", _LL), ("b", _I), ("c", _I), ("n", _I), ("mode", _I),
+                ("mean", _P), ("rstd", _P), ("scale", _P), ("shift", _P), ("s1", _P), ("s2", _P)]
+
+
+class TrWpack(ctypes.Structure):
+    """Mirror of dcl_tr_wpack (include/dcl_b200.h)."""
+    _fields_ = [("src", _P), ("dst", _P), ("rows", _I), ("cols", _I), ("rows_pad", _I), ("k_pad", _I), ("nt", _I),
+                ("transpose", _I)]
 
 
 class FdaJob(ctypes.Structure):
@@ -149,7 +182,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if lib.dcl_b200_abi_version() != 4:
+        if lib.dcl_b200_abi_version() != 5:
             raise RuntimeError("libdcl_b200.so ABI version mismatch with dcl_net_b200/_lib.py")
         _lib = lib
     return _lib

@@ -95,8 +95,10 @@ __device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, %0;
 
 template <int NT, int EPI>
 __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_in, int mt, int nti, uint32_t tmem_acc,
-                                                 int ewarp, int lane, GmColParams& cp, float* s_dot) {
-    const dcl_pm_gemm_problem pr = pr_in;  // registers, not repeated constant-bank loads with a dynamic index
+                                                 int ewarp, int lane, GmColParams& cp, float* s_dot, int inst = 0) {
+    dcl_pm_gemm_problem pr = pr_in;  // registers, not repeated constant-bank loads with a dynamic index
+    if (inst != 0)  // split-K slice `inst` of a strided-batch problem (weight-gradient launches): its own fp32 output
+        pr.out_cm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(pr.out_cm) + (size_t)inst * pr.out_cm_inst_stride);
     const int quad = ewarp & 3;            // ewarp = warp index - 2; (ewarp + 2) % 4 is the TMEM quadrant this warp may read
     const int half = ewarp >> 2;           // which half of the columns (always 0 with 128 epilogue threads)
     constexpr int HALVES = EPI / 128;
@@ -259,7 +261,7 @@ __device__ __forceinline__ void gm_epilogue_tile(const dcl_pm_gemm_problem& pr_i
 }
 
 template <int NT, int STAGES, int FMT>
-__global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch) {
+__global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_constant__ PmGemmBatch batch, int nprob) {
     using Cfg = GmCfg<NT, STAGES, FMT>;
     constexpr int A_BLOB = Cfg::A_BLOB;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
     // grid = (problems, n-tiles, m-tiles): CTAs that read the same A blobs (same m-tile: the other n-tiles of a
     // layer, the other problems sharing the input) are launched next to each other, so each blob comes from DRAM
     // once and is an L2 hit for the rest (with the m-tile fastest, ncu showed 3x the unique bytes read from DRAM).
-    const dcl_pm_gemm_problem& pr = batch.p[blockIdx.x];
+    const dcl_pm_gemm_problem& pr = batch.p[blockIdx.x % nprob];
+    const int inst = blockIdx.x / nprob;   // slice of a strided-batch problem (0 unless inst_count > 1)
     const int mt = blockIdx.z, nti = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = pr.kb_total;
@@ -293,10 +296,12 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
 
     if (warp == 0) {
         if (dcl_elect_one()) {
-            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB;
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB +
+                                      (size_t)inst * pr.a_inst_stride;
             const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
                                       (size_t)mt * (KB - pr.kb0) * A_BLOB;
-            const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB;
+            const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB +
+                                     (size_t)inst * pr.w_inst_stride;
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((kb / STAGES) - 1) & 1));
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) pm_gemm_kernel(const __grid_con
         // ===================== epilogue =====================
         dcl_mbar_wait(acc_full, 0);
         tc_fence_after();
-        gm_epilogue_tile<NT, 128>(pr, mt, nti, tmem_base, warp - 2, lane, s_colp, nullptr);
+        gm_epilogue_tile<NT, 128>(pr, mt, nti, tmem_base, warp - 2, lane, s_colp, nullptr, inst);
         tc_fence_before();
     }
     __syncwarp();
@@ -508,7 +513,7 @@ struct GmP2Cfg {
 
 template <int NT, int STAGES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
-    pm_gemm_pair_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m) {
+    pm_gemm_pair_kernel(const __grid_constant__ PmGemmBatch batch, int nprob, int ntiles_n, int npairs_m, int ninst) {
     using Cfg = GmP2Cfg<NT, STAGES, FMT>;
     constexpr int A_BLOB = Cfg::A_BLOB;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -524,7 +529,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     const uint32_t rank = dcl_cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-    const int total_units = npairs_m * ntiles_n * nprob;   // unit = (m-tile pair, n-tile, problem); problem fastest
+    // unit = (m-tile pair, slice, n-tile, problem), problem fastest: CTAs running side by side read the same A blobs
+    // (the problems / n-tiles sharing an input); `slice` = the split-K instance of a strided-batch problem
+    const int total_units = npairs_m * ntiles_n * nprob * ninst;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -549,14 +556,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
         if (dcl_elect_one()) {
             int it = 0;
             for (int u = cluster_id; u < total_units; u += nclusters) {
-                const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+                const int prob = u % nprob, nti = (u / nprob) % ntiles_n, inst = (u / (nprob * ntiles_n)) % ninst;
+                const int mt = 2 * (u / (nprob * ntiles_n * ninst)) + (int)rank;
                 const dcl_pm_gemm_problem& pr = batch.p[prob];
                 const int KB = pr.kb_total;
-                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB;
+                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(pr.a0) + (size_t)mt * pr.kb0 * A_BLOB +
+                                          (size_t)inst * pr.a_inst_stride;
                 const unsigned char* a1 = reinterpret_cast<const unsigned char*>(pr.a1) +
                                           (size_t)mt * (KB - pr.kb0) * A_BLOB;
                 const unsigned char* w = reinterpret_cast<const unsigned char*>(pr.w) + (size_t)nti * KB * Cfg::B_BLOB +
-                                         rank * Cfg::B_HALF_ROWS;
+                                         rank * Cfg::B_HALF_ROWS + (size_t)inst * pr.w_inst_stride;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % STAGES;
                     if (it >= STAGES) dcl_mbar_wait(empty + s, (uint32_t)(((it / STAGES) - 1) & 1));
@@ -617,11 +626,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
     } else {
         int tl = 0;
         for (int u = cluster_id; u < total_units; u += nclusters, ++tl) {
-            const int prob = u % nprob, nti = (u / nprob) % ntiles_n, mt = 2 * (u / (nprob * ntiles_n)) + (int)rank;
+            const int prob = u % nprob, nti = (u / nprob) % ntiles_n, inst = (u / (nprob * ntiles_n)) % ninst;
+            const int mt = 2 * (u / (nprob * ntiles_n * ninst)) + (int)rank;
             const int acc = tl & 1;
             dcl_mbar_wait(acc_full + acc, (uint32_t)((tl >> 1) & 1));
             tc_fence_after();
-            gm_epilogue_tile<NT, GM_P_EPI>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp - 2, lane, s_colp, s_dot);
+            gm_epilogue_tile<NT, GM_P_EPI>(batch.p[prob], mt, nti, tmem_base + acc * NT, warp - 2, lane, s_colp, s_dot,
+                                           inst);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) dcl_mbar_arrive_remote(acc_empty + acc, 0);
@@ -637,7 +648,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_P_THREADS, 1)
 }
 
 template <int NT, int STAGES, int FMT>
-int launch_gemm_pair(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
+int launch_gemm_pair(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st, int ninst) {
     using Cfg = GmP2Cfg<NT, STAGES, FMT>;
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -649,11 +660,11 @@ int launch_gemm_pair(const PmGemmBatch& batch, int nprob, int rows, int cout, cu
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int ntiles_n = cout / NT, npairs_m = rows / (2 * GM_BM);
-    const int units = npairs_m * ntiles_n * nprob;
+    const int units = npairs_m * ntiles_n * nprob * ninst;
     int clusters = num_sms / 2;
     if (clusters > units) clusters = units;
     pm_gemm_pair_kernel<NT, STAGES, FMT><<<2 * clusters, GM_P_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob, ntiles_n,
-                                                                                             npairs_m);
+                                                                                             npairs_m, ninst);
     return dcl_launch_status();
 }
 
@@ -783,13 +794,13 @@ __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout
 }
 
 template <int NT, int STAGES, int FMT>
-int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st) {
+int launch_gemm(const PmGemmBatch& batch, int nprob, int rows, int cout, cudaStream_t st, int ninst) {
     using Cfg = GmCfg<NT, STAGES, FMT>;
     cudaError_t e = cudaFuncSetAttribute(pm_gemm_kernel<NT, STAGES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid(nprob, cout / NT, rows / GM_BM);
-    pm_gemm_kernel<NT, STAGES, FMT><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch);
+    dim3 grid(nprob * ninst, cout / NT, rows / GM_BM);
+    pm_gemm_kernel<NT, STAGES, FMT><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(batch, nprob);
     return dcl_launch_status();
 }
 
@@ -800,12 +811,20 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
     DCL_RETURN_IF_BAD(rows > 0 && rows % GM_BM == 0 && rows / GM_BM <= 65535);
     PmGemmBatch batch;
     const int cout = problems[0].cout, nt = problems[0].nt, a_fmt = problems[0].a_fmt;
+    const int ninst = problems[0].inst_count > 1 ? problems[0].inst_count : 1;
     DCL_RETURN_IF_BAD((nt == 64 || nt == 128 || nt == 256) && cout % nt == 0);
+    DCL_RETURN_IF_BAD((long)nproblems * ninst <= 65535);
     DCL_RETURN_IF_BAD(a_fmt == FMT_BF16X2 || a_fmt == FMT_F16);
     for (int i = 0; i < nproblems; ++i) {
         const dcl_pm_gemm_problem& p = problems[i];
         DCL_RETURN_IF_BAD(p.cout == cout && p.nt == nt && p.kb_total >= 1 && p.kb0 >= 0 && p.kb0 <= p.kb_total);
         DCL_RETURN_IF_BAD(p.a_fmt == a_fmt && (p.out_fmt == FMT_BF16X2 || p.out_fmt == FMT_F16));
+        // strided-batch problems (split-K slices with their own fp32 output): one operand image per slice, fp32 output only
+        DCL_RETURN_IF_BAD((p.inst_count > 1 ? p.inst_count : 1) == ninst);
+        DCL_RETURN_IF_BAD(ninst == 1 || (p.kb0 == p.kb_total && p.out_cm != nullptr && p.out_pm == nullptr &&
+                                         p.pool_out == nullptr && p.dot_out == nullptr && p.out_qk == nullptr &&
+                                         p.out_v == nullptr && p.a_inst_stride % 16 == 0 && p.w_inst_stride % 16 == 0 &&
+                                         p.out_cm_inst_stride % 4 == 0));
         DCL_RETURN_IF_BAD(p.a0 != nullptr && p.w != nullptr && (p.kb0 == p.kb_total || p.a1 != nullptr));
         DCL_RETURN_IF_BAD((p.post_scale == nullptr) == (p.post_shift == nullptr));
         DCL_RETURN_IF_BAD(p.out_cm == nullptr || (p.rows_per_inst > 0 && p.rows_per_inst % 32 == 0 && rows % p.rows_per_inst == 0));
@@ -827,27 +846,27 @@ DCL_API int dcl_pm_gemm(int nproblems, const dcl_pm_gemm_problem* problems, int 
     const bool paired = (rows / GM_BM) % 2 == 0;
     if (a_fmt == FMT_F16) {
         if (!force_simple && paired) {
-            if (nt == 256) return launch_gemm_pair<256, 8, FMT_F16>(batch, nproblems, rows, cout, st);
-            if (nt == 128) return launch_gemm_pair<128, 12, FMT_F16>(batch, nproblems, rows, cout, st);
-            return launch_gemm_pair<64, 12, FMT_F16>(batch, nproblems, rows, cout, st);
+            if (nt == 256) return launch_gemm_pair<256, 8, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
+            if (nt == 128) return launch_gemm_pair<128, 12, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
+            return launch_gemm_pair<64, 12, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
         }
-        if (nt == 256) return launch_gemm<256, 2, FMT_F16>(batch, nproblems, rows, cout, st);
-        if (nt == 128) return launch_gemm<128, 4, FMT_F16>(batch, nproblems, rows, cout, st);
-        return launch_gemm<64, 6, FMT_F16>(batch, nproblems, rows, cout, st);
+        if (nt == 256) return launch_gemm<256, 2, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
+        if (nt == 128) return launch_gemm<128, 4, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
+        return launch_gemm<64, 6, FMT_F16>(batch, nproblems, rows, cout, st, ninst);
     }
     if (!force_simple && !force_mcast && paired) {
-        if (nt == 256) return launch_gemm_pair<256, 6, FMT_BF16X2>(batch, nproblems, rows, cout, st);
-        if (nt == 128) return launch_gemm_pair<128, 8, FMT_BF16X2>(batch, nproblems, rows, cout, st);
-        return launch_gemm_pair<64, 9, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+        if (nt == 256) return launch_gemm_pair<256, 6, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
+        if (nt == 128) return launch_gemm_pair<128, 8, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
+        return launch_gemm_pair<64, 9, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
     }
-    if (!force_simple && paired) {
+    if (!force_simple && paired && ninst == 1) {
         if (nt == 256) return launch_gemm_cluster<256, 4>(batch, nproblems, rows, cout, st);
         if (nt == 128) return launch_gemm_cluster<128, 6>(batch, nproblems, rows, cout, st);
         return launch_gemm_cluster<64, 8>(batch, nproblems, rows, cout, st);
     }
-    if (nt == 256) return launch_gemm<256, 2, FMT_BF16X2>(batch, nproblems, rows, cout, st);
-    if (nt == 128) return launch_gemm<128, 3, FMT_BF16X2>(batch, nproblems, rows, cout, st);
-    return launch_gemm<64, 4, FMT_BF16X2>(batch, nproblems, rows, cout, st);
+    if (nt == 256) return launch_gemm<256, 2, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
+    if (nt == 128) return launch_gemm<128, 3, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
+    return launch_gemm<64, 4, FMT_BF16X2>(batch, nproblems, rows, cout, st, ninst);
 }
 
 DCL_API int dcl_pm_pack_rows(int rows, int c, int ld, const float* src, void* dst_pm, int fmt, void* stream) {

@@ -1,0 +1,354 @@
+// Training path of the pointwise MLP stacks (models/DCL_Net.py:56-151, models/Modules.py:58-97,173-201 in train
+// mode; the reference runs them as cuDNN/cuBLAS calls under autograd).  The three GEMMs of every layer
+//      forward  U  = X W^T (+ bias, ReLU)             dcl_pm_gemm on the PM image of X
+//      dgrad    dX = dZ W                             dcl_pm_gemm on the PM image of dZ, "weights" = packed W^T
+//      wgrad    dW = dZ^T X = sum_b dZ_b^T X_b        dcl_pm_gemm, strided batch: per instance b the TRANSPOSED images
+//                                                     of dZ_b (rows = channels, K = points) and of X_b; a PM image with
+//                                                     128-row tiles is byte-identical to packed weights of n-tile 128
+// run on the tcgen05 kernel of pm_gemm.cu with bf16 hi/lo operands (3 MMAs per product: fp32-faithful, no loss
+// scaling needed for the gradients).  This file holds what surrounds them — everything HBM-bound and elementwise:
+//   * tr_tile_kernel: one pass over an fp32 activation (or gradient) that applies the layer's pointwise transform
+//     (train-mode BatchNorm affine, ReLU, their backward) and emits the operand images the GEMMs read: the PM image,
+//     the per-instance transposed images, optionally the fp32 tensor and per-tile column sums (bias gradient).
+//     A CTA owns a tile of 32 channels x 128 points staged in shared memory, so that both images leave as whole
+//     16-byte units in runs of >= 512 contiguous bytes whatever the layout of the source.
+//   * tr_bn_stats_kernel / tr_bn_bwd_reduce_kernel: per-channel batch statistics and the two sums of the BatchNorm
+//     backward, accumulated in fp64 per thread and reduced in a fixed order (deterministic).
+//   * tr_pack_weights_kernel: fp32 weights (or their transpose, zero-padded) -> packed bf16 hi/lo blobs.
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/dcl_b200.h"
+
+namespace {
+
+constexpr int TR_MAX_ITEMS = 8;
+constexpr int TR_TC = 32;          // channels per tile
+constexpr int TR_TP = 128;         // points per tile
+constexpr int TR_LD = TR_TP + 1;   // shared-memory row stride (floats): conflict-free for both image writers
+constexpr int TR_BLOB = 16384;     // PM blob: bf16 hi image (8 KB) + lo image (8 KB) of 128 rows x 32 channels
+
+struct TrTileBatch { dcl_tr_tile it[TR_MAX_ITEMS]; };
+struct TrBnBatch { dcl_tr_bn it[TR_MAX_ITEMS]; };
+struct TrBnBwdBatch { dcl_tr_bn_bwd it[TR_MAX_ITEMS]; };
+struct TrWpackBatch { dcl_tr_wpack it[TR_MAX_ITEMS]; };
+
+__device__ __forceinline__ uint4 pack8_hi_lo(const float* v, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2_bf16(v[2 * e], v[2 * e + 1], h[e], l[e]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    return make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+// ------------------------------------------------------------------ tile transform + operand images
+__global__ void __launch_bounds__(256) tr_tile_kernel(const __grid_constant__ TrTileBatch batch) {
+    __shared__ float tile[TR_TC * TR_LD];
+    const dcl_tr_tile& it = batch.it[blockIdx.z];
+    const int tiles_per_inst = it.n / TR_TP;
+    const int inst = blockIdx.x / tiles_per_inst, n0 = (blockIdx.x % tiles_per_inst) * TR_TP;
+    const int c0 = blockIdx.y * TR_TC;
+    if (c0 >= it.c || inst >= it.b) return;      // items of a launch may differ in width / batch
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int mode = it.mode;
+    const float inv_cnt = 1.f / ((float)it.b * (float)it.n);
+
+    // ---- load + transform -> tile[ch][pt]
+    // x has element strides (x_sb, x_sc, x_sn); u (backward modes) is a contiguous (b, c, n) tensor
+    const float* xb = it.x + (size_t)inst * it.x_sb + (size_t)c0 * it.x_sc + (size_t)n0 * it.x_sn;
+    const float* ub = it.u != nullptr ? it.u + ((size_t)inst * it.c + c0) * it.n + n0 : nullptr;
+#pragma unroll 4
+    for (int j = 0; j < (TR_TC * TR_TP) / 256; ++j) {
+        int ch, pt;
+        if (it.x_sc == 1) {           // row-major source (points x channels): 32 consecutive channels per point
+            const int idx = t + 256 * j;
+            ch = idx & 31;
+            pt = idx >> 5;
+        } else {                      // channel-major source: 128 consecutive points per channel
+            const int idx = t + 256 * j;
+            ch = idx >> 7;
+            pt = idx & 127;
+        }
+        float x = __ldg(xb + (size_t)ch * it.x_sc + (size_t)pt * it.x_sn);
+        const int cg = c0 + ch;
+        float y;
+        if (mode == DCL_TR_COPY) {
+            y = x;
+        } else if (mode == DCL_TR_AFFINE || mode == DCL_TR_AFFINE_RELU) {
+            y = __fmaf_rn(x, __ldg(it.scale + cg), __ldg(it.shift + cg));
+            if (mode == DCL_TR_AFFINE_RELU) y = fmaxf(y, 0.f);
+        } else {
+            const float u = __ldg(ub + (size_t)ch * it.n + pt);
+            if (mode == DCL_TR_BWD_RELU) {
+                y = u > 0.f ? x : 0.f;
+            } else {
+                const float sc = __ldg(it.scale + cg), sh = __ldg(it.shift + cg);
+                const float xhat = (u - __ldg(it.mean + cg)) * __ldg(it.rstd + cg);
+                const float k1 = __ldg(it.s1 + cg) * inv_cnt, k2 = __ldg(it.s2 + cg) * inv_cnt;
+                if (mode == DCL_TR_BWD_BN_RELU) {
+                    const float g = __fmaf_rn(u, sc, sh) > 0.f ? x : 0.f;
+                    y = sc * (g - k1 - xhat * k2);
+                } else {  // DCL_TR_BWD_RELU_BN
+                    y = u > 0.f ? sc * (x - k1 - xhat * k2) : 0.f;
+                }
+            }
+        }
+        tile[ch * TR_LD + pt] = y;
+    }
+    __syncthreads();
+
+    // ---- fp32 channel-major copy of the result
+    if (it.out_cm != nullptr) {
+        float* o = it.out_cm + ((size_t)inst * it.c + c0) * it.n + n0;
+#pragma unroll 4
+        for (int j = 0; j < (TR_TC * TR_TP) / 256; ++j) {
+            const int idx = t + 256 * j, ch = idx >> 7, pt = idx & 127;
+            o[(size_t)ch * it.n + pt] = tile[ch * TR_LD + pt];
+        }
+    }
+    // ---- PM image of the (b*n x c) matrix: this tile is exactly one blob
+    if (it.out_k != nullptr) {
+        unsigned char* blob = reinterpret_cast<unsigned char*>(it.out_k) +
+                              ((size_t)((size_t)inst * it.n + n0) / 128 * (it.c / 32) + blockIdx.y) * TR_BLOB;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int uu = t + 256 * h;                     // unit = (row r, 8-channel chunk q); byte offset uu*16
+            const int r = (uu >> 5) * 8 + (uu & 7), q = (uu >> 3) & 3;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = tile[(q * 8 + e) * TR_LD + r];
+            uint4 lo;
+            const uint4 hi = pack8_hi_lo(v, lo);
+            *reinterpret_cast<uint4*>(blob + uu * 16) = hi;
+            *reinterpret_cast<uint4*>(blob + TR_BLOB / 2 + uu * 16) = lo;
+        }
+    }
+    // ---- transposed image of instance `inst`: PM image of the (t_rows x n) matrix [channel][point]
+    if (it.out_t != nullptr) {
+        const int row0 = it.t_row0 + c0;                    // first of this tile's 32 channel rows
+        const int kbs = it.n / 32;
+        unsigned char* img = reinterpret_cast<unsigned char*>(it.out_t) + (size_t)inst * it.t_rows * it.n * 4 +
+                             ((size_t)(row0 / 128) * kbs + n0 / 32) * TR_BLOB + ((row0 % 128) / 8) * 512;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int uu = t + 256 * h;                     // unit = (k-block kbl, row group rgl, 8-point chunk q8, row e)
+            const int kbl = uu >> 7, rgl = (uu >> 5) & 3, q8 = (uu >> 3) & 3, e = uu & 7;
+            const float* src = tile + (rgl * 8 + e) * TR_LD + kbl * 32 + q8 * 8;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = src[k];
+            uint4 lo;
+            const uint4 hi = pack8_hi_lo(v, lo);
+            unsigned char* d = img + (size_t)kbl * TR_BLOB + rgl * 512 + q8 * 128 + e * 16;
+            *reinterpret_cast<uint4*>(d) = hi;
+            *reinterpret_cast<uint4*>(d + TR_BLOB / 2) = lo;
+        }
+    }
+    // ---- per-tile column sums (bias gradient partials), fixed order
+    if (it.col_partial != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ch = warp * 4 + k;
+            float s = (tile[ch * TR_LD + lane] + tile[ch * TR_LD + lane + 32]) +
+                      (tile[ch * TR_LD + lane + 64] + tile[ch * TR_LD + lane + 96]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) it.col_partial[(size_t)blockIdx.x * it.c + c0 + ch] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ block reduction of two fp64 sums (fixed order)
+__device__ __forceinline__ void tr_block_reduce2(double& a, double& b, double* s_a, double* s_b) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_a[warp] = a;
+        s_b[warp] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            ta += s_a[w];
+            tb += s_b[w];
+        }
+        a = ta;
+        b = tb;
+    }
+}
+
+// Train-mode BatchNorm statistics of channel blockIdx.x of a contiguous (b, c, n) tensor.
+__global__ void __launch_bounds__(256) tr_bn_stats_kernel(const __grid_constant__ TrBnBatch batch) {
+    __shared__ double s_a[8], s_b[8];
+    const dcl_tr_bn& it = batch.it[blockIdx.y];
+    const int ch = blockIdx.x;
+    if (ch >= it.c) return;
+    double sum = 0.0, sq = 0.0;
+    const int n4 = it.n / 4;
+    for (int inst = 0; inst < it.b; ++inst) {
+        const float4* row = reinterpret_cast<const float4*>(it.u + ((size_t)inst * it.c + ch) * it.n);
+        for (int i = threadIdx.x; i < n4; i += 256) {
+            const float4 v = __ldg(row + i);
+            sum += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+            sq += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        }
+    }
+    tr_block_reduce2(sum, sq, s_a, s_b);
+    if (threadIdx.x == 0) {
+        const double cnt = (double)it.b * it.n;
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)it.eps));
+        const float g = it.gamma != nullptr ? it.gamma[ch] : 1.f, bt = it.beta != nullptr ? it.beta[ch] : 0.f;
+        const float scale = g * rstd;
+        it.mean[ch] = (float)mean;
+        it.rstd[ch] = rstd;
+        it.scale[ch] = scale;
+        it.shift[ch] = bt - (float)mean * scale;
+        if (it.running_mean != nullptr) {
+            const float m = it.momentum;
+            it.running_mean[ch] = (1.f - m) * it.running_mean[ch] + m * (float)mean;
+            it.running_var[ch] = (1.f - m) * it.running_var[ch] + m * (float)(var * cnt / (cnt - 1.0));
+        }
+    }
+}
+
+// The two per-channel sums of the BatchNorm backward:  s1 = sum g (= d beta),  s2 = sum g * xhat (= d gamma), where
+// g = dY masked by the ReLU that follows the BatchNorm (mode DCL_TR_BWD_BN_RELU) or dY itself (DCL_TR_BWD_RELU_BN).
+__global__ void __launch_bounds__(256) tr_bn_bwd_reduce_kernel(const __grid_constant__ TrBnBwdBatch batch) {
+    __shared__ double s_a[8], s_b[8];
+    const dcl_tr_bn_bwd& it = batch.it[blockIdx.y];
+    const int ch = blockIdx.x;
+    if (ch >= it.c) return;
+    const float mean = it.mean[ch], rstd = it.rstd[ch], sc = it.scale[ch], sh = it.shift[ch];
+    const bool masked = it.mode == DCL_TR_BWD_BN_RELU;
+    double s1 = 0.0, s2 = 0.0;
+    for (int inst = 0; inst < it.b; ++inst) {
+        const float* urow = it.u + ((size_t)inst * it.c + ch) * it.n;
+        const float* drow = it.dy + (size_t)inst * it.dy_sb + (size_t)ch * it.dy_sc;
+        for (int i = threadIdx.x; i < it.n; i += 256) {
+            const float u = __ldg(urow + i);
+            float g = __ldg(drow + i);
+            if (masked && !(__fmaf_rn(u, sc, sh) > 0.f)) g = 0.f;
+            s1 += (double)g;
+            s2 += (double)g * (double)((u - mean) * rstd);
+        }
+    }
+    tr_block_reduce2(s1, s2, s_a, s_b);
+    if (threadIdx.x == 0) {
+        it.s1[ch] = (float)s1;
+        it.s2[ch] = (float)s2;
+    }
+}
+
+// fp32 weights (rows x cols, row-major; transpose != 0: the source holds the matrix transposed, cols x rows) ->
+// packed bf16 hi/lo blobs of the (rows_pad x k_pad) matrix with n-tile nt (include/dcl_b200.h: packed weights);
+// elements outside (rows x cols) are zero.  Thread = one 16-byte unit (row o, 8 consecutive k).
+__global__ void __launch_bounds__(256) tr_pack_weights_kernel(const __grid_constant__ TrWpackBatch batch) {
+    const dcl_tr_wpack& it = batch.it[blockIdx.y];
+    const int kchunks = it.k_pad / 8;
+    const long g = (long)blockIdx.x * 256 + threadIdx.x;
+    if (g >= (long)it.rows_pad * kchunks) return;
+    const int o = (int)(g % it.rows_pad), kc = (int)(g / it.rows_pad);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kc * 8 + e;
+        float x = 0.f;
+        if (o < it.rows && k < it.cols)
+            x = it.transpose ? __ldg(it.src + (size_t)k * it.rows + o) : __ldg(it.src + (size_t)o * it.cols + k);
+        v[e] = x;
+    }
+    uint4 lo;
+    const uint4 hi = pack8_hi_lo(v, lo);
+    const int nt = it.nt;
+    unsigned char* d = reinterpret_cast<unsigned char*>(it.dst) +
+                       ((size_t)(o / nt) * (it.k_pad / 32) + kc / 4) * ((size_t)nt * 128) + ((o % nt) / 8) * 512 +
+                       (kc & 3) * 128 + (o & 7) * 16;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + (size_t)nt * 64) = lo;
+}
+
+}  // namespace
+
+DCL_API int dcl_tr_tile_pass(int nitems, const dcl_tr_tile* items, void* stream) {
+    DCL_RETURN_IF_BAD(nitems >= 1 && nitems <= TR_MAX_ITEMS && items != nullptr);
+    TrTileBatch batch;
+    int max_tiles = 0, max_cb = 0;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_tile& it = items[i];
+        DCL_RETURN_IF_BAD(it.x != nullptr && it.b > 0 && it.c > 0 && it.c % TR_TC == 0 && it.n > 0 && it.n % TR_TP == 0);
+        DCL_RETURN_IF_BAD(it.mode >= DCL_TR_COPY && it.mode <= DCL_TR_BWD_RELU_BN);
+        const bool affine = it.mode != DCL_TR_COPY && it.mode != DCL_TR_BWD_RELU;
+        DCL_RETURN_IF_BAD(!affine || (it.scale != nullptr && it.shift != nullptr));
+        DCL_RETURN_IF_BAD(it.mode < DCL_TR_BWD_RELU || it.u != nullptr);
+        DCL_RETURN_IF_BAD(it.mode < DCL_TR_BWD_BN_RELU ||
+                          (it.mean != nullptr && it.rstd != nullptr && it.s1 != nullptr && it.s2 != nullptr));
+        DCL_RETURN_IF_BAD(it.out_t == nullptr || (it.t_rows % 128 == 0 && it.t_row0 >= 0 && it.t_row0 % TR_TC == 0 &&
+                                                  it.t_row0 + it.c <= it.t_rows));
+        DCL_RETURN_IF_BAD(((((uintptr_t)it.out_k) | ((uintptr_t)it.out_t)) & 15u) == 0);
+        batch.it[i] = it;
+        const int tiles = it.b * (it.n / TR_TP);
+        max_tiles = tiles > max_tiles ? tiles : max_tiles;
+        max_cb = it.c / TR_TC > max_cb ? it.c / TR_TC : max_cb;
+    }
+    tr_tile_kernel<<<dim3(max_tiles, max_cb, nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_tr_bn_stats(int nitems, const dcl_tr_bn* items, void* stream) {
+    DCL_RETURN_IF_BAD(nitems >= 1 && nitems <= TR_MAX_ITEMS && items != nullptr);
+    TrBnBatch batch;
+    int max_c = 0;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_bn& it = items[i];
+        DCL_RETURN_IF_BAD(it.u != nullptr && it.b > 0 && it.c > 0 && it.n > 0 && it.n % 4 == 0 && (long)it.b * it.n > 1);
+        DCL_RETURN_IF_BAD(it.mean != nullptr && it.rstd != nullptr && it.scale != nullptr && it.shift != nullptr);
+        DCL_RETURN_IF_BAD((it.running_mean == nullptr) == (it.running_var == nullptr));
+        DCL_RETURN_IF_BAD((((uintptr_t)it.u) & 15u) == 0);
+        batch.it[i] = it;
+        max_c = it.c > max_c ? it.c : max_c;
+    }
+    tr_bn_stats_kernel<<<dim3(max_c, nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_tr_bn_bwd_reduce(int nitems, const dcl_tr_bn_bwd* items, void* stream) {
+    DCL_RETURN_IF_BAD(nitems >= 1 && nitems <= TR_MAX_ITEMS && items != nullptr);
+    TrBnBwdBatch batch;
+    int max_c = 0;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_bn_bwd& it = items[i];
+        DCL_RETURN_IF_BAD(it.dy != nullptr && it.u != nullptr && it.b > 0 && it.c > 0 && it.n > 0);
+        DCL_RETURN_IF_BAD(it.mode == DCL_TR_BWD_BN_RELU || it.mode == DCL_TR_BWD_RELU_BN);
+        DCL_RETURN_IF_BAD(it.mean != nullptr && it.rstd != nullptr && it.scale != nullptr && it.shift != nullptr &&
+                          it.s1 != nullptr && it.s2 != nullptr);
+        batch.it[i] = it;
+        max_c = it.c > max_c ? it.c : max_c;
+    }
+    tr_bn_bwd_reduce_kernel<<<dim3(max_c, nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* stream) {
+    DCL_RETURN_IF_BAD(nitems >= 1 && nitems <= TR_MAX_ITEMS && items != nullptr);
+    TrWpackBatch batch;
+    long max_units = 0;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_wpack& it = items[i];
+        DCL_RETURN_IF_BAD(it.src != nullptr && it.dst != nullptr && it.rows > 0 && it.cols > 0);
+        DCL_RETURN_IF_BAD((it.nt == 64 || it.nt == 128 || it.nt == 256) && it.rows_pad >= it.rows &&
+                          it.rows_pad % it.nt == 0 && it.k_pad >= it.cols && it.k_pad % 32 == 0);
+        DCL_RETURN_IF_BAD((((uintptr_t)it.dst) & 15u) == 0);
+        batch.it[i] = it;
+        const long units = (long)it.rows_pad * (it.k_pad / 8);
+        max_units = units > max_units ? units : max_units;
+    }
+    tr_pack_weights_kernel<<<dim3((unsigned)DCL_DIVUP(max_units, 256L), nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    return dcl_launch_status();
+}

@@ -253,6 +253,8 @@ class Network(nn.Module):
         if fused is not None:
             from .fused_tail import pm_pack_rows
             return fused.forward(pm_pack_rows(F_Xc, fused.fmt), pm_pack_rows(F_Yo, fused.fmt), b)
+        if self._train_kernels(F_Xc):
+            return self._forward_train(F_Xc, F_Yo, b)
         F_Xc = F_Xc.view(b, self.n_inp, -1).transpose(1, 2)[:, :, :, None, None]
         F_Yo = F_Yo.view(b, self.n_tmp, -1).transpose(1, 2)[:, :, :, None, None]
         sq = lambda t: t.squeeze(-1).squeeze(-1)
@@ -280,6 +282,61 @@ class Network(nn.Module):
         rot_pred = ortho9d2matrix(ortho9d_pred[:, :3], ortho9d_pred[:, 3:6], ortho9d_pred[:, 6:])
         trans_pred = self.regressor_trans(F_p_wei).squeeze(-1)
 
+        prediction = {"trans_pred": trans_pred, "rot_pred": rot_pred, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p}
+        if self.mode != "test":
+            prediction.update({"Xo_pred": Xo_pred.transpose(1, 2), "Yc_pred": Yc_pred.transpose(1, 2)})
+        prediction["_debug"] = {"F_Yc_p": F_Yc_p, "F_Xo_m": F_Xo_m, "F_Yc_m": F_Yc_m, "ortho9d": ortho9d_pred}
+        return prediction
+
+    def _train_kernels(self, F_Xc):
+        """Training runs on the tensor-core training path (train_tail.py) when the module is in train mode
+        (BatchNorm on batch statistics) and the shapes fit its tiles; `use_train_kernels = False` selects the
+        PyTorch layer modules (library GEMMs) instead, e.g. for A/B runs."""
+        if not (self.training and torch.is_grad_enabled() and getattr(self, "use_train_kernels", True)):
+            return False
+        ok = (F_Xc.is_cuda and F_Xc.dtype == torch.float32 and self.n_inp == self.n_tmp and self.n_inp % 128 == 0
+              and F_Xc.shape[1] % 32 == 0 and self.disengage_Xc_m1[1].layers[0].out_channels in (64, 128))
+        if not ok:
+            L.warn_once("train_kernels", "dcl_net_b200.Network: training falls back to PyTorch layer modules "
+                                         "(needs CUDA fp32 inputs, n_inp == n_tmp, n % 128 == 0, c_m in {64, 128})")
+        return ok
+
+    def _forward_train(self, F_Xc, F_Yo, b):
+        """models/DCL_Net.py:187-235 in train mode with every pointwise MLP stack — forward and backward — on the
+        tcgen05 GEMM (train_tail.mlp_stacks) and the fused FDA kernels; same modules, parameters and BatchNorm
+        buffers as the layer path below."""
+        from .train_tail import StackSpec, disengage_layers, head_layers, mlp_stacks
+        n = self.n_inp
+        names = ("Xc_p1", "Xc_m1", "Xc_p2", "Xc_m2", "Yo_p1", "Yo_m1", "Yo_p2", "Yo_m2")
+        F_Xc, F_Yo = F_Xc.contiguous(), F_Yo.contiguous()
+        dis = mlp_stacks([StackSpec([(F_Xc if k.startswith("Xc") else F_Yo, "rm")],
+                                    disengage_layers(getattr(self, "disengage_" + k))) for k in names], b, n)
+        F_Xc_p1, F_Xc_m1, F_Xc_p2, F_Xc_m2, F_Yo_p1, F_Yo_m1, F_Yo_p2, F_Yo_m2 = dis
+
+        F_Xo_p, F_Xo_m = fda_align(F_Xc_m1, F_Yo_m1, F_Yo_p1)
+        F_Yc_p, F_Yc_m = fda_align(F_Yo_m2, F_Xc_m2, F_Xc_p2)
+        Xo_pred = Yc_pred = None
+        if self.mode != "test":
+            (lx, wx), (ly, wy) = head_layers(self.regressor_Xo), head_layers(self.regressor_Yc)
+            xo, yc = mlp_stacks([StackSpec([(F_Xo_p, "cm")], lx), StackSpec([(F_Yc_p, "cm")], ly)], b, n)
+            Xo_pred, Yc_pred = xo[:, :wx], yc[:, :wy]
+
+        (l1, w1), (l2, w2) = head_layers(self.regressor_conf), head_layers(self.regressor_conf_bi)
+        c1, c2 = mlp_stacks([StackSpec([(F_Xc_m1, "cm"), (F_Xo_m, "cm")], l1),
+                             StackSpec([(F_Yc_m, "cm"), (F_Yo_m2, "cm")], l2)], b, n)
+        conf = torch.sigmoid(torch.cat([c1[:, :w1], c2[:, :w2]], dim=2))
+        conf_softmax = torch.softmax(conf, dim=2)
+
+        (f1, _), (f2, _) = head_layers(self.neck_fuser), head_layers(self.neck_fuser_bi)
+        F_p1, F_p2 = mlp_stacks([StackSpec([(F_Xc_p1, "cm"), (F_Xo_p, "cm")], f1),
+                                 StackSpec([(F_Yc_p, "cm"), (F_Yo_p2, "cm")], f2)], b, n)
+        # confidence-weighted pooling over the 2n correspondences (DCL_Net.py:228) without the (b,1024,2n) concat
+        F_p_wei = (torch.bmm(F_p1, conf_softmax[:, 0, :n].unsqueeze(2)) +
+                   torch.bmm(F_p2, conf_softmax[:, 0, n:].unsqueeze(2)))
+
+        ortho9d_pred = self.regressor_rot(F_p_wei).squeeze(-1)
+        rot_pred = ortho9d2matrix(ortho9d_pred[:, :3], ortho9d_pred[:, 3:6], ortho9d_pred[:, 6:])
+        trans_pred = self.regressor_trans(F_p_wei).squeeze(-1)
         prediction = {"trans_pred": trans_pred, "rot_pred": rot_pred, "conf": conf.squeeze(1), "F_Xo_p": F_Xo_p}
         if self.mode != "test":
             prediction.update({"Xo_pred": Xo_pred.transpose(1, 2), "Yc_pred": Yc_pred.transpose(1, 2)})

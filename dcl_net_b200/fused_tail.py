@@ -168,6 +168,8 @@ def run_gemm(problems, rows):
         slot.out_qk, slot.qk_tile_rows = _addr(p.get("out_qk")), p.get("qk_tile_rows", 0)
         slot.out_v, slot.v_row0, slot.v_rows = _addr(p.get("out_v")), p.get("v_row0", 0), p.get("v_rows", 0)
         slot.a_fmt, slot.out_fmt = lay.fmt, p.get("out_fmt", lay.fmt)
+        # strided batch (weight-gradient launches of train_tail.py): (slices, a / w / out_cm strides in bytes)
+        slot.inst_count, slot.a_inst_stride, slot.w_inst_stride, slot.out_cm_inst_stride = p.get("inst", (0, 0, 0, 0))
         keep.append(p)
     if GEMM_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

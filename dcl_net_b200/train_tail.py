@@ -1,0 +1,432 @@
+"""Training path of the pointwise MLP stacks of Network.forward (models/DCL_Net.py:56-151,187-235 in train mode):
+forward AND backward on the tcgen05 GEMM of csrc/pm_gemm.cu instead of the cuDNN/cuBLAS calls autograd makes for
+nn.Conv3d / nn.Conv1d / nn.BatchNorm (reference step: tools/train_YCBV_stage1.py:168-191).
+
+`mlp_stacks(stacks)` runs S parallel stacks of pointwise layers as ONE autograd node.  Per layer, three GEMMs on
+bf16 hi/lo operand images (3 MMAs per product: fp32-faithful, so gradients need no loss scaling):
+
+    forward   U  = X W^T (+ bias, ReLU)      dcl_pm_gemm, A = PM image of X
+    dgrad     dX = dZ W                      dcl_pm_gemm, A = PM image of dZ, packed W^T as the weights
+    wgrad     dW = sum_b dZ_b^T X_b          dcl_pm_gemm strided batch over the per-instance transposed images
+
+and the HBM-bound passes of csrc/train_ops.cu around them (train-mode BatchNorm statistics, the pointwise
+transforms and their backward, operand-image writers, deterministic bias / weight gradient reductions).  The module
+tree, parameter names and BatchNorm running statistics are the reference's; only the kernels differ.
+
+Layer kinds (what follows the 1x1 convolution):
+    "linear"   conv (+bias)                               last layer of the regressors
+    "relu"     conv + bias -> ReLU                        Head_MultiLayerPerceptron without BatchNorm
+    "bn_relu"  conv -> BatchNorm -> ReLU                  BasicBlock_3DCONV (disengage blocks)
+    "relu_bn"  conv + bias -> ReLU -> BatchNorm           Head_MultiLayerPerceptron with BatchNorm (neck fusers)
+"""
+import ctypes
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .fused_tail import pick_nt, pm_empty, run_gemm
+
+TR_COPY, TR_AFFINE, TR_AFFINE_RELU, TR_BWD_RELU, TR_BWD_BN_RELU, TR_BWD_RELU_BN = range(6)
+_FWD_MODE = {"linear": TR_COPY, "relu": TR_COPY, "bn_relu": TR_AFFINE_RELU, "relu_bn": TR_AFFINE}
+_BWD_MODE = {"linear": TR_COPY, "relu": TR_BWD_RELU, "bn_relu": TR_BWD_BN_RELU, "relu_bn": TR_BWD_RELU_BN}
+
+
+def _pad(x, m):
+    return (x + m - 1) // m * m
+
+
+def _batched(fn_name, struct, items, what):
+    """Launch `items` (lists of field dicts) through a dcl_tr_* entry point, 8 per launch."""
+    fn = getattr(L.load(), fn_name)
+    for i in range(0, len(items), 8):
+        chunk = items[i:i + 8]
+        arr = (struct * len(chunk))()
+        for slot, fields in zip(arr, chunk):
+            for k, v in fields.items():
+                setattr(slot, k, L.ptr(v) if isinstance(v, torch.Tensor) or v is None else v)
+        L.check(fn(len(chunk), ctypes.cast(arr, ctypes.c_void_p), L.stream_ptr()), what)
+
+
+def tile_pass(items):
+    """csrc/train_ops.cu:tr_tile_kernel.  items: dicts with x (tensor), fmt ('cm' (b,c,n) view | 'rm' (b*n,c) matrix),
+    b, c, n, mode and the optional fields of dcl_tr_tile."""
+    out = []
+    for it in items:
+        x, b, c, n = it["x"], it["b"], it["c"], it["n"]
+        if it["fmt"] == "cm":
+            assert x.shape == (b, c, n) and x.stride(2) == 1
+            sb, sc, sn = x.stride(0), x.stride(1), 1
+        else:
+            assert x.shape == (b * n, c) and x.stride(1) == 1
+            sb, sc, sn = n * x.stride(0), 1, x.stride(0)
+        f = {"x": ctypes.c_void_p(x.data_ptr()), "x_sb": sb, "x_sc": sc, "x_sn": sn, "b": b, "c": c, "n": n,
+             "mode": it["mode"], "t_row0": it.get("t_row0", 0), "t_rows": it.get("t_rows", 0)}
+        for k in ("u", "scale", "shift", "mean", "rstd", "s1", "s2", "out_k", "out_t", "out_cm", "col_partial"):
+            f[k] = it.get(k)
+        out.append(f)
+    _batched("dcl_tr_tile_pass", L.TrTile, out, "tr_tile")
+
+
+def pack_weights(items):
+    """items: (src (rows, cols) fp32 contiguous — or its transpose when `transpose` —, rows, cols, rows_pad, k_pad, nt,
+    transpose) -> list of packed uint8 tensors."""
+    outs, fields = [], []
+    for src, rows, cols, rows_pad, k_pad, nt, transpose in items:
+        dst = torch.empty(rows_pad * k_pad * 4, dtype=torch.uint8, device=src.device)
+        outs.append(dst)
+        fields.append({"src": src, "dst": dst, "rows": rows, "cols": cols, "rows_pad": rows_pad, "k_pad": k_pad,
+                       "nt": nt, "transpose": int(transpose)})
+    _batched("dcl_tr_pack_weights", L.TrWpack, fields, "tr_pack_weights")
+    return outs
+
+
+def _gemm_layer(w_packed, cout, cin, nt, bias=None, relu=False):
+    return SimpleNamespace(cout=cout, cin=cin, nt=nt, fmt=L.FMT_BF16X2, w=w_packed, bias=bias, relu=int(relu),
+                           post_scale=None, post_shift=None)
+
+
+def _run_gemm_groups(problems, rows):
+    """dcl_pm_gemm takes up to 8 problems of equal (cout, nt) per launch."""
+    groups = {}
+    for p in problems:
+        groups.setdefault((p["layer"].cout, p["layer"].nt), []).append(p)
+    for plist in groups.values():
+        for i in range(0, len(plist), 8):
+            run_gemm(plist[i:i + 8], rows)
+
+
+# Tests set this to a list to record the ReLU gates of a forward pass: entries (layer, stack, bool mask (b, c, n)).
+GATE_LOG = None
+
+
+class StackSpec:
+    """One stack: inputs = [(tensor, 'cm' | 'rm')] (one tensor, or two concatenated along channels), layers =
+    [(kind, weight (cout, cin), bias | None, bn module | None)]."""
+
+    def __init__(self, inputs, layers):
+        self.inputs, self.layers = inputs, layers
+
+
+class _MlpStacksFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *tensors):
+        b, n = plan.b, plan.n
+        rows = b * n
+        dev = tensors[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        nl = plan.nlayers
+        # ---- K-images of the distinct input tensors
+        in_imgs = {}
+        items = []
+        for st in plan.stacks:
+            for ti, fmt, c in st.inputs:
+                if ti not in in_imgs:
+                    in_imgs[ti] = pm_empty(rows, c, dev)
+                    items.append({"x": tensors[ti], "fmt": fmt, "b": b, "c": c, "n": n, "mode": TR_COPY,
+                                  "out_k": in_imgs[ti]})
+        tile_pass(items)
+        cur = [[in_imgs[ti] for ti, _, _ in st.inputs] for st in plan.stacks]   # per stack: the A images
+        cur_c0 = [st.inputs[0][2] for st in plan.stacks]
+        saved_u, saved_bn = [], []
+        for l in range(nl):
+            lays = [st.layers[l] for st in plan.stacks]
+            wp = pack_weights([(tensors[la.w], la.cout, la.cin, la.cout, la.cin, pick_nt(la.cout), False) for la in lays])
+            last = l == nl - 1
+            us, nxt, probs = [], [], []
+            for s, (la, w) in enumerate(zip(lays, wp)):
+                u = torch.empty(b, la.cout, n, **f32)
+                bias = tensors[la.bias] if la.bias is not None else None
+                lay = _gemm_layer(w, la.cout, la.cin, pick_nt(la.cout), bias, la.kind in ("relu", "relu_bn"))
+                p = {"a0": cur[s][0], "layer": lay, "out_cm": u, "rows_per_inst": n}
+                if len(cur[s]) == 2:
+                    p.update(a1=cur[s][1], c0=cur_c0[s])
+                if la.kind in ("linear", "relu") and not last:
+                    p["out_pm"] = pm_empty(rows, la.cout, dev)     # Y = U: the next layer's operand straight away
+                    nxt.append([p["out_pm"]])
+                else:
+                    nxt.append(None)
+                us.append(u)
+                probs.append(p)
+            _run_gemm_groups(probs, rows)
+            # ---- train-mode BatchNorm: batch statistics, then the affine (+ReLU) pass writing the next operand
+            bn_items, tiles, bns = [], [], []
+            for s, la in enumerate(lays):
+                if la.kind not in ("bn_relu", "relu_bn"):
+                    bns.append(None)
+                    continue
+                bn = la.bn
+                stat = torch.empty(4, la.cout, **f32)            # mean, rstd, scale, shift
+                upd = bn.training and bn.track_running_stats
+                bn_items.append({"u": us[s], "b": b, "c": la.cout, "n": n, "gamma": tensors[la.gamma],
+                                 "beta": tensors[la.beta], "eps": float(bn.eps),
+                                 "momentum": float(bn.momentum if bn.momentum is not None else 0.0),
+                                 "running_mean": bn.running_mean if upd else None,
+                                 "running_var": bn.running_var if upd else None,
+                                 "mean": stat[0], "rstd": stat[1], "scale": stat[2], "shift": stat[3]})
+                bns.append(stat)
+                t = {"x": us[s], "fmt": "cm", "b": b, "c": la.cout, "n": n, "mode": _FWD_MODE[la.kind],
+                     "scale": stat[2], "shift": stat[3]}
+                if last or (GATE_LOG is not None and la.kind == "bn_relu"):
+                    t["out_cm"] = torch.empty(b, la.cout, n, **f32)
+                if not last:
+                    t["out_k"] = pm_empty(rows, la.cout, dev)
+                    nxt[s] = [t["out_k"]]
+                tiles.append((s, t))
+            if bn_items:
+                _batched("dcl_tr_bn_stats", L.TrBn, bn_items, "tr_bn_stats")
+                tile_pass([t for _, t in tiles])
+            saved_u.append(us)
+            saved_bn.append(bns)
+            if GATE_LOG is not None:
+                ys = {s: t["out_cm"] for s, t in tiles if "out_cm" in t}
+                for s, la in enumerate(lays):
+                    if la.kind != "linear":
+                        GATE_LOG.append((l, s, (ys[s] if la.kind == "bn_relu" else us[s]) > 0))
+            if last:
+                outs = list(us)
+                for s, t in tiles:
+                    outs[s] = t["out_cm"]
+            else:
+                cur = nxt
+                cur_c0 = [la.cout for la in lays]
+        for st in plan.stacks:
+            for la in st.layers:
+                if la.bn is not None and la.bn.training and la.bn.track_running_stats:
+                    la.bn.num_batches_tracked += 1
+        ctx.plan = plan
+        # everything the backward reads goes through save_for_backward (outputs included: no reference cycles)
+        flat, ctx.u_idx, ctx.bn_idx = list(tensors), [], []
+        for us, bns in zip(saved_u, saved_bn):
+            ctx.u_idx.append([len(flat) + i for i in range(len(us))])
+            flat += us
+            row = []
+            for st in bns:
+                row.append(None if st is None else len(flat))
+                if st is not None:
+                    flat.append(st)
+            ctx.bn_idx.append(row)
+        ctx.ntensors = len(tensors)
+        ctx.save_for_backward(*flat)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan, flat = ctx.plan, ctx.saved_tensors
+        tensors = flat[:ctx.ntensors]
+        saved_u = [[flat[i] for i in row] for row in ctx.u_idx]
+        saved_bn = [[None if i is None else flat[i] for i in row] for row in ctx.bn_idx]
+        b, n = plan.b, plan.n
+        rows = b * n
+        dev = tensors[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        nl, ns = plan.nlayers, len(plan.stacks)
+        lib = L.load()
+        out_grads = [None] * len(tensors)
+
+        def acc(idx, g):
+            out_grads[idx] = g if out_grads[idx] is None else out_grads[idx] + g
+
+        dys = []
+        for s, g in enumerate(grads):
+            c = plan.stacks[s].layers[-1].cout
+            dys.append(torch.zeros(b, c, n, **f32) if g is None else (g if g.stride(2) == 1 else g.contiguous()))
+        for l in range(nl - 1, -1, -1):
+            lays = [st.layers[l] for st in plan.stacks]
+            us, bns = saved_u[l], saved_bn[l]
+            need_dx = l > 0 or any(ctx.needs_input_grad[1 + ti] for st in plan.stacks for ti, _, _ in st.inputs)
+            # ---- BatchNorm backward sums (= d beta, d gamma)
+            red, sums = [], [None] * ns
+            for s, la in enumerate(lays):
+                if bns[s] is None:
+                    continue
+                sums[s] = torch.empty(2, la.cout, **f32)
+                dy = dys[s]
+                assert dy.stride(2) == 1
+                red.append({"dy": ctypes.c_void_p(dy.data_ptr()), "u": us[s], "dy_sb": dy.stride(0), "dy_sc": dy.stride(1),
+                            "b": b, "c": la.cout, "n": n, "mode": _BWD_MODE[la.kind], "mean": bns[s][0], "rstd": bns[s][1],
+                            "scale": bns[s][2], "shift": bns[s][3], "s1": sums[s][0], "s2": sums[s][1]})
+            if red:
+                _batched("dcl_tr_bn_bwd_reduce", L.TrBnBwd, red, "tr_bn_bwd_reduce")
+            # ---- dZ: PM image (dgrad), transposed images (wgrad), bias-gradient partials
+            items, dz_k, dz_t, colp = [], [], [], []
+            for s, la in enumerate(lays):
+                cp_rows = _pad(la.cout, 128)
+                alloc = torch.empty if cp_rows == la.cout else torch.zeros
+                dzt = alloc(b * cp_rows * n * 4, dtype=torch.uint8, device=dev)
+                it = {"x": dys[s], "fmt": "cm", "b": b, "c": la.cout, "n": n, "mode": _BWD_MODE[la.kind],
+                      "out_t": dzt, "t_rows": cp_rows}
+                if la.kind != "linear":
+                    it["u"] = us[s]
+                if bns[s] is not None:
+                    it.update(scale=bns[s][2], shift=bns[s][3], mean=bns[s][0], rstd=bns[s][1], s1=sums[s][0], s2=sums[s][1])
+                if need_dx:
+                    it["out_k"] = pm_empty(rows, la.cout, dev)
+                if la.bias is not None:
+                    it["col_partial"] = torch.empty(rows // 128, la.cout, **f32)
+                items.append(it)
+                dz_k.append(it.get("out_k"))
+                dz_t.append((dzt, cp_rows))
+                colp.append(it.get("col_partial"))
+            tile_pass(items)
+            # ---- transposed images of the layer inputs (recomputed from what the forward saved)
+            items, x_t, shared = [], [], {}
+            for s, st in enumerate(plan.stacks):
+                la = lays[s]
+                cin_pad = _pad(la.cin, 128)
+                key = tuple(ti for ti, _, _ in st.inputs)
+                if l == 0 and key in shared:                  # stacks reading the same input share its image
+                    x_t.append(shared[key])
+                    continue
+                alloc = torch.empty if cin_pad == la.cin else torch.zeros
+                xt = alloc(b * cin_pad * n * 4, dtype=torch.uint8, device=dev)
+                x_t.append((xt, cin_pad))
+                if l == 0:
+                    shared[key] = (xt, cin_pad)
+                    row0 = 0
+                    for ti, fmt, c in st.inputs:
+                        items.append({"x": tensors[ti], "fmt": fmt, "b": b, "c": c, "n": n, "mode": TR_COPY,
+                                      "out_t": xt, "t_row0": row0, "t_rows": cin_pad})
+                        row0 += c
+                else:
+                    pl = st.layers[l - 1]
+                    it = {"x": saved_u[l - 1][s], "fmt": "cm", "b": b, "c": pl.cout, "n": n,
+                          "mode": _FWD_MODE[pl.kind], "out_t": xt, "t_rows": cin_pad}
+                    pbn = saved_bn[l - 1][s]
+                    if pbn is not None:
+                        it.update(scale=pbn[2], shift=pbn[3])
+                    items.append(it)
+            tile_pass(items)
+            # ---- wgrad: per (stack, instance) slice  dW_b^T (cin_pad x cout_pad) = X_b^T-image x dZ_b^T-image, then the
+            # fixed-order sum over instances
+            probs, parts = [], []
+            for s, la in enumerate(lays):
+                (dzt, cp_rows), (xt, cin_pad) = dz_t[s], x_t[s]
+                part = torch.empty(b, cin_pad, cp_rows, **f32)
+                parts.append(part)
+                lay = _gemm_layer(xt, cin_pad, n, 128)           # the X^T image read as packed weights (n-tile 128)
+                probs.append({"a0": dzt, "layer": lay, "out_cm": part, "rows_per_inst": cp_rows,
+                              "inst": (b, cp_rows * n * 4, cin_pad * n * 4, cin_pad * cp_rows * 4), "_rows": cp_rows})
+            by_rows = {}
+            for p in probs:
+                by_rows.setdefault(p["_rows"], []).append(p)
+            for r, plist in by_rows.items():
+                _run_gemm_groups(plist, r)
+            for s, la in enumerate(lays):
+                (_, cp_rows), (_, cin_pad) = dz_t[s], x_t[s]
+                dwt = torch.empty(cin_pad, cp_rows, **f32)
+                L.check(lib.dcl_pm_pool_reduce(1, cin_pad * cp_rows, b, L.ptr(parts[s]), None, L.ptr(dwt), 0, L.stream_ptr()),
+                        "wgrad reduce")
+                acc(la.w, dwt[:la.cin, :la.cout].t().reshape(tensors[la.w].shape))
+                if la.bias is not None:
+                    db = torch.empty(la.cout, **f32)
+                    L.check(lib.dcl_pm_pool_reduce(1, la.cout, rows // 128, L.ptr(colp[s]), None, L.ptr(db), 0,
+                                                   L.stream_ptr()), "bias reduce")
+                    acc(la.bias, db)
+                if bns[s] is not None:
+                    acc(la.beta, sums[s][0])
+                    acc(la.gamma, sums[s][1])
+            # ---- dgrad: dX (b, cin_pad, n) = dZ W
+            if need_dx:
+                wt = pack_weights([(tensors[la.w], la.cin, la.cout, _pad(la.cin, 64), la.cout, pick_nt(_pad(la.cin, 64)), True)
+                                   for la in lays])
+                probs, dxs = [], []
+                for s, la in enumerate(lays):
+                    cin_pad = _pad(la.cin, 64)
+                    dx = torch.empty(b, cin_pad, n, **f32)
+                    dxs.append(dx)
+                    lay = _gemm_layer(wt[s], cin_pad, la.cout, pick_nt(cin_pad))
+                    probs.append({"a0": dz_k[s], "layer": lay, "out_cm": dx, "rows_per_inst": n})
+                _run_gemm_groups(probs, rows)
+                if l > 0:
+                    dys = [dx[:, :la.cin] for dx, la in zip(dxs, lays)]
+                else:
+                    for s, st in enumerate(plan.stacks):
+                        c0 = 0
+                        for ti, fmt, c in st.inputs:
+                            if ctx.needs_input_grad[1 + ti]:
+                                g = dxs[s][:, c0:c0 + c]
+                                acc(ti, g if fmt == "cm" else g.permute(0, 2, 1).reshape(rows, c))
+                            c0 += c
+        return (None,) + tuple(out_grads)
+
+
+def mlp_stacks(stacks, b, n):
+    """stacks: list of StackSpec.  Returns one fp32 (b, cout, n) tensor per stack (the last layer's output)."""
+    tensors, index = [], {}
+
+    def reg(t):
+        if t is None:
+            return None
+        k = id(t)
+        if k not in index:
+            index[k] = len(tensors)
+            tensors.append(t)
+        return index[k]
+
+    plan = SimpleNamespace(b=b, n=n, stacks=[], nlayers=len(stacks[0].layers))
+    for st in stacks:
+        assert len(st.layers) == plan.nlayers and 1 <= len(st.inputs) <= 2
+        ins = []
+        for t, fmt in st.inputs:
+            c = t.shape[1]
+            assert c % 32 == 0 and t.dtype == torch.float32 and t.is_cuda
+            if fmt == "cm" and t.stride(2) != 1 or fmt == "rm" and t.stride(1) != 1:
+                t = t.contiguous()
+            ins.append((reg(t), fmt, c))
+        cin = sum(c for _, _, c in ins)
+        lays = []
+        for kind, w, bias, bn in st.layers:
+            cout = w.shape[0]
+            w2 = w.reshape(cout, -1)
+            assert w2.shape[1] == cin and cout % 64 == 0 and cin % 32 == 0, (cout, cin, w.shape)
+            assert (bn is not None) == (kind in ("bn_relu", "relu_bn"))
+            if bn is not None:
+                assert bn.affine and bn.momentum is not None
+            lays.append(SimpleNamespace(kind=kind, cout=cout, cin=cin, w=reg(w2.contiguous() if not w2.is_contiguous() else w2),
+                                        bias=reg(bias), bn=bn, gamma=reg(bn.weight) if bn is not None else None,
+                                        beta=reg(bn.bias) if bn is not None else None))
+            cin = cout
+        plan.stacks.append(SimpleNamespace(inputs=ins, layers=lays))
+    assert n % 128 == 0 and (b * n) % 128 == 0
+    return _MlpStacksFn.apply(plan, *tensors)
+
+
+# ------------------------------------------------------------------ module tree -> stack specs
+def disengage_layers(stack):
+    """nn.Sequential of BasicBlock_3DCONV (Conv3d 1x1x1 without bias -> BatchNorm3d -> ReLU)."""
+    out = []
+    for block in stack:
+        mods = list(block.layers)
+        conv, bn = mods[0], mods[1]
+        assert isinstance(conv, nn.Conv3d) and conv.bias is None and isinstance(bn, nn.BatchNorm3d) and \
+            isinstance(mods[2], nn.ReLU) and len(mods) == 3
+        out.append(("bn_relu", conv.weight, None, bn))
+    return out
+
+
+def head_layers(head, pad_last_to=64):
+    """Head_MultiLayerPerceptron: Conv1d(k=1) -> [ReLU] -> [BatchNorm1d] per layer.  A last layer narrower than 64
+    outputs is zero-padded to `pad_last_to` rows (differentiable torch ops); returns (layers, true output width)."""
+    mods = list(head.layers)
+    out, i, width = [], 0, None
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, nn.Conv1d)
+        relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+        j = i + 1 + int(relu)
+        bn = mods[j] if j < len(mods) and isinstance(mods[j], nn.BatchNorm1d) else None
+        j += int(bn is not None)
+        w, bias = conv.weight.reshape(conv.out_channels, conv.in_channels), conv.bias
+        width = conv.out_channels
+        if width % 64 != 0:
+            assert j == len(mods) and bn is None
+            padn = _pad(width, pad_last_to) - width
+            w = torch.nn.functional.pad(w, (0, 0, 0, padn))
+            bias = torch.nn.functional.pad(bias, (0, padn)) if bias is not None else None
+        kind = ("relu_bn" if bn is not None else "relu") if relu else "linear"
+        assert not (bn is not None and not relu)
+        out.append((kind, w, bias, bn))
+        i = j
+    return out, width

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header; bumped on any signature change. */
-#define DCL_B200_ABI_VERSION 4
+#define DCL_B200_ABI_VERSION 5
 int dcl_b200_abi_version(void);
 /* Compiled-for architecture as an integer (100 for sm_100a). */
 int dcl_b200_arch(void);
@@ -305,6 +305,14 @@ typedef struct dcl_pm_gemm_problem {
      * logits of the FDA softmax keep split operands). */
     int a_fmt;
     int out_fmt;
+    /* Strided batch (the weight-gradient launches of the training path, dcl_tr_*): inst_count > 1 turns the problem
+     * into inst_count independent slices s = 0..inst_count-1 reading a0 + s*a_inst_stride and w + s*w_inst_stride
+     * (bytes) and writing out_cm + s*out_cm_inst_stride (bytes): split-K over instances, one fp32 partial per slice.
+     * Needs kb0 == kb_total and out_cm as the only output; equal inst_count for all problems of a launch. */
+    int inst_count;
+    long long a_inst_stride;
+    long long w_inst_stride;
+    long long out_cm_inst_stride;
 } dcl_pm_gemm_problem;
 #define DCL_PM_FMT_BF16X2 0
 #define DCL_PM_FMT_F16 1
@@ -505,6 +513,100 @@ int dcl_spb_avgpool(int b, int c, int ntowers, const dcl_spb_pool* pools, void* 
 /* replaces voxelize_fp_cuda (libs/pointgroup_ops/src/voxelize/voxelize.cu:10-31) for mode 4 (mean):
  * feats (n,c), rules (m,width) int32 rows [count, i_1 .. i_count, ...] -> out (m,c), summed in rule order. */
 int dcl_voxelize_mean(int m, int width, int c, const float* feats, const int* rules, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Group 5: training path of the pointwise MLP stacks (BASELINE.json configs[4])  */
+/* ------------------------------------------------------------------------- */
+/* Replaces, in train mode, the cuDNN/cuBLAS calls autograd makes for the Conv3d/Conv1d(k=1) + BatchNorm + ReLU
+ * layers of models/DCL_Net.py:56-151 and models/Modules.py:58-97,173-201 (forward and backward), stepped by
+ * tools/train_YCBV_stage1.py:168-191.  Every layer is three dcl_pm_gemm calls on bf16 hi/lo operand images
+ * (forward; dgrad dX = dZ W with the packed transpose of W as "weights"; wgrad dW = sum_b dZ_b^T X_b as a strided
+ * batch over the per-instance TRANSPOSED images, split-K over instances) plus the HBM-bound passes below.
+ * Layer kinds: conv(+bias); conv+bias -> ReLU; conv -> BN -> ReLU (disengage blocks); conv+bias -> ReLU -> BN
+ * (neck fusers).  U = what the GEMM epilogue writes (fp32 (b,c,n): conv output after bias / ReLU where they follow
+ * the conv directly); BN scale = gamma*rstd, shift = beta - mean*scale from the batch statistics. */
+#define DCL_TR_COPY         0   /* y = x */
+#define DCL_TR_AFFINE       1   /* y = x*scale + shift                      (forward: ReLU -> BN layers)   */
+#define DCL_TR_AFFINE_RELU  2   /* y = relu(x*scale + shift)                (forward: BN -> ReLU layers)   */
+#define DCL_TR_BWD_RELU     3   /* dZ = dY * [u > 0]                        (conv+bias -> ReLU)            */
+#define DCL_TR_BWD_BN_RELU  4   /* dZ = scale*(g - s1/cnt - xhat*s2/cnt), g = dY*[u*scale+shift > 0]       */
+#define DCL_TR_BWD_RELU_BN  5   /* dZ = [u > 0] * scale*(dY - s1/cnt - xhat*s2/cnt)                        */
+/* One pass over an activation (or gradient): the pointwise transform `mode`, then any of the operand images the
+ * GEMMs read.  x: fp32 with element strides (x_sb, x_sc, x_sn) over (instance, channel, point) — channel-major
+ * (b,c,n) tensors and their channel slices, or point-major (b*n, c) matrices (x_sc == 1); u: contiguous (b,c,n)
+ * (backward modes); xhat = (u - mean)*rstd, cnt = b*n.  c % 32 == 0, n % 128 == 0.  Outputs (NULL = skipped):
+ *   out_k       PM image of the (b*n x c) result (A operand of the forward / dgrad GEMM);
+ *   out_t       per instance the PM image of the (t_rows x n) matrix [channel][point], this tensor's channels at rows
+ *               [t_row0, t_row0+c) (t_rows % 128 == 0, t_row0 % 32 == 0; rows never written must be zeroed by the
+ *               caller once) — operands of the wgrad GEMM; instance stride t_rows*n*4 bytes;
+ *   out_cm      the result as fp32 (b,c,n);
+ *   col_partial (b*n/128, c) sums of the result over each 128-point tile (bias gradient; reduce with
+ *               dcl_pm_pool_reduce). */
+typedef struct dcl_tr_tile {
+    const float* x;
+    const float* u;
+    long long x_sb, x_sc, x_sn;
+    int b, c, n;
+    int mode;
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* rstd;
+    const float* s1;
+    const float* s2;
+    void* out_k;
+    void* out_t;
+    int t_row0, t_rows;
+    float* out_cm;
+    float* col_partial;
+} dcl_tr_tile;
+/* Up to 8 items per launch. */
+int dcl_tr_tile_pass(int nitems, const dcl_tr_tile* items, void* stream);
+/* Train-mode BatchNorm statistics (torch.nn.BatchNorm1d/3d forward in training): per channel of the contiguous
+ * (b,c,n) tensor u the batch mean and rstd = 1/sqrt(biased var + eps), scale / shift as above, and — when
+ * running_mean is given — the running statistics update with `momentum` (unbiased variance), in place. */
+typedef struct dcl_tr_bn {
+    const float* u;
+    int b, c, n;
+    const float* gamma;
+    const float* beta;
+    float eps, momentum;
+    float* running_mean;
+    float* running_var;
+    float* mean;
+    float* rstd;
+    float* scale;
+    float* shift;
+} dcl_tr_bn;
+int dcl_tr_bn_stats(int nitems, const dcl_tr_bn* items, void* stream);
+/* BatchNorm backward sums per channel: s1 = sum g (= d beta), s2 = sum g*xhat (= d gamma); g as in the modes
+ * DCL_TR_BWD_BN_RELU / DCL_TR_BWD_RELU_BN.  dy: fp32 (b,c,n) with instance / channel strides dy_sb / dy_sc. */
+typedef struct dcl_tr_bn_bwd {
+    const float* dy;
+    const float* u;
+    long long dy_sb, dy_sc;
+    int b, c, n;
+    int mode;
+    const float* mean;
+    const float* rstd;
+    const float* scale;
+    const float* shift;
+    float* s1;
+    float* s2;
+} dcl_tr_bn_bwd;
+int dcl_tr_bn_bwd_reduce(int nitems, const dcl_tr_bn_bwd* items, void* stream);
+/* fp32 weights -> packed bf16 hi/lo blobs of dcl_pm_gemm (n-tile nt): the (rows x cols) matrix src (row-major), or —
+ * transpose != 0 — the transpose of the (cols x rows) matrix src (the dgrad "weights" W^T), zero-padded to
+ * (rows_pad x k_pad); rows_pad % nt == 0, k_pad % 32 == 0. */
+typedef struct dcl_tr_wpack {
+    const float* src;
+    void* dst;
+    int rows, cols;
+    int rows_pad, k_pad;
+    int nt;
+    int transpose;
+} dcl_tr_wpack;
+int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Bring-up / test hook                                                       */

@@ -28,7 +28,9 @@ def test_struct_layouts_match_the_header(tmp_path):
     """The ctypes mirrors in _lib.py have the size and field offsets a C compiler gives the structs of the header."""
     import subprocess
     structs = {"dcl_pm_gemm_problem": _lib.PmGemmProblem, "dcl_pose_head_mlp": _lib.PoseHeadMlp,
-               "dcl_sp_level": _lib.SpLevel, "dcl_sp_tower": _lib.SpTower, "dcl_fda_job": _lib.FdaJob}
+               "dcl_sp_level": _lib.SpLevel, "dcl_sp_tower": _lib.SpTower, "dcl_fda_job": _lib.FdaJob,
+               "dcl_tr_tile": _lib.TrTile, "dcl_tr_bn": _lib.TrBn, "dcl_tr_bn_bwd": _lib.TrBnBwd,
+               "dcl_tr_wpack": _lib.TrWpack}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER_PATH}"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -48,7 +50,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 def test_version_and_arch():
     lib = _lib.load()
-    assert lib.dcl_b200_abi_version() == 4
+    assert lib.dcl_b200_abi_version() == 5
     assert lib.dcl_b200_arch() == 100
 
 
