@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps alternate over (each step is still one whole pass over its own "
                          "batch; with 2 the tail of one step's kernels overlaps the head of the next step's)")
+    ap.add_argument("--train-layers", action="store_true",
+                    help="--config train on the nn layer modules (cuDNN/cuBLAS) instead of the training kernels: A/B figure")
     ap.add_argument("--config", default="stage1", choices=["stage1", "stage2", "train"],
                     help="stage1 = BASELINE.json configs[2] (the headline); stage2 = configs[3]: stage 1 + 2 refiner "
                          "iterations over --batch-total instances sharded across the GPUs (strong scaling); "
@@ -593,7 +595,8 @@ def main():
     if args.config == "train":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import train_step_ddp
-        train_step_ddp.run(args.batch, args.steps, max(args.warmup, 3), rank, world, local_rank, contract=True)
+        train_step_ddp.run(args.batch, args.steps, max(args.warmup, 3), rank, world, local_rank, contract=True,
+                           layers=args.train_layers)
         return
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

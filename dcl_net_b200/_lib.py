@@ -73,6 +73,7 @@ SIGNATURES = {
     "dcl_tr_bn_stats": (_I, [_I, _P, _P]),
     "dcl_tr_bn_bwd_reduce": (_I, [_I, _P, _P]),
     "dcl_tr_pack_weights": (_I, [_I, _P, _P]),
+    "dcl_fda_bwd": (_I, [_I, _P, _I, _I, _I, _I, _I, _P]),
     "dcl_debug_spconv_set_trace": (_I, [_P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "dcl_debug_umma_pair_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
@@ -99,7 +100,8 @@ class TrTile(ctypes.Structure):
     """Mirror of dcl_tr_tile (include/dcl_b200.h)."""
     _fields_ = [("x", _P), ("u", _P), ("x_sb", _LL), ("x_sc", _LL), ("x_sn", _LL), ("b", _I), ("c", _I), ("n", _I),
                 ("mode", _I), ("scale", _P), ("shift", _P), ("mean", _P), ("rstd", _P), ("s1", _P), ("s2", _P),
-                ("out_k", _P), ("out_t", _P), ("t_row0", _I), ("t_rows", _I), ("out_cm", _P), ("col_partial", _P)]
+                ("out_k", _P), ("out_t", _P), ("t_row0", _I), ("t_rows", _I), ("out_cm", _P), ("col_partial", _P),
+                ("k_col0", _I), ("k_cols", _I), ("t_group", _I)]
 
 
 class TrBn(ctypes.Structure):
@@ -118,6 +120,11 @@ class TrWpack(ctypes.Structure):
     """Mirror of dcl_tr_wpack (include/dcl_b200.h)."""
     _fields_ = [("src", _P), ("dst", _P), ("rows", _I), ("cols", _I), ("rows_pad", _I), ("k_pad", _I), ("nt", _I),
                 ("transpose", _I)]
+
+
+class FdaBwdJob(ctypes.Structure):
+    """Mirror of dcl_fda_bwd_job (include/dcl_b200.h)."""
+    _fields_ = [(k, _P) for k in ("q_k", "k_k", "g_k", "v_k", "q_t", "k_t", "g_t", "lse", "dsum", "d_q", "d_k", "d_v")]
 
 
 class FdaJob(ctypes.Structure):

@@ -24,7 +24,7 @@ namespace {
 constexpr int TR_MAX_ITEMS = 8;
 constexpr int TR_TC = 32;          // channels per tile
 constexpr int TR_TP = 128;         // points per tile
-constexpr int TR_LD = TR_TP + 1;   // shared-memory row stride (floats): conflict-free for both image writers
+constexpr int TR_LD = TR_TP + 4;   // shared-memory row stride (floats): 16-byte aligned rows, conflict-free float4 accesses
 constexpr int TR_BLOB = 16384;     // PM blob: bf16 hi image (8 KB) + lo image (8 KB) of 128 rows x 32 channels
 
 struct TrTileBatch { dcl_tr_tile it[TR_MAX_ITEMS]; };
@@ -41,8 +41,42 @@ __device__ __forceinline__ uint4 pack8_hi_lo(const float* v, uint4& lo) {
 }
 
 // ------------------------------------------------------------------ tile transform + operand images
+// the pointwise transform of one element; `cg` = its channel
+struct TrChan { float sc, sh, mean, rstd, k1, k2; };
+__device__ __forceinline__ TrChan tr_chan(const dcl_tr_tile& it, int cg, float inv_cnt) {
+    TrChan p = {1.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+    if (it.mode != DCL_TR_COPY && it.mode != DCL_TR_BWD_RELU) {
+        p.sc = __ldg(it.scale + cg);
+        p.sh = __ldg(it.shift + cg);
+    }
+    if (it.mode >= DCL_TR_BWD_BN_RELU) {
+        p.mean = __ldg(it.mean + cg);
+        p.rstd = __ldg(it.rstd + cg);
+        p.k1 = __ldg(it.s1 + cg) * inv_cnt;
+        p.k2 = __ldg(it.s2 + cg) * inv_cnt;
+    }
+    return p;
+}
+__device__ __forceinline__ float tr_apply(int mode, float x, float u, const TrChan& p) {
+    switch (mode) {
+        case DCL_TR_COPY: return x;
+        case DCL_TR_AFFINE: return __fmaf_rn(x, p.sc, p.sh);
+        case DCL_TR_AFFINE_RELU: return fmaxf(__fmaf_rn(x, p.sc, p.sh), 0.f);
+        case DCL_TR_BWD_RELU: return u > 0.f ? x : 0.f;
+        case DCL_TR_BWD_BN_RELU: {
+            const float g = __fmaf_rn(u, p.sc, p.sh) > 0.f ? x : 0.f;
+            return p.sc * (g - p.k1 - (u - p.mean) * p.rstd * p.k2);
+        }
+        default:  // DCL_TR_BWD_RELU_BN
+            return u > 0.f ? p.sc * (x - p.k1 - (u - p.mean) * p.rstd * p.k2) : 0.f;
+    }
+}
+
+// VEC: 0 = scalar loads (any strides), 1 = channel-major source read as float4 along the points, 2 = point-major
+// source read as float4 along the channels (16-byte aligned rows; checked on the host).
+template <int VEC>
 __global__ void __launch_bounds__(256) tr_tile_kernel(const __grid_constant__ TrTileBatch batch) {
-    __shared__ float tile[TR_TC * TR_LD];
+    __shared__ __align__(16) float tile[TR_TC * TR_LD];
     const dcl_tr_tile& it = batch.it[blockIdx.z];
     const int tiles_per_inst = it.n / TR_TP;
     const int inst = blockIdx.x / tiles_per_inst, n0 = (blockIdx.x % tiles_per_inst) * TR_TP;
@@ -56,59 +90,74 @@ __global__ void __launch_bounds__(256) tr_tile_kernel(const __grid_constant__ Tr
     // x has element strides (x_sb, x_sc, x_sn); u (backward modes) is a contiguous (b, c, n) tensor
     const float* xb = it.x + (size_t)inst * it.x_sb + (size_t)c0 * it.x_sc + (size_t)n0 * it.x_sn;
     const float* ub = it.u != nullptr ? it.u + ((size_t)inst * it.c + c0) * it.n + n0 : nullptr;
+    const bool need_u = mode >= DCL_TR_BWD_RELU;
+    if (VEC == 1) {
+        float4 xv[4], uv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {            // thread -> (channel t/32 + 8j, points 4*(t%32) .. +3)
+            const int ch = (t >> 5) + 8 * j, pt = (t & 31) * 4;
+            xv[j] = dcl_ld_stream_f4(xb + (size_t)ch * it.x_sc + pt);
+            uv[j] = need_u ? dcl_ld_stream_f4(ub + (size_t)ch * it.n + pt) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = (t >> 5) + 8 * j, pt = (t & 31) * 4;
+            const TrChan p = tr_chan(it, c0 + ch, inv_cnt);
+            float4 y;
+            y.x = tr_apply(mode, xv[j].x, uv[j].x, p);
+            y.y = tr_apply(mode, xv[j].y, uv[j].y, p);
+            y.z = tr_apply(mode, xv[j].z, uv[j].z, p);
+            y.w = tr_apply(mode, xv[j].w, uv[j].w, p);
+            *reinterpret_cast<float4*>(tile + ch * TR_LD + pt) = y;
+        }
+    } else if (VEC == 2) {
+        float4 xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {            // thread -> (point t/8 + 32j, channels 4*(t%8) .. +3); forward modes only
+            const int pt = (t >> 3) + 32 * j, ch = (t & 7) * 4;
+            xv[j] = dcl_ld_stream_f4(xb + (size_t)pt * it.x_sn + ch);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pt = (t >> 3) + 32 * j, ch = (t & 7) * 4;
+            const float v[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                tile[(ch + e) * TR_LD + pt] = tr_apply(mode, v[e], 0.f, tr_chan(it, c0 + ch + e, inv_cnt));
+        }
+    } else {
 #pragma unroll 4
-    for (int j = 0; j < (TR_TC * TR_TP) / 256; ++j) {
-        int ch, pt;
-        if (it.x_sc == 1) {           // row-major source (points x channels): 32 consecutive channels per point
+        for (int j = 0; j < (TR_TC * TR_TP) / 256; ++j) {
+            int ch, pt;
             const int idx = t + 256 * j;
-            ch = idx & 31;
-            pt = idx >> 5;
-        } else {                      // channel-major source: 128 consecutive points per channel
-            const int idx = t + 256 * j;
-            ch = idx >> 7;
-            pt = idx & 127;
-        }
-        float x = __ldg(xb + (size_t)ch * it.x_sc + (size_t)pt * it.x_sn);
-        const int cg = c0 + ch;
-        float y;
-        if (mode == DCL_TR_COPY) {
-            y = x;
-        } else if (mode == DCL_TR_AFFINE || mode == DCL_TR_AFFINE_RELU) {
-            y = __fmaf_rn(x, __ldg(it.scale + cg), __ldg(it.shift + cg));
-            if (mode == DCL_TR_AFFINE_RELU) y = fmaxf(y, 0.f);
-        } else {
-            const float u = __ldg(ub + (size_t)ch * it.n + pt);
-            if (mode == DCL_TR_BWD_RELU) {
-                y = u > 0.f ? x : 0.f;
-            } else {
-                const float sc = __ldg(it.scale + cg), sh = __ldg(it.shift + cg);
-                const float xhat = (u - __ldg(it.mean + cg)) * __ldg(it.rstd + cg);
-                const float k1 = __ldg(it.s1 + cg) * inv_cnt, k2 = __ldg(it.s2 + cg) * inv_cnt;
-                if (mode == DCL_TR_BWD_BN_RELU) {
-                    const float g = __fmaf_rn(u, sc, sh) > 0.f ? x : 0.f;
-                    y = sc * (g - k1 - xhat * k2);
-                } else {  // DCL_TR_BWD_RELU_BN
-                    y = u > 0.f ? sc * (x - k1 - xhat * k2) : 0.f;
-                }
+            if (it.x_sc == 1) {       // point-major source: 32 consecutive channels per point
+                ch = idx & 31;
+                pt = idx >> 5;
+            } else {                  // channel-major source: 128 consecutive points per channel
+                ch = idx >> 7;
+                pt = idx & 127;
             }
+            const float x = __ldg(xb + (size_t)ch * it.x_sc + (size_t)pt * it.x_sn);
+            const float u = need_u ? __ldg(ub + (size_t)ch * it.n + pt) : 0.f;
+            tile[ch * TR_LD + pt] = tr_apply(mode, x, u, tr_chan(it, c0 + ch, inv_cnt));
         }
-        tile[ch * TR_LD + pt] = y;
     }
     __syncthreads();
 
     // ---- fp32 channel-major copy of the result
     if (it.out_cm != nullptr) {
         float* o = it.out_cm + ((size_t)inst * it.c + c0) * it.n + n0;
-#pragma unroll 4
-        for (int j = 0; j < (TR_TC * TR_TP) / 256; ++j) {
-            const int idx = t + 256 * j, ch = idx >> 7, pt = idx & 127;
-            o[(size_t)ch * it.n + pt] = tile[ch * TR_LD + pt];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = (t >> 5) + 8 * j, pt = (t & 31) * 4;
+            *reinterpret_cast<float4*>(o + (size_t)ch * it.n + pt) = *reinterpret_cast<const float4*>(tile + ch * TR_LD + pt);
         }
     }
     // ---- PM image of the (b*n x c) matrix: this tile is exactly one blob
     if (it.out_k != nullptr) {
+        const int kcols = it.k_cols > 0 ? it.k_cols : it.c;
         unsigned char* blob = reinterpret_cast<unsigned char*>(it.out_k) +
-                              ((size_t)((size_t)inst * it.n + n0) / 128 * (it.c / 32) + blockIdx.y) * TR_BLOB;
+                              ((size_t)((size_t)inst * it.n + n0) / 128 * (kcols / 32) + it.k_col0 / 32 + blockIdx.y) * TR_BLOB;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int uu = t + 256 * h;                     // unit = (row r, 8-channel chunk q); byte offset uu*16
@@ -125,17 +174,18 @@ __global__ void __launch_bounds__(256) tr_tile_kernel(const __grid_constant__ Tr
     // ---- transposed image of instance `inst`: PM image of the (t_rows x n) matrix [channel][point]
     if (it.out_t != nullptr) {
         const int row0 = it.t_row0 + c0;                    // first of this tile's 32 channel rows
-        const int kbs = it.n / 32;
-        unsigned char* img = reinterpret_cast<unsigned char*>(it.out_t) + (size_t)inst * it.t_rows * it.n * 4 +
-                             ((size_t)(row0 / 128) * kbs + n0 / 32) * TR_BLOB + ((row0 % 128) / 8) * 512;
+        const int grp = it.t_group > 1 ? it.t_group : 1;
+        const int kbs = grp * (it.n / 32);
+        unsigned char* img = reinterpret_cast<unsigned char*>(it.out_t) + (size_t)(inst / grp) * it.t_rows * kbs * 128 +
+                             ((size_t)(row0 / 128) * kbs + (inst % grp) * (it.n / 32) + n0 / 32) * TR_BLOB +
+                             ((row0 % 128) / 8) * 512;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int uu = t + 256 * h;                     // unit = (k-block kbl, row group rgl, 8-point chunk q8, row e)
             const int kbl = uu >> 7, rgl = (uu >> 5) & 3, q8 = (uu >> 3) & 3, e = uu & 7;
             const float* src = tile + (rgl * 8 + e) * TR_LD + kbl * 32 + q8 * 8;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = src[k];
+            const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             uint4 lo;
             const uint4 hi = pack8_hi_lo(v, lo);
             unsigned char* d = img + (size_t)kbl * TR_BLOB + rgl * 512 + q8 * 128 + e * 16;
@@ -228,15 +278,33 @@ __global__ void __launch_bounds__(256) tr_bn_bwd_reduce_kernel(const __grid_cons
     const float mean = it.mean[ch], rstd = it.rstd[ch], sc = it.scale[ch], sh = it.shift[ch];
     const bool masked = it.mode == DCL_TR_BWD_BN_RELU;
     double s1 = 0.0, s2 = 0.0;
+    const bool vec = it.n % 4 == 0 && it.dy_sb % 4 == 0 && it.dy_sc % 4 == 0 && ((((uintptr_t)it.dy) | ((uintptr_t)it.u)) & 15u) == 0;
     for (int inst = 0; inst < it.b; ++inst) {
         const float* urow = it.u + ((size_t)inst * it.c + ch) * it.n;
         const float* drow = it.dy + (size_t)inst * it.dy_sb + (size_t)ch * it.dy_sc;
-        for (int i = threadIdx.x; i < it.n; i += 256) {
-            const float u = __ldg(urow + i);
-            float g = __ldg(drow + i);
-            if (masked && !(__fmaf_rn(u, sc, sh) > 0.f)) g = 0.f;
-            s1 += (double)g;
-            s2 += (double)g * (double)((u - mean) * rstd);
+        if (vec) {
+            for (int i = threadIdx.x; i < it.n / 4; i += 256) {
+                const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow) + i);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(drow) + i);
+                const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                float a1 = 0.f, a2 = 0.f;      // four terms in fp32, then into the fp64 running sums
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float g = (masked && !(__fmaf_rn(uu[e], sc, sh) > 0.f)) ? 0.f : gg[e];
+                    a1 += g;
+                    a2 = __fmaf_rn(g, (uu[e] - mean) * rstd, a2);
+                }
+                s1 += (double)a1;
+                s2 += (double)a2;
+            }
+        } else {
+            for (int i = threadIdx.x; i < it.n; i += 256) {
+                const float u = __ldg(urow + i);
+                float g = __ldg(drow + i);
+                if (masked && !(__fmaf_rn(u, sc, sh) > 0.f)) g = 0.f;
+                s1 += (double)g;
+                s2 += (double)g * (double)((u - mean) * rstd);
+            }
         }
     }
     tr_block_reduce2(s1, s2, s_a, s_b);
@@ -292,12 +360,32 @@ DCL_API int dcl_tr_tile_pass(int nitems, const dcl_tr_tile* items, void* stream)
         DCL_RETURN_IF_BAD(it.out_t == nullptr || (it.t_rows % 128 == 0 && it.t_row0 >= 0 && it.t_row0 % TR_TC == 0 &&
                                                   it.t_row0 + it.c <= it.t_rows));
         DCL_RETURN_IF_BAD(((((uintptr_t)it.out_k) | ((uintptr_t)it.out_t)) & 15u) == 0);
+        DCL_RETURN_IF_BAD(it.out_cm == nullptr || (((uintptr_t)it.out_cm) & 15u) == 0);
+        DCL_RETURN_IF_BAD(it.t_group <= 1 || it.b % it.t_group == 0);
+        DCL_RETURN_IF_BAD(it.k_cols == 0 ? it.k_col0 == 0
+                                         : (it.k_cols % 32 == 0 && it.k_col0 >= 0 && it.k_col0 % 32 == 0 &&
+                                            it.k_col0 + it.c <= it.k_cols));
         batch.it[i] = it;
         const int tiles = it.b * (it.n / TR_TP);
         max_tiles = tiles > max_tiles ? tiles : max_tiles;
         max_cb = it.c / TR_TC > max_cb ? it.c / TR_TC : max_cb;
     }
-    tr_tile_kernel<<<dim3(max_tiles, max_cb, nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    // vector path of the loads: all items channel-major with 16-byte aligned rows (1), all point-major forward
+    // transforms with aligned rows (2), scalar otherwise
+    bool v1 = true, v2 = true;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_tile& it = items[i];
+        const bool al = (((uintptr_t)it.x) & 15u) == 0 && it.x_sb % 4 == 0;
+        v1 = v1 && al && it.x_sn == 1 && it.x_sc % 4 == 0 && (it.u == nullptr || (((uintptr_t)it.u) & 15u) == 0);
+        v2 = v2 && al && it.x_sc == 1 && it.x_sn % 4 == 0 && it.mode < DCL_TR_BWD_RELU;
+        v1 = v1 && (it.out_cm == nullptr || (((uintptr_t)it.out_cm) & 15u) == 0);
+        v2 = v2 && (it.out_cm == nullptr || (((uintptr_t)it.out_cm) & 15u) == 0);
+    }
+    const dim3 grid(max_tiles, max_cb, nitems);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v1) tr_tile_kernel<1><<<grid, 256, 0, st>>>(batch);
+    else if (v2) tr_tile_kernel<2><<<grid, 256, 0, st>>>(batch);
+    else tr_tile_kernel<0><<<grid, 256, 0, st>>>(batch);
     return dcl_launch_status();
 }
 

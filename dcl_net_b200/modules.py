@@ -31,34 +31,78 @@ def _fda_workspace(nbytes, device):
 
 
 class FdaAlignFunction(torch.autograd.Function):
-    """Autograd wrapper of the fused kernel (training path).  Forward = the fused tcgen05 kernel, saving only the
-    inputs and the per-query log-sum-exp; backward rebuilds A = exp(S - lse) with dcl_fda_attention_map (the
-    reference keeps A alive instead, models/Modules.py:167-169) and forms the five gradient products with library
-    GEMMs:  dA = RE_2^T gE + RI_2^T gI;  dS = A o (dA - sum_m A o dA);
+    """Autograd wrapper of the fused kernels (training path).  Forward = the fused tcgen05 kernel, saving the inputs,
+    the outputs and the per-query log-sum-exp; backward = dcl_fda_bwd (csrc/fda_bwd.cu), which rebuilds
+    A = exp(S - lse) tile by tile on chip (the reference keeps A (B,M,N) alive instead, models/Modules.py:167-169)
+    and forms the five gradient products on tensor cores:
+            dA = RE_2^T gE + RI_2^T gI;  dS = A o (dA - sum_m A o dA);
             dRE_2 = gE A^T;  dRI_2 = gI A^T + RI_1 dS^T;  dRI_1 = RI_2 dS."""
 
     @staticmethod
     def forward(ctx, RI_1, RI_2, RE_2):
         RE_embed, RI_embed, lse = _fda_align_kernel(RI_1, RI_2, RE_2, True)
-        ctx.save_for_backward(RI_1, RI_2, RE_2, lse)
+        ctx.save_for_backward(RI_1, RI_2, RE_2, lse, RE_embed, RI_embed)
         ctx.mark_non_differentiable(lse)
         return RE_embed, RI_embed, lse
 
     @staticmethod
     def backward(ctx, gE, gI, _g_lse):
-        RI_1, RI_2, RE_2, lse = ctx.saved_tensors
-        A = fda_attention_map(RI_1, RI_2, lse)                       # (B, M, N)
-        # The forward's lse comes out of the split-bf16 logits; the fp32 logits recomputed here differ from those by
-        # ~|S| 2^-17, a common factor per query column that the renormalisation removes exactly.
-        A = A / A.sum(dim=1, keepdim=True)
-        gE = torch.zeros_like(RE_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gE is None else gE
-        gI = torch.zeros_like(RI_2[:, :, :1]).expand(-1, -1, RI_1.shape[2]) if gI is None else gI
-        dA = torch.bmm(RE_2.transpose(1, 2), gE) + torch.bmm(RI_2.transpose(1, 2), gI)
-        dS = A * (dA - (A * dA).sum(dim=1, keepdim=True))
-        d_RE_2 = torch.bmm(gE, A.transpose(1, 2))
-        d_RI_2 = torch.bmm(gI, A.transpose(1, 2)) + torch.bmm(RI_1, dS.transpose(1, 2))
-        d_RI_1 = torch.bmm(RI_2, dS)
-        return d_RI_1, d_RI_2, d_RE_2
+        RI_1, RI_2, RE_2, lse, RE_embed, RI_embed = ctx.saved_tensors
+        gE = torch.zeros_like(RE_embed) if gE is None else gE.contiguous()
+        gI = torch.zeros_like(RI_embed) if gI is None else gI.contiguous()
+        if RI_2.shape[2] % 128 == 0 and USE_FUSED_FDA_BACKWARD:
+            return fda_backward(RI_1, RI_2, RE_2, lse, RE_embed, RI_embed, gE, gI)
+        L.warn_once("fda_bwd", "dcl_net_b200: FDA backward on library GEMMs (needs m % 128 == 0 for csrc/fda_bwd.cu)")
+        return _fda_backward_unfused(RI_1, RI_2, RE_2, lse, gE, gI)
+
+
+USE_FUSED_FDA_BACKWARD = True     # False: the unfused backward below (A/B runs, tests)
+
+
+def _fda_backward_unfused(RI_1, RI_2, RE_2, lse, gE, gI):
+    """The same gradients with A (B,M,N) materialised in fp32 and library GEMMs."""
+    A = fda_attention_map(RI_1, RI_2, lse)                       # (B, M, N)
+    # The forward's lse comes out of the split-bf16 logits; the fp32 logits recomputed here differ from those by
+    # ~|S| 2^-17, a common factor per query column that the renormalisation removes exactly.
+    A = A / A.sum(dim=1, keepdim=True)
+    dA = torch.bmm(RE_2.transpose(1, 2), gE) + torch.bmm(RI_2.transpose(1, 2), gI)
+    dS = A * (dA - (A * dA).sum(dim=1, keepdim=True))
+    d_RE_2 = torch.bmm(gE, A.transpose(1, 2))
+    d_RI_2 = torch.bmm(gI, A.transpose(1, 2)) + torch.bmm(RI_1, dS.transpose(1, 2))
+    d_RI_1 = torch.bmm(RI_2, dS)
+    return d_RI_1, d_RI_2, d_RE_2
+
+
+def fda_backward(RI_1, RI_2, RE_2, lse, RE_embed, RI_embed, gE, gI):
+    """(d RI_1, d RI_2, d RE_2) through dcl_fda_bwd.  Operand images are written by one dcl_tr_tile_pass launch."""
+    import ctypes
+    from .train_tail import TR_COPY, tile_pass
+    B, C, N = RI_1.shape
+    M, P = RI_2.shape[2], RE_2.shape[1]
+    VC = P + C
+    dev = RI_1.device
+    u8 = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    cpad, vpad = (C + 127) // 128 * 128, (VC + 127) // 128 * 128
+    q_k, k_k = u8(B * N * C * 4), u8(B * M * C * 4)
+    v_k, g_k = u8(B * M * VC * 4), u8(B * N * VC * 4)
+    q_t, k_t, g_t = u8(B * cpad * N * 4), u8(B * cpad * M * 4), u8(B * vpad * N * 4)
+    dsum = (gE * RE_embed).sum(dim=1) + (gI * RI_embed).sum(dim=1)          # D (B, N)
+    item = lambda x, n, **kw: dict({"x": x, "fmt": "cm", "b": B, "c": x.shape[1], "n": n, "mode": TR_COPY}, **kw)
+    tile_pass([item(RI_1, N, out_k=q_k, out_t=q_t, t_rows=cpad),
+               item(RI_2, M, out_k=k_k, out_t=k_t, t_rows=cpad),
+               item(RI_2, M, out_k=v_k, k_col0=P, k_cols=VC),
+               item(RE_2, M, out_k=v_k, k_col0=0, k_cols=VC),
+               item(gE, N, out_k=g_k, k_col0=0, k_cols=VC, out_t=g_t, t_row0=0, t_rows=vpad),
+               item(gI, N, out_k=g_k, k_col0=P, k_cols=VC, out_t=g_t, t_row0=P, t_rows=vpad)])
+    d_q = torch.empty(B, C, N, dtype=torch.float32, device=dev)
+    d_k = torch.empty(B, C, M, dtype=torch.float32, device=dev)
+    d_v = torch.empty(B, VC, M, dtype=torch.float32, device=dev)
+    job = (L.FdaBwdJob * 1)()
+    for name, t in (("q_k", q_k), ("k_k", k_k), ("g_k", g_k), ("v_k", v_k), ("q_t", q_t), ("k_t", k_t), ("g_t", g_t),
+                    ("lse", lse.contiguous()), ("dsum", dsum.contiguous()), ("d_q", d_q), ("d_k", d_k), ("d_v", d_v)):
+        setattr(job[0], name, L.ptr(t))
+    L.check(L.load().dcl_fda_bwd(1, ctypes.cast(job, ctypes.c_void_p), B, C, P, N, M, L.stream_ptr()), "fda_bwd")
+    return d_q, d_k + d_v[:, P:], d_v[:, :P]
 
 
 def fda_align(RI_1, RI_2, RE_2, return_lse=False):

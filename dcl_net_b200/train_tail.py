@@ -62,7 +62,8 @@ def tile_pass(items):
             assert x.shape == (b * n, c) and x.stride(1) == 1
             sb, sc, sn = n * x.stride(0), 1, x.stride(0)
         f = {"x": ctypes.c_void_p(x.data_ptr()), "x_sb": sb, "x_sc": sc, "x_sn": sn, "b": b, "c": c, "n": n,
-             "mode": it["mode"], "t_row0": it.get("t_row0", 0), "t_rows": it.get("t_rows", 0)}
+             "mode": it["mode"], "t_row0": it.get("t_row0", 0), "t_rows": it.get("t_rows", 0),
+             "k_col0": it.get("k_col0", 0), "k_cols": it.get("k_cols", 0), "t_group": it.get("t_group", 0)}
         for k in ("u", "scale", "shift", "mean", "rstd", "s1", "s2", "out_k", "out_t", "out_cm", "col_partial"):
             f[k] = it.get(k)
         out.append(f)
@@ -97,13 +98,14 @@ def _run_gemm_groups(problems, rows):
             run_gemm(plist[i:i + 8], rows)
 
 
-# Tests set this to a list to record the ReLU gates of a forward pass: entries (layer, stack, bool mask (b, c, n)).
+# Tests set this to a list to record the ReLU gates of a forward pass: entries (layer, stack, bool mask (b, c, n),
+# the nn.ReLU module of the layer or None).
 GATE_LOG = None
 
 
 class StackSpec:
     """One stack: inputs = [(tensor, 'cm' | 'rm')] (one tensor, or two concatenated along channels), layers =
-    [(kind, weight (cout, cin), bias | None, bn module | None)]."""
+    [(kind, weight (cout, cin), bias | None, bn module | None[, the layer's nn.ReLU module — only for GATE_LOG])]."""
 
     def __init__(self, inputs, layers):
         self.inputs, self.layers = inputs, layers
@@ -183,7 +185,7 @@ class _MlpStacksFn(torch.autograd.Function):
                 ys = {s: t["out_cm"] for s, t in tiles if "out_cm" in t}
                 for s, la in enumerate(lays):
                     if la.kind != "linear":
-                        GATE_LOG.append((l, s, (ys[s] if la.kind == "bn_relu" else us[s]) > 0))
+                        GATE_LOG.append((l, s, (ys[s] if la.kind == "bn_relu" else us[s]) > 0, la.relu_mod))
             if last:
                 outs = list(us)
                 for s, t in tiles:
@@ -223,6 +225,9 @@ class _MlpStacksFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         nl, ns = plan.nlayers, len(plan.stacks)
         lib = L.load()
+        # wgrad split-K: one slice per group of `grp` instances (K = grp*n points): partial sums to write and reduce
+        # shrink by grp while the launch still has several waves of tiles
+        grp = next(g for g in (4, 2, 1) if b % g == 0)
         out_grads = [None] * len(tensors)
 
         def acc(idx, g):
@@ -256,7 +261,7 @@ class _MlpStacksFn(torch.autograd.Function):
                 alloc = torch.empty if cp_rows == la.cout else torch.zeros
                 dzt = alloc(b * cp_rows * n * 4, dtype=torch.uint8, device=dev)
                 it = {"x": dys[s], "fmt": "cm", "b": b, "c": la.cout, "n": n, "mode": _BWD_MODE[la.kind],
-                      "out_t": dzt, "t_rows": cp_rows}
+                      "out_t": dzt, "t_rows": cp_rows, "t_group": grp}
                 if la.kind != "linear":
                     it["u"] = us[s]
                 if bns[s] is not None:
@@ -287,12 +292,12 @@ class _MlpStacksFn(torch.autograd.Function):
                     row0 = 0
                     for ti, fmt, c in st.inputs:
                         items.append({"x": tensors[ti], "fmt": fmt, "b": b, "c": c, "n": n, "mode": TR_COPY,
-                                      "out_t": xt, "t_row0": row0, "t_rows": cin_pad})
+                                      "out_t": xt, "t_row0": row0, "t_rows": cin_pad, "t_group": grp})
                         row0 += c
                 else:
                     pl = st.layers[l - 1]
                     it = {"x": saved_u[l - 1][s], "fmt": "cm", "b": b, "c": pl.cout, "n": n,
-                          "mode": _FWD_MODE[pl.kind], "out_t": xt, "t_rows": cin_pad}
+                          "mode": _FWD_MODE[pl.kind], "out_t": xt, "t_rows": cin_pad, "t_group": grp}
                     pbn = saved_bn[l - 1][s]
                     if pbn is not None:
                         it.update(scale=pbn[2], shift=pbn[3])
@@ -300,25 +305,33 @@ class _MlpStacksFn(torch.autograd.Function):
             tile_pass(items)
             # ---- wgrad: per (stack, instance) slice  dW_b^T (cin_pad x cout_pad) = X_b^T-image x dZ_b^T-image, then the
             # fixed-order sum over instances
-            probs, parts = [], []
+            # stacks of equal (cin_pad, cout_pad) share one partial buffer and one reduction launch
+            shape_groups = {}
             for s, la in enumerate(lays):
-                (dzt, cp_rows), (xt, cin_pad) = dz_t[s], x_t[s]
-                part = torch.empty(b, cin_pad, cp_rows, **f32)
-                parts.append(part)
-                lay = _gemm_layer(xt, cin_pad, n, 128)           # the X^T image read as packed weights (n-tile 128)
-                probs.append({"a0": dzt, "layer": lay, "out_cm": part, "rows_per_inst": cp_rows,
-                              "inst": (b, cp_rows * n * 4, cin_pad * n * 4, cin_pad * cp_rows * 4), "_rows": cp_rows})
+                shape_groups.setdefault((x_t[s][1], dz_t[s][1]), []).append(s)
+            probs, parts = [], {}
+            for (cin_pad, cp_rows), members in shape_groups.items():
+                part = torch.empty(len(members), b // grp, cin_pad, cp_rows, **f32)
+                for k, s in enumerate(members):
+                    parts[s] = (part, k)
+                    lay = _gemm_layer(x_t[s][0], cin_pad, grp * n, 128)   # the X^T image read as packed weights (n-tile 128)
+                    probs.append({"a0": dz_t[s][0], "layer": lay, "out_cm": part[k], "rows_per_inst": cp_rows,
+                                  "inst": (b // grp, cp_rows * grp * n * 4, cin_pad * grp * n * 4, cin_pad * cp_rows * 4),
+                                  "_rows": cp_rows})
             by_rows = {}
             for p in probs:
                 by_rows.setdefault(p["_rows"], []).append(p)
             for r, plist in by_rows.items():
                 _run_gemm_groups(plist, r)
+            for (cin_pad, cp_rows), members in shape_groups.items():
+                part = parts[members[0]][0]
+                dwt = torch.empty(len(members), cin_pad, cp_rows, **f32)
+                L.check(lib.dcl_pm_pool_reduce(len(members), cin_pad * cp_rows, b // grp, L.ptr(part), None, L.ptr(dwt), 0,
+                                               L.stream_ptr()), "wgrad reduce")
+                for k, s in enumerate(members):
+                    la = lays[s]
+                    acc(la.w, dwt[k, :la.cin, :la.cout].t().reshape(tensors[la.w].shape))
             for s, la in enumerate(lays):
-                (_, cp_rows), (_, cin_pad) = dz_t[s], x_t[s]
-                dwt = torch.empty(cin_pad, cp_rows, **f32)
-                L.check(lib.dcl_pm_pool_reduce(1, cin_pad * cp_rows, b, L.ptr(parts[s]), None, L.ptr(dwt), 0, L.stream_ptr()),
-                        "wgrad reduce")
-                acc(la.w, dwt[:la.cin, :la.cout].t().reshape(tensors[la.w].shape))
                 if la.bias is not None:
                     db = torch.empty(la.cout, **f32)
                     L.check(lib.dcl_pm_pool_reduce(1, la.cout, rows // 128, L.ptr(colp[s]), None, L.ptr(db), 0,
@@ -377,7 +390,7 @@ def mlp_stacks(stacks, b, n):
             ins.append((reg(t), fmt, c))
         cin = sum(c for _, _, c in ins)
         lays = []
-        for kind, w, bias, bn in st.layers:
+        for kind, w, bias, bn, *rest in st.layers:
             cout = w.shape[0]
             w2 = w.reshape(cout, -1)
             assert w2.shape[1] == cin and cout % 64 == 0 and cin % 32 == 0, (cout, cin, w.shape)
@@ -385,7 +398,8 @@ def mlp_stacks(stacks, b, n):
             if bn is not None:
                 assert bn.affine and bn.momentum is not None
             lays.append(SimpleNamespace(kind=kind, cout=cout, cin=cin, w=reg(w2.contiguous() if not w2.is_contiguous() else w2),
-                                        bias=reg(bias), bn=bn, gamma=reg(bn.weight) if bn is not None else None,
+                                        bias=reg(bias), bn=bn, relu_mod=rest[0] if rest else None,
+                                        gamma=reg(bn.weight) if bn is not None else None,
                                         beta=reg(bn.bias) if bn is not None else None))
             cin = cout
         plan.stacks.append(SimpleNamespace(inputs=ins, layers=lays))
@@ -402,7 +416,7 @@ def disengage_layers(stack):
         conv, bn = mods[0], mods[1]
         assert isinstance(conv, nn.Conv3d) and conv.bias is None and isinstance(bn, nn.BatchNorm3d) and \
             isinstance(mods[2], nn.ReLU) and len(mods) == 3
-        out.append(("bn_relu", conv.weight, None, bn))
+        out.append(("bn_relu", conv.weight, None, bn, mods[2]))
     return out
 
 
@@ -427,6 +441,6 @@ def head_layers(head, pad_last_to=64):
             bias = torch.nn.functional.pad(bias, (0, padn)) if bias is not None else None
         kind = ("relu_bn" if bn is not None else "relu") if relu else "linear"
         assert not (bn is not None and not relu)
-        out.append((kind, w, bias, bn))
+        out.append((kind, w, bias, bn, mods[i + 1] if relu else None))
         i = j
     return out, width

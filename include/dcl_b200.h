@@ -535,7 +535,8 @@ int dcl_voxelize_mean(int m, int width, int c, const float* feats, const int* ru
  * GEMMs read.  x: fp32 with element strides (x_sb, x_sc, x_sn) over (instance, channel, point) — channel-major
  * (b,c,n) tensors and their channel slices, or point-major (b*n, c) matrices (x_sc == 1); u: contiguous (b,c,n)
  * (backward modes); xhat = (u - mean)*rstd, cnt = b*n.  c % 32 == 0, n % 128 == 0.  Outputs (NULL = skipped):
- *   out_k       PM image of the (b*n x c) result (A operand of the forward / dgrad GEMM);
+ *   out_k       PM image of the (b*n x c) result (A operand of the forward / dgrad GEMM); with k_cols > 0 the result
+ *               becomes columns [k_col0, k_col0+c) of a (b*n x k_cols) image (k_col0 % 32 == 0): concatenations;
  *   out_t       per instance the PM image of the (t_rows x n) matrix [channel][point], this tensor's channels at rows
  *               [t_row0, t_row0+c) (t_rows % 128 == 0, t_row0 % 32 == 0; rows never written must be zeroed by the
  *               caller once) — operands of the wgrad GEMM; instance stride t_rows*n*4 bytes;
@@ -559,6 +560,9 @@ typedef struct dcl_tr_tile {
     int t_row0, t_rows;
     float* out_cm;
     float* col_partial;
+    int k_col0, k_cols;
+    int t_group;   /* > 1: out_t holds one image per GROUP of t_group consecutive instances, (t_rows x t_group*n), the
+                    * instances side by side along the points (fewer, longer split-K slices for the wgrad GEMM) */
 } dcl_tr_tile;
 /* Up to 8 items per launch. */
 int dcl_tr_tile_pass(int nitems, const dcl_tr_tile* items, void* stream);
@@ -607,6 +611,33 @@ typedef struct dcl_tr_wpack {
     int transpose;
 } dcl_tr_wpack;
 int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* stream);
+
+/* Fused backward of the FDA (models/Modules.py:166-169 under autograd; forward = dcl_fda_align_fwd): with
+ * S = RI_2^T RI_1, A = softmax_m S, RE_embed = RE_2 A, RI_embed = RI_2 A and the output gradients gE (b,p,n), gI (b,c,n):
+ *   d_q (b,c,n)      = d RI_1                 = RI_2 dS,          dS = A o (dA - D),  dA = [RE_2; RI_2]^T [gE; gI]
+ *   d_k (b,c,m)      = d RI_2 (key role)      = RI_1 dS^T
+ *   d_v (b,p+c,m)    = [d RE_2; d RI_2 (value role)] = [gE; gI] A^T
+ * with A rebuilt on chip from the forward's lse (b,n) and D = dsum (b,n) = sum_p gE o RE_embed + sum_c gI o RI_embed;
+ * no (m x n) matrix is written to memory.  Operands are bf16 hi/lo PM images written by dcl_tr_tile_pass:
+ * "_k" = PM image of the (b*points x channels) matrix, "_t" = per-instance PM images of the (channels x points)
+ * matrix with the channel rows padded to a multiple of 128 (zero rows):
+ *   q_k, q_t: RI_1 (c wide);  k_k, k_t: RI_2;  v_k: [RE_2 | RI_2] (p+c wide);  g_k, g_t: [gE | gI] (p+c wide).
+ * c in {64,128}, p = 256, n % 128 == 0, m % 128 == 0.  Up to two jobs of equal shape per call (the two directions). */
+typedef struct dcl_fda_bwd_job {
+    const void* q_k;
+    const void* k_k;
+    const void* g_k;
+    const void* v_k;
+    const void* q_t;
+    const void* k_t;
+    const void* g_t;
+    const float* lse;
+    const float* dsum;
+    float* d_q;
+    float* d_k;
+    float* d_v;
+} dcl_fda_bwd_job;
+int dcl_fda_bwd(int njobs, const dcl_fda_bwd_job* jobs, int b, int c, int p, int n, int m, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Bring-up / test hook                                                       */

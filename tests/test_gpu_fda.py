@@ -235,3 +235,53 @@ def test_fda_pv16_needs_cta_pairs(cuda_dev):
     x = torch.zeros(1, 64, 128, device=cuda_dev)
     with pytest.raises(RuntimeError):
         fda_align_formats(x, x, torch.zeros(1, 256, 128, device=cuda_dev), pv_fmt=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,c,n,m,kind", [(2, 64, 128, 128, "relu"), (3, 64, 256, 384, "relu"), (2, 128, 384, 128, "relu"),
+                                          (2, 128, 256, 256, "sharp"), (1, 64, 1024, 1024, "relu")])
+def test_fda_backward_fused_vs_fp64(cuda_dev, b, c, n, m, kind):
+    """dcl_fda_bwd (csrc/fda_bwd.cu: A rebuilt on chip from lse, the five gradient products on tcgen05) against
+    autograd through the reference's graph (models/Modules.py:166-169: bmm -> softmax -> bmm) evaluated in fp64.
+    Bar: 5e-5 of each gradient's max, the figure the unfused backward was held to."""
+    g = torch.Generator().manual_seed(100 + n + m)
+    scale = 1.0 if kind == "relu" else 3.0        # "sharp": logits up to ~100, near one-hot attention rows
+    ri1 = (torch.randn(b, c, n, generator=g).relu() * scale).to(cuda_dev).requires_grad_(True)
+    ri2 = (torch.randn(b, c, m, generator=g).relu() * scale).to(cuda_dev).requires_grad_(True)
+    re2 = torch.randn(b, 256, m, generator=g).to(cuda_dev).requires_grad_(True)
+    ge, gi = torch.randn(b, 256, n, generator=g).to(cuda_dev), torch.randn(b, c, n, generator=g).to(cuda_dev)
+    e, i = fda_align(ri1, ri2, re2)
+    ((e * ge).sum() + (i * gi).sum()).backward()
+    got = [t.grad.clone() for t in (ri1, ri2, re2)]
+    x64 = [t.detach().double().requires_grad_(True) for t in (ri1, ri2, re2)]
+    a = torch.softmax(torch.bmm(x64[1].transpose(1, 2), x64[0]), dim=1)
+    ((torch.bmm(x64[2], a) * ge.double()).sum() + (torch.bmm(x64[1], a) * gi.double()).sum()).backward()
+    # "sharp": the logits are recomputed by the same split product as in the forward (|S| 2^-17 ~ 8e-4 absolute at
+    # |S| ~ 100), which moves individual attention weights by that relative amount: the forward's 5e-4 bar applies
+    tol = 5e-5 if kind == "relu" else 5e-4
+    for name, gg, t in zip(("d RI_1", "d RI_2", "d RE_2"), got, x64):
+        assert rel_err(gg, t.grad) < tol, f"{name}: {rel_err(gg, t.grad):.2e}"
+
+
+@pytest.mark.gpu
+def test_fda_backward_fused_matches_unfused(cuda_dev):
+    """Same gradients from the fused kernel and from the materialised-A backward, one output gradient absent."""
+    from dcl_net_b200 import modules
+    g = torch.Generator().manual_seed(7)
+    ri1 = torch.randn(2, 64, 256, generator=g).relu().to(cuda_dev).requires_grad_(True)
+    ri2 = torch.randn(2, 64, 256, generator=g).relu().to(cuda_dev).requires_grad_(True)
+    re2 = torch.randn(2, 256, 256, generator=g).to(cuda_dev).requires_grad_(True)
+    ge = torch.randn(2, 256, 256, generator=g).to(cuda_dev)
+    res = []
+    for fused in (True, False):
+        modules.USE_FUSED_FDA_BACKWARD = fused
+        try:
+            e, _ = fda_align(ri1, ri2, re2)
+            (e * ge).sum().backward()
+        finally:
+            modules.USE_FUSED_FDA_BACKWARD = True
+        res.append([t.grad.clone() for t in (ri1, ri2, re2)])
+        for t in (ri1, ri2, re2):
+            t.grad = None
+    for a, b_ in zip(*res):
+        assert rel_err(a, b_) < 5e-5

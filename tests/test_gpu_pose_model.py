@@ -296,19 +296,41 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         return l_pose + 5 * l_xo.mean() + l_yc.mean() + l_conf
 
     # Four runs of the same step: this implementation, the fp32 reference graph, the reference graph in fp64, and the
-    # fp64 graph with its aligned features (Aligner outputs) perturbed by 1e-5 (relative to their max; 100x below the 1e-3 forward bar).
-    # The step is badly conditioned — train-mode BatchNorm and ReLU gates near zero make some weight gradients jump
-    # by percents under a 1e-6 perturbation (tools/diag_train_grad.py) — so gradient parity is defined against the
-    # fp64 result with that perturbation response as the floor: this implementation must be as close to fp64 as the
-    # fp32 reference graph is, or within 3x of what a 1e-5 forward perturbation does.  The FDA gradients on their
-    # own are checked at 5e-5 in test_fda_align_function_gradcheck_like below.
+    # fp64 graph with its aligned features (Aligner outputs) perturbed by 1e-5 (relative to their max; 100x below the
+    # 1e-3 forward bar).  The reference graphs take the ReLU gates this implementation took (forward hooks on their
+    # nn.ReLU modules; train_tail.GATE_LOG): a pre-activation within rounding of zero otherwise opens in one graph and
+    # closes in the other, and train-mode BatchNorm spreads that one flipped element over the whole batch — measured
+    # ~1e-2 on whole weight gradients, which says nothing about the arithmetic.  With matched gates the step is still
+    # well enough conditioned for a fixed bar against fp64 (see check below); the fp32 reference graph's own distance
+    # to fp64 and the response to a 1e-5 perturbation of the aligned features are printed beside it for scale.
     import copy
+    from dcl_net_b200 import train_tail
     oracle64 = copy.deepcopy(oracle_net).double()
     a = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
     bb = f_xc.clone().requires_grad_(True), f_yo.clone().requires_grad_(True)
     cc = f_xc.double().requires_grad_(True), f_yo.double().requires_grad_(True)
     dd = f_xc.double().requires_grad_(True), f_yo.double().requires_grad_(True)
-    loss_mine = loss_fn(net.forward_from_point_feats(a[0], a[1], b))
+    train_tail.GATE_LOG = log = []
+    try:
+        loss_mine = loss_fn(net.forward_from_point_feats(a[0], a[1], b))
+    finally:
+        train_tail.GATE_LOG = None
+    name_of = {m: name for name, m in net.named_modules()}
+    gates = {name_of[mod]: mask for _, _, mask, mod in log}
+    assert len(gates) == 8 * 2 + 4 * 2 + 2 * 3, len(gates)
+
+    def force_gates(model):
+        def hook(name):
+            def fn(_mod, inp, _out):
+                g_ = gates[name]
+                return inp[0] * g_.view(g_.shape + (1,) * (inp[0].dim() - 3)).to(inp[0].dtype)
+            return fn
+        for name, mod in model.named_modules():
+            if name in gates:
+                mod.register_forward_hook(hook(name))
+
+    force_gates(oracle_net)
+    force_gates(oracle64)
     loss_ref = loss_fn(oracle_net(bb[0], bb[1], b, n, n))
     pts_tmp, rot_gt, trans_gt = pts_tmp.double(), rot_gt.double(), trans_gt.double()
     loss_64 = loss_fn(oracle64(cc[0], cc[1], b, n, n))
@@ -332,6 +354,7 @@ def test_training_step_gradients_match_oracle(cuda_dev):
     finally:
         T.aligner = exact_aligner
     gpert = {name: p.grad for name, p in oracle64.named_parameters() if p.grad is not None}
+    report = []
 
     def check(mine, ref32, ref64, pert64, what):
         scale = ref64.abs().max().item()
@@ -340,7 +363,10 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         e_mine = (mine.double() - ref64).abs().max().item() / scale
         e_ref = (ref32.double() - ref64).abs().max().item() / scale
         e_floor = (pert64 - ref64).abs().max().item() / scale
-        assert e_mine <= max(4.0 * e_ref, 3.0 * e_floor, 1e-4), \
+        report.append((e_mine, e_ref, e_floor, what))
+        # fixed bar: 2e-4 of the gradient's max (measured worst 8.7e-5: split-bf16 products, ~2^-17 each, through
+        # ~10 layers and two BatchNorm-coupled stacks); the fp32 graph and the perturbation response are reported only
+        assert e_mine <= 2e-4, \
             f"{what}: {e_mine:.3e} vs fp32 reference graph {e_ref:.3e}, 1e-5 perturbation response {e_floor:.3e}"
 
     for mine, r32, r64, rp in zip(a, bb, cc, dd):
@@ -353,6 +379,7 @@ def test_training_step_gradients_match_oracle(cuda_dev):
         assert p32[name].grad is not None, name
         check(p.grad, p32[name].grad, g64[name], gpert[name], name)
         checked += 1
+    print("worst (e_mine, e_ref32, e_floor):", sorted(report, reverse=True)[:6])
     assert checked > 40
 
 

@@ -108,7 +108,7 @@ def test_mlp_stacks_vs_fp64(cuda_dev, case):
             st.append(StackSpec([(t, "cm") for t in x], lays))
         outs = [o[:, :w] for o, w in zip(mlp_stacks(st, b, n), widths)]
     train_tail.GATE_LOG = None
-    gates = [[m for l, s, m in sorted(log, key=lambda e: e[0]) if s == si] for si in range(len(mods))]
+    gates = [[m for l, s, m, _ in sorted(log, key=lambda e: e[0]) if s == si] for si in range(len(mods))]
     gouts = [torch.randn(o.shape, generator=g).to(dev) for o in outs]
     loss = sum((o * go).sum() for o, go in zip(outs, gouts))
     loss.backward()

@@ -50,7 +50,7 @@ class FromPointFeats(torch.nn.Module):
         return self.inner.forward_from_point_feats(f_xc, f_yo, nb)
 
 
-def run(batch, steps, warmup, rank, world, local, contract=False):
+def run(batch, steps, warmup, rank, world, local, contract=False, layers=False):
     """One process per GPU.  Times `steps` training steps (max over ranks), then — multi-GPU — the same steps with
     the gradient all-reduce switched off (DDP.no_sync) and the all-reduce of a gradient-sized buffer on its own:
     exposed all-reduce time = synced step - unsynced step; overlap = 1 - exposed / standalone."""
@@ -63,6 +63,7 @@ def run(batch, steps, warmup, rank, world, local, contract=False):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     net = Network(Cfg, mode="train").to(dev).train()
+    net.use_train_kernels = not layers      # layers=True: the nn layer modules on library GEMMs (A/B figure)
     wrapped = FromPointFeats(net)
     model = torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local]) if world > 1 else wrapped
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
@@ -102,9 +103,13 @@ def run(batch, steps, warmup, rank, world, local, contract=False):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), loss
 
+    from dcl_net_b200 import _lib
     for _ in range(warmup):
         step()
+    torch.cuda.synchronize()
+    launches0 = _lib.load().dcl_b200_launch_count()
     ms, loss = timed(steps)
+    launches = (_lib.load().dcl_b200_launch_count() - launches0) // steps
     nparam = sum(p.numel() for p in net.parameters())
     extra = {}
     if world > 1:
@@ -131,14 +136,19 @@ def run(batch, steps, warmup, rank, world, local, contract=False):
         if contract:
             line = {"metric": "training instances/s (N=M=1024)", "value": value, "unit": "instances/s", "n_gpus": world,
                     "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": "fp32 (FDA forward: bf16 hi/lo split tensor-core kernel)",
+                    "vs_baseline": None,
+                    "dtype": ("fp32 layer modules on cuDNN/cuBLAS (FDA: fused kernels)" if layers else
+                              "bf16 hi/lo split operands (3 MMAs per product), fp32 accumulate: every pointwise-MLP GEMM "
+                              "(forward, dgrad, wgrad) and the FDA forward / backward on tcgen05"),
                     "data": "synthetic",
                     "config": {"workload": "config_LM-shaped training step through the FDA section: fwd + bwd + Adam, "
                                            "train-mode BatchNorm, losses of models/DCL_Net.py:265-303; entry = point "
-                                           "features (b*n, 480) per tower", "B_per_gpu": b, "N": n, "M": n, "C": 64,
+                                           "features (b*n, 480) per tower",
+                               "path": "nn layer modules (A/B)" if layers else "train_tail.mlp_stacks + dcl_fda_bwd",
+                               "B_per_gpu": b, "N": n, "M": n, "C": 64,
                                "parallelism": f"DDP x{world} (NCCL all-reduce of {nparam} fp32 gradients, bucketed, "
                                               "overlapped with backward)"},
-                    "impl": "b200", "loss": float(loss.item()), "params": nparam}
+                    "impl": "b200", "loss": float(loss.item()), "params": nparam, "gpu_launches": int(launches)}
             line.update(extra)
         else:
             line = dict({"what": "training step (fwd+bwd+Adam) through the FDA section, train mode", "n_gpus": world,
@@ -154,9 +164,10 @@ def main():
     ap.add_argument("--batch", type=int, default=40)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--layers", action="store_true", help="nn layer modules on library GEMMs instead of the training kernels")
     args = ap.parse_args()
     run(args.batch, args.steps, args.warmup, int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
-        int(os.environ.get("LOCAL_RANK", 0)))
+        int(os.environ.get("LOCAL_RANK", 0)), layers=args.layers)
 
 
 if __name__ == "__main__":
