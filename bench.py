@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the timed steps alternate over (each step is still one whole pass over its own "
                          "batch; with 2 the tail of one step's kernels overlaps the head of the next step's)")
+    ap.add_argument("--train-entry", default="backbone", choices=["backbone", "feats"],
+                    help="--config train: enter at the towers' pyramid levels (interpolation forward + backward included) "
+                         "or at the (b*n, 480) point features")
     ap.add_argument("--train-layers", action="store_true",
                     help="--config train on the nn layer modules (cuDNN/cuBLAS) instead of the training kernels: A/B figure")
     ap.add_argument("--config", default="stage1", choices=["stage1", "stage2", "train"],
@@ -596,7 +599,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import train_step_ddp
         train_step_ddp.run(args.batch, args.steps, max(args.warmup, 3), rank, world, local_rank, contract=True,
-                           layers=args.train_layers)
+                           layers=args.train_layers, entry=args.train_entry)
         return
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

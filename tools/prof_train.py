@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=40)
     ap.add_argument("--rows", type=int, default=45)
     ap.add_argument("--layers", action="store_true", help="PyTorch layer modules instead of the training kernels")
+    ap.add_argument("--entry", default="feats", choices=["feats", "backbone"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -36,9 +37,25 @@ def main():
     rot_gt = q * torch.det(q).sign().view(b, 1, 1)
     trans_gt = (torch.rand(b, 3, device=dev, generator=g) - 0.5) * 0.1
 
+    if args.entry == "backbone":
+        from dcl_net_b200.synthetic import backbone_levels, levels_to, object_clouds
+        p_inp, p_tmp = object_clouds(2000, b, n, partial=True), object_clouds(3000, b, n)
+        lv_inp = levels_to(backbone_levels(4000, p_inp, b), dev)
+        lv_tmp = levels_to(backbone_levels(5000, p_tmp, b), dev)
+        for lv in lv_inp + lv_tmp:
+            lv.features.requires_grad_(True)
+        p_inp, p_tmp = p_inp.to(dev), p_tmp.to(dev)
+        pts_inp, pts_tmp = p_inp.view(b, n, 3), p_tmp.view(b, n, 3)
+
     def step():
         opt.zero_grad(set_to_none=True)
-        loss = losses(net.forward_from_point_feats(f_xc, f_yo, b), pts_tmp, pts_inp, rot_gt, trans_gt)
+        if args.entry == "backbone":
+            for lv in lv_inp + lv_tmp:
+                lv.features.grad = None
+            out = net.forward_from_backbone(lv_inp, lv_tmp, p_inp, p_tmp, b)
+        else:
+            out = net.forward_from_point_feats(f_xc, f_yo, b)
+        loss = losses(out, pts_tmp, pts_inp, rot_gt, trans_gt)
         loss.backward()
         opt.step()
 

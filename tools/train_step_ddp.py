@@ -50,7 +50,19 @@ class FromPointFeats(torch.nn.Module):
         return self.inner.forward_from_point_feats(f_xc, f_yo, nb)
 
 
-def run(batch, steps, warmup, rank, world, local, contract=False, layers=False):
+class FromBackbone(torch.nn.Module):
+    """Entry at the towers' pyramid levels: pointnet_sp three_nn + three_interpolate (with their backward kernels:
+    the level features carry gradients, as they do when the towers train) -> FDA section."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, levels_inp, levels_tmp, points_inp, points_tmp, nb):
+        return self.inner.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, nb)
+
+
+def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, entry="backbone"):
     """One process per GPU.  Times `steps` training steps (max over ranks), then — multi-GPU — the same steps with
     the gradient all-reduce switched off (DDP.no_sync) and the all-reduce of a gradient-sized buffer on its own:
     exposed all-reduce time = synced step - unsynced step; overlap = 1 - exposed / standalone."""
@@ -64,24 +76,39 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False):
     torch.manual_seed(0)
     net = Network(Cfg, mode="train").to(dev).train()
     net.use_train_kernels = not layers      # layers=True: the nn layer modules on library GEMMs (A/B figure)
-    wrapped = FromPointFeats(net)
+    wrapped = FromBackbone(net) if entry == "backbone" else FromPointFeats(net)
     model = torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local]) if world > 1 else wrapped
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
     b, n = batch, 1024
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    f_xc = torch.randn(b * n, 480, device=dev, generator=g)
-    f_yo = torch.randn(b * n, 480, device=dev, generator=g)
-    pts_tmp = (torch.rand(b, n, 3, device=dev, generator=g) - 0.5) * 0.2
-    pts_inp = (torch.rand(b, n, 3, device=dev, generator=g) - 0.5) * 0.2
+    if entry == "backbone":
+        from dcl_net_b200.synthetic import backbone_levels, levels_to, object_clouds
+        p_inp, p_tmp = object_clouds(2000 + rank, b, n, partial=True), object_clouds(3000 + rank, b, n)
+        lv_inp = levels_to(backbone_levels(4000 + rank, p_inp, b), dev)
+        lv_tmp = levels_to(backbone_levels(5000 + rank, p_tmp, b), dev)
+        for lv in lv_inp + lv_tmp:
+            lv.features.requires_grad_(True)
+        p_inp, p_tmp = p_inp.to(dev), p_tmp.to(dev)
+        pts_inp, pts_tmp = p_inp.view(b, n, 3), p_tmp.view(b, n, 3)
+        fwd = lambda: model(lv_inp, lv_tmp, p_inp, p_tmp, b)
+    else:
+        f_xc = torch.randn(b * n, 480, device=dev, generator=g)
+        f_yo = torch.randn(b * n, 480, device=dev, generator=g)
+        pts_tmp = (torch.rand(b, n, 3, device=dev, generator=g) - 0.5) * 0.2
+        pts_inp = (torch.rand(b, n, 3, device=dev, generator=g) - 0.5) * 0.2
+        fwd = lambda: model(f_xc, f_yo, b)
     q, _ = torch.linalg.qr(torch.randn(b, 3, 3, device=dev, generator=g))
     rot_gt = q * torch.det(q).sign().view(b, 1, 1)
     trans_gt = (torch.rand(b, 3, device=dev, generator=g) - 0.5) * 0.1
 
     def step(sync=True):
         opt.zero_grad(set_to_none=True)
+        if entry == "backbone":
+            for lv in lv_inp + lv_tmp:
+                lv.features.grad = None
         ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
         with ctx:
-            loss = losses(model(f_xc, f_yo, b), pts_tmp, pts_inp, rot_gt, trans_gt)
+            loss = losses(fwd(), pts_tmp, pts_inp, rot_gt, trans_gt)
             loss.backward()
         opt.step()
         return loss
@@ -142,8 +169,11 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False):
                               "(forward, dgrad, wgrad) and the FDA forward / backward on tcgen05"),
                     "data": "synthetic",
                     "config": {"workload": "config_LM-shaped training step through the FDA section: fwd + bwd + Adam, "
-                                           "train-mode BatchNorm, losses of models/DCL_Net.py:265-303; entry = point "
-                                           "features (b*n, 480) per tower",
+                                           "train-mode BatchNorm, losses of models/DCL_Net.py:265-303; entry = " +
+                                           ("the towers' four pyramid levels per cloud (pointnet_sp three_nn + "
+                                            "three_interpolate forward and backward: the level features carry gradients)"
+                                            if entry == "backbone" else "point features (b*n, 480) per tower"),
+                               "entry": entry,
                                "path": "nn layer modules (A/B)" if layers else "train_tail.mlp_stacks + dcl_fda_bwd",
                                "B_per_gpu": b, "N": n, "M": n, "C": 64,
                                "parallelism": f"DDP x{world} (NCCL all-reduce of {nparam} fp32 gradients, bucketed, "
@@ -165,9 +195,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--layers", action="store_true", help="nn layer modules on library GEMMs instead of the training kernels")
+    ap.add_argument("--entry", default="backbone", choices=["backbone", "feats"])
     args = ap.parse_args()
     run(args.batch, args.steps, args.warmup, int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
-        int(os.environ.get("LOCAL_RANK", 0)), layers=args.layers)
+        int(os.environ.get("LOCAL_RANK", 0)), layers=args.layers, entry=args.entry)
 
 
 if __name__ == "__main__":
