@@ -12,6 +12,8 @@
 #include "../../include/dcl_b200.h"
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int NN_THREADS = 128;
@@ -220,6 +222,103 @@ __global__ void __launch_bounds__(NN_THREADS) knn_big_kernel(int n, int m, int k
             }
         }
         pipe.release(t);
+    }
+}
+
+// ---- warp-cooperative k-NN (k <= 32, known cloud resident in shared memory) ----
+// A warp owns KW_Q queries at a time and scans 32 candidates per step (lane = candidate): coordinates are read once per
+// step and tested against each query's current k-th distance.  The sorted list of a query is spread over the lanes
+// (lane l = l-th neighbour); a candidate that beats the k-th distance is inserted where the sequential rule puts it —
+// behind every entry with distance <= its own — by one ballot and two shuffles, candidates of a step in ascending
+// order, each re-tested against the updated k-th distance: the list equals the reference's (interpolate_gpu.cu:42-52)
+// element for element.  The thread-per-query kernel above keeps the list in one thread's registers and runs its
+// ~6*KMAX-instruction bubble whenever ANY lane of the warp inserts, which with 32 independent queries per warp is
+// nearly every candidate.  The CTA stages the whole known cloud once (m <= KW_MAX_M) and walks KW_ITERS query groups.
+constexpr int KW_Q = 2;
+constexpr int KW_WARPS = 8;
+constexpr int KW_ITERS = 8;
+constexpr int KW_THREADS = KW_WARPS * 32;
+constexpr int KW_QPC = KW_WARPS * KW_Q * KW_ITERS;   // queries per CTA
+constexpr int KW_MAX_M = 4096;                       // 48 KB of shared memory
+
+__global__ void __launch_bounds__(KW_THREADS) knn_warp_kernel(int n, int m, int k, const float* __restrict__ unknown,
+                                                              const float* __restrict__ known,
+                                                              float* __restrict__ dist2, int* __restrict__ idx) {
+    extern __shared__ __align__(16) float s_known[];
+    __shared__ uint64_t s_bar;
+    const int bs = blockIdx.y;
+    unknown += (size_t)bs * n * 3;
+    known += (size_t)bs * m * 3;
+    dist2 += (size_t)bs * n * k;
+    idx += (size_t)bs * n * k;
+    const int nfl = m * 3;
+    if (((((uintptr_t)known) & 15u) == 0) && ((nfl & 3) == 0)) {
+        if (threadIdx.x == 0) {
+            dcl_mbar_init(&s_bar, 1);
+            dcl_fence_barrier_init();
+            dcl_mbar_arrive_expect_tx(&s_bar, (uint32_t)nfl * 4u);
+            dcl_bulk_g2s(s_known, known, (uint32_t)nfl * 4u, &s_bar);
+        }
+        __syncthreads();
+        dcl_mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < nfl; i += KW_THREADS) s_known[i] = __ldg(known + i);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_list = lane < k;
+    for (int it = 0; it < KW_ITERS; ++it) {
+        const int q0 = blockIdx.x * KW_QPC + (it * KW_WARPS + warp) * KW_Q;
+        if (q0 >= n) break;
+        float ux[KW_Q], uy[KW_Q], uz[KW_Q], bd[KW_Q], worst[KW_Q];
+        int bi[KW_Q];
+#pragma unroll
+        for (int q = 0; q < KW_Q; ++q) {
+            const int qc = min(q0 + q, n - 1);
+            ux[q] = __ldg(unknown + qc * 3 + 0);
+            uy[q] = __ldg(unknown + qc * 3 + 1);
+            uz[q] = __ldg(unknown + qc * 3 + 2);
+            bd[q] = CUDART_INF_F;
+            bi[q] = 0;
+            worst[q] = CUDART_INF_F;
+        }
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            const int j = j0 + lane;
+            const bool in = j < m;
+            const int jc = in ? j : m - 1;
+            const float x = s_known[jc * 3 + 0], y = s_known[jc * 3 + 1], z = s_known[jc * 3 + 2];
+#pragma unroll
+            for (int q = 0; q < KW_Q; ++q) {
+                const float d = dcl_dist2(ux[q], uy[q], uz[q], x, y, z);
+                uint32_t mask = __ballot_sync(0xffffffffu, in && d < worst[q]);
+                while (mask != 0u) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    const float dc = __shfl_sync(0xffffffffu, d, src);
+                    if (dc < worst[q]) {                                   // warp-uniform
+                        // position = number of list entries with distance <= dc (equal distances keep arrival order)
+                        const int p = __popc(__ballot_sync(0xffffffffu, in_list && bd[q] <= dc));
+                        const float nd = __shfl_up_sync(0xffffffffu, bd[q], 1);
+                        const int ni = __shfl_up_sync(0xffffffffu, bi[q], 1);
+                        if (in_list && lane > p) {
+                            bd[q] = nd;
+                            bi[q] = ni;
+                        } else if (lane == p) {
+                            bd[q] = dc;
+                            bi[q] = j0 + src;
+                        }
+                        worst[q] = __shfl_sync(0xffffffffu, bd[q], k - 1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KW_Q; ++q) {
+            if (q0 + q < n && in_list) {
+                dist2[(size_t)(q0 + q) * k + lane] = bd[q];
+                idx[(size_t)(q0 + q) * k + lane] = bi[q];
+            }
+        }
     }
 }
 
@@ -490,6 +589,15 @@ DCL_API int dcl_lib_knn_kernel_launcher_fast(int b, int n, int m, int k, const f
     DCL_RETURN_IF_BAD(b >= 0 && n >= 0 && m >= 0 && k >= 1 && k <= 200);
     if (b == 0 || n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    // warp-cooperative kernel when the known cloud fits in shared memory; DCL_KNN_THREAD=1 keeps the thread-per-query
+    // kernels (A/B runs)
+    static const bool force_thread = getenv("DCL_KNN_THREAD") != nullptr;
+    if (!force_thread && k <= 32 && m >= 1 && m <= KW_MAX_M) {
+        const size_t smem = (size_t)m * 3 * 4;
+        if (smem > 40 * 1024) cudaFuncSetAttribute(knn_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        knn_warp_kernel<<<dim3(DCL_DIVUP(n, KW_QPC), b), KW_THREADS, smem, st>>>(n, m, k, unknown, known, dist2, idx);
+        return dcl_launch_status();
+    }
     dim3 grid(DCL_DIVUP(n, NN_THREADS), b);
     if (k <= 4)
         knn_reg_kernel<4><<<grid, NN_THREADS, 0, st>>>(n, m, k, unknown, known, dist2, idx);

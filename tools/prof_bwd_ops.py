@@ -1,5 +1,6 @@
-"""Driver for ncu: the gather-type ops of the microbench shape (BASELINE.json configs[1]) once each after a warm-up:
-grouping fwd / bwd, three_interpolate fwd / bwd, gather fwd / bwd, pointnet_sp three_interpolate fwd / bwd."""
+"""Driver for ncu: every neighbourhood op at the microbench shape (BASELINE.json configs[1]), twice (the second pass is
+the warm one): FPS, ball_query, knn, three_nn, grouping fwd / bwd, three_interpolate fwd / bwd, gather fwd / bwd,
+pointnet_sp three_nn + three_interpolate fwd / bwd.  Summarise the log with tools/summarize_ops_ncu.py."""
 import os
 import sys
 
@@ -29,6 +30,10 @@ kf = torch.randn(B * 300, 128, generator=g).to(dev).requires_grad_(True)
 for it in range(2):
     for t in (feats, known_f, kf):
         t.grad = None
+    pu.furthest_point_sample(xyz, NP)
+    pu.ball_query(0.05, NS, xyz, new_xyz)
+    pu.knn(16, xyz, new_xyz)
+    pu.three_nn(xyz, new_xyz)
     out = pu.grouping_operation(feats, bq)
     out.backward(torch.ones_like(out))
     o2 = pu.three_interpolate(known_f, i3, w)
