@@ -6,22 +6,30 @@
         bench.py --gpus N --steps K --warmup W
 
 Metric (BASELINE.json): pose instances/s at N=M=1024.  One step = one stage-1 inference pass over a batch of
-B=32 object instances per GPU (configs[2]: config_YCBV_bs32 shape), entered where this path starts: the voxel
-pyramids of the two sparse-conv towers (synthetic, random features) ->
+B=32 object instances per GPU (configs[2]: config_YCBV_bs32 shape), entered at the raw clouds (`--entry points`, default):
+    device voxelisation -> two sparse-conv towers (tcgen05, output-stationary) ->
     pointnet_sp three_nn + three_interpolate (4 levels x 2 towers, fused) -> 8 disengage stacks ->
     dual fused FDA (tcgen05) -> confidence / fuser / regressor heads -> SVD pose projection.
-Random-init weights (no checkpoints offline), eval mode, fp32 (TF32 off) outside the FDA contraction.
-Multi-GPU: instances are sharded, one process per GPU, B per GPU fixed (weak scaling); the only exchange is the
-all_gather of the (B,12) poses, which is inside the timed region.
+`--entry pyramids` is round 1's entry (synthetic outputs of the towers as input; 30 MB of host input per step).
+Random-init weights (no checkpoints offline), eval mode.  Operand precision `--precision fp16` (default: activations
+rounded once to fp16, fp16 hi/lo weights, 2 MMAs per product; FDA logits on bf16 hi/lo operands) or `fp32-faithful`
+(bf16 hi/lo everywhere, 3 MMAs); both are held to the same parity bars by the GPU tests.
+Multi-GPU: instances are sharded, one process per GPU, B per GPU fixed (weak scaling); no data-path collective — the
+poses are gathered once at the end of the timed region (`--gather step` gathers every step).
+`--config stage2`: configs[3], stage 1 + the refiner loop, --batch-total instances sharded over the ranks (strong
+scaling).  `--config train`: configs[4], one training step (fwd + bwd + Adam; DDP all-reduce for N > 1) at --batch
+instances per GPU on the tensor-core training kernels (tools/train_step_ddp.py).
 
-`value`  : device-resident throughput — inputs already in HBM, CUDA events, max over ranks.
-`e2e`    : the same pass through PoseEngine.infer() from pinned HOST buffers: H2D copies of that step's batch and
+`value`  : device-resident throughput — inputs already in HBM, CUDA events, max over ranks; the timed step is one
+           CUDA-graph replay, consecutive steps alternating over two streams.
+`e2e`    : the same pass through PipelinedPoseEngine from pinned HOST buffers: H2D copies of that step's batch and
            the D2H read of the poses are inside the timed region.
 `roofline`: the dominant kernel — the persistent CTA-pair tensor-core GEMM of the pointwise MLP stacks
-           (pm_gemm_pair_kernel<256,6>, 5 launches per step) — timed live with CUDA events around each of its launches
-           in an eager pass of the same K steps; algorithmic FLOPs = sum of 2*rows*cin*cout over the layers in those
-           launches; peak = the measured cuBLAS bf16 BURST figure (the timed region is tens of milliseconds).
-           `roofline_fda`: the same for the fused FDA kernel, 2*N*M*(C + P + C) FLOPs per instance and direction.
+           (pm_gemm_pair_kernel<256,8,fp16>, 5 launches per step) — timed live with CUDA events around each of its
+           launches in an eager pass of the same K steps; algorithmic FLOPs = sum of 2*rows*cin*cout over the layers in
+           those launches; peak = the measured cuBLAS bf16 BURST figure (the kernel is timed alone, the region is
+           tens of milliseconds).  `roofline_fda`: the same for the fused FDA kernel, 2*N*M*(C + P + C) FLOPs per
+           instance and direction.
 `cpu_baseline`: the oracle port (pure PyTorch restatement of the same pass, oracle/torch_oracle.py) timed on this
            box's host cores on a bounded sample.  `--impl reference` prints that arm as its own line.
 """

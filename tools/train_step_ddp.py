@@ -77,7 +77,8 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
     net = Network(Cfg, mode="train").to(dev).train()
     net.use_train_kernels = not layers      # layers=True: the nn layer modules on library GEMMs (A/B figure)
     wrapped = FromBackbone(net) if entry == "backbone" else FromPointFeats(net)
-    model = torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local]) if world > 1 else wrapped
+    model = (torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local], gradient_as_bucket_view=True)
+             if world > 1 else wrapped)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
     b, n = batch, 1024
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
