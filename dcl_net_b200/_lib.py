@@ -73,6 +73,7 @@ SIGNATURES = {
     "dcl_tr_bn_stats": (_I, [_I, _P, _P]),
     "dcl_tr_bn_bwd_reduce": (_I, [_I, _P, _P]),
     "dcl_tr_pack_weights": (_I, [_I, _P, _P]),
+    "dcl_tr_colsum_reduce": (_I, [_I, _P, _P]),
     "dcl_fda_bwd": (_I, [_I, _P, _I, _I, _I, _I, _I, _P]),
     "dcl_debug_spconv_set_trace": (_I, [_P]),
     "dcl_debug_umma_gemm": (_I, [_I, _I, _P, _P, _P, _I, _P]),
@@ -120,6 +121,11 @@ class TrWpack(ctypes.Structure):
     """Mirror of dcl_tr_wpack (include/dcl_b200.h)."""
     _fields_ = [("src", _P), ("dst", _P), ("rows", _I), ("cols", _I), ("rows_pad", _I), ("k_pad", _I), ("nt", _I),
                 ("transpose", _I)]
+
+
+class TrColsum(ctypes.Structure):
+    """Mirror of dcl_tr_colsum (include/dcl_b200.h)."""
+    _fields_ = [("partial", _P), ("out", _P), ("parts", _I), ("c", _I)]
 
 
 class FdaBwdJob(ctypes.Structure):
@@ -196,7 +202,36 @@ def load():
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream of the current device as a void* (the raw-handle query: torch.cuda.current_stream()
+    builds a Stream object and costs ~6 us, which adds up over the ~400 launches of a training step)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+def fill_structs(struct, items):
+    """ctypes array of `struct` from a list of field dicts (missing pointer fields = NULL, missing numbers = 0;
+    tensors must be contiguous CUDA tensors and are passed by address).  Built positionally: a setattr per field is
+    several times slower, and these arrays are rebuilt for every launch."""
+    spec = _STRUCT_SPECS.get(struct)
+    if spec is None:
+        spec = _STRUCT_SPECS[struct] = [(name, typ is _P) for name, typ in struct._fields_]
+    rows = []
+    for f in items:
+        vals = []
+        for name, is_ptr in spec:
+            v = f.get(name)
+            if v is None:
+                vals.append(None if is_ptr else 0)
+            elif isinstance(v, torch.Tensor):
+                if not (v.is_cuda and v.is_contiguous()):
+                    raise RuntimeError(f"dcl_net_b200: field {name} needs a contiguous CUDA tensor")
+                vals.append(v.data_ptr())
+            else:
+                vals.append(v)
+        rows.append(struct(*vals))
+    return (struct * len(rows))(*rows)
+
+
+_STRUCT_SPECS = {}
 
 
 def ptr(t):

@@ -781,15 +781,20 @@ __global__ void __launch_bounds__(256) pm_pool_reduce_kernel(int insts, int cout
     if (g >= insts * cout) return;
     const int inst = g / cout, col = g % cout;
     float acc = accumulate ? out[g] : 0.f;
-    const float* p = partials + (size_t)inst * parts * cout + col;
-    // the additions stay in index order; unrolling only puts 16 independent loads in flight per thread
-#pragma unroll 16
-    for (int i = 0; i < parts; ++i) acc += __ldg(p + (size_t)i * cout);
-    if (partials2 != nullptr) {
-        const float* q = partials2 + (size_t)inst * parts * cout + col;
-#pragma unroll 16
-        for (int i = 0; i < parts; ++i) acc += __ldg(q + (size_t)i * cout);
-    }
+    // the additions stay in index order; the loads of a batch of 16 are independent of the running sum, so they are
+    // all in flight together whatever `parts` is (a plain loop serialises load -> add when it is not unrolled)
+    auto add_set = [&](const float* p) {
+        for (int i0 = 0; i0 < parts; i0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (i0 + u < parts) ? __ldg(p + (size_t)(i0 + u) * cout) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (i0 + u < parts) acc += v[u];
+        }
+    };
+    add_set(partials + (size_t)inst * parts * cout + col);
+    if (partials2 != nullptr) add_set(partials2 + (size_t)inst * parts * cout + col);
     out[g] = acc;
 }
 

@@ -31,6 +31,7 @@ struct TrTileBatch { dcl_tr_tile it[TR_MAX_ITEMS]; };
 struct TrBnBatch { dcl_tr_bn it[TR_MAX_ITEMS]; };
 struct TrBnBwdBatch { dcl_tr_bn_bwd it[TR_MAX_ITEMS]; };
 struct TrWpackBatch { dcl_tr_wpack it[TR_MAX_ITEMS]; };
+struct TrColsumBatch { dcl_tr_colsum it[TR_MAX_ITEMS]; };
 
 __device__ __forceinline__ uint4 pack8_hi_lo(const float* v, uint4& lo) {
     uint32_t h[4], l[4];
@@ -342,6 +343,29 @@ __global__ void __launch_bounds__(256) tr_pack_weights_kernel(const __grid_const
     *reinterpret_cast<uint4*>(d + (size_t)nt * 64) = lo;
 }
 
+// out[c] = sum over `parts` rows of partial[parts][c], lane = channel (coalesced 128-byte rows), the rows dealt to the
+// CTA's 8 warps round-robin and the 8 warp sums added in warp order: a fixed order, hence deterministic.
+__global__ void __launch_bounds__(256) tr_colsum_kernel(const __grid_constant__ TrColsumBatch batch) {
+    __shared__ float s_part[8][33];
+    const dcl_tr_colsum& it = batch.it[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    if (blockIdx.x * 32 >= it.c) return;
+    float acc = 0.f;
+    if (ch < it.c) {
+#pragma unroll 4
+        for (int p = warp; p < it.parts; p += 8) acc += __ldg(it.partial + (size_t)p * it.c + ch);
+    }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && ch < it.c) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_part[w][lane];
+        it.out[ch] = t;
+    }
+}
+
 }  // namespace
 
 DCL_API int dcl_tr_tile_pass(int nitems, const dcl_tr_tile* items, void* stream) {
@@ -438,5 +462,19 @@ DCL_API int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* str
         max_units = units > max_units ? units : max_units;
     }
     tr_pack_weights_kernel<<<dim3((unsigned)DCL_DIVUP(max_units, 256L), nitems), 256, 0, (cudaStream_t)stream>>>(batch);
+    return dcl_launch_status();
+}
+
+DCL_API int dcl_tr_colsum_reduce(int nitems, const dcl_tr_colsum* items, void* stream) {
+    DCL_RETURN_IF_BAD(nitems >= 1 && nitems <= TR_MAX_ITEMS && items != nullptr);
+    TrColsumBatch batch;
+    int max_c = 0;
+    for (int i = 0; i < nitems; ++i) {
+        const dcl_tr_colsum& it = items[i];
+        DCL_RETURN_IF_BAD(it.partial != nullptr && it.out != nullptr && it.parts > 0 && it.c > 0);
+        batch.it[i] = it;
+        max_c = it.c > max_c ? it.c : max_c;
+    }
+    tr_colsum_kernel<<<dim3(DCL_DIVUP(max_c, 32), nitems), 256, 0, (cudaStream_t)stream>>>(batch);
     return dcl_launch_status();
 }

@@ -149,28 +149,24 @@ GEMM_EVENTS = None
 
 def run_gemm(problems, rows):
     """problems: list of dicts with keys a0, [a1], layer, [out_pm], [out_cm], [rows_per_inst], [pool_w], [pool_out]."""
-    arr = (L.PmGemmProblem * len(problems))()
-    keep = []
-    for slot, p in zip(arr, problems):
+    rows_ = []
+    for p in problems:
         lay = p["layer"]
         a1 = p.get("a1")
         kb_total = lay.cin // 32
         c0 = p.get("c0", lay.cin if a1 is None else None)
-        slot.a0, slot.a1 = L.ptr(p["a0"]), L.ptr(a1)
-        slot.kb0, slot.kb_total = c0 // 32, kb_total
-        slot.w, slot.bias = L.ptr(lay.w), L.ptr(lay.bias)
-        slot.post_scale, slot.post_shift = L.ptr(lay.post_scale), L.ptr(lay.post_shift)
-        slot.relu, slot.cout, slot.nt = lay.relu, lay.cout, lay.nt
-        slot.out_pm, slot.out_cm = L.ptr(p.get("out_pm")), L.ptr(p.get("out_cm"))
-        slot.rows_per_inst = p.get("rows_per_inst", 0)
-        slot.pool_w, slot.pool_out = L.ptr(p.get("pool_w")), L.ptr(p.get("pool_out"))
-        slot.dot_w, slot.dot_out = L.ptr(p.get("dot_w")), L.ptr(p.get("dot_out"))
-        slot.out_qk, slot.qk_tile_rows = _addr(p.get("out_qk")), p.get("qk_tile_rows", 0)
-        slot.out_v, slot.v_row0, slot.v_rows = _addr(p.get("out_v")), p.get("v_row0", 0), p.get("v_rows", 0)
-        slot.a_fmt, slot.out_fmt = lay.fmt, p.get("out_fmt", lay.fmt)
-        # strided batch (weight-gradient launches of train_tail.py): (slices, a / w / out_cm strides in bytes)
-        slot.inst_count, slot.a_inst_stride, slot.w_inst_stride, slot.out_cm_inst_stride = p.get("inst", (0, 0, 0, 0))
-        keep.append(p)
+        inst = p.get("inst", (0, 0, 0, 0))
+        # strided batch (weight-gradient launches of train_tail.py): inst = (slices, a / w / out_cm strides in bytes)
+        rows_.append({"a0": p["a0"], "a1": a1, "kb0": c0 // 32, "kb_total": kb_total, "w": lay.w, "bias": lay.bias,
+                      "post_scale": lay.post_scale, "post_shift": lay.post_shift, "relu": lay.relu, "cout": lay.cout,
+                      "nt": lay.nt, "out_pm": p.get("out_pm"), "out_cm": p.get("out_cm"),
+                      "rows_per_inst": p.get("rows_per_inst", 0), "pool_w": p.get("pool_w"), "pool_out": p.get("pool_out"),
+                      "dot_w": p.get("dot_w"), "dot_out": p.get("dot_out"), "out_qk": p.get("out_qk"),
+                      "qk_tile_rows": p.get("qk_tile_rows", 0), "out_v": p.get("out_v"), "v_row0": p.get("v_row0", 0),
+                      "v_rows": p.get("v_rows", 0), "a_fmt": lay.fmt, "out_fmt": p.get("out_fmt", lay.fmt),
+                      "inst_count": inst[0], "a_inst_stride": inst[1], "w_inst_stride": inst[2],
+                      "out_cm_inst_stride": inst[3]})
+    arr = L.fill_structs(L.PmGemmProblem, rows_)
     if GEMM_EVENTS is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

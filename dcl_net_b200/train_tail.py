@@ -40,13 +40,10 @@ def _pad(x, m):
 def _batched(fn_name, struct, items, what):
     """Launch `items` (lists of field dicts) through a dcl_tr_* entry point, 8 per launch."""
     fn = getattr(L.load(), fn_name)
+    st = L.stream_ptr()
     for i in range(0, len(items), 8):
-        chunk = items[i:i + 8]
-        arr = (struct * len(chunk))()
-        for slot, fields in zip(arr, chunk):
-            for k, v in fields.items():
-                setattr(slot, k, L.ptr(v) if isinstance(v, torch.Tensor) or v is None else v)
-        L.check(fn(len(chunk), ctypes.cast(arr, ctypes.c_void_p), L.stream_ptr()), what)
+        arr = L.fill_structs(struct, items[i:i + 8])
+        L.check(fn(len(arr), ctypes.cast(arr, ctypes.c_void_p), st), what)
 
 
 def tile_pass(items):
@@ -61,7 +58,7 @@ def tile_pass(items):
         else:
             assert x.shape == (b * n, c) and x.stride(1) == 1
             sb, sc, sn = n * x.stride(0), 1, x.stride(0)
-        f = {"x": ctypes.c_void_p(x.data_ptr()), "x_sb": sb, "x_sc": sc, "x_sn": sn, "b": b, "c": c, "n": n,
+        f = {"x": x.data_ptr(), "x_sb": sb, "x_sc": sc, "x_sn": sn, "b": b, "c": c, "n": n,
              "mode": it["mode"], "t_row0": it.get("t_row0", 0), "t_rows": it.get("t_rows", 0),
              "k_col0": it.get("k_col0", 0), "k_cols": it.get("k_cols", 0), "t_group": it.get("t_group", 0)}
         for k in ("u", "scale", "shift", "mean", "rstd", "s1", "s2", "out_k", "out_t", "out_cm", "col_partial"):
@@ -249,7 +246,7 @@ class _MlpStacksFn(torch.autograd.Function):
                 sums[s] = torch.empty(2, la.cout, **f32)
                 dy = dys[s]
                 assert dy.stride(2) == 1
-                red.append({"dy": ctypes.c_void_p(dy.data_ptr()), "u": us[s], "dy_sb": dy.stride(0), "dy_sc": dy.stride(1),
+                red.append({"dy": dy.data_ptr(), "u": us[s], "dy_sb": dy.stride(0), "dy_sc": dy.stride(1),
                             "b": b, "c": la.cout, "n": n, "mode": _BWD_MODE[la.kind], "mean": bns[s][0], "rstd": bns[s][1],
                             "scale": bns[s][2], "shift": bns[s][3], "s1": sums[s][0], "s2": sums[s][1]})
             if red:
@@ -331,12 +328,15 @@ class _MlpStacksFn(torch.autograd.Function):
                 for k, s in enumerate(members):
                     la = lays[s]
                     acc(la.w, dwt[k, :la.cin, :la.cout].t().reshape(tensors[la.w].shape))
+            sums_items = []
             for s, la in enumerate(lays):
                 if la.bias is not None:
                     db = torch.empty(la.cout, **f32)
-                    L.check(lib.dcl_pm_pool_reduce(1, la.cout, rows // 128, L.ptr(colp[s]), None, L.ptr(db), 0,
-                                                   L.stream_ptr()), "bias reduce")
+                    sums_items.append({"partial": colp[s], "out": db, "parts": rows // 128, "c": la.cout})
                     acc(la.bias, db)
+            if sums_items:
+                _batched("dcl_tr_colsum_reduce", L.TrColsum, sums_items, "tr_colsum")
+            for s, la in enumerate(lays):
                 if bns[s] is not None:
                     acc(la.beta, sums[s][0])
                     acc(la.gamma, sums[s][1])

@@ -611,6 +611,14 @@ typedef struct dcl_tr_wpack {
     int transpose;
 } dcl_tr_wpack;
 int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* stream);
+/* out[c] = sum over the `parts` rows of partial (parts x c), in a fixed order: the bias gradients from the per-tile
+ * column sums of dcl_tr_tile_pass (col_partial).  Up to 8 items per launch. */
+typedef struct dcl_tr_colsum {
+    const float* partial;
+    float* out;
+    int parts, c;
+} dcl_tr_colsum;
+int dcl_tr_colsum_reduce(int nitems, const dcl_tr_colsum* items, void* stream);
 
 /* Fused backward of the FDA (models/Modules.py:166-169 under autograd; forward = dcl_fda_align_fwd): with
  * S = RI_2^T RI_1, A = softmax_m S, RE_embed = RE_2 A, RI_embed = RI_2 A and the output gradients gE (b,p,n), gI (b,c,n):

@@ -30,7 +30,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     structs = {"dcl_pm_gemm_problem": _lib.PmGemmProblem, "dcl_pose_head_mlp": _lib.PoseHeadMlp,
                "dcl_sp_level": _lib.SpLevel, "dcl_sp_tower": _lib.SpTower, "dcl_fda_job": _lib.FdaJob,
                "dcl_tr_tile": _lib.TrTile, "dcl_tr_bn": _lib.TrBn, "dcl_tr_bn_bwd": _lib.TrBnBwd,
-               "dcl_tr_wpack": _lib.TrWpack, "dcl_fda_bwd_job": _lib.FdaBwdJob}
+               "dcl_tr_wpack": _lib.TrWpack, "dcl_tr_colsum": _lib.TrColsum, "dcl_fda_bwd_job": _lib.FdaBwdJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER_PATH}"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

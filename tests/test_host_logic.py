@@ -86,3 +86,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_train_tail_layer_specs():
+    """train_tail maps the reference's module trees to layer kinds without touching a GPU: disengage blocks are
+    conv -> BN -> ReLU, Head_MultiLayerPerceptron layers conv -> [ReLU] -> [BN], a narrow last layer is zero-padded to
+    64 outputs by differentiable torch ops (so its gradient flows back to the unpadded parameter)."""
+    import torch
+    from dcl_net_b200.dcl_net import Network
+    from dcl_net_b200.train_tail import disengage_layers, head_layers
+
+    class Cfg:
+        n_inp = n_tmp = 256
+        unit_voxel_extent = [0.006] * 3
+
+    net = Network(Cfg, mode="train")
+    dis = disengage_layers(net.disengage_Xc_m1)
+    assert [l[0] for l in dis] == ["bn_relu", "bn_relu"]
+    assert dis[0][1].shape[:2] == (256, 480) and dis[1][1].shape[:2] == (64, 256) and dis[0][2] is None
+    assert isinstance(dis[0][4], torch.nn.ReLU)
+    lays, width = head_layers(net.regressor_conf)
+    assert [l[0] for l in lays] == ["relu", "relu", "linear"] and width == 1
+    assert lays[2][1].shape == (64, 128) and lays[2][2].shape == (64,)
+    assert torch.equal(lays[2][1][:1], net.regressor_conf.layers[4].weight.reshape(1, 128)) and not lays[2][1][1:].any()
+    lays[2][1].sum().backward()
+    assert net.regressor_conf.layers[4].weight.grad is not None
+    lays, width = head_layers(net.neck_fuser)
+    assert [l[0] for l in lays] == ["relu_bn"] * 3 and width == 1024
+    assert all(isinstance(l[3], torch.nn.BatchNorm1d) for l in lays)
+    lays, width = head_layers(net.regressor_Xo)
+    assert width == 3 and lays[-1][1].shape == (64, 128)

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--rows", type=int, default=45)
     ap.add_argument("--layers", action="store_true", help="PyTorch layer modules instead of the training kernels")
     ap.add_argument("--entry", default="feats", choices=["feats", "backbone"])
+    ap.add_argument("--cprofile", action="store_true", help="host-side profile (cProfile) of three steps")
+    ap.add_argument("--ncu", action="store_true", help="two plain steps and exit (run under ncu; summarise the second half)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -59,6 +61,27 @@ def main():
         loss.backward()
         opt.step()
 
+    if args.ncu:
+        step()
+        step()
+        torch.cuda.synchronize()
+        return
+    if args.cprofile:
+        import cProfile
+        import pstats
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        st = pstats.Stats(pr)
+        st.sort_stats("cumulative").print_stats(45)
+        st.sort_stats("tottime").print_stats(25)
+        return
     for _ in range(3):
         step()
     torch.cuda.synchronize()
