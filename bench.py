@@ -81,6 +81,10 @@ def parse_args():
     ap.add_argument("--train-entry", default="backbone", choices=["backbone", "feats"],
                     help="--config train: enter at the towers' pyramid levels (interpolation forward + backward included) "
                          "or at the (b*n, 480) point features")
+    ap.add_argument("--train-eager", action="store_true",
+                    help="--config train launches the step eagerly (torch DDP for N > 1).  Default: forward + backward "
+                         "(+ Adam on one GPU) replayed as one CUDA graph; with N > 1 the gradients are averaged by one "
+                         "NCCL all-reduce of a flat buffer after the replay")
     ap.add_argument("--train-layers", action="store_true",
                     help="--config train on the nn layer modules (cuDNN/cuBLAS) instead of the training kernels: A/B figure")
     ap.add_argument("--config", default="stage1", choices=["stage1", "stage2", "train"],
@@ -607,7 +611,8 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import train_step_ddp
         train_step_ddp.run(args.batch, args.steps, max(args.warmup, 3), rank, world, local_rank, contract=True,
-                           layers=args.train_layers, entry=args.train_entry)
+                           layers=args.train_layers, entry=args.train_entry,
+                           graph=not (args.train_eager or args.train_layers))
         return
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

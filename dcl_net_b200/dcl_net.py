@@ -70,15 +70,59 @@ def pose_heads(pooled, rot_head, trans_head):
     return o9, t3
 
 
+class ProjectSO3Function(torch.autograd.Function):
+    """R = U diag(1,1,det(UV^T)) V^T of a (B,3,3) matrix M, forward on the dcl_svd3_project kernel, backward in closed
+    form without an SVD: R^T M = P is symmetric at the optimum, so a perturbation dM turns R by the skew matrix Omega
+    solving Omega P + P Omega = R^T dM - dM^T R, i.e. (tr(P) I - P) omega = axial(R^T dM - dM^T R); transposing that
+    linear map gives  dL/dM = R [gamma]x^T-type skew matrix  with  gamma = (tr(P) I - P)^-1 alpha,
+    alpha_k = eps_ijk (R^T G)_ij.  Agrees with autograd through the reference's torch.svd formula
+    (models/DCL_Net.py:22-35) to rounding, reflections included (tests/test_oracle_golden.py), and — unlike torch.svd —
+    is a handful of elementwise / bmm launches that a CUDA graph can capture."""
+
+    @staticmethod
+    def forward(ctx, m):
+        r = svd3_project(m.reshape(m.shape[0], 9), False)
+        ctx.save_for_backward(m, r)
+        return r
+
+    @staticmethod
+    def backward(ctx, g):
+        m, r = ctx.saved_tensors
+        return so3_projection_backward(m, r, g)
+
+
+def so3_projection_backward(m, r, g):
+    """dL/dM of R = project_SO3(M) given G = dL/dR; plain torch ops on (B,3,3) tensors (any device / dtype)."""
+    rt = r.transpose(1, 2)
+    a = rt @ g
+    alpha = torch.stack((a[:, 1, 2] - a[:, 2, 1], a[:, 2, 0] - a[:, 0, 2], a[:, 0, 1] - a[:, 1, 0]), 1)
+    p = rt @ m
+    k = p.diagonal(dim1=1, dim2=2).sum(1).view(-1, 1, 1) * torch.eye(3, dtype=m.dtype, device=m.device) - p
+    r0, r1, r2 = k[:, 0], k[:, 1], k[:, 2]
+    c0, c1, c2 = torch.cross(r1, r2, dim=1), torch.cross(r2, r0, dim=1), torch.cross(r0, r1, dim=1)
+    det = (r0 * c0).sum(1, keepdim=True)
+    gamma = (c0 * alpha[:, 0:1] + c1 * alpha[:, 1:2] + c2 * alpha[:, 2:3]) / det      # K^-1 alpha (K symmetric)
+    z = torch.zeros_like(gamma[:, 0])
+    skew = torch.stack((torch.stack((z, gamma[:, 2], -gamma[:, 1]), 1), torch.stack((-gamma[:, 2], z, gamma[:, 0]), 1),
+                        torch.stack((gamma[:, 1], -gamma[:, 0], z), 1)), 1)
+    return r @ skew
+
+
+USE_TORCH_SVD_AUTOGRAD = False   # True: differentiate through torch.svd as the reference does (A/B, tests)
+
+
 def ortho9d2matrix(x_raw, y_raw, z_raw):
     """Rotation from three raw 3-vectors: columns normalised by (|v| + 1e-8), then the SO(3) projection
-    U diag(1,1,det(UV^T)) V^T.  Runs the dcl_svd3_project kernel; when autograd is recording a gradient through
-    it (training) the same formula is evaluated with torch's differentiable SVD, as the reference does
-    (models/DCL_Net.py:22-35)."""
+    U diag(1,1,det(UV^T)) V^T (models/DCL_Net.py:22-35).  Runs the dcl_svd3_project kernel; when autograd is recording
+    a gradient through it (training), the column normalisation is differentiated by autograd and the projection by
+    ProjectSO3Function (same kernel forward, closed-form backward) — or, with USE_TORCH_SVD_AUTOGRAD, through
+    torch.svd exactly as the reference does."""
     if torch.is_grad_enabled() and (x_raw.requires_grad or y_raw.requires_grad or z_raw.requires_grad):
         def unit(v):
             return v / (torch.sqrt(v.pow(2).sum(1, keepdim=True)) + 1e-8)
         m = torch.stack((unit(x_raw), unit(y_raw), unit(z_raw)), dim=2)
+        if not USE_TORCH_SVD_AUTOGRAD and m.is_cuda and m.dtype == torch.float32:
+            return ProjectSO3Function.apply(m.contiguous())
         u, _, v = torch.svd(m)
         sigma = torch.ones(m.shape[0], 3, dtype=m.dtype, device=m.device)
         sigma[:, -1] = torch.bmm(u, v.transpose(1, 2)).det()

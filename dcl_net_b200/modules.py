@@ -257,11 +257,24 @@ class Head_MultiLayerPerceptron(nn.Module):
         return self.layers(input)
 
 
+_const_cache = {}
+
+
+def _const_tensor(values, device):
+    """fp32 device tensor of a small host constant, created once per (values, device): a host-to-device copy per
+    call would also keep a training step from being captured in a CUDA graph."""
+    key = (tuple(float(v) for v in np.asarray(values).reshape(-1)), str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        t = _const_cache[key] = torch.tensor(key[0], dtype=torch.float32, device=device)
+    return t
+
+
 def Ops_tensor2points(tensor, offset=(0., -40., -3.), voxel_extent=(.1, .1, .2)):
     """Sparse tensor (.features (Mv,C), .indices (Mv,4) int bxyz) -> (features, voxel centres bxyz)."""
     indices = tensor.indices.float()
-    offset = torch.as_tensor(np.asarray(offset), dtype=torch.float32, device=indices.device)
-    voxel_extent = torch.as_tensor(np.asarray(voxel_extent), dtype=torch.float32, device=indices.device)
+    offset = _const_tensor(offset, indices.device)
+    voxel_extent = _const_tensor(voxel_extent, indices.device)
     indices[:, 1:] = indices[:, 1:] * voxel_extent + offset + .5 * voxel_extent
     return tensor.features, indices
 

@@ -186,3 +186,68 @@ def test_network_train_path_matches_layer_path(cuda_dev):
     assert errs[0][0] < 5e-2, errs[:5]
     for (name, p), (_, q) in zip(net.named_buffers(), ref.named_buffers()):
         assert _rel(p.float(), q.float()) < 1e-4, name
+
+
+def test_training_step_graph_replay_equals_eager(cuda_dev):
+    """The whole training step (forward, backward, optimizer) captured in one CUDA graph (tools/train_step_ddp.py
+    --graph) moves the parameters and BatchNorm buffers as the eagerly launched step does.  Plain SGD on purpose: its
+    update is linear in the gradient, so rounding-level differences stay rounding-level (Adam's first steps move every
+    weight by ~lr whatever the gradient's size, which turns a last-bit difference of a near-zero gradient into 2*lr)."""
+    from dcl_net_b200.dcl_net import Network
+
+    class Cfg:
+        n_inp = n_tmp = 256
+        unit_voxel_extent = [0.006] * 3
+
+    b, n = 4, 256
+    g = torch.Generator().manual_seed(5)
+    f_xc = torch.randn(b * n, 480, generator=g).to(cuda_dev)
+    f_yo = torch.randn(b * n, 480, generator=g).to(cuda_dev)
+    tgt = torch.randn(b, 3, 3, generator=g).to(cuda_dev)
+
+    def loss_fn(out):
+        return (out["Xo_pred"].square().mean() + out["Yc_pred"].square().mean() + out["conf"].mean() +
+                out["trans_pred"].square().mean() + (out["rot_pred"] * tgt).sum(dim=(1, 2)).mean())
+
+    torch.manual_seed(9)
+    net_e = Network(Cfg, mode="train").to(cuda_dev).train()
+    net_g = copy.deepcopy(net_e)
+    opt_e = torch.optim.SGD(net_e.parameters(), lr=1e-2)
+    for _ in range(5):
+        opt_e.zero_grad(set_to_none=True)
+        loss_fn(net_e.forward_from_point_feats(f_xc, f_yo, b)).backward()
+        opt_e.step()
+
+    opt_g = torch.optim.SGD(net_g.parameters(), lr=1e-2)
+    params = list(net_g.parameters())
+    flat = torch.zeros(sum(p.numel() for p in params), device=cuda_dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    def fwd_bwd():
+        flat.zero_()
+        loss = loss_fn(net_g.forward_from_point_feats(f_xc, f_yo, b))
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fwd_bwd()
+            opt_g.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fwd_bwd()
+        opt_g.step()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for (name, p), (_, q) in zip(net_g.named_parameters(), net_e.named_parameters()):
+        assert _relmax(p, q) < 1e-4, (name, _relmax(p, q))
+    for (name, p), (_, q) in zip(net_g.named_buffers(), net_e.named_buffers()):
+        assert _relmax(p.float(), q.float()) < 1e-5, name

@@ -116,3 +116,26 @@ def test_train_tail_layer_specs():
     assert all(isinstance(l[3], torch.nn.BatchNorm1d) for l in lays)
     lays, width = head_layers(net.regressor_Xo)
     assert width == 3 and lays[-1][1].shape == (64, 128)
+
+
+def test_so3_projection_backward_closed_form_matches_svd_autograd():
+    """dcl_net.so3_projection_backward (what ProjectSO3Function.backward runs) against autograd through the
+    reference's torch.svd formula (models/DCL_Net.py:22-35), fp64 on CPU, proper and reflected inputs."""
+    import torch
+    from dcl_net_b200.dcl_net import so3_projection_backward
+    from oracle import torch_oracle as T
+    g = torch.Generator().manual_seed(3)
+    for reflect in (False, True):
+        m = torch.randn(16, 3, 3, generator=g, dtype=torch.float64)
+        if reflect:
+            m = m * torch.where(torch.det(m) > 0, -1.0, 1.0).view(-1, 1, 1)
+        m.requires_grad_(True)
+        u, _, v = torch.svd(m)
+        sigma = torch.ones(16, 3, dtype=torch.float64)
+        sigma[:, -1] = torch.bmm(u, v.transpose(1, 2)).det()
+        r = u @ torch.diag_embed(sigma) @ v.transpose(1, 2)
+        gr = torch.randn(16, 3, 3, generator=g, dtype=torch.float64)
+        (r * gr).sum().backward()
+        mine = so3_projection_backward(m.detach(), r.detach(), gr)
+        assert (mine - m.grad).abs().max().item() < 1e-10 * max(1.0, m.grad.abs().max().item())
+        assert torch.allclose(r.detach(), T.project_so3(m.detach()), atol=1e-12)

@@ -62,7 +62,7 @@ class FromBackbone(torch.nn.Module):
         return self.inner.forward_from_backbone(levels_inp, levels_tmp, points_inp, points_tmp, nb)
 
 
-def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, entry="backbone"):
+def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, entry="backbone", graph=False):
     """One process per GPU.  Times `steps` training steps (max over ranks), then — multi-GPU — the same steps with
     the gradient all-reduce switched off (DDP.no_sync) and the all-reduce of a gradient-sized buffer on its own:
     exposed all-reduce time = synced step - unsynced step; overlap = 1 - exposed / standalone."""
@@ -77,9 +77,13 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
     net = Network(Cfg, mode="train").to(dev).train()
     net.use_train_kernels = not layers      # layers=True: the nn layer modules on library GEMMs (A/B figure)
     wrapped = FromBackbone(net) if entry == "backbone" else FromPointFeats(net)
+    # graph mode: forward + backward (+ Adam on one GPU) replayed as ONE CUDA graph; data parallelism is then a single
+    # NCCL all-reduce of the flat gradient buffer after the replay instead of DDP's bucket hooks (the step issues ~750
+    # small launches and is otherwise paced by the host; the 19.5 MB all-reduce takes 0.11 ms over NVLink)
+    use_ddp = world > 1 and not graph
     model = (torch.nn.parallel.DistributedDataParallel(wrapped, device_ids=[local], gradient_as_bucket_view=True)
-             if world > 1 else wrapped)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+             if use_ddp else wrapped)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=graph and world == 1)
     b, n = batch, 1024
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     if entry == "backbone":
@@ -107,12 +111,54 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
         if entry == "backbone":
             for lv in lv_inp + lv_tmp:
                 lv.features.grad = None
-        ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
+        ctx = contextlib.nullcontext() if (sync or not use_ddp) else model.no_sync()
         with ctx:
             loss = losses(fwd(), pts_tmp, pts_inp, rot_gt, trans_gt)
             loss.backward()
         opt.step()
         return loss
+
+    if graph:
+        params = list(net.parameters())
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        off = 0
+        for p in params:                      # gradients accumulate in place into one flat buffer (static addresses)
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+        def fwd_bwd():
+            flat.zero_()
+            if entry == "backbone":
+                for lv in lv_inp + lv_tmp:
+                    lv.features.grad = None
+            loss = losses(fwd(), pts_tmp, pts_inp, rot_gt, trans_gt)
+            loss.backward()
+            return loss
+
+        def reduce_and_step(sync=True):
+            if world > 1 and sync:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            opt.step()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fwd_bwd()
+                reduce_and_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cuda_graph):
+            static_loss = fwd_bwd()
+            if world == 1:
+                opt.step()
+
+        def step(sync=True):  # noqa: F811
+            cuda_graph.replay()
+            if world > 1:
+                reduce_and_step(sync)
+            return static_loss
 
     def timed(k, sync=True):
         if world > 1:
@@ -176,9 +222,14 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
                                             if entry == "backbone" else "point features (b*n, 480) per tower"),
                                "entry": entry,
                                "path": "nn layer modules (A/B)" if layers else "train_tail.mlp_stacks + dcl_fda_bwd",
+                               "launch_mode": ("cuda_graph (forward + backward" + (" + Adam" if world == 1 else "") +
+                                               " in one graph" + ("; flat-gradient NCCL all-reduce + Adam after the replay)"
+                                                                  if world > 1 else ")")) if graph else "eager",
                                "B_per_gpu": b, "N": n, "M": n, "C": 64,
-                               "parallelism": f"DDP x{world} (NCCL all-reduce of {nparam} fp32 gradients, bucketed, "
-                                              "overlapped with backward)"},
+                               "parallelism": (f"data parallel x{world}: one NCCL all-reduce (AVG) of the flat {nparam}-element "
+                                               "fp32 gradient buffer per step, after the graph replay" if graph else
+                                               f"DDP x{world} (NCCL all-reduce of {nparam} fp32 gradients, bucketed, "
+                                               "overlapped with backward)")},
                     "impl": "b200", "loss": float(loss.item()), "params": nparam, "gpu_launches": int(launches)}
             line.update(extra)
         else:
@@ -197,9 +248,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--layers", action="store_true", help="nn layer modules on library GEMMs instead of the training kernels")
     ap.add_argument("--entry", default="backbone", choices=["backbone", "feats"])
+    ap.add_argument("--graph", action="store_true", help="replay forward + backward as one CUDA graph")
     args = ap.parse_args()
     run(args.batch, args.steps, args.warmup, int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
-        int(os.environ.get("LOCAL_RANK", 0)), layers=args.layers, entry=args.entry)
+        int(os.environ.get("LOCAL_RANK", 0)), layers=args.layers, entry=args.entry, graph=args.graph)
 
 
 if __name__ == "__main__":
