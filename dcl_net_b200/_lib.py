@@ -120,7 +120,7 @@ class TrBnBwd(ctypes.Structure):
 class TrWpack(ctypes.Structure):
     """Mirror of dcl_tr_wpack (include/dcl_b200.h)."""
     _fields_ = [("src", _P), ("dst", _P), ("rows", _I), ("cols", _I), ("rows_pad", _I), ("k_pad", _I), ("nt", _I),
-                ("transpose", _I)]
+                ("transpose", _I), ("k_col0", _I), ("k_total", _I)]
 
 
 class TrColsum(ctypes.Structure):

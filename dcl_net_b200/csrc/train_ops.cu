@@ -336,9 +336,10 @@ __global__ void __launch_bounds__(256) tr_pack_weights_kernel(const __grid_const
     uint4 lo;
     const uint4 hi = pack8_hi_lo(v, lo);
     const int nt = it.nt;
+    const int k_total = it.k_total > 0 ? it.k_total : it.k_pad;
     unsigned char* d = reinterpret_cast<unsigned char*>(it.dst) +
-                       ((size_t)(o / nt) * (it.k_pad / 32) + kc / 4) * ((size_t)nt * 128) + ((o % nt) / 8) * 512 +
-                       (kc & 3) * 128 + (o & 7) * 16;
+                       ((size_t)(o / nt) * (k_total / 32) + it.k_col0 / 32 + kc / 4) * ((size_t)nt * 128) +
+                       ((o % nt) / 8) * 512 + (kc & 3) * 128 + (o & 7) * 16;
     *reinterpret_cast<uint4*>(d) = hi;
     *reinterpret_cast<uint4*>(d + (size_t)nt * 64) = lo;
 }
@@ -457,6 +458,9 @@ DCL_API int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* str
         DCL_RETURN_IF_BAD((it.nt == 64 || it.nt == 128 || it.nt == 256) && it.rows_pad >= it.rows &&
                           it.rows_pad % it.nt == 0 && it.k_pad >= it.cols && it.k_pad % 32 == 0);
         DCL_RETURN_IF_BAD((((uintptr_t)it.dst) & 15u) == 0);
+        DCL_RETURN_IF_BAD(it.k_total == 0 ? it.k_col0 == 0
+                                          : (it.k_total % 32 == 0 && it.k_col0 >= 0 && it.k_col0 % 32 == 0 &&
+                                             it.k_col0 + it.k_pad <= it.k_total));
         batch.it[i] = it;
         const long units = (long)it.rows_pad * (it.k_pad / 8);
         max_units = units > max_units ? units : max_units;

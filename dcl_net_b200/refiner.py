@@ -36,11 +36,29 @@ class Refiner(nn.Module):
             self._fused_refiner = None
         return super().train(mode)
 
+    def _mlp_share(self, x):
+        """MLP_share (Conv1d 259 -> 512 -> 512 -> 1024, ReLU after each; models/refiner.py:61-63).  In training on CUDA it
+        runs — forward and backward — on the tensor-core training kernels (train_tail.mlp_stacks), like the stage-1
+        stacks: the 3 coordinate channels are zero-padded to a 32-channel block (input and the matching weight
+        columns, by differentiable torch ops), the 256 feature channels follow as a second input."""
+        b, c, n = x.shape
+        if not (self.training and torch.is_grad_enabled() and getattr(self, "use_train_kernels", True) and x.is_cuda
+                and x.dtype == torch.float32 and c == 259 and n % 128 == 0):
+            return self.MLP_share(x)
+        from .train_tail import StackSpec, head_layers, mlp_stacks
+        lays, _ = head_layers(self.MLP_share)
+        kind, w, bias, bn, relu_mod = lays[0]
+        w = torch.cat([w[:, :3], w.new_zeros(w.shape[0], 29), w[:, 3:]], dim=1)          # (512, 288)
+        pts = torch.nn.functional.pad(x[:, :3], (0, 0, 0, 29))                            # (b, 32, n)
+        out, = mlp_stacks([StackSpec([(pts, "cm"), (x[:, 3:].contiguous(), "cm")],
+                                     [(kind, w, bias, bn, relu_mod)] + lays[1:])], b, n)
+        return out
+
     def forward(self, input_dict):
         input_features = input_dict["input_features"]
         conf = input_dict["conf"]
         conf_softmax = torch.softmax(conf.unsqueeze(1), dim=2)[:, :, :1024]
-        shared_feature = self.MLP_share(input_features)
+        shared_feature = self._mlp_share(input_features)
         shared_feature = (shared_feature * conf_softmax).sum(dim=2, keepdim=True)
         if torch.is_grad_enabled():
             ortho9d_pred2 = self.regressor_rot2(shared_feature).squeeze(-1)

@@ -37,6 +37,11 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
+def _wgrad_group(b):
+    """Instances per split-K slice of the weight-gradient GEMMs (K = group * n points)."""
+    return next(g for g in (4, 2, 1) if b % g == 0)
+
+
 def _batched(fn_name, struct, items, what):
     """Launch `items` (lists of field dicts) through a dcl_tr_* entry point, 8 per launch."""
     fn = getattr(L.load(), fn_name)
@@ -69,13 +74,16 @@ def tile_pass(items):
 
 def pack_weights(items):
     """items: (src (rows, cols) fp32 contiguous — or its transpose when `transpose` —, rows, cols, rows_pad, k_pad, nt,
-    transpose) -> list of packed uint8 tensors."""
+    transpose[, dst, k_col0, k_total]) -> list of packed uint8 tensors.  With dst / k_col0 / k_total the matrix becomes
+    a column block of a wider packed matrix (weights concatenated along the reduction axis)."""
     outs, fields = [], []
-    for src, rows, cols, rows_pad, k_pad, nt, transpose in items:
-        dst = torch.empty(rows_pad * k_pad * 4, dtype=torch.uint8, device=src.device)
+    for src, rows, cols, rows_pad, k_pad, nt, transpose, *into in items:
+        dst, k_col0, k_total = into if into else (None, 0, 0)
+        if dst is None:
+            dst = torch.empty(rows_pad * k_pad * 4, dtype=torch.uint8, device=src.device)
         outs.append(dst)
         fields.append({"src": src, "dst": dst, "rows": rows, "cols": cols, "rows_pad": rows_pad, "k_pad": k_pad,
-                       "nt": nt, "transpose": int(transpose)})
+                       "nt": nt, "transpose": int(transpose), "k_col0": k_col0, "k_total": k_total})
     _batched("dcl_tr_pack_weights", L.TrWpack, fields, "tr_pack_weights")
     return outs
 
@@ -128,7 +136,8 @@ class _MlpStacksFn(torch.autograd.Function):
         tile_pass(items)
         cur = [[in_imgs[ti] for ti, _, _ in st.inputs] for st in plan.stacks]   # per stack: the A images
         cur_c0 = [st.inputs[0][2] for st in plan.stacks]
-        saved_u, saved_bn = [], []
+        saved_u, saved_bn, saved_t = [], [], []
+        grp = _wgrad_group(b)
         for l in range(nl):
             lays = [st.layers[l] for st in plan.stacks]
             wp = pack_weights([(tensors[la.w], la.cout, la.cin, la.cout, la.cin, pick_nt(la.cout), False) for la in lays])
@@ -172,12 +181,19 @@ class _MlpStacksFn(torch.autograd.Function):
                 if not last:
                     t["out_k"] = pm_empty(rows, la.cout, dev)
                     nxt[s] = [t["out_k"]]
+                    # the same pass writes the transposed images the NEXT layer's weight gradient reads (kept for the
+                    # backward: one read of U saved per activation)
+                    cpad = _pad(la.cout, 128)
+                    alloc = torch.empty if cpad == la.cout else torch.zeros
+                    t.update(out_t=alloc(b * cpad * n * 4, dtype=torch.uint8, device=dev), t_rows=cpad, t_group=grp)
                 tiles.append((s, t))
             if bn_items:
                 _batched("dcl_tr_bn_stats", L.TrBn, bn_items, "tr_bn_stats")
                 tile_pass([t for _, t in tiles])
             saved_u.append(us)
             saved_bn.append(bns)
+            t_of = {s: t.get("out_t") for s, t in tiles}
+            saved_t.append([t_of.get(s) for s in range(len(lays))])
             if GATE_LOG is not None:
                 ys = {s: t["out_cm"] for s, t in tiles if "out_cm" in t}
                 for s, la in enumerate(lays):
@@ -196,16 +212,17 @@ class _MlpStacksFn(torch.autograd.Function):
                     la.bn.num_batches_tracked += 1
         ctx.plan = plan
         # everything the backward reads goes through save_for_backward (outputs included: no reference cycles)
-        flat, ctx.u_idx, ctx.bn_idx = list(tensors), [], []
-        for us, bns in zip(saved_u, saved_bn):
+        flat, ctx.u_idx, ctx.bn_idx, ctx.t_idx = list(tensors), [], [], []
+        for us, bns, ts in zip(saved_u, saved_bn, saved_t):
             ctx.u_idx.append([len(flat) + i for i in range(len(us))])
             flat += us
-            row = []
-            for st in bns:
-                row.append(None if st is None else len(flat))
-                if st is not None:
-                    flat.append(st)
-            ctx.bn_idx.append(row)
+            for dst, src in ((ctx.bn_idx, bns), (ctx.t_idx, ts)):
+                row = []
+                for st in src:
+                    row.append(None if st is None else len(flat))
+                    if st is not None:
+                        flat.append(st)
+                dst.append(row)
         ctx.ntensors = len(tensors)
         ctx.save_for_backward(*flat)
         return tuple(outs)
@@ -216,6 +233,7 @@ class _MlpStacksFn(torch.autograd.Function):
         tensors = flat[:ctx.ntensors]
         saved_u = [[flat[i] for i in row] for row in ctx.u_idx]
         saved_bn = [[None if i is None else flat[i] for i in row] for row in ctx.bn_idx]
+        saved_t = [[None if i is None else flat[i] for i in row] for row in ctx.t_idx]
         b, n = plan.b, plan.n
         rows = b * n
         dev = tensors[0].device
@@ -224,7 +242,7 @@ class _MlpStacksFn(torch.autograd.Function):
         lib = L.load()
         # wgrad split-K: one slice per group of `grp` instances (K = grp*n points): partial sums to write and reduce
         # shrink by grp while the launch still has several waves of tiles
-        grp = next(g for g in (4, 2, 1) if b % g == 0)
+        grp = _wgrad_group(b)
         out_grads = [None] * len(tensors)
 
         def acc(idx, g):
@@ -252,6 +270,22 @@ class _MlpStacksFn(torch.autograd.Function):
             if red:
                 _batched("dcl_tr_bn_bwd_reduce", L.TrBnBwd, red, "tr_bn_bwd_reduce")
             # ---- dZ: PM image (dgrad), transposed images (wgrad), bias-gradient partials
+            # layer 0: stacks reading the same input share ONE input-gradient GEMM, dX = [dZ_1 | dZ_2 | ..] [W_1; W_2; ..]
+            # (their dZ images are column blocks of one image), instead of one GEMM each and a sum of the results
+            share = {}
+            if l == 0 and need_dx:
+                for s, st in enumerate(plan.stacks):
+                    share.setdefault(tuple(ti for ti, _, _ in st.inputs), []).append(s)
+                share = {k: v for k, v in share.items() if len(v) > 1}
+            cat_img, cat_of = {}, {}
+            for key, members in share.items():
+                ktot = sum(lays[s].cout for s in members)
+                img = pm_empty(rows, ktot, dev)
+                col = 0
+                for s in members:
+                    cat_of[s] = (key, col, ktot)
+                    col += lays[s].cout
+                cat_img[key] = img
             items, dz_k, dz_t, colp = [], [], [], []
             for s, la in enumerate(lays):
                 cp_rows = _pad(la.cout, 128)
@@ -263,7 +297,10 @@ class _MlpStacksFn(torch.autograd.Function):
                     it["u"] = us[s]
                 if bns[s] is not None:
                     it.update(scale=bns[s][2], shift=bns[s][3], mean=bns[s][0], rstd=bns[s][1], s1=sums[s][0], s2=sums[s][1])
-                if need_dx:
+                if need_dx and s in cat_of:
+                    key, col, ktot = cat_of[s]
+                    it.update(out_k=cat_img[key], k_col0=col, k_cols=ktot)
+                elif need_dx:
                     it["out_k"] = pm_empty(rows, la.cout, dev)
                 if la.bias is not None:
                     it["col_partial"] = torch.empty(rows // 128, la.cout, **f32)
@@ -280,6 +317,9 @@ class _MlpStacksFn(torch.autograd.Function):
                 key = tuple(ti for ti, _, _ in st.inputs)
                 if l == 0 and key in shared:                  # stacks reading the same input share its image
                     x_t.append(shared[key])
+                    continue
+                if l > 0 and saved_t[l - 1][s] is not None:   # written by the forward's BatchNorm pass
+                    x_t.append((saved_t[l - 1][s], cin_pad))
                     continue
                 alloc = torch.empty if cin_pad == la.cin else torch.zeros
                 xt = alloc(b * cin_pad * n * 4, dtype=torch.uint8, device=dev)
@@ -342,24 +382,44 @@ class _MlpStacksFn(torch.autograd.Function):
                     acc(la.gamma, sums[s][1])
             # ---- dgrad: dX (b, cin_pad, n) = dZ W
             if need_dx:
-                wt = pack_weights([(tensors[la.w], la.cin, la.cout, _pad(la.cin, 64), la.cout, pick_nt(_pad(la.cin, 64)), True)
-                                   for la in lays])
-                probs, dxs = [], []
-                for s, la in enumerate(lays):
+                solo = [s for s in range(ns) if s not in cat_of]
+                wt = pack_weights([(tensors[lays[s].w], lays[s].cin, lays[s].cout, _pad(lays[s].cin, 64), lays[s].cout,
+                                    pick_nt(_pad(lays[s].cin, 64)), True) for s in solo])
+                probs, dxs = [], {}
+                for s, w in zip(solo, wt):
+                    la = lays[s]
                     cin_pad = _pad(la.cin, 64)
-                    dx = torch.empty(b, cin_pad, n, **f32)
-                    dxs.append(dx)
-                    lay = _gemm_layer(wt[s], cin_pad, la.cout, pick_nt(cin_pad))
-                    probs.append({"a0": dz_k[s], "layer": lay, "out_cm": dx, "rows_per_inst": n})
+                    dxs[s] = torch.empty(b, cin_pad, n, **f32)
+                    probs.append({"a0": dz_k[s], "layer": _gemm_layer(w, cin_pad, la.cout, pick_nt(cin_pad)),
+                                  "out_cm": dxs[s], "rows_per_inst": n})
+                shared_dx = {}
+                for key, members in share.items():
+                    la0 = lays[members[0]]
+                    cin_pad, ktot = _pad(la0.cin, 64), cat_of[members[0]][2]
+                    wcat = torch.empty(cin_pad * ktot * 4, dtype=torch.uint8, device=dev)
+                    pack_weights([(tensors[lays[s].w], la0.cin, lays[s].cout, cin_pad, lays[s].cout, pick_nt(cin_pad), True,
+                                   wcat, cat_of[s][1], ktot) for s in members])
+                    shared_dx[key] = torch.empty(b, cin_pad, n, **f32)
+                    probs.append({"a0": cat_img[key], "layer": _gemm_layer(wcat, cin_pad, ktot, pick_nt(cin_pad)),
+                                  "out_cm": shared_dx[key], "rows_per_inst": n})
                 _run_gemm_groups(probs, rows)
                 if l > 0:
-                    dys = [dx[:, :la.cin] for dx, la in zip(dxs, lays)]
+                    dys = [dxs[s][:, :lays[s].cin] for s in range(ns)]
                 else:
+                    done = set()
                     for s, st in enumerate(plan.stacks):
+                        key = tuple(ti for ti, _, _ in st.inputs)
+                        if key in shared_dx:
+                            if key in done:
+                                continue
+                            done.add(key)
+                            dx = shared_dx[key]
+                        else:
+                            dx = dxs[s]
                         c0 = 0
                         for ti, fmt, c in st.inputs:
                             if ctx.needs_input_grad[1 + ti]:
-                                g = dxs[s][:, c0:c0 + c]
+                                g = dx[:, c0:c0 + c]
                                 acc(ti, g if fmt == "cm" else g.permute(0, 2, 1).reshape(rows, c))
                             c0 += c
         return (None,) + tuple(out_grads)

@@ -609,6 +609,8 @@ typedef struct dcl_tr_wpack {
     int rows_pad, k_pad;
     int nt;
     int transpose;
+    int k_col0, k_total;   /* k_total > 0: the matrix becomes columns [k_col0, k_col0+k_pad) of a (rows_pad x k_total)
+                            * packed matrix (k_col0 % 32 == 0): weights concatenated along the reduction axis */
 } dcl_tr_wpack;
 int dcl_tr_pack_weights(int nitems, const dcl_tr_wpack* items, void* stream);
 /* out[c] = sum over the `parts` rows of partial (parts x c), in a fixed order: the bias gradients from the per-tile

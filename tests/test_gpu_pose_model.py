@@ -267,6 +267,17 @@ def test_conf_weights_kernel_vs_torch(cuda_dev, b, n):
     assert rel_err(torch.cat([w1.view(b, n), w2.view(b, n)], 1), want_sm) < 2e-6
 
 
+def _force_relu_gates(model, gates):
+    """Forward hooks that replace every nn.ReLU named in `gates` (name -> bool mask (b,c,n)) by a multiplication with
+    that mask: the comparison graph then takes the ReLU decisions of the implementation under test."""
+    def hook(name):
+        def fn(_mod, inp, _out):
+            g_ = gates[name]
+            return inp[0] * g_.view(g_.shape + (1,) * (inp[0].dim() - 3)).to(inp[0].dtype)
+        return fn
+    return [mod.register_forward_hook(hook(name)) for name, mod in model.named_modules() if name in gates]
+
+
 def test_training_step_gradients_match_oracle(cuda_dev):
     """Train mode (autograd on): the drop-in Network — fused FDA forward + FdaAlignFunction backward, torch-SVD pose
     — against the restated reference graph (bmm/softmax/svd autograd), same weights, same loss.  SURVEY.md config #5
@@ -319,18 +330,8 @@ def test_training_step_gradients_match_oracle(cuda_dev):
     gates = {name_of[mod]: mask for _, _, mask, mod in log}
     assert len(gates) == 8 * 2 + 4 * 2 + 2 * 3, len(gates)
 
-    def force_gates(model):
-        def hook(name):
-            def fn(_mod, inp, _out):
-                g_ = gates[name]
-                return inp[0] * g_.view(g_.shape + (1,) * (inp[0].dim() - 3)).to(inp[0].dtype)
-            return fn
-        for name, mod in model.named_modules():
-            if name in gates:
-                mod.register_forward_hook(hook(name))
-
-    force_gates(oracle_net)
-    force_gates(oracle64)
+    _force_relu_gates(oracle_net, gates)
+    _force_relu_gates(oracle64, gates)
     loss_ref = loss_fn(oracle_net(bb[0], bb[1], b, n, n))
     pts_tmp, rot_gt, trans_gt = pts_tmp.double(), rot_gt.double(), trans_gt.double()
     loss_64 = loss_fn(oracle64(cc[0], cc[1], b, n, n))
@@ -490,7 +491,19 @@ def test_refiner_backward_reaches_rotation_head(cuda_dev):
 
     def loss(out):
         return ((out["rot_pred"] - target) ** 2).sum() + out["trans_pred"].pow(2).sum()
-    loss(ref(inp)).backward()
+    # the shared MLP trains on the tensor-core kernels; the comparison graphs take its ReLU gates (6 M of them here: a
+    # few pre-activations always sit within rounding of zero — see test_training_step_gradients_match_oracle)
+    from dcl_net_b200 import train_tail
+    train_tail.GATE_LOG = log = []
+    try:
+        out_mine = ref(inp)
+    finally:
+        train_tail.GATE_LOG = None
+    name_of = {m: name for name, m in ref.named_modules()}
+    gates = {name_of[mod]: mask for _, _, mask, mod in log}
+    assert len(gates) == 3
+    _force_relu_gates(oracle_ref, gates)
+    loss(out_mine).backward()
     loss(oracle_ref(inp)).backward()
     want = dict(oracle_ref.named_parameters())
     seen = 0
@@ -501,6 +514,17 @@ def test_refiner_backward_reaches_rotation_head(cuda_dev):
             seen += 1
         assert rel_err(p.grad, want[name].grad) < 1e-3, name
     assert seen >= 6
+    # the same step with the shared MLP on the nn layer modules instead of the training kernels
+    import copy
+    layer_ref = copy.deepcopy(ref)
+    layer_ref.use_train_kernels = False
+    _force_relu_gates(layer_ref, gates)
+    for m_ in (ref, layer_ref):
+        m_.zero_grad()
+    loss(ref(inp)).backward()
+    loss(layer_ref(inp)).backward()
+    for (name, p), (_, q) in zip(ref.named_parameters(), layer_ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 1e-3, name
 
 
 def test_nearest_dist_propagates_nan(cuda_dev):
