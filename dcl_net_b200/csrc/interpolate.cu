@@ -373,6 +373,54 @@ __global__ void __launch_bounds__(IP_THREADS) three_interpolate_kernel(int c, in
     }
 }
 
+// Channel-interleaved form of the kernel above for groups of 8 channels: the staged rows are stored point-major,
+// s_il[point][8 channels] = two 16-byte halves per point, so that one query's three gathers are 6 LDS.128 instead of
+// 24 LDS.32 — the ~3.5-way bank conflicts of 32 random 4-byte gathers per instruction (ncu: 16 M conflict cycles per
+// launch at the microbench shape, the kernel's limiter at 38 % of the HBM roofline) become the ~2.4-way conflicts of 8
+// random 16-byte gathers per quarter-warp phase on a quarter of the instructions.  The two halves of a point are
+// swizzled (half h of point j at 16-byte slot 2j + (h ^ ((j >> 2) & 1))) so that a phase's eight lanes spread over all
+// eight slots mod 8, for the staging stores (consecutive j) as well as for the gathers.  Same fma order as above:
+// bit-identical results.
+__global__ void __launch_bounds__(IP_THREADS) three_interpolate_il8_kernel(int c, int m, int n, int n_per_cta,
+                                                                           const float* __restrict__ points,
+                                                                           const int* __restrict__ idx,
+                                                                           const float* __restrict__ weight,
+                                                                           float* __restrict__ out) {
+    extern __shared__ __align__(16) float4 s_il[];     // [m][2]
+    const int bs = blockIdx.z;
+    const int c0 = blockIdx.y * 8;
+    const int ncg = min(8, c - c0);
+    const float* src = points + ((size_t)bs * c + c0) * m;
+    for (int j = threadIdx.x; j < m; j += IP_THREADS) {
+        float v[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) v[cc] = cc < ncg ? __ldg(src + (size_t)cc * m + j) : 0.f;
+        const int sw = (j >> 2) & 1;
+        s_il[2 * j + sw] = make_float4(v[0], v[1], v[2], v[3]);
+        s_il[2 * j + (sw ^ 1)] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    idx += (size_t)bs * n * 3;
+    weight += (size_t)bs * n * 3;
+    out += ((size_t)bs * c + c0) * n;
+    const int i_begin = blockIdx.x * n_per_cta;
+    const int i_end = min(n, i_begin + n_per_cta);
+    for (int i = i_begin + threadIdx.x; i < i_end; i += IP_THREADS) {
+        const int j0 = idx[i * 3 + 0], j1 = idx[i * 3 + 1], j2 = idx[i * 3 + 2];
+        const float w0 = weight[i * 3 + 0], w1 = weight[i * 3 + 1], w2 = weight[i * 3 + 2];
+        const int s0 = (j0 >> 2) & 1, s1 = (j1 >> 2) & 1, s2 = (j2 >> 2) & 1;
+        const float4 a0 = s_il[2 * j0 + s0], a1 = s_il[2 * j1 + s1], a2 = s_il[2 * j2 + s2];
+        const float4 b0 = s_il[2 * j0 + (s0 ^ 1)], b1 = s_il[2 * j1 + (s1 ^ 1)], b2 = s_il[2 * j2 + (s2 ^ 1)];
+        const float r[8] = {dcl_interp3(w0, a0.x, w1, a1.x, w2, a2.x), dcl_interp3(w0, a0.y, w1, a1.y, w2, a2.y),
+                            dcl_interp3(w0, a0.z, w1, a1.z, w2, a2.z), dcl_interp3(w0, a0.w, w1, a1.w, w2, a2.w),
+                            dcl_interp3(w0, b0.x, w1, b1.x, w2, b2.x), dcl_interp3(w0, b0.y, w1, b1.y, w2, b2.y),
+                            dcl_interp3(w0, b0.z, w1, b1.z, w2, b2.z), dcl_interp3(w0, b0.w, w1, b1.w, w2, b2.w)};
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+            if (cc < ncg) dcl_st_stream_f1(out + (size_t)cc * n + i, r[cc]);
+    }
+}
+
 // ---- lane-per-channel backward (used when 32 transposed rows fit in shared memory) ----
 // The CG-row backward above scatters into row[j] with 32 random j per warp instruction: ~3.5-way conflicting
 // shared-memory atomics, three per element.  Here a CTA accumulates into acc_t[point][channel] (stride 33) and a
@@ -628,6 +676,13 @@ DCL_API int dcl_lib_three_interpolate_kernel_launcher_fast(int b, int c, int m, 
     const int per = pick_n_per_cta(n, ngroups * b);
     dim3 grid(DCL_DIVUP(n, per), ngroups, b);
     const size_t smem = (size_t)cg * m * 4;
+    // groups of 8 channels: the channel-interleaved kernel; DCL_INTERP_ROWS=1 keeps the row-staged one (A/B runs)
+    static const bool force_rows = getenv("DCL_INTERP_ROWS") != nullptr;
+    if (cg == 8 && !force_rows) {
+        allow_smem(three_interpolate_il8_kernel, smem);
+        three_interpolate_il8_kernel<<<grid, IP_THREADS, smem, st>>>(c, m, n, per, points, idx, weight, out);
+        return dcl_launch_status();
+    }
 #define DCL_LAUNCH_IP(CG)                                                                                       \
     allow_smem(three_interpolate_kernel<CG>, smem);                                                             \
     three_interpolate_kernel<CG><<<grid, IP_THREADS, smem, st>>>(c, m, n, per, points, idx, weight, out)
