@@ -1,7 +1,9 @@
 """Aggregate an ncu --csv metrics log of a step (training or inference) per kernel: launches, total duration, DRAM
 read / write, achieved DRAM GB/s, L2 bytes, warp instructions, tensor-pipe activity (duration-weighted).
-    python tools/summarize_step_ncu.py LOG.csv "title" [--last-fraction F]   (F: keep the last 1/F of the launches,
-    e.g. 2 for a log that holds a warm-up pass and the measured one)"""
+    python tools/summarize_step_ncu.py LOG.csv "title" [--last-fraction F] [--lib-only] [--last-n N]
+    --last-fraction F: keep the last 1/F of the launches (2 for a log holding a warm-up pass and the measured one);
+    --lib-only: this library's kernels only (anonymous-namespace names); --last-n N: the last N launches after that;
+    --from-last NAME: everything from the last launch whose kernel name contains NAME (the first kernel of a pass)."""
 import collections
 import csv
 import sys
@@ -19,7 +21,15 @@ def main():
         if len(r) > vi:
             d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = r[vi]
     items = sorted(d.items())
+    if "--lib-only" in sys.argv:
+        items = [it for it in items if "<unnamed>::" in it[0][1]]
     items = items[len(items) - len(items) // frac:]
+    if "--from-last" in sys.argv:
+        key = sys.argv[sys.argv.index("--from-last") + 1]
+        starts = [i for i, it in enumerate(items) if key in it[0][1]]
+        items = items[starts[-1]:]
+    if "--last-n" in sys.argv:
+        items = items[-int(sys.argv[sys.argv.index("--last-n") + 1]):]
     agg = collections.OrderedDict()
     for (_, k), m in items:
         g = lambda n: float(m.get(n, "0").replace(",", ""))
