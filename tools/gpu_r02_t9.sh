@@ -4,5 +4,5 @@ set +e
 N=$1
 O=gpurun_out
 if [ "$N" = "1" ]; then RUN="python"; else RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"; fi
-timeout 300 $RUN bench.py --gpus $N --config train --train-graph --steps 10 --warmup 3 > $O/r02z_train_graph_${N}gpu.json 2> $O/r02z_train_graph_${N}gpu.err
+timeout 300 $RUN bench.py --gpus $N --config train --steps 10 --warmup 3 > $O/r02z_train_graph_${N}gpu.json 2> $O/r02z_train_graph_${N}gpu.err
 cut -c1-250 $O/r02z_train_graph_${N}gpu.json; grep -o '"ms_per_step_without_allreduce.*' $O/r02z_train_graph_${N}gpu.json; grep -v Warning $O/r02z_train_graph_${N}gpu.err | tail -3
