@@ -189,3 +189,22 @@ def test_fda_arithmetic_emulated_on_cpu():
         for got, want in ((got_e, want_e), (got_i, want_i)):
             err = (got.double() - want).abs().max().item() / want.abs().max().item()
             assert err <= tol, (name, err)
+
+
+def test_pm_image_equals_packed_weights_of_ntile_128():
+    """What the training path's weight-gradient GEMM rests on (train_tail.py, csrc/train_ops.cu): the PM image of an
+    (R x C) matrix — byte(r,c,half) = ((r/128)(C/32) + c/32)*16384 + half*8192 + ((r%128)/8)*512 + ((c%32)/8)*128 +
+    (r%8)*16 + (c%8)*2 — is byte for byte the packed-weight layout with n-tile 128, so an operand image written by
+    the tile pass can be read by dcl_pm_gemm as its `w` operand."""
+    g = torch.Generator().manual_seed(1)
+    rows, c = 384, 96
+    x = torch.randn(rows, c, generator=g)
+    packed = FT.pack_weight(x, 128).view(torch.int16)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    r = torch.arange(rows).view(-1, 1).expand(rows, c)
+    ch = torch.arange(c).view(1, -1).expand(rows, c)
+    base = ((r // 128) * (c // 32) + ch // 32) * 16384 + ((r % 128) // 8) * 512 + ((ch % 32) // 8) * 128 + (r % 8) * 16 + (ch % 8) * 2
+    for half, img in ((0, hi), (1, lo)):
+        got = packed[((base + half * 8192) // 2).reshape(-1)].reshape(rows, c)
+        assert torch.equal(got, img.view(torch.int16))
