@@ -455,6 +455,9 @@ def run_b200_arm(args, rank, world, local_rank):
         #      count of this library's kernel launches per step
         modules.FDA_KERNEL_EVENTS = []
         fused_tail.GEMM_EVENTS = []
+        if from_points:
+            from dcl_net_b200 import backbone as backbone_mod
+            backbone_mod.CONV_EVENTS = []
         launches0 = lib.dcl_b200_launch_count()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -469,6 +472,9 @@ def run_b200_arm(args, rank, world, local_rank):
         fda_events, modules.FDA_KERNEL_EVENTS = modules.FDA_KERNEL_EVENTS, None
         fda_ms = [a.elapsed_time(bb) for a, bb, _ in fda_events]
         fda_jobs_per_launch = max([nj for _, _, nj in fda_events] or [1])
+        conv_events = []
+        if from_points:
+            conv_events, backbone_mod.CONV_EVENTS = backbone_mod.CONV_EVENTS, None
         gemm_events, fused_tail.GEMM_EVENTS = fused_tail.GEMM_EVENTS, None
         gemm = [(a.elapsed_time(bb), fl) for a, bb, fl, nt in gemm_events if nt == 256]   # the 256-wide-tile kernel
         # ---- timed region 1: device-resident, the step replayed as a CUDA graph (same kernels, one launch)
@@ -578,6 +584,29 @@ def run_b200_arm(args, rank, world, local_rank):
                     "launches_timed": len(fda_ms), "algorithmic_flops_per_launch": flops_per_launch,
                     "directions_per_launch": fda_jobs_per_launch,
                     "share_of_step": (sum(fda_ms) / ms_eager) if fda_ms else None}
+    roofline_spconv = None
+    if conv_events:
+        # the 16 sparse convolutions of both towers (8 launches per step, one per layer for the pair of towers):
+        # algorithmic FLOPs = 2 * (output row, kernel offset) pairs with an input voxel * c_in * c_out, pairs counted from
+        # the rulebooks of the timed inputs; fp16 activations x fp16 hi/lo weights = 2 MMAs per product
+        tw = engines[0].towers
+        pairs = {op: tw.rulebook_pairs(op) for op in sorted({op for _, _, op, _, _ in conv_events})}
+        conv_ms = [a.elapsed_time(bb) for a, bb, _, _, _ in conv_events]
+        conv_flops = sum(2.0 * pairs[op] * ci * co for _, _, op, ci, co in conv_events)
+        gather_bytes = sum(2.0 * pairs[op] * ci for _, _, op, ci, _ in conv_events)     # fp16 input rows gathered
+        conv_tf = conv_flops / (sum(conv_ms) * 1e-3) / 1e12
+        roofline_spconv = {"kernel": "sparse_conv3_kernel (8 launches per step: both towers per layer)", "bound": "tensor",
+                           "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
+                           "executed_frac": 2 * conv_tf / peak_tf, "mmas_per_product": 2,
+                           "algorithmic_flops_per_step": conv_flops / args.steps,
+                           "rulebook_pairs_per_step": sum(pairs[op] for _, _, op, _, _ in conv_events) / args.steps,
+                           "rulebook_pairs_source": "rulebooks of the last timed input set (the sets rotate; synthetic clouds "
+                                                    "of equal statistics)",
+                           "gathered_input_GBps": gather_bytes / (sum(conv_ms) * 1e-3) / 1e9,
+                           "ms_per_step": sum(conv_ms) / args.steps, "launches_timed": len(conv_ms),
+                           "share_of_step": sum(conv_ms) / ms_eager,
+                           "note": "the A operand is gathered row by row (16-byte cp.async pieces) from L2: the gather, "
+                                   "not the tensor pipe, paces these kernels (profiles/r02_trace_spconv_8warps.txt)"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -592,6 +621,8 @@ def run_b200_arm(args, rank, world, local_rank):
                 "streams": nstreams, "pose_gather": args.gather if world > 1 else None,
                 "ms_per_step_eager": ms_eager / args.steps, "clocks": clocks, "roofline": roofline,
                 "roofline_fda": roofline_fda}
+        if roofline_spconv is not None:
+            line["roofline_spconv"] = roofline_spconv
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)

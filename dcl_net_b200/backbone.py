@@ -27,6 +27,8 @@ import torch.nn as nn
 from . import _lib as L
 
 NSETS, NOPS = 9, 12
+# bench.py sets this to a list to collect (start event, end event, rulebook op, c_in, c_out) around every sparse-conv launch
+CONV_EVENTS = None
 DIMS = (7, 16, 32, 32, 64, 64, 128, 128, 256)
 
 
@@ -227,12 +229,16 @@ class SparseTowers:
                 w, shift = self.weights[k].layers[level][0]
                 src = t.feat16 if level == 0 else t.pool16[level - 1]
                 self._fill_conv(convs[k], t, src, 3 * level, s_out, w, shift, t.conv16[level], None)
+            ev = self._conv_event()
             L.check(lib.dcl_spb_conv3(b, 16 if level == 0 else c_in, c_mid, 2, ctypes.cast(convs, ctypes.c_void_p), st()),
                     "spb_conv3")
+            self._conv_event(ev, 3 * level, c_in, c_mid)
             for k, t in enumerate(self.t):
                 w, shift = self.weights[k].layers[level][1]
                 self._fill_conv(convs[k], t, t.conv16[level], 3 * level + 1, s_out, w, shift, None, t.subm32[level])
+            ev = self._conv_event()
             L.check(lib.dcl_spb_conv3(b, c_mid, c_out, 2, ctypes.cast(convs, ctypes.c_void_p), st()), "spb_conv3 (subm)")
+            self._conv_event(ev, 3 * level + 1, c_mid, c_out)
             pools = (L.SpbPool * 2)()
             for k, t in enumerate(self.t):
                 pools[k].inp, pools[k].nbr = L.ptr(t.subm32[level]), L.ptr(t.nbr[3 * level + 2])
@@ -242,6 +248,22 @@ class SparseTowers:
             L.check(lib.dcl_spb_avgpool(b, c_out, 2, ctypes.cast(pools, ctypes.c_void_p), st()), "spb_avgpool")
         return tuple([types.SimpleNamespace(features=t.pool32[level], indices=t.indices[2 * level + 2])
                       for level in range(4)] for t in self.t)
+
+    @staticmethod
+    def _conv_event(start=None, op=None, c_in=None, c_out=None):
+        """CONV_EVENTS bookkeeping: called without arguments before a launch (returns the start event) and with it after."""
+        if CONV_EVENTS is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            CONV_EVENTS.append((start, ev, op, c_in, c_out))
+        return ev
+
+    def rulebook_pairs(self, op):
+        """(output row, kernel offset) pairs with an input voxel in rulebook `op`, both towers: the multiply-accumulate
+        count of that layer is pairs * c_in * c_out (slot 27 of the tile-transposed table holds each row's count)."""
+        return int(sum(t.nbr[op].view(-1, 32, 128)[:, 27, :].sum().item() for t in self.t))
 
     def _fill_conv(self, slot, t, src16, op, s_out, w, shift, out16, out32):
         slot.in16, slot.nbr, slot.anymask = L.ptr(src16), L.ptr(t.nbr[op]), L.ptr(t.anymask[op])
