@@ -3,7 +3,9 @@
 Every op on the path is per object instance, so inference shards by contiguous instance ranges,
 one process per GPU, weights replicated, and needs no data-path collective; the only exchange is
 an optional all_gather of the (B/G, 12) poses.  The flat pointnet_sp tensors carry a batch id in
-column 0, which is re-based to the rank-local range.
+column 0, which is re-based to the rank-local range.  Training is data parallel: every rank steps on its own
+instances and the gradients are averaged by ONE all-reduce of a flat buffer (flat_grad_buffer / average_gradients) —
+what DDP's bucketed all-reduce computes, without per-bucket host work, so that the step itself can be a CUDA graph.
 """
 import torch
 import torch.distributed as dist
@@ -47,3 +49,29 @@ def gather_poses(rot, trans, total=None, equal_shards=False):
     dist.all_gather(bufs, padded)
     full = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
     return full[:, :9].reshape(-1, 3, 3), full[:, 9:]
+
+
+def flat_grad_buffer(params):
+    """One flat fp32 buffer holding every parameter's gradient: sets p.grad to views of it (autograd then accumulates
+    in place, at addresses that never change — what a captured CUDA graph needs) and returns the buffer.  Zero it at
+    the start of every step instead of calling zero_grad(set_to_none=True)."""
+    params = list(params)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
+
+
+def average_gradients(flat):
+    """In-place mean of the flat gradient buffer over the ranks: one all-reduce (NCCL: ReduceOp.AVG; backends without
+    AVG, e.g. gloo in the CPU tests: SUM then divide).  No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+    return flat

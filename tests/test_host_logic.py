@@ -139,3 +139,34 @@ def test_so3_projection_backward_closed_form_matches_svd_autograd():
         mine = so3_projection_backward(m.detach(), r.detach(), gr)
         assert (mine - m.grad).abs().max().item() < 1e-10 * max(1.0, m.grad.abs().max().item())
         assert torch.allclose(r.detach(), T.project_so3(m.detach()), atol=1e-12)
+
+
+def _dp_worker(rank, world, port):
+    """Data-parallel step with the flat gradient buffer (sharding.flat_grad_buffer / average_gradients): after the
+    all-reduce every rank holds the mean of the per-rank gradients, in the parameters' own .grad views."""
+    import torch.distributed as dist
+    from dcl_net_b200.sharding import average_gradients, flat_grad_buffer
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                                    # same parameters on every rank
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        flat = flat_grad_buffer(model.parameters())
+        assert flat.numel() == sum(p.numel() for p in model.parameters())
+        views = [p.grad.data_ptr() for p in model.parameters()]
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 + rank))   # different data per rank
+        for _ in range(2):                                      # second step: the buffer is zeroed, not replaced
+            flat.zero_()
+            model(x).square().sum().backward()
+            assert [p.grad.data_ptr() for p in model.parameters()] == views          # accumulated in place
+            local = flat.clone()
+            average_gradients(flat)
+            gathered = [torch.zeros_like(local) for _ in range(world)]
+            dist.all_gather(gathered, local)
+            assert torch.allclose(flat, sum(gathered) / world, atol=1e-6)
+            assert torch.equal(torch.cat([p.grad.reshape(-1) for p in model.parameters()]), flat)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_data_parallel_world2_gloo():
+    mp.spawn(_dp_worker, args=(2, _free_port()), nprocs=2, join=True)

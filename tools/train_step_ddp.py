@@ -119,12 +119,8 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
         return loss
 
     if graph:
-        params = list(net.parameters())
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-        off = 0
-        for p in params:                      # gradients accumulate in place into one flat buffer (static addresses)
-            p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        from dcl_net_b200.sharding import average_gradients, flat_grad_buffer
+        flat = flat_grad_buffer(net.parameters())   # gradients accumulate in place into one flat buffer (static addresses)
 
         def fwd_bwd():
             flat.zero_()
@@ -137,7 +133,7 @@ def run(batch, steps, warmup, rank, world, local, contract=False, layers=False, 
 
         def reduce_and_step(sync=True):
             if world > 1 and sync:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+                average_gradients(flat)
             opt.step()
 
         side = torch.cuda.Stream()
