@@ -170,3 +170,44 @@ def _dp_worker(rank, world, port):
 
 def test_flat_gradient_data_parallel_world2_gloo():
     mp.spawn(_dp_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_training_pointwise_backward_formulas():
+    """The pointwise backward transforms of csrc/train_ops.cu (modes DCL_TR_BWD_BN_RELU / DCL_TR_BWD_RELU_BN, with the
+    sums of tr_bn_bwd_reduce_kernel), restated in torch fp64, against autograd through train-mode BatchNorm + ReLU in
+    the two orders the reference uses (models/Modules.py:58-97: conv -> BN -> ReLU; :173-201: conv -> ReLU -> BN)."""
+    import torch
+    g = torch.Generator().manual_seed(11)
+    b, c, n, eps = 3, 8, 40, 1e-5
+    gamma = torch.rand(c, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(c, generator=g, dtype=torch.float64) * 0.3
+    dy = torch.randn(b, c, n, generator=g, dtype=torch.float64)
+    cnt = b * n
+
+    def stats(u):
+        mean = u.mean(dim=(0, 2))
+        rstd = 1.0 / torch.sqrt(u.var(dim=(0, 2), unbiased=False) + eps)
+        scale = gamma * rstd
+        return mean, rstd, scale, beta - mean * scale
+
+    v = lambda t: t.view(1, c, 1)
+    # conv -> BN -> ReLU: U = conv output
+    u = torch.randn(b, c, n, generator=g, dtype=torch.float64, requires_grad=True)
+    y = torch.relu(torch.nn.functional.batch_norm(u, None, None, gamma, beta, True, 0.1, eps))
+    y.backward(dy)
+    mean, rstd, scale, shift = stats(u.detach())
+    xhat = (u.detach() - v(mean)) * v(rstd)
+    gte = torch.where(u.detach() * v(scale) + v(shift) > 0, dy, torch.zeros_like(dy))
+    s1, s2 = gte.sum(dim=(0, 2)), (gte * xhat).sum(dim=(0, 2))
+    dz = v(scale) * (gte - v(s1) / cnt - xhat * v(s2) / cnt)
+    assert torch.allclose(dz, u.grad, atol=1e-12)
+    # conv + bias -> ReLU -> BN: U = relu(conv output + bias); z = the pre-activation
+    z = torch.randn(b, c, n, generator=g, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.batch_norm(torch.relu(z), None, None, gamma, beta, True, 0.1, eps)
+    y.backward(dy)
+    uu = torch.relu(z.detach())
+    mean, rstd, scale, shift = stats(uu)
+    xhat = (uu - v(mean)) * v(rstd)
+    s1, s2 = dy.sum(dim=(0, 2)), (dy * xhat).sum(dim=(0, 2))
+    dz = torch.where(uu > 0, v(scale) * (dy - v(s1) / cnt - xhat * v(s2) / cnt), torch.zeros_like(dy))
+    assert torch.allclose(dz, z.grad, atol=1e-12)
