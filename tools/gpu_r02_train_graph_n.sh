@@ -1,5 +1,5 @@
 #!/bin/bash
-# graph-mode training step on N GPUs (N=1: plain python): bash tools/gpu_r02_t9.sh N
+# graph-mode training step (one CUDA graph + flat-gradient all-reduce) on N GPUs (N=1: plain python): bash tools/gpu_r02_train_graph_n.sh N
 set +e
 N=$1
 O=gpurun_out
